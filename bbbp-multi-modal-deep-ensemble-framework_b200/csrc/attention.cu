@@ -1,0 +1,336 @@
+// Cross-molecule self-attention of the fingerprint encoder: nn.TransformerEncoder is built
+// with batch_first=False at 20250113.py:75-78 and fed (B,1,F) at :110-111, so the sequence axis IS the
+// reference mini-batch.  One launch covers `groups` independent reference batches of `seq` molecules.
+// Streaming (online) softmax, fp32 CUDA cores: S x S scores are never materialised.
+#include <math.h>
+#include "common.cuh"
+
+namespace bbbp {
+
+constexpr int KT = 32;      // keys (or queries) per shared-memory tile
+constexpr int MAX_DT = 8;   // head_dim <= 256
+constexpr int ATT_WARPS = 4;
+
+// Keep mask of attention-probability dropout: one Philox-4x32-10 block per (row, key, head) triple.
+__device__ __forceinline__ uint32_t philox_first_word(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr.x;
+}
+// multiplier applied to probability (query row, key row) of head h: 0 or 1/(1-p); 1 when p == 0
+__device__ __forceinline__ float keep_scale(float p, float inv_keep, uint64_t seed, size_t qrow, size_t krow, int h) {
+  if (p <= 0.0f) return 1.0f;
+  uint32_t r = philox_first_word(make_uint4((uint32_t)qrow, (uint32_t)krow, (uint32_t)h, (uint32_t)(qrow >> 32)),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return (r * 2.3283064365386963e-10f) >= p ? inv_keep : 0.0f;
+}
+
+// dynamic smem layout (floats): Ks[KT][ld] | Vs[KT][ld] | qs[ATT_WARPS][ld]
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const float* __restrict__ qkv,
+                                                                       float* __restrict__ out, float* __restrict__ lse,
+                                                                       int seq, int heads, int d, int q_per_block,
+                                                                       float drop_p, uint64_t seed) {
+  extern __shared__ float smem[];
+  const int ld = d | 1;  // odd pitch: conflict-free row-per-lane reads
+  float* Ks = smem;
+  float* Vs = Ks + KT * ld;
+  float* qs = Vs + KT * ld;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int h = blockIdx.y, g = blockIdx.z;
+  const int E = heads * d, ldq = 3 * E;
+  const size_t row0 = (size_t)g * seq;
+  const float scale = rsqrtf((float)d);
+  const float inv_keep = 1.0f / (1.0f - drop_p);
+  const int qbase = blockIdx.x * q_per_block;
+  const int nq = min(q_per_block, seq - qbase);
+  const int q_iters = ceil_div(nq, ATT_WARPS);
+
+  for (int it = 0; it < q_iters; ++it) {
+    const int qi = qbase + it * ATT_WARPS + warp;
+    const bool active = qi < qbase + nq;
+    if (active)
+      for (int dd = lane; dd < d; dd += 32) qs[warp * ld + dd] = qkv[(row0 + qi) * ldq + h * d + dd] * scale;
+    float m = -INFINITY, l = 0.0f, o[MAX_DT];
+#pragma unroll
+    for (int t = 0; t < MAX_DT; ++t) o[t] = 0.0f;
+
+    for (int k0 = 0; k0 < seq; k0 += KT) {
+      __syncthreads();  // previous tile fully consumed (and qs visible)
+      for (int i = threadIdx.x; i < KT * d; i += ATT_WARPS * 32) {
+        int j = i / d, dd = i % d;
+        bool ok = k0 + j < seq;
+        const float* src = qkv + (row0 + k0 + j) * ldq + h * d + dd;
+        Ks[j * ld + dd] = ok ? src[E] : 0.0f;
+        Vs[j * ld + dd] = ok ? src[2 * E] : 0.0f;
+      }
+      __syncthreads();
+      if (!active) continue;
+      float s = 0.0f;
+      for (int dd = 0; dd < d; ++dd) s = fmaf(qs[warp * ld + dd], Ks[lane * ld + dd], s);
+      if (k0 + lane >= seq) s = -INFINITY;
+      const float m_new = fmaxf(m, warp_max(s));
+      const float alpha = __expf(m - m_new);  // m == -inf on the first tile -> 0
+      const float p = __expf(s - m_new);
+      l = l * alpha + warp_sum(p);
+      m = m_new;
+      // dropout acts on the normalised probabilities: the normaliser l keeps every key
+      const float pd = p * keep_scale(drop_p, inv_keep, seed, row0 + qi, row0 + k0 + lane, h);
+#pragma unroll
+      for (int t = 0; t < MAX_DT; ++t) o[t] *= alpha;
+      for (int j = 0; j < KT; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, pd, j);
+#pragma unroll
+        for (int t = 0; t < MAX_DT; ++t) {
+          int dd = lane + 32 * t;
+          if (dd < d) o[t] = fmaf(pj, Vs[j * ld + dd], o[t]);
+        }
+      }
+    }
+    if (active) {
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int t = 0; t < MAX_DT; ++t) {
+        int dd = lane + 32 * t;
+        if (dd < d) out[(row0 + qi) * E + h * d + dd] = o[t] * inv;
+      }
+      if (lse && lane == 0) lse[(row0 + qi) * heads + h] = m + __logf(l);
+    }
+  }
+}
+
+// dQ: one warp per query row, streaming over key tiles.
+// smem: Ks | Vs | qs[W][ld] | dos[W][ld]
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dq_kernel(const float* __restrict__ qkv,
+                                                                          const float* __restrict__ out,
+                                                                          const float* __restrict__ lse,
+                                                                          const float* __restrict__ dout,
+                                                                          float* __restrict__ dqkv, int seq, int heads,
+                                                                          int d, int q_per_block, float drop_p,
+                                                                          uint64_t seed) {
+  const float inv_keep = 1.0f / (1.0f - drop_p);
+  extern __shared__ float smem[];
+  const int ld = d | 1;
+  float* Ks = smem;
+  float* Vs = Ks + KT * ld;
+  float* qs = Vs + KT * ld;
+  float* dos = qs + ATT_WARPS * ld;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int h = blockIdx.y, g = blockIdx.z;
+  const int E = heads * d, ldq = 3 * E;
+  const size_t row0 = (size_t)g * seq;
+  const float scale = rsqrtf((float)d);
+  const int qbase = blockIdx.x * q_per_block;
+  const int nq = min(q_per_block, seq - qbase);
+  const int q_iters = ceil_div(nq, ATT_WARPS);
+
+  for (int it = 0; it < q_iters; ++it) {
+    const int qi = qbase + it * ATT_WARPS + warp;
+    const bool active = qi < qbase + nq;
+    float D = 0.0f, L = 0.0f;
+    if (active) {
+      for (int dd = lane; dd < d; dd += 32) {
+        qs[warp * ld + dd] = qkv[(row0 + qi) * ldq + h * d + dd] * scale;
+        float go = dout[(row0 + qi) * E + h * d + dd];
+        dos[warp * ld + dd] = go;
+        D = fmaf(go, out[(row0 + qi) * E + h * d + dd], D);
+      }
+      D = warp_sum(D);
+      L = lse[(row0 + qi) * heads + h];
+    }
+    float dq[MAX_DT];
+#pragma unroll
+    for (int t = 0; t < MAX_DT; ++t) dq[t] = 0.0f;
+    for (int k0 = 0; k0 < seq; k0 += KT) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < KT * d; i += ATT_WARPS * 32) {
+        int j = i / d, dd = i % d;
+        bool ok = k0 + j < seq;
+        const float* src = qkv + (row0 + k0 + j) * ldq + h * d + dd;
+        Ks[j * ld + dd] = ok ? src[E] : 0.0f;
+        Vs[j * ld + dd] = ok ? src[2 * E] : 0.0f;
+      }
+      __syncthreads();
+      if (!active) continue;
+      float s = 0.0f, dp = 0.0f;
+      for (int dd = 0; dd < d; ++dd) {
+        s = fmaf(qs[warp * ld + dd], Ks[lane * ld + dd], s);
+        dp = fmaf(dos[warp * ld + dd], Vs[lane * ld + dd], dp);
+      }
+      const float p = (k0 + lane < seq) ? __expf(s - L) : 0.0f;
+      const float ds = p * (dp * keep_scale(drop_p, inv_keep, seed, row0 + qi, row0 + k0 + lane, h) - D);
+      for (int j = 0; j < KT; ++j) {
+        const float dsj = __shfl_sync(0xffffffffu, ds, j);
+#pragma unroll
+        for (int t = 0; t < MAX_DT; ++t) {
+          int dd = lane + 32 * t;
+          if (dd < d) dq[t] = fmaf(dsj, Ks[j * ld + dd], dq[t]);
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < MAX_DT; ++t) {
+        int dd = lane + 32 * t;
+        if (dd < d) dqkv[(row0 + qi) * ldq + h * d + dd] = dq[t] * scale;
+      }
+    }
+  }
+}
+
+// dK, dV: one warp per key row, streaming over query tiles.
+// smem: Qs[KT][ld] (pre-scaled) | dOs[KT][ld] | ks[W][ld] | vs[W][ld] | Ls[KT] | Ds[KT]
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dkv_kernel(const float* __restrict__ qkv,
+                                                                           const float* __restrict__ out,
+                                                                           const float* __restrict__ lse,
+                                                                           const float* __restrict__ dout,
+                                                                           float* __restrict__ dqkv, int seq, int heads,
+                                                                           int d, int k_per_block, float drop_p,
+                                                                           uint64_t seed) {
+  const float inv_keep = 1.0f / (1.0f - drop_p);
+  extern __shared__ float smem[];
+  const int ld = d | 1;
+  float* Qs = smem;
+  float* dOs = Qs + KT * ld;
+  float* ks = dOs + KT * ld;
+  float* vs = ks + ATT_WARPS * ld;
+  float* Ls = vs + ATT_WARPS * ld;
+  float* Ds = Ls + KT;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int h = blockIdx.y, g = blockIdx.z;
+  const int E = heads * d, ldq = 3 * E;
+  const size_t row0 = (size_t)g * seq;
+  const float scale = rsqrtf((float)d);
+  const int kbase = blockIdx.x * k_per_block;
+  const int nk = min(k_per_block, seq - kbase);
+  const int k_iters = ceil_div(nk, ATT_WARPS);
+
+  for (int it = 0; it < k_iters; ++it) {
+    const int kj = kbase + it * ATT_WARPS + warp;
+    const bool active = kj < kbase + nk;
+    if (active)
+      for (int dd = lane; dd < d; dd += 32) {
+        ks[warp * ld + dd] = qkv[(row0 + kj) * ldq + E + h * d + dd];
+        vs[warp * ld + dd] = qkv[(row0 + kj) * ldq + 2 * E + h * d + dd];
+      }
+    float dk[MAX_DT], dv[MAX_DT];
+#pragma unroll
+    for (int t = 0; t < MAX_DT; ++t) dk[t] = dv[t] = 0.0f;
+    for (int q0 = 0; q0 < seq; q0 += KT) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < KT * d; i += ATT_WARPS * 32) {
+        int j = i / d, dd = i % d;
+        bool ok = q0 + j < seq;
+        Qs[j * ld + dd] = ok ? qkv[(row0 + q0 + j) * ldq + h * d + dd] * scale : 0.0f;
+        dOs[j * ld + dd] = ok ? dout[(row0 + q0 + j) * E + h * d + dd] : 0.0f;
+      }
+      __syncthreads();
+      // D_i = <dO_i, O_i> and lse_i for the tile: warp w covers queries w*8 .. w*8+7
+      for (int jj = 0; jj < KT / ATT_WARPS; ++jj) {
+        int j = warp * (KT / ATT_WARPS) + jj;
+        float acc = 0.0f;
+        if (q0 + j < seq)
+          for (int dd = lane; dd < d; dd += 32) acc = fmaf(dOs[j * ld + dd], out[(row0 + q0 + j) * E + h * d + dd], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          Ds[j] = acc;
+          Ls[j] = (q0 + j < seq) ? lse[(row0 + q0 + j) * heads + h] : 0.0f;
+        }
+      }
+      __syncthreads();
+      if (!active) continue;
+      float s = 0.0f, dp = 0.0f;
+      for (int dd = 0; dd < d; ++dd) {
+        s = fmaf(Qs[lane * ld + dd], ks[warp * ld + dd], s);
+        dp = fmaf(dOs[lane * ld + dd], vs[warp * ld + dd], dp);
+      }
+      const float p = (q0 + lane < seq) ? __expf(s - Ls[lane]) : 0.0f;
+      const float keep = keep_scale(drop_p, inv_keep, seed, row0 + q0 + lane, row0 + kj, h);
+      const float ds = p * (dp * keep - Ds[lane]);
+      const float pk = p * keep;
+      for (int i = 0; i < KT; ++i) {
+        const float pi = __shfl_sync(0xffffffffu, pk, i);
+        const float dsi = __shfl_sync(0xffffffffu, ds, i);
+#pragma unroll
+        for (int t = 0; t < MAX_DT; ++t) {
+          int dd = lane + 32 * t;
+          if (dd < d) {
+            dv[t] = fmaf(pi, dOs[i * ld + dd], dv[t]);
+            dk[t] = fmaf(dsi, Qs[i * ld + dd], dk[t]);  // Qs already carries the 1/sqrt(d) factor
+          }
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < MAX_DT; ++t) {
+        int dd = lane + 32 * t;
+        if (dd < d) {
+          dqkv[(row0 + kj) * ldq + E + h * d + dd] = dk[t];
+          dqkv[(row0 + kj) * ldq + 2 * E + h * d + dd] = dv[t];
+        }
+      }
+    }
+  }
+}
+
+static int attention_args_ok(const char* who, int groups, int seq, int heads, int d) {
+  if (groups < 0 || seq <= 0 || heads <= 0 || d <= 0 || d > 32 * MAX_DT) {
+    set_error("%s: groups=%d seq=%d heads=%d head_dim=%d unsupported (head_dim <= %d)", who, groups, seq, heads, d,
+              32 * MAX_DT);
+    return 0;
+  }
+  if (heads > 65535 || groups > 65535) {
+    set_error("%s: heads/groups exceed 65535", who);
+    return 0;
+  }
+  return 1;
+}
+
+}  // namespace bbbp
+
+extern "C" int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, int groups, int seq, int heads,
+                                      int head_dim, float dropout_p, uint64_t seed, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(qkv && out, "attention_fwd: null operand");
+  BBBP_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f, "attention_fwd: dropout_p must be in [0,1)");
+  if (!attention_args_ok("attention_fwd", groups, seq, heads, head_dim)) return BBBP_EINVAL;
+  if (groups == 0) return BBBP_OK;
+  const int ld = head_dim | 1;
+  const int qpb = 16;
+  size_t smem = (size_t)(2 * KT + ATT_WARPS) * ld * sizeof(float);
+  cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(ceil_div(seq, qpb), heads, groups);
+  attention_fwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(qkv, out, lse, seq, heads, head_dim, qpb,
+                                                                          dropout_p, seed);
+  return launch_status("attention_fwd");
+}
+
+extern "C" int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout,
+                                      float* dqkv, int groups, int seq, int heads, int head_dim, float dropout_p,
+                                      uint64_t seed, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(qkv && out && lse && dout && dqkv, "attention_bwd: null operand");
+  if (!attention_args_ok("attention_bwd", groups, seq, heads, head_dim)) return BBBP_EINVAL;
+  if (groups == 0) return BBBP_OK;
+  const int ld = head_dim | 1;
+  const int per_block = 16;
+  dim3 grid(ceil_div(seq, per_block), heads, groups);
+  size_t smem_q = (size_t)(2 * KT + 2 * ATT_WARPS) * ld * sizeof(float);
+  cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
+  attention_bwd_dq_kernel<<<grid, ATT_WARPS * 32, smem_q, as_stream(stream)>>>(qkv, out, lse, dout, dqkv, seq, heads,
+                                                                               head_dim, per_block, dropout_p, seed);
+  int st = launch_status("attention_bwd dq");
+  if (st != BBBP_OK) return st;
+  size_t smem_kv = ((size_t)(2 * KT + 2 * ATT_WARPS) * ld + 2 * KT) * sizeof(float);
+  cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
+  attention_bwd_dkv_kernel<<<grid, ATT_WARPS * 32, smem_kv, as_stream(stream)>>>(qkv, out, lse, dout, dqkv, seq, heads,
+                                                                                 head_dim, per_block, dropout_p, seed);
+  return launch_status("attention_bwd dkv");
+}

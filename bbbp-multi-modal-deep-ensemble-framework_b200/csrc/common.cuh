@@ -1,0 +1,48 @@
+// Shared helpers for the bbbp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/bbbp_b200.h"
+
+namespace bbbp {
+
+// thread-local error string behind bbbp_last_error()
+void set_error(const char* fmt, ...);
+// cudaGetLastError() after a launch -> BBBP_OK / BBBP_ECUDA (message recorded)
+int launch_status(const char* what);
+
+inline cudaStream_t as_stream(bbbp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kWarp = 32;
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == BBBP_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == BBBP_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+}  // namespace bbbp
+
+#define BBBP_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      bbbp::set_error(__VA_ARGS__);          \
+      return BBBP_EINVAL;                    \
+    }                                        \
+  } while (0)

@@ -1,0 +1,254 @@
+// fp32 CUDA-core 3x3 convolution family (validation / training path).
+// Forward: conv(k3,s1,p1) + bias + ReLU + MaxPool2d(2) fused -- the pre-pool activation (2 MB per molecule
+// for conv1) never reaches HBM.  Reference call sites: 20250113.py:85-90, 20250107_network.py:133-141.
+#include "common.cuh"
+
+namespace bbbp {
+
+constexpr int CI_CHUNK = 8;
+
+// block: 256 threads = 64 pooling windows (16x16 pre-pool tile) x 4 channel groups of CPT channels
+template <int CPT>
+__global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y,
+                                                          uint8_t* __restrict__ argmax, int Cin, int Cout, int H, int W,
+                                                          int pool) {
+  constexpr int CB = 4 * CPT;  // channels per block
+  __shared__ float xs[CI_CHUNK][18][18];
+  __shared__ float ws[CI_CHUNK][9][CB];
+  const int tid = threadIdx.x;
+  const int tiles_x = W / 16;
+  const int tx0 = (blockIdx.x % tiles_x) * 16, ty0 = (blockIdx.x / tiles_x) * 16;
+  const int co0 = blockIdx.y * CB;
+  const int n = blockIdx.z;
+  const int wq = tid % 64, cg = tid / 64;
+  const int wx = wq % 8, wy = wq / 8;
+  float acc[CPT][4];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[c][p] = 0.0f;
+
+  const float* xn = x + (size_t)n * Cin * H * W;
+  for (int ci0 = 0; ci0 < Cin; ci0 += CI_CHUNK) {
+    const int nci = min(CI_CHUNK, Cin - ci0);
+    for (int i = tid; i < nci * 324; i += 256) {
+      int ci = i / 324, r = (i % 324) / 18, c = i % 18;
+      int gy = ty0 + r - 1, gx = tx0 + c - 1;
+      xs[ci][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xn[((size_t)(ci0 + ci) * H + gy) * W + gx] : 0.0f;
+    }
+    for (int i = tid; i < nci * 9 * CB; i += 256) {
+      int co = i % CB, tap = (i / CB) % 9, ci = i / (CB * 9);
+      ws[ci][tap][co] = w[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + tap];
+    }
+    __syncthreads();
+    for (int ci = 0; ci < nci; ++ci) {
+      float p[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[i][j] = xs[ci][2 * wy + i][2 * wx + j];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            float wv = ws[ci][kh * 3 + kw][cg * CPT + c];
+            acc[c][0] = fmaf(p[kh][kw], wv, acc[c][0]);
+            acc[c][1] = fmaf(p[kh][kw + 1], wv, acc[c][1]);
+            acc[c][2] = fmaf(p[kh + 1][kw], wv, acc[c][2]);
+            acc[c][3] = fmaf(p[kh + 1][kw + 1], wv, acc[c][3]);
+          }
+    }
+    __syncthreads();
+  }
+
+  const int gy = ty0 + 2 * wy, gx = tx0 + 2 * wx;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int co = co0 + cg * CPT + c;
+    const float b = bias ? bias[co] : 0.0f;
+    if (pool) {
+      float best = fmaxf(acc[c][0] + b, 0.0f);
+      int arg = 0;
+#pragma unroll
+      for (int p = 1; p < 4; ++p) {
+        float v = fmaxf(acc[c][p] + b, 0.0f);
+        if (v > best) { best = v; arg = p; }
+      }
+      size_t o = (((size_t)n * Cout + co) * (H / 2) + gy / 2) * (W / 2) + gx / 2;
+      y[o] = best;
+      if (argmax) argmax[o] = (uint8_t)arg;
+    } else {
+      float* yo = y + (((size_t)n * Cout + co) * H + gy) * W + gx;
+      yo[0] = acc[c][0] + b;
+      yo[1] = acc[c][1] + b;
+      yo[W] = acc[c][2] + b;
+      yo[W + 1] = acc[c][3] + b;
+    }
+  }
+}
+
+__global__ void relu_pool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                     const uint8_t* __restrict__ argmax, float* __restrict__ dpre, size_t total, int H,
+                                     int W) {
+  // one thread per pooled element; writes its 2x2 window
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int PW = W / 2, PH = H / 2;
+  int pw = i % PW, ph = (i / PW) % PH;
+  size_t plane = i / ((size_t)PW * PH);
+  float g = y[i] > 0.0f ? dy[i] : 0.0f;
+  int a = argmax[i];
+  float* o = dpre + (plane * H + 2 * ph) * W + 2 * pw;
+  o[0] = a == 0 ? g : 0.0f;
+  o[1] = a == 1 ? g : 0.0f;
+  o[W] = a == 2 ? g : 0.0f;
+  o[W + 1] = a == 3 ? g : 0.0f;
+}
+
+// per-image partial weight gradient: block = (ci tile of 16, co tile of 16, image); thread = (co, ci), 9 taps
+__global__ void __launch_bounds__(256) conv3x3_wgrad_partial_kernel(const float* __restrict__ dpre,
+                                                                    const float* __restrict__ x,
+                                                                    float* __restrict__ part, int Cin, int Cout, int H,
+                                                                    int W) {
+  __shared__ float ds[16][256];
+  __shared__ float xs[16][18][18];
+  const int tid = threadIdx.x;
+  const int ci0 = blockIdx.x * 16, co0 = blockIdx.y * 16, n = blockIdx.z;
+  const int ci_l = tid % 16, co_l = tid / 16;
+  float acc[9] = {};
+  const float* xn = x + (size_t)n * Cin * H * W;
+  const float* dn = dpre + (size_t)n * Cout * H * W;
+  const int nci = min(16, Cin - ci0);
+  for (int ty0 = 0; ty0 < H; ty0 += 16)
+    for (int tx0 = 0; tx0 < W; tx0 += 16) {
+      for (int i = tid; i < 16 * 256; i += 256) {
+        int co = i / 256, p = i % 256;
+        ds[co][p] = dn[((size_t)(co0 + co) * H + ty0 + p / 16) * W + tx0 + p % 16];
+      }
+      for (int i = tid; i < 16 * 324; i += 256) {
+        int ci = i / 324, r = (i % 324) / 18, c = i % 18;
+        int gy = ty0 + r - 1, gx = tx0 + c - 1;
+        xs[ci][r][c] =
+            (ci < nci && gy >= 0 && gy < H && gx >= 0 && gx < W) ? xn[((size_t)(ci0 + ci) * H + gy) * W + gx] : 0.0f;
+      }
+      __syncthreads();
+      for (int p = 0; p < 256; ++p) {
+        const float d = ds[co_l][p];
+        const int py = p / 16, px = p % 16;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf(d, xs[ci_l][py + kh][px + kw], acc[kh * 3 + kw]);
+      }
+      __syncthreads();
+    }
+  if (ci_l < nci) {
+    float* o = part + (((size_t)n * Cout + co0 + co_l) * Cin + ci0 + ci_l) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) o[t] = acc[t];
+  }
+}
+
+// bias-gradient partial: block = (co, n) -> part_b[n][co] = sum over the plane, fixed reduction tree
+__global__ void __launch_bounds__(256) conv_bgrad_partial_kernel(const float* __restrict__ dpre, float* __restrict__ part_b,
+                                                                 int Cout, int HW) {
+  __shared__ float red[8];
+  const int co = blockIdx.x, n = blockIdx.y;
+  const float* d = dpre + ((size_t)n * Cout + co) * HW;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < HW; i += 256) s += d[i];
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    part_b[(size_t)n * Cout + co] = t;
+  }
+}
+
+__global__ void sum_over_images_kernel(const float* __restrict__ part, float* __restrict__ out, int N, size_t per_image) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= per_image) return;
+  float s = 0.0f;
+  for (int n = 0; n < N; ++n) s += part[(size_t)n * per_image + i];
+  out[i] = s;
+}
+
+__global__ void flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cin * Cout * 9) return;
+  int tap = i % 9, co = (i / 9) % Cout, ci = i / (9 * Cout);  // wt[ci][co][tap]
+  wt[i] = w[((size_t)co * Cin + ci) * 9 + (8 - tap)];
+}
+
+}  // namespace bbbp
+
+extern "C" int bbbp_conv3x3_f32(const float* x, const float* w, const float* b, float* y, uint8_t* argmax, int N,
+                                int Cin, int Cout, int H, int W, int pool, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(x && w && y, "conv3x3_f32: null operand");
+  BBBP_CHECK_ARG(N >= 0 && Cin > 0 && Cout > 0 && Cout % 32 == 0, "conv3x3_f32: Cout=%d must be a multiple of 32", Cout);
+  BBBP_CHECK_ARG(H > 0 && W > 0 && H % 16 == 0 && W % 16 == 0, "conv3x3_f32: H=%d W=%d must be multiples of 16", H, W);
+  if (N == 0) return BBBP_OK;
+  BBBP_CHECK_ARG(N <= 65535, "conv3x3_f32: N=%d exceeds 65535 images per launch", N);
+  cudaStream_t s = as_stream(stream);
+  if (Cout % 64 == 0) {
+    dim3 grid((H / 16) * (W / 16), Cout / 64, N);
+    conv3x3_f32_kernel<16><<<grid, 256, 0, s>>>(x, w, b, y, argmax, Cin, Cout, H, W, pool);
+  } else {
+    dim3 grid((H / 16) * (W / 16), Cout / 32, N);
+    conv3x3_f32_kernel<8><<<grid, 256, 0, s>>>(x, w, b, y, argmax, Cin, Cout, H, W, pool);
+  }
+  return launch_status("conv3x3_f32");
+}
+
+extern "C" int bbbp_relu_pool_bwd_f32(const float* dy, const float* y, const uint8_t* argmax, float* dpre, int N, int C,
+                                      int H, int W, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(dy && y && argmax && dpre, "relu_pool_bwd: null operand");
+  BBBP_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "relu_pool_bwd: odd plane");
+  size_t total = (size_t)N * C * (H / 2) * (W / 2);
+  if (total == 0) return BBBP_OK;
+  relu_pool_bwd_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(dy, y, argmax, dpre, total,
+                                                                                               H, W);
+  return launch_status("relu_pool_bwd");
+}
+
+extern "C" int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* dw, float* db, int N, int Cin, int Cout,
+                                      int H, int W, float* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(dpre && x && dw, "conv3x3_wgrad: null operand");
+  BBBP_CHECK_ARG(Cout % 16 == 0 && H % 16 == 0 && W % 16 == 0, "conv3x3_wgrad: Cout/H/W must be multiples of 16");
+  BBBP_CHECK_ARG(N > 0 && N <= 65535, "conv3x3_wgrad: N=%d out of range", N);
+  size_t per_w = (size_t)Cout * Cin * 9, per_b = Cout;
+  size_t need = (size_t)N * (per_w + per_b) * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("conv3x3_wgrad: needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    return BBBP_EWORKSPACE;
+  }
+  cudaStream_t s = as_stream(stream);
+  float* part_w = workspace;
+  float* part_b = workspace + (size_t)N * per_w;
+  dim3 grid(ceil_div(Cin, 16), Cout / 16, N);
+  conv3x3_wgrad_partial_kernel<<<grid, 256, 0, s>>>(dpre, x, part_w, Cin, Cout, H, W);
+  int st = launch_status("conv3x3_wgrad partial");
+  if (st != BBBP_OK) return st;
+  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)256), 256, 0, s>>>(part_w, dw, N, per_w);
+  st = launch_status("conv3x3_wgrad reduce");
+  if (st != BBBP_OK || !db) return st;
+  conv_bgrad_partial_kernel<<<dim3(Cout, N), 256, 0, s>>>(dpre, part_b, Cout, H * W);
+  sum_over_images_kernel<<<(unsigned)ceil_div(per_b, (size_t)256), 256, 0, s>>>(part_b, db, N, per_b);
+  return launch_status("conv3x3 bias grad");
+}
+
+extern "C" int bbbp_conv3x3_flip_weights_f32(const float* w, float* w_t, int Cin, int Cout, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(w && w_t && Cin > 0 && Cout > 0, "flip_weights: bad argument");
+  int total = Cin * Cout * 9;
+  flip_weights_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, w_t, Cin, Cout);
+  return launch_status("flip_weights");
+}

@@ -1,0 +1,436 @@
+// Memory-bound kernels of the hot path: fusion-block mixing, activation gradients, column reductions,
+// dropout, losses, fused multi-tensor AdamW, and the packed-input contracts.  All single pass, coalesced,
+// warp-shuffle reductions, deterministic (no floating-point atomics anywhere).
+#include <math.h>
+#include "common.cuh"
+
+namespace bbbp {
+
+// ---- fusion: softmax over n head scores, out = sum_h w_h * c (20250113.py:60-65) -------------------------------
+__global__ void __launch_bounds__(128) fusion_softmax_mix_fwd_kernel(const float* __restrict__ scores,
+                                                                     const float* __restrict__ c, float* __restrict__ out,
+                                                                     float* __restrict__ w_out, int rows, int n, int dim) {
+  const int row = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float sc = lane < n ? scores[(size_t)row * n + lane] : -INFINITY;
+  const float mx = warp_max(sc);
+  const float e = lane < n ? expf(sc - mx) : 0.0f;
+  const float w = e / warp_sum(e);
+  if (w_out && lane < n) w_out[(size_t)row * n + lane] = w;
+  for (int i0 = 0; i0 < dim; i0 += 32) {  // uniform trip count: the shuffles need the whole warp
+    const int i = i0 + lane;
+    const float cv = i < dim ? c[(size_t)row * dim + i] : 0.0f;
+    float acc = 0.0f;
+    for (int h = 0; h < n; ++h) acc += __shfl_sync(0xffffffffu, w, h) * cv;
+    if (i < dim) out[(size_t)row * dim + i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(128) fusion_softmax_mix_bwd_kernel(const float* __restrict__ w, const float* __restrict__ c,
+                                                                     const float* __restrict__ dout, float* __restrict__ dc,
+                                                                     float* __restrict__ dscores, int rows, int n, int dim) {
+  const int row = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float wl = lane < n ? w[(size_t)row * n + lane] : 0.0f;
+  const float wsum = warp_sum(wl);
+  float t = 0.0f;
+  for (int i0 = 0; i0 < dim; i0 += 32) {
+    const int i = i0 + lane;
+    const float g = i < dim ? dout[(size_t)row * dim + i] : 0.0f;
+    if (i < dim) t = fmaf(g, c[(size_t)row * dim + i], t);
+    float acc = 0.0f;
+    for (int h = 0; h < n; ++h) acc += __shfl_sync(0xffffffffu, wl, h) * g;
+    if (i < dim) dc[(size_t)row * dim + i] = acc;
+  }
+  t = warp_sum(t);  // d out / d w_h is the same inner product for every head
+  if (lane < n) dscores[(size_t)row * n + lane] = wl * (t - wsum * t);
+}
+
+// ---- scaled column mean (big variant, 20250107_network.py:85-96) -------------------------------------------------
+__device__ __forceinline__ float strip_reduce(float v, float (*red)[33]) {
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) scaled_colmean_fwd_kernel(const float* __restrict__ x, int ldx,
+                                                                 const float* __restrict__ scale, int ld_scale,
+                                                                 float* __restrict__ out, int ld_out,
+                                                                 float* __restrict__ colmean_out, int rows, int cols) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < cols;
+  float s = 0.0f;
+  if (ok)
+    for (int r = threadIdx.y; r < rows; r += 8) s += x[(size_t)r * ldx + c];
+  const float mean = strip_reduce(s, red) / rows;
+  if (!ok) return;
+  if (colmean_out && threadIdx.y == 0) colmean_out[c] = mean;
+  for (int r = threadIdx.y; r < rows; r += 8) out[(size_t)r * ld_out + c] = scale[(size_t)r * ld_scale] * mean;
+}
+
+__global__ void __launch_bounds__(256) scaled_colmean_bwd_dx_kernel(const float* __restrict__ dout, int ld_dout,
+                                                                    const float* __restrict__ scale, int ld_scale,
+                                                                    float* __restrict__ dx, int ldx, int rows, int cols) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < cols;
+  float s = 0.0f;
+  if (ok)
+    for (int r = threadIdx.y; r < rows; r += 8) s = fmaf(scale[(size_t)r * ld_scale], dout[(size_t)r * ld_dout + c], s);
+  const float t = strip_reduce(s, red) / rows;
+  if (!ok) return;
+  for (int r = threadIdx.y; r < rows; r += 8) dx[(size_t)r * ldx + c] = t;
+}
+
+__global__ void __launch_bounds__(128) rowdot_vec_kernel(const float* __restrict__ a, int lda, const float* __restrict__ v,
+                                                         float* __restrict__ out, int rows, int cols) {
+  const int row = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float t = 0.0f;
+  for (int i = lane; i < cols; i += 32) t = fmaf(a[(size_t)row * lda + i], v[i], t);
+  t = warp_sum(t);
+  if (lane == 0) out[row] = t;
+}
+
+// ---- elementwise ------------------------------------------------------------------------------------------------
+__global__ void act_bwd_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ y, int ld_y,
+                               float* __restrict__ dx, int ld_dx, int rows, int cols, int act) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  int r = i / cols, c = i % cols;
+  float g = dy[(size_t)r * ld_dy + c], o = y[(size_t)r * ld_y + c];
+  float d = act == BBBP_ACT_RELU ? (o > 0.0f ? g : 0.0f) : act == BBBP_ACT_TANH ? g * (1.0f - o * o) : g;
+  dx[(size_t)r * ld_dx + c] = d;
+}
+
+__global__ void scale_by_device_scalar_kernel(const float* __restrict__ x, const float* __restrict__ scalar,
+                                              float* __restrict__ y, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * scalar[0];
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int rows,
+                                                     int cols) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.0f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 8) s += x[(size_t)r * ldx + c];
+  s = strip_reduce(s, red);
+  if (c < cols && threadIdx.y == 0) out[c] = s;
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst, int rows,
+                              int cols) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  int r = i / cols, c = i % cols;
+  dst[(size_t)r * ld_dst + c] = src[(size_t)r * ld_src + c];
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                 int rows, int cols, int cols_pad) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols_pad) return;
+  int r = i / cols_pad, c = i % cols_pad;
+  dst[(size_t)r * ld_dst + c] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.0f);
+}
+
+// ---- Philox-4x32-10 dropout -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, float p, float inv_keep,
+                               uint64_t seed, uint64_t offset) {
+  size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // one Philox block = 4 elements
+  if (q * 4 >= n) return;
+  uint64_t ctr = q + offset;
+  uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    size_t i = q * 4 + k;
+    if (i < n) {
+      float u = bits[k] * 2.3283064365386963e-10f;  // [0,1)
+      y[i] = u >= p ? x[i] * inv_keep : 0.0f;
+    }
+  }
+}
+
+// ---- losses (single block: n is a batch size) -------------------------------------------------------------------
+template <int KIND>  // 0 = MSE, 1 = BCE with logits
+__global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                    float* __restrict__ loss, float* __restrict__ dpred, int n,
+                                                    float grad_scale) {
+  __shared__ float red[32];
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const float z = pred[i], t = target[i];
+    if (KIND == 0) {
+      const float d = z - t;
+      s = fmaf(d, d, s);
+      if (dpred) dpred[i] = 2.0f * d / n * grad_scale;
+    } else {
+      // max(z,0) - z t + log1p(exp(-|z|)): torch's stable binary_cross_entropy_with_logits
+      s += fmaxf(z, 0.0f) - z * t + log1pf(expf(-fabsf(z)));
+      if (dpred) dpred[i] = (1.0f / (1.0f + expf(-z)) - t) / n * grad_scale;
+    }
+  }
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = warp_sum(red[threadIdx.x]);
+    if (threadIdx.x == 0) loss[0] = t / n;
+  }
+}
+
+// ---- fused multi-tensor AdamW (torch.optim.AdamW single-tensor semantics, 20250113.py:172,191) -------------------
+constexpr int ADAMW_CHUNK = 65536;
+__global__ void __launch_bounds__(256) adamw_kernel(void* const* __restrict__ ptrs, const int64_t* __restrict__ sizes,
+                                                    const int32_t* __restrict__ chunk_tensor,
+                                                    const int64_t* __restrict__ chunk_offset, int ntensors, float lr,
+                                                    float beta1, float beta2, float eps, float decay_mul, float step_size,
+                                                    float bc2_sqrt, float grad_scale) {
+  const int t = chunk_tensor[blockIdx.x];
+  const int64_t off = chunk_offset[blockIdx.x];
+  float* __restrict__ p = static_cast<float*>(ptrs[t]) + off;
+  const float* __restrict__ g = static_cast<const float*>(ptrs[ntensors + t]) + off;
+  float* __restrict__ m = static_cast<float*>(ptrs[2 * ntensors + t]) + off;
+  float* __restrict__ v = static_cast<float*>(ptrs[3 * ntensors + t]) + off;
+  const int64_t left = sizes[t] - off;
+  const int n = left < ADAMW_CHUNK ? (int)left : ADAMW_CHUNK;
+  auto update = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= grad_scale;
+    pp *= decay_mul;
+    mm = mm + (gg - mm) * (1.0f - beta1);
+    vv = vv * beta2 + (1.0f - beta2) * gg * gg;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (vec) {
+    const int n4 = n / 4;
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+      const float4 gg = reinterpret_cast<const float4*>(g)[i];
+      update(pp.x, gg.x, mm.x, vv.x);
+      update(pp.y, gg.y, mm.y, vv.y);
+      update(pp.z, gg.z, mm.z, vv.z);
+      update(pp.w, gg.w, mm.w, vv.w);
+      reinterpret_cast<float4*>(p)[i] = pp;
+      reinterpret_cast<float4*>(m)[i] = mm;
+      reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += 256) update(p[i], g[i], m[i], v[i]);
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) update(p[i], g[i], m[i], v[i]);
+  }
+}
+
+// ---- input contracts --------------------------------------------------------------------------------------------
+// one warp per molecule: popcount -> mean/std in double (as sklearn StandardScaler on the 0/1 column) -> two values
+__global__ void __launch_bounds__(128) unpack_zscore_kernel(const uint8_t* __restrict__ packed, int bytes_per_row,
+                                                            float* __restrict__ out, int ld_out, int rows, int n_bits) {
+  const int row = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const uint8_t* pr = packed + (size_t)row * bytes_per_row;
+  int pop = 0;
+  for (int b = lane; b < bytes_per_row; b += 32) {
+    uint32_t byte = pr[b];
+    int valid = n_bits - b * 8;
+    if (valid < 8) byte &= (1u << (valid > 0 ? valid : 0)) - 1u;
+    pop += __popc(byte);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
+  const double mean = (double)pop / n_bits;
+  // population variance of a 0/1 vector, written as the mean of squared deviations
+  const double var = ((double)pop * (1.0 - mean) * (1.0 - mean) + (double)(n_bits - pop) * mean * mean) / n_bits;
+  double sd = sqrt(var);
+  if (sd == 0.0) sd = 1.0;
+  const float v0 = (float)((0.0 - mean) / sd), v1 = (float)((1.0 - mean) / sd);
+  for (int i = lane; i < n_bits; i += 32) out[(size_t)row * ld_out + i] = ((pr[i >> 3] >> (i & 7)) & 1) ? v1 : v0;
+}
+
+__device__ __forceinline__ double block_sum_double(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)blockDim.x / 32; ++i) t += red[i];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) u8_zscore_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int n) {
+  __shared__ double red[8];
+  const uint8_t* src = img + (size_t)blockIdx.x * n;
+  float* dst = out + (size_t)blockIdx.x * n;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)((float)src[i] / 255.0f);
+  const double mean = block_sum_double(s, red) / n;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    double d = (double)((float)src[i] / 255.0f) - mean;
+    q += d * d;
+  }
+  double sd = sqrt(block_sum_double(q, red) / n);
+  if (sd == 0.0) sd = 1.0;
+  for (int i = threadIdx.x; i < n; i += 256) dst[i] = (float)(((double)((float)src[i] / 255.0f) - mean) / sd);
+}
+
+}  // namespace bbbp
+
+using namespace bbbp;
+
+extern "C" int bbbp_fusion_softmax_mix_fwd_f32(const float* scores, const float* c, float* out, float* w_out, int rows,
+                                               int n, int dim, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(scores && c && out && rows >= 0 && n > 0 && n <= 32 && dim > 0, "fusion_softmax_mix_fwd: bad argument");
+  if (rows == 0) return BBBP_OK;
+  fusion_softmax_mix_fwd_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(scores, c, out, w_out, rows, n, dim);
+  return launch_status("fusion_softmax_mix_fwd");
+}
+
+extern "C" int bbbp_fusion_softmax_mix_bwd_f32(const float* w, const float* c, const float* dout, float* dc,
+                                               float* dscores, int rows, int n, int dim, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(w && c && dout && dc && dscores && rows >= 0 && n > 0 && n <= 32 && dim > 0,
+                 "fusion_softmax_mix_bwd: bad argument");
+  if (rows == 0) return BBBP_OK;
+  fusion_softmax_mix_bwd_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(w, c, dout, dc, dscores, rows, n, dim);
+  return launch_status("fusion_softmax_mix_bwd");
+}
+
+extern "C" int bbbp_scaled_colmean_fwd_f32(const float* x, int ldx, const float* scale, int ld_scale, float* out,
+                                           int ld_out, float* colmean_out, int rows, int cols, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x && scale && out && rows > 0 && cols > 0, "scaled_colmean_fwd: bad argument");
+  scaled_colmean_fwd_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, as_stream(stream)>>>(x, ldx, scale, ld_scale, out, ld_out,
+                                                                                     colmean_out, rows, cols);
+  return launch_status("scaled_colmean_fwd");
+}
+
+extern "C" int bbbp_scaled_colmean_bwd_f32(const float* dout, int ld_dout, const float* scale, int ld_scale,
+                                           const float* colmean, float* dx, int ldx, float* dscale, int rows, int cols,
+                                           bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(dout && scale && colmean && dx && dscale && rows > 0 && cols > 0, "scaled_colmean_bwd: bad argument");
+  scaled_colmean_bwd_dx_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, as_stream(stream)>>>(dout, ld_dout, scale, ld_scale, dx,
+                                                                                        ldx, rows, cols);
+  rowdot_vec_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(dout, ld_dout, colmean, dscale, rows, cols);
+  return launch_status("scaled_colmean_bwd");
+}
+
+extern "C" int bbbp_act_bwd_f32(const float* dy, int ld_dy, const float* y, int ld_y, float* dx, int ld_dx, int rows,
+                                int cols, int act, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(dy && y && dx && rows >= 0 && cols >= 0, "act_bwd: bad argument");
+  size_t total = (size_t)rows * cols;
+  if (total == 0) return BBBP_OK;
+  act_bwd_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(dy, ld_dy, y, ld_y, dx, ld_dx, rows,
+                                                                                         cols, act);
+  return launch_status("act_bwd");
+}
+
+extern "C" int bbbp_scale_by_device_scalar_f32(const float* x, const float* scalar, float* y, size_t n,
+                                               bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x && scalar && y, "scale_by_device_scalar: null operand");
+  if (n == 0) return BBBP_OK;
+  scale_by_device_scalar_kernel<<<(unsigned)ceil_div(n, (size_t)256), 256, 0, as_stream(stream)>>>(x, scalar, y, n);
+  return launch_status("scale_by_device_scalar");
+}
+
+extern "C" int bbbp_colsum_f32(const float* x, int ldx, float* out, int rows, int cols, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x && out && rows >= 0 && cols > 0, "colsum: bad argument");
+  colsum_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, as_stream(stream)>>>(x, ldx, out, rows, cols);
+  return launch_status("colsum");
+}
+
+extern "C" int bbbp_copy2d_f32(const float* src, int ld_src, float* dst, int ld_dst, int rows, int cols,
+                               bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(src && dst && rows >= 0 && cols >= 0, "copy2d: bad argument");
+  size_t total = (size_t)rows * cols;
+  if (total == 0) return BBBP_OK;
+  copy2d_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(src, ld_src, dst, ld_dst, rows, cols);
+  return launch_status("copy2d");
+}
+
+extern "C" int bbbp_cast_bf16(const float* src, int ld_src, void* dst_bf16, int ld_dst, int rows, int cols, int cols_pad,
+                              bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(src && dst_bf16 && rows >= 0 && cols >= 0 && cols_pad >= cols && ld_dst >= cols_pad, "cast_bf16: bad argument");
+  size_t total = (size_t)rows * cols_pad;
+  if (total == 0) return BBBP_OK;
+  cast_bf16_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
+      src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst, rows, cols, cols_pad);
+  return launch_status("cast_bf16");
+}
+
+extern "C" int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset,
+                                bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x && y && p >= 0.0f && p < 1.0f, "dropout: p must be in [0,1)");
+  if (n == 0) return BBBP_OK;
+  size_t quads = ceil_div(n, (size_t)4);
+  dropout_kernel<<<(unsigned)ceil_div(quads, (size_t)256), 256, 0, as_stream(stream)>>>(x, y, n, p, 1.0f / (1.0f - p), seed,
+                                                                                         offset);
+  return launch_status("dropout");
+}
+
+extern "C" int bbbp_mse_loss_f32(const float* pred, const float* target, float* loss, float* dpred, int n,
+                                 float grad_scale, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(pred && target && loss && n > 0, "mse_loss: bad argument");
+  loss_kernel<0><<<1, 1024, 0, as_stream(stream)>>>(pred, target, loss, dpred, n, grad_scale);
+  return launch_status("mse_loss");
+}
+
+extern "C" int bbbp_bce_logits_loss_f32(const float* logit, const float* target, float* loss, float* dlogit, int n,
+                                        float grad_scale, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(logit && target && loss && n > 0, "bce_logits_loss: bad argument");
+  loss_kernel<1><<<1, 1024, 0, as_stream(stream)>>>(logit, target, loss, dlogit, n, grad_scale);
+  return launch_status("bce_logits_loss");
+}
+
+extern "C" int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor,
+                              const int64_t* chunk_offset, int ntensors, int nchunks, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, int step, float grad_scale, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(ptrs && sizes && chunk_tensor && chunk_offset && ntensors > 0 && nchunks > 0 && step >= 1,
+                 "adamw: bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float decay_mul = (float)(1.0 - (double)lr * (double)weight_decay);
+  adamw_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(ptrs, sizes, chunk_tensor, chunk_offset, ntensors, lr, beta1, beta2,
+                                                       eps, decay_mul, step_size, bc2_sqrt, grad_scale);
+  return launch_status("adamw");
+}
+
+extern "C" int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, float* out, int ld_out, int rows,
+                                      int n_bits, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(packed && out && rows >= 0 && n_bits > 0 && bytes_per_row * 8 >= n_bits && ld_out >= n_bits,
+                 "unpack_zscore: bad argument");
+  if (rows == 0) return BBBP_OK;
+  unpack_zscore_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(packed, bytes_per_row, out, ld_out, rows, n_bits);
+  return launch_status("unpack_zscore");
+}
+
+extern "C" int bbbp_u8_zscore_f32(const uint8_t* img, float* out, int rows, int n, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img && out && rows >= 0 && n > 0, "u8_zscore: bad argument");
+  if (rows == 0) return BBBP_OK;
+  u8_zscore_kernel<<<rows, 256, 0, as_stream(stream)>>>(img, out, n);
+  return launch_status("u8_zscore");
+}

@@ -1,0 +1,125 @@
+// fp32 CUDA-core GEMM with fused bias/activation epilogue.  Validation-grade arithmetic (plain
+// fmaf chain in k order, deterministic) for BBBP_PREC_FP32 and for the training path's dgrad/wgrad.
+// Replaces the ATen addmm calls behind nn.Linear at 20250113.py:80,92,53-55,99-106 and the encoder
+// projections (torch.nn.TransformerEncoderLayer via 20250113.py:75-78).
+#include "common.cuh"
+
+namespace bbbp {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+// element (m,k) of A at A[m*sAm + k*sAk]; element (k,n) of B at B[k*sBk + n*sBn]
+__global__ void __launch_bounds__(256) gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long sAm,
+                                                       long sAk, const float* __restrict__ B, long sBk, long sBn,
+                                                       float* __restrict__ C, int ldc, const float* __restrict__ bias,
+                                                       int act, int accumulate, int k_per_split,
+                                                       float* __restrict__ partial) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = tid % 16, ty = tid / 16;  // 16x16 threads, 4x4 outputs each
+  float acc[4][4] = {};
+
+  const bool a_k_fast = (sAk == 1);
+  const bool b_n_fast = (sBn == 1);
+
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256;
+      int mm, kk;
+      if (a_k_fast) { kk = idx % TK; mm = idx / TK; } else { mm = idx % TM; kk = idx / TM; }
+      int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < kend) ? A[gm * sAm + gk * sAk] : 0.0f;
+      int nn, kb;
+      if (b_n_fast) { nn = idx % TN; kb = idx / TN; } else { kb = idx % TK; nn = idx / TK; }
+      int gn = n0 + nn, gkb = k0 + kb;
+      Bs[kb][nn] = (gn < N && gkb < kend) ? B[gkb * sBk + gn * sBn] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      if (partial) {
+        partial[((size_t)blockIdx.z * M + gm) * N + gn] = acc[i][j];
+      } else {
+        float v = acc[i][j] + (bias ? bias[gn] : 0.0f);
+        v = apply_act(v, act);
+        float* dst = C + (size_t)gm * ldc + gn;
+        *dst = accumulate ? (*dst + v) : v;
+      }
+    }
+  }
+}
+
+__global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C,
+                                     int ldc, const float* __restrict__ bias, int act, int accumulate) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  int m = i / N, n = i % N;
+  float v = 0.0f;
+  for (int s = 0; s < splits; ++s) v += partial[(size_t)s * M * N + i];
+  v += bias ? bias[n] : 0.0f;
+  v = apply_act(v, act);
+  float* dst = C + (size_t)m * ldc + n;
+  *dst = accumulate ? (*dst + v) : v;
+}
+
+}  // namespace bbbp
+
+extern "C" int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+                             int ldb, float* C, int ldc, const float* bias, int act, int accumulate, int split_k,
+                             float* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_f32: negative dimension");
+  BBBP_CHECK_ARG(A && B && C, "gemm_f32: null operand");
+  if (M == 0 || N == 0) return BBBP_OK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > K) split_k = K > 0 ? K : 1;
+  long sAm = transA ? 1 : lda, sAk = transA ? lda : 1;
+  long sBk = transB ? 1 : ldb, sBn = transB ? ldb : 1;
+  int k_per_split = ceil_div(ceil_div(K, split_k), TK) * TK;
+  if (k_per_split == 0) k_per_split = TK;
+  split_k = K > 0 ? ceil_div(K, k_per_split) : 1;
+  float* partial = nullptr;
+  if (split_k > 1) {
+    size_t need = (size_t)split_k * M * N * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("gemm_f32: split_k=%d needs %zu workspace bytes, got %zu", split_k, need, workspace_bytes);
+      return BBBP_EWORKSPACE;
+    }
+    partial = workspace;
+  }
+  dim3 grid(ceil_div(N, TN), ceil_div(M, TM), split_k);
+  gemm_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, bias, act,
+                                                        accumulate, k_per_split, partial);
+  int st = launch_status("gemm_f32");
+  if (st != BBBP_OK || !partial) return st;
+  size_t total = (size_t)M * N;
+  splitk_finish_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(partial, split_k, M, N, C,
+                                                                                             ldc, bias, act, accumulate);
+  return launch_status("gemm_f32 split-k finish");
+}

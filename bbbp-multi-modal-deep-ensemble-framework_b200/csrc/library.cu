@@ -1,0 +1,41 @@
+// Library-level entry points: ABI version, error string, device check.
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+namespace bbbp {
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return BBBP_ECUDA;
+  }
+  return BBBP_OK;
+}
+}  // namespace bbbp
+
+extern "C" int bbbp_abi_version(void) { return BBBP_ABI_VERSION; }
+extern "C" const char* bbbp_last_error(void) { return bbbp::g_error; }
+
+extern "C" int bbbp_device_check(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    bbbp::set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return BBBP_ECUDA;
+  }
+  if (prop.major != 10) {
+    bbbp::set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    return BBBP_EUNSUPPORTED;
+  }
+  return BBBP_OK;
+}

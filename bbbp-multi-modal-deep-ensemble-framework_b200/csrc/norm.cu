@@ -1,0 +1,251 @@
+// LayerNorm (post-norm residual blocks of nn.TransformerEncoderLayer, eps 1e-5, via 20250113.py:75-78)
+// and BatchNorm1d (20250113.py:101).  Memory-bound single-purpose kernels: one warp per row for LN
+// (warp-shuffle statistics over the TRUE width, never a padded one), column-strip blocks for BN.
+#include "common.cuh"
+
+namespace bbbp {
+
+constexpr int LN_WARPS = 4;
+
+__global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ sum_out, float* __restrict__ mean_out,
+    float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y16, int ld16, int rows, int dim, float eps) {
+  const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * dim;
+  const float* rr = res ? res + (size_t)row * dim : nullptr;
+  float s = 0.0f;
+  for (int i = lane; i < dim; i += 32) s += xr[i] + (rr ? rr[i] : 0.0f);
+  const float mean = warp_sum(s) / dim;
+  float v = 0.0f;
+  for (int i = lane; i < dim; i += 32) {
+    float t = xr[i] + (rr ? rr[i] : 0.0f) - mean;
+    v = fmaf(t, t, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / dim + eps);
+  for (int i = lane; i < dim; i += 32) {
+    float t = xr[i] + (rr ? rr[i] : 0.0f);
+    float o = (t - mean) * rstd * gamma[i] + beta[i];
+    y[(size_t)row * dim + i] = o;
+    if (sum_out) sum_out[(size_t)row * dim + i] = t;
+    if (y16) y16[(size_t)row * ld16 + i] = __float2bfloat16(o);
+  }
+  if (y16)
+    for (int i = dim + lane; i < ld16; i += 32) y16[(size_t)row * ld16 + i] = __float2bfloat16(0.0f);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_dx_kernel(const float* __restrict__ dy,
+                                                                         const float* __restrict__ s,
+                                                                         const float* __restrict__ mean,
+                                                                         const float* __restrict__ rstd,
+                                                                         const float* __restrict__ gamma,
+                                                                         float* __restrict__ dx, int rows, int dim) {
+  const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  const float* dyr = dy + (size_t)row * dim;
+  const float* sr = s + (size_t)row * dim;
+  float c1 = 0.0f, c2 = 0.0f;
+  for (int i = lane; i < dim; i += 32) {
+    float g = dyr[i] * gamma[i];
+    c1 += g;
+    c2 = fmaf(g, (sr[i] - mu) * rs, c2);
+  }
+  c1 = warp_sum(c1) / dim;
+  c2 = warp_sum(c2) / dim;
+  for (int i = lane; i < dim; i += 32) {
+    float g = dyr[i] * gamma[i];
+    dx[(size_t)row * dim + i] = rs * (g - c1 - (sr[i] - mu) * rs * c2);
+  }
+}
+
+constexpr int LN_PARTS = 64;
+__global__ void layernorm_bwd_param_partial_kernel(const float* __restrict__ dy, const float* __restrict__ s,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   float* __restrict__ part, int rows, int dim) {
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col >= dim) return;
+  float dg = 0.0f, db = 0.0f;
+  for (int r = blockIdx.x; r < rows; r += LN_PARTS) {
+    float d = dy[(size_t)r * dim + col];
+    dg = fmaf(d, (s[(size_t)r * dim + col] - mean[r]) * rstd[r], dg);
+    db += d;
+  }
+  part[(size_t)blockIdx.x * dim + col] = dg;
+  part[(size_t)(LN_PARTS + blockIdx.x) * dim + col] = db;
+}
+__global__ void layernorm_bwd_param_final_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
+                                                 float* __restrict__ dbeta, int dim) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= dim) return;
+  float dg = 0.0f, db = 0.0f;
+  for (int p = 0; p < LN_PARTS; ++p) {
+    dg += part[(size_t)p * dim + col];
+    db += part[(size_t)(LN_PARTS + p) * dim + col];
+  }
+  dgamma[col] = dg;
+  dbeta[col] = db;
+}
+
+// ---- BatchNorm1d: block = 32 channels x 8 row lanes -------------------------------------------------------------
+__device__ __forceinline__ float bn_col_reduce(float v, float (*red)[33]) {
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) batchnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ rmean,
+                                                            float* __restrict__ rvar, float* __restrict__ y,
+                                                            float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                            int rows, int C, int training, float momentum, float eps) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  float mean, rstd;
+  if (training) {
+    float s = 0.0f;
+    if (ok)
+      for (int r = threadIdx.y; r < rows; r += 8) s += x[(size_t)r * C + c];
+    mean = bn_col_reduce(s, red) / rows;
+    float v = 0.0f;
+    if (ok)
+      for (int r = threadIdx.y; r < rows; r += 8) {
+        float t = x[(size_t)r * C + c] - mean;
+        v = fmaf(t, t, v);
+      }
+    const float var = bn_col_reduce(v, red) / rows;  // biased: used to normalise
+    rstd = rsqrtf(var + eps);
+    if (ok && threadIdx.y == 0) {
+      save_mean[c] = mean;
+      save_rstd[c] = rstd;
+      const float unbiased = rows > 1 ? var * rows / (rows - 1) : var;
+      rmean[c] = (1.0f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.0f - momentum) * rvar[c] + momentum * unbiased;
+    }
+  } else {
+    mean = ok ? rmean[c] : 0.0f;
+    rstd = ok ? rsqrtf(rvar[c] + eps) : 0.0f;
+  }
+  if (!ok) return;
+  const float g = gamma[c], b = beta[c];
+  for (int r = threadIdx.y; r < rows; r += 8) y[(size_t)r * C + c] = (x[(size_t)r * C + c] - mean) * rstd * g + b;
+}
+
+// training != 0: batch-statistics backward; else running statistics are constants
+__global__ void __launch_bounds__(256) batchnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, const float* __restrict__ rvar,
+                                                            float* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int rows, int C, int training,
+                                                            float eps) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  const float mean = ok ? mean_in[c] : 0.0f;
+  const float rstd = ok ? (training ? rstd_in[c] : rsqrtf(rvar[c] + eps)) : 0.0f;
+  float sg = 0.0f, sb = 0.0f;
+  if (ok)
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      float d = dy[(size_t)r * C + c];
+      sg = fmaf(d, (x[(size_t)r * C + c] - mean) * rstd, sg);
+      sb += d;
+    }
+  sg = bn_col_reduce(sg, red);
+  sb = bn_col_reduce(sb, red);
+  if (!ok) return;
+  if (threadIdx.y == 0) {
+    dgamma[c] = sg;
+    dbeta[c] = sb;
+  }
+  const float g = gamma[c];
+  for (int r = threadIdx.y; r < rows; r += 8) {
+    float d = dy[(size_t)r * C + c];
+    if (training) {
+      float xh = (x[(size_t)r * C + c] - mean) * rstd;
+      dx[(size_t)r * C + c] = g * rstd * (d - sb / rows - xh * sg / rows);
+    } else {
+      dx[(size_t)r * C + c] = d * g * rstd;
+    }
+  }
+}
+
+}  // namespace bbbp
+
+extern "C" int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, const float* gamma, const float* beta,
+                                          float* y, float* sum_out, float* mean, float* rstd, void* y_bf16, int ld_bf16,
+                                          int rows, int dim, float eps, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(x && gamma && beta && y && rows >= 0 && dim > 0, "add_layernorm_fwd: bad argument");
+  BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd: ld_bf16 < dim");
+  if (rows == 0) return BBBP_OK;
+  add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
+      x, res, gamma, beta, y, sum_out, mean, rstd, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf16, rows, dim, eps);
+  return launch_status("add_layernorm_fwd");
+}
+
+extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const float* mean, const float* rstd,
+                                      const float* gamma, float* dx, float* dgamma, float* dbeta, int rows, int dim,
+                                      float* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(dy && s && mean && rstd && gamma && dx && dgamma && dbeta && rows > 0 && dim > 0,
+                 "layernorm_bwd: bad argument");
+  size_t need = (size_t)2 * LN_PARTS * dim * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("layernorm_bwd: needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    return BBBP_EWORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  layernorm_bwd_dx_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, st>>>(dy, s, mean, rstd, gamma, dx, rows, dim);
+  layernorm_bwd_param_partial_kernel<<<dim3(LN_PARTS, ceil_div(dim, 128)), 128, 0, st>>>(dy, s, mean, rstd, workspace,
+                                                                                         rows, dim);
+  layernorm_bwd_param_final_kernel<<<ceil_div(dim, 128), 128, 0, st>>>(workspace, dgamma, dbeta, dim);
+  return launch_status("layernorm_bwd");
+}
+
+extern "C" int bbbp_batchnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, float* y, float* save_mean, float* save_rstd, int rows,
+                                      int channels, int training, float momentum, float eps, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(x && gamma && beta && running_mean && running_var && y && rows > 0 && channels > 0,
+                 "batchnorm_fwd: bad argument");
+  BBBP_CHECK_ARG(!training || (save_mean && save_rstd), "batchnorm_fwd: training needs save_mean/save_rstd");
+  BBBP_CHECK_ARG(!training || rows > 1, "batchnorm_fwd: Expected more than 1 value per channel when training");
+  batchnorm_fwd_kernel<<<ceil_div(channels, 32), dim3(32, 8), 0, as_stream(stream)>>>(
+      x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, rows, channels, training, momentum, eps);
+  return launch_status("batchnorm_fwd");
+}
+
+extern "C" int bbbp_batchnorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                                      const float* save_rstd, float* dx, float* dgamma, float* dbeta, int rows,
+                                      int channels, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(dy && x && gamma && save_mean && save_rstd && dx && dgamma && dbeta && rows > 0 && channels > 0,
+                 "batchnorm_bwd: bad argument");
+  batchnorm_bwd_kernel<<<ceil_div(channels, 32), dim3(32, 8), 0, as_stream(stream)>>>(
+      dy, x, gamma, save_mean, save_rstd, nullptr, dx, dgamma, dbeta, rows, channels, 1, 0.0f);
+  return launch_status("batchnorm_bwd");
+}
+
+extern "C" int bbbp_batchnorm_eval_bwd_f32(const float* dy, const float* x, const float* gamma,
+                                           const float* running_mean, const float* running_var, float* dx,
+                                           float* dgamma, float* dbeta, int rows, int channels, float eps,
+                                           bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(dy && x && gamma && running_mean && running_var && dx && dgamma && dbeta && rows > 0 && channels > 0,
+                 "batchnorm_eval_bwd: bad argument");
+  batchnorm_bwd_kernel<<<ceil_div(channels, 32), dim3(32, 8), 0, as_stream(stream)>>>(
+      dy, x, gamma, running_mean, nullptr, running_var, dx, dgamma, dbeta, rows, channels, 0, eps);
+  return launch_status("batchnorm_eval_bwd");
+}

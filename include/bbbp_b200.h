@@ -1,0 +1,228 @@
+/*
+ * bbbp_b200.h -- C ABI of the B200 (sm_100a) kernels behind the reference's
+ * MixedInputModel hot path (forward / backward / batched inference / AdamW).
+ *
+ * Conventions:
+ *   - extern "C", plain pointers and sizes, no torch types.  Every pointer is a DEVICE
+ *     pointer on the current device unless a comment says "host".
+ *   - The caller owns every buffer, including workspaces.  The library allocates nothing
+ *     persistent and keeps no global state besides a thread-local error string.
+ *   - All work is enqueued on the stream argument (a cudaStream_t passed as void*); no
+ *     entry point synchronises.
+ *   - Return 0 on success, a negative BBBP_E* code on failure; bbbp_last_error() gives
+ *     the message.  Nothing throws or exits.
+ *   - Matrices are row-major.  "ld*" is the row pitch in ELEMENTS.
+ *
+ * Reference = /root/reference (FengDushuo/BBBP-Multi-Modal-Deep-Ensemble-Framework).
+ * "C:" below abbreviates Models/multi_input_data_regression_opt_transformer_cnn_20250113.py.
+ */
+#ifndef BBBP_B200_H
+#define BBBP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBBP_ABI_VERSION 1
+
+enum { BBBP_OK = 0, BBBP_EINVAL = -1, BBBP_ECUDA = -2, BBBP_EWORKSPACE = -3, BBBP_EUNSUPPORTED = -4 };
+
+/* activation fused into a linear epilogue */
+enum { BBBP_ACT_NONE = 0, BBBP_ACT_RELU = 1, BBBP_ACT_TANH = 2 };
+
+/* arithmetic mode of the fused forward */
+enum {
+  BBBP_PREC_FP32 = 0, /* CUDA-core fp32 FMA everywhere (validation mode, 1e-4 class parity)       */
+  BBBP_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 TMEM accumulation, fp32 statistics (default)  */
+};
+
+typedef void* bbbp_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int bbbp_abi_version(void);
+const char* bbbp_last_error(void);
+/* 0 when the current device is compute capability 10.x, BBBP_EUNSUPPORTED otherwise. */
+int bbbp_device_check(void);
+
+/* ---- dense layers: nn.Linear call sites C:80,92,53-55,99-106; encoder in_proj/out_proj/
+ *      linear1/linear2 (torch.nn.TransformerEncoderLayer via C:75-78); PCA transform
+ *      Models/..._transformer_cnn_opt.py:30-33 ------------------------------------------------ */
+
+/* C[M,N] = act( opA(A)[M,K] * opB(B)[K,N] + bias[N] ) (+ C_in when accumulate != 0), fp32 CUDA cores.
+ * transA == 0: A stored [M,K] (lda >= K); != 0: A stored [K,M] (lda >= M).  Same for B with [K,N]/[N,K].
+ * nn.Linear forward is transA=0, transB=1 with B = weight[N,K].  bias may be NULL.
+ * split_k > 1 needs workspace of split_k*M*N floats (deterministic two-pass reduction). */
+int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                  float* C, int ldc, const float* bias, int act, int accumulate, int split_k, float* workspace,
+                  size_t workspace_bytes, bbbp_stream_t stream);
+
+/* dst[r, 0:cols_pad) = bf16(src[r, 0:cols)) with zero fill of [cols, cols_pad); ld_dst in bf16 elements. */
+int bbbp_cast_bf16(const float* src, int ld_src, void* dst_bf16, int ld_dst, int rows, int cols, int cols_pad,
+                   bbbp_stream_t stream);
+
+/* tcgen05 / TMEM / TMA GEMM: out = act( A[M,K] * W[N,K]^T + bias ) (+ residual), bf16 operands, fp32
+ * accumulate.  A and W are bf16 row-major with K contiguous; lda/ldw in elements, multiples of 8, 16-byte
+ * aligned bases.  Columns >= K are never read (TMA zero fill), so K need not be padded.
+ * out_f32 and/or out_bf16 may be NULL (at least one must be given).  residual (fp32, ld = ld_res) may be NULL.
+ * split_k >= 1; split_k > 1 needs workspace of split_k*M_pad*N_pad floats where *_pad round up to 128.
+ * bbbp_gemm_bf16_workspace() returns the bytes needed. */
+size_t bbbp_gemm_bf16_workspace(int M, int N, int split_k);
+int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, const void* W_bf16, int ldw, const float* bias,
+                   const float* residual, int ld_res, float* out_f32, int ld_out, void* out_bf16, int ld_out16,
+                   int act, int split_k, void* workspace, size_t workspace_bytes, bbbp_stream_t stream);
+
+/* ---- image branch: nn.Conv2d(k3,s1,p1) + ReLU + MaxPool2d(2) C:85-90 (and 20250107_network.py:133-141) */
+
+/* y[N,Cout,H/2,W/2] = maxpool2(relu(conv3x3(x[N,Cin,H,W], w[Cout,Cin,3,3]) + b)), NCHW fp32, CUDA cores.
+ * argmax (uint8 in 0..3 = 2*dh+dw of the first maximum in torch's scan order) may be NULL.
+ * pool == 0 gives the plain convolution (+bias when b != NULL, no ReLU) at full resolution.
+ * Cout must be a multiple of 32; H, W multiples of 16. */
+int bbbp_conv3x3_f32(const float* x, const float* w, const float* b, float* y, uint8_t* argmax, int N, int Cin,
+                     int Cout, int H, int W, int pool, bbbp_stream_t stream);
+/* dpre[N,C,H,W] = scatter of dy[N,C,H/2,W/2] to the arg-max position, zero where y <= 0 (ReLU) */
+int bbbp_relu_pool_bwd_f32(const float* dy, const float* y, const uint8_t* argmax, float* dpre, int N, int C, int H,
+                           int W, bbbp_stream_t stream);
+/* dw[Cout,Cin,3,3] and db[Cout] from dpre[N,Cout,H,W] and x[N,Cin,H,W]; deterministic two-pass.
+ * workspace: N * (Cout*Cin*9 + Cout) floats. */
+int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* dw, float* db, int N, int Cin, int Cout, int H,
+                           int W, float* workspace, size_t workspace_bytes, bbbp_stream_t stream);
+/* w_t[Cin,Cout,3,3] = spatially flipped, channel-transposed w[Cout,Cin,3,3] (weights of the data-gradient conv) */
+int bbbp_conv3x3_flip_weights_f32(const float* w, float* w_t, int Cin, int Cout, bbbp_stream_t stream);
+
+/* ---- encoder self-attention across the molecules of a reference batch: the (B,1,F)
+ *      input of C:110-111 is read by nn.TransformerEncoder as seq_len = B, batch = 1.  ``groups``
+ *      independent reference batches of ``seq`` molecules each are processed in one launch. ------ */
+
+/* qkv[groups*seq, 3E] = [q | k | v], E = heads*head_dim (nn.MultiheadAttention in_proj layout).
+ * out[groups*seq, E]; lse[groups*seq, heads] (log-sum-exp of the scaled scores, may be NULL). */
+/* dropout_p > 0 drops attention probabilities after the softmax (nn.MultiheadAttention dropout, train mode);
+ * the keep mask is Philox(seed; group, head, query, key), so backward regenerates it from the same seed. */
+int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, int groups, int seq, int heads, int head_dim,
+                           float dropout_p, uint64_t seed, bbbp_stream_t stream);
+int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
+                           int groups, int seq, int heads, int head_dim, float dropout_p, uint64_t seed,
+                           bbbp_stream_t stream);
+
+/* ---- normalisation: nn.LayerNorm (post-norm residual, eps 1e-5) and nn.BatchNorm1d C:101 ------- */
+
+/* s = x + res (res may be NULL); y = LN(s)*gamma + beta.  Optional outputs: sum_out (= s), mean[rows],
+ * rstd[rows], y_bf16 (pitch ld_bf16, zero filled up to it). */
+int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                               float* sum_out, float* mean, float* rstd, void* y_bf16, int ld_bf16, int rows,
+                               int dim, float eps, bbbp_stream_t stream);
+/* dx (= gradient wrt s, which is also the gradient of both x and res), dgamma[dim], dbeta[dim].
+ * workspace: 2 * 64 * dim floats. */
+int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
+                           float* dx, float* dgamma, float* dbeta, int rows, int dim, float* workspace,
+                           size_t workspace_bytes, bbbp_stream_t stream);
+/* training != 0: batch statistics, running stats updated in place (momentum, unbiased variance), save_mean /
+ * save_rstd written.  training == 0: running statistics, save_* untouched (may be NULL). */
+int bbbp_batchnorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, float* y, float* save_mean, float* save_rstd, int rows, int channels,
+                           int training, float momentum, float eps, bbbp_stream_t stream);
+int bbbp_batchnorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* save_mean,
+                           const float* save_rstd, float* dx, float* dgamma, float* dbeta, int rows, int channels,
+                           bbbp_stream_t stream);
+/* eval-mode backward (running statistics are constants): dx = dy * gamma * rsqrt(var + eps) */
+int bbbp_batchnorm_eval_bwd_f32(const float* dy, const float* x, const float* gamma, const float* running_mean,
+                                const float* running_var, float* dx, float* dgamma, float* dbeta, int rows,
+                                int channels, float eps, bbbp_stream_t stream);
+
+/* ---- fusion blocks C:48-65, _rdkit.py:53-66, 20250107_network.py:51-105 ------------------------ */
+
+/* w = softmax over the last axis of scores[rows, n] (n <= 32); out[rows, dim] = sum_h w[r,h] * c[r, :]
+ * accumulated in head order.  w_out[rows, n] optional. */
+int bbbp_fusion_softmax_mix_fwd_f32(const float* scores, const float* c, float* out, float* w_out, int rows, int n,
+                                    int dim, bbbp_stream_t stream);
+/* dc[rows, dim] and dscores[rows, n] from dout */
+int bbbp_fusion_softmax_mix_bwd_f32(const float* w, const float* c, const float* dout, float* dc, float* dscores,
+                                    int rows, int n, int dim, bbbp_stream_t stream);
+/* out[r, c] = scale[r*ld_scale] * colmean(x)[c]  (the (B,1,1)*(B,D) -> mean(dim=1) broadcast of the big variant);
+ * colmean_out[cols] optional. */
+int bbbp_scaled_colmean_fwd_f32(const float* x, int ldx, const float* scale, int ld_scale, float* out, int ld_out,
+                                float* colmean_out, int rows, int cols, bbbp_stream_t stream);
+/* dscale[r] = <dout[r,:], colmean>;  dx[r', c] = (1/rows) * sum_r scale[r] * dout[r, c]  (same for every r') */
+int bbbp_scaled_colmean_bwd_f32(const float* dout, int ld_dout, const float* scale, int ld_scale, const float* colmean,
+                                float* dx, int ldx, float* dscale, int rows, int cols, bbbp_stream_t stream);
+
+/* ---- elementwise / reductions ------------------------------------------------------------------ */
+/* dx = dy * act'(y) computed from the activation OUTPUT y (relu: y > 0; tanh: 1 - y^2); pitches in elements */
+int bbbp_act_bwd_f32(const float* dy, int ld_dy, const float* y, int ld_y, float* dx, int ld_dx, int rows, int cols,
+                     int act, bbbp_stream_t stream);
+/* y[i] = x[i] * scalar[0] with the scalar read from DEVICE memory (chain-rule factor of a loss, no host sync) */
+int bbbp_scale_by_device_scalar_f32(const float* x, const float* scalar, float* y, size_t n, bbbp_stream_t stream);
+/* out[c] = sum_r x[r, c] (bias gradients), deterministic */
+int bbbp_colsum_f32(const float* x, int ldx, float* out, int rows, int cols, bbbp_stream_t stream);
+/* dst[r, 0:cols) = src[r, 0:cols) with independent pitches (concatenation / slicing) */
+int bbbp_copy2d_f32(const float* src, int ld_src, float* dst, int ld_dst, int rows, int cols, bbbp_stream_t stream);
+/* Philox-4x32-10 dropout: y = x * keep / (1-p); the mask is a function of (seed, element index).  Not
+ * stream-compatible with torch's generator (SURVEY hard part f). */
+int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset, bbbp_stream_t stream);
+
+/* ---- loss C:143,189 and optimiser C:172,191 ----------------------------------------------------- */
+/* loss[0] = mean((pred - target)^2); dpred = 2 (pred - target) / n * grad_scale (dpred may be NULL) */
+int bbbp_mse_loss_f32(const float* pred, const float* target, float* loss, float* dpred, int n, float grad_scale,
+                      bbbp_stream_t stream);
+/* extension (no reference code): mean BCE-with-logits, dlogit = (sigmoid(z) - t) / n * grad_scale */
+int bbbp_bce_logits_loss_f32(const float* logit, const float* target, float* loss, float* dlogit, int n,
+                             float grad_scale, bbbp_stream_t stream);
+/* torch.optim.AdamW semantics, one launch for all tensors.  ptrs is a DEVICE array of 4*ntensors pointers
+ * laid out [param | grad | exp_avg | exp_avg_sq] and sizes a DEVICE array of ntensors element counts;
+ * chunk_tensor / chunk_offset (DEVICE, nchunks entries) enumerate 64Ki-element chunks. step is 1-based. */
+int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor, const int64_t* chunk_offset,
+                   int ntensors, int nchunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int step, float grad_scale, bbbp_stream_t stream);
+
+/* ---- input contracts P1/P2 (extensions; oracle = oracle/preprocess.py) --------------------------- */
+/* packed little-endian bit rows (bytes_per_row = ceil(n_bits/8)) -> per-molecule z-scored fp32 rows */
+int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, float* out, int ld_out, int rows, int n_bits,
+                           bbbp_stream_t stream);
+/* uint8 depictions (rows x n values) -> x/255 -> per-molecule z-score, fp32 */
+int bbbp_u8_zscore_f32(const uint8_t* img, float* out, int rows, int n, bbbp_stream_t stream);
+
+/* ---- fused batched inference of the canonical transformer-CNN (C:109-119, eval mode) -------------- */
+typedef struct {
+  int32_t fingerprint_size; /* F: 167 (MACCS) or 2048 (Morgan / RDKFingerprint)                         */
+  int32_t heads;            /* encoder heads (C:71-73)                                                   */
+  int32_t layers;           /* 6                                                                         */
+  int32_t ffn;              /* 2048                                                                      */
+  int32_t groups;           /* independent reference batches in this call                               */
+  int32_t seq;              /* molecules per reference batch (attention scope)               */
+  int32_t precision;        /* BBBP_PREC_*                                                               */
+  int32_t reserved;
+} bbbp_tcnn_desc;
+
+/* Parameter pointer table for bbbp_tcnn_forward, fp32 tensors in the reference's state_dict layout.
+ * Index = BBBP_P_* ; per encoder layer l the 12 tensors start at BBBP_P_LAYER0 + 12*l. */
+enum {
+  BBBP_L_IN_W = 0, BBBP_L_IN_B, BBBP_L_OUT_W, BBBP_L_OUT_B, BBBP_L_FF1_W, BBBP_L_FF1_B, BBBP_L_FF2_W, BBBP_L_FF2_B,
+  BBBP_L_LN1_G, BBBP_L_LN1_B, BBBP_L_LN2_G, BBBP_L_LN2_B, BBBP_L_COUNT
+};
+enum {
+  BBBP_P_FPFC_W = 0, BBBP_P_FPFC_B, BBBP_P_CONV1_W, BBBP_P_CONV1_B, BBBP_P_CONV2_W, BBBP_P_CONV2_B, BBBP_P_IMGFC_W,
+  BBBP_P_IMGFC_B, BBBP_P_FUS_W1 /* 4 heads x (128,256), contiguous per head: +0..3 */, BBBP_P_FUS_B1 = BBBP_P_FUS_W1 + 4,
+  BBBP_P_FUS_W2 = BBBP_P_FUS_B1 + 4, BBBP_P_FUS_B2 = BBBP_P_FUS_W2 + 4, BBBP_P_FC0_W = BBBP_P_FUS_B2 + 4, BBBP_P_FC0_B,
+  BBBP_P_BN_G, BBBP_P_BN_B, BBBP_P_BN_MEAN, BBBP_P_BN_VAR, BBBP_P_FC3_W, BBBP_P_FC3_B, BBBP_P_FC5_W, BBBP_P_FC5_B,
+  BBBP_P_FC7_W, BBBP_P_FC7_B, BBBP_P_LAYER0
+};
+
+/* Bytes of the derived-weight cache (bf16 copies / re-laid-out conv and fc weights) and of the
+ * per-call activation workspace for ``groups*seq`` molecules. */
+size_t bbbp_tcnn_prepared_bytes(const bbbp_tcnn_desc* desc);
+size_t bbbp_tcnn_workspace_bytes(const bbbp_tcnn_desc* desc);
+/* Build the derived-weight cache from the fp32 parameters (call again whenever they change). */
+int bbbp_tcnn_prepare(const bbbp_tcnn_desc* desc, const void* const* params /* host array */, void* prepared,
+                      size_t prepared_bytes, bbbp_stream_t stream);
+/* out[groups*seq] = model(fingerprint[groups*seq, F], image[groups*seq, 3*128*128]) in eval mode.
+ * aux_stream (may be NULL) lets the fingerprint branch overlap the image branch. */
+int bbbp_tcnn_forward(const bbbp_tcnn_desc* desc, const void* const* params /* host array */, const void* prepared,
+                      const float* fingerprint, const float* image, float* out, void* workspace,
+                      size_t workspace_bytes, bbbp_stream_t stream, bbbp_stream_t aux_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBBP_B200_H */
