@@ -1,0 +1,308 @@
+"""torch.autograd.Function wrappers: the reference's ``loss.backward()`` (20250113.py:190) keeps working
+because every op of the forward registers its hand-written backward kernels here.  The autograd ENGINE
+(graph walk, .grad accumulation) is torch plumbing; every arithmetic step is a bbbp_* kernel.
+"""
+from __future__ import annotations
+
+import itertools
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+_seed_counter = itertools.count(1)
+
+
+def next_seed() -> int:
+    """Dropout seed: torch's global seed mixed with a process-wide counter (no device sync)."""
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def contig(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous float32 copy of a 2-D strided view through the copy2d kernel (no torch arithmetic)."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 2 and t.stride(1) == 1:
+        out = torch.empty(t.shape, device=t.device, dtype=t.dtype)
+        return ops.copy2d(t, out)
+    return t.contiguous()
+
+
+# bf16 copies of weights for the tcgen05 GEMMs, refreshed when the parameter is updated in place
+_W16_CACHE: dict = {}
+
+
+def weight_bf16(w: torch.Tensor) -> torch.Tensor:
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _W16_CACHE.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    w2 = w.detach().reshape(w.shape[0], -1)
+    w16 = ops.cast_bf16(w2)
+    _W16_CACHE[key] = (w._version, w16)
+    return w16
+
+
+def clear_weight_cache() -> None:
+    _W16_CACHE.clear()
+
+
+class Linear(Function):
+    """y = act(x W^T + b); precision "fp32" (CUDA-core FMA) or "bf16" (tcgen05, fp32 accumulate)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, precision):
+        x = contig(x)
+        M, K = x.shape
+        N = weight.shape[0]
+        if precision == "bf16":
+            a16 = ops.cast_bf16(x)
+            split = ops.pick_split_k(M, N, K, x.device, 128, 128, 1024)
+            y, _ = ops.gemm_bf16(a16, K, weight_bf16(weight), N, bias=bias, act=act, split_k=split)
+        else:
+            split = ops.pick_split_k(M, N, K, x.device)
+            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=split)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = contig(dy)
+        dpre = ops.act_bwd(dy, y, ctx.act) if ctx.act else dy
+        M, K = x.shape
+        N = weight.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_f32(dpre, weight, split_k=ops.pick_split_k(M, K, N, x.device))
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm_f32(dpre, x, trans_a=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dpre)
+        return dx, dw, db, None, None
+
+
+class ConvReluPool(Function):
+    """maxpool2(relu(conv3x3(x) + b)), NCHW (20250113.py:85-90)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x if x.is_contiguous() else x.contiguous()
+        need = x.requires_grad or weight.requires_grad
+        y, arg = ops.conv3x3(x, weight, bias, pool=True, want_argmax=need)
+        ctx.save_for_backward(x, weight, y, arg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y, arg = ctx.saved_tensors
+        N, Cin, H, W = x.shape
+        Cout = weight.shape[0]
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        dpre = ops.relu_pool_bwd(dy, y, arg, H, W)
+        dw, db = ops.conv3x3_wgrad(dpre, x, Cout, Cin)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = ops.conv3x3(dpre, ops.conv3x3_flip_weights(weight), None, pool=False)
+        return dx, dw, db
+
+
+class Attention(Function):
+    """Self-attention over the molecules of each reference batch; qkv rows = groups*seq."""
+
+    @staticmethod
+    def forward(ctx, qkv, groups, seq, heads, head_dim, dropout_p, seed):
+        qkv = contig(qkv)
+        out, lse = ops.attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p, seed, want_lse=qkv.requires_grad)
+        ctx.cfg = (groups, seq, heads, head_dim, dropout_p, seed)
+        ctx.save_for_backward(qkv, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        return (ops.attention_bwd(qkv, out, lse, contig(dout), *ctx.cfg),) + (None,) * 6
+
+
+class AddLayerNorm(Function):
+    """LN(x + res) * gamma + beta (post-norm residual block)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        x = contig(x)
+        res = None if res is None else contig(res)
+        save = x.requires_grad or gamma.requires_grad or (res is not None and res.requires_grad)
+        y, s, mean, rstd, _ = ops.add_layernorm_fwd(x, res, gamma, beta, eps, save=save)
+        ctx.has_res = res is not None
+        ctx.save_for_backward(s, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, mean, rstd, gamma = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(contig(dy), s, mean, rstd, gamma)
+        return dx, (dx if ctx.has_res else None), dg, db, None
+
+
+class BatchNorm(Function):
+    """nn.BatchNorm1d: batch statistics + running update when training, running statistics otherwise."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):
+        x = contig(x)
+        y, sm, sr = ops.batchnorm_fwd(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+        ctx.training, ctx.eps = training, eps
+        if training:
+            ctx.save_for_backward(x, gamma, sm, sr)
+        else:
+            ctx.save_for_backward(x, gamma, running_mean, running_var)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, a, b = ctx.saved_tensors
+        dy = contig(dy)
+        if ctx.training:
+            dx, dg, db = ops.batchnorm_bwd(dy, x, gamma, a, b)
+        else:
+            dx, dg, db = ops.batchnorm_eval_bwd(dy, x, gamma, a, b, ctx.eps)
+        return dx, dg, db, None, None, None, None, None
+
+
+class FusionMix(Function):
+    """out = sum_h softmax_h(scores) * c  (20250113.py:62-64)."""
+
+    @staticmethod
+    def forward(ctx, scores, c):
+        scores, c = contig(scores), contig(c)
+        out, w = ops.fusion_softmax_mix_fwd(scores, c, want_w=True)
+        ctx.save_for_backward(w, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, c = ctx.saved_tensors
+        dc, ds = ops.fusion_softmax_mix_bwd(w, c, contig(dout))
+        return ds, dc
+
+
+class SoftmaxRows(Function):
+    @staticmethod
+    def forward(ctx, scores):
+        w = ops.softmax_rows_fwd(contig(scores))
+        ctx.save_for_backward(w)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        (w,) = ctx.saved_tensors
+        return ops.softmax_rows_bwd(w, contig(dw))
+
+
+class ScaledColmean(Function):
+    """out[r, :] = scale[r] * mean_rows(x)  (the broadcast quirk of 20250107_network.py:85-96)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = contig(x)
+        scale = scale.reshape(-1)
+        out, cm = ops.scaled_colmean_fwd(x, scale)
+        ctx.save_for_backward(scale, cm)
+        ctx.scale_shape = scale.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        scale, cm = ctx.saved_tensors
+        dx, dscale = ops.scaled_colmean_bwd(contig(dout), scale, cm)
+        return dx, dscale
+
+
+class Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(x if x.is_contiguous() else x.contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(dy if dy.is_contiguous() else dy.contiguous(), ctx.p, ctx.seed), None, None
+
+
+class ConcatCols(Function):
+    """cat(tensors, dim=1) of 2-D float32 tensors through the pitched copy kernel."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        rows = tensors[0].shape[0]
+        widths = [t.shape[1] for t in tensors]
+        out = torch.empty((rows, sum(widths)), device=tensors[0].device, dtype=torch.float32)
+        col = 0
+        for t, w in zip(tensors, widths):
+            ops.copy2d(t if t.stride(1) == 1 else t.contiguous(), out[:, col:col + w])
+            col += w
+        ctx.widths = widths
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads, col = [], 0
+        for w in ctx.widths:
+            grads.append(dout[:, col:col + w])
+            col += w
+        return tuple(grads)
+
+
+class MSELoss(Function):
+    """mean((pred - target)^2) with the gradient produced by the same kernel (20250113.py:143,189)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        p = pred.reshape(-1)
+        p = p if p.is_contiguous() else p.contiguous()
+        t = target.reshape(-1)
+        t = t if t.is_contiguous() else t.contiguous()
+        loss, dpred = ops.mse_loss(p, t, want_grad=pred.requires_grad)
+        ctx.shape = pred.shape
+        ctx.save_for_backward(dpred)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dpred,) = ctx.saved_tensors
+        return ops.scale_by_device_scalar(dpred, dloss.reshape(1).contiguous()).reshape(ctx.shape), None
+
+
+class BCEWithLogitsLoss(Function):
+    """Extension (no reference NN uses it): oracle = F.binary_cross_entropy_with_logits."""
+
+    @staticmethod
+    def forward(ctx, logit, target):
+        z = logit.reshape(-1).contiguous()
+        t = target.reshape(-1).contiguous()
+        loss, d = ops.bce_logits_loss(z, t, want_grad=logit.requires_grad)
+        ctx.shape = logit.shape
+        ctx.save_for_backward(d)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (d,) = ctx.saved_tensors
+        return ops.scale_by_device_scalar(d, dloss.reshape(1).contiguous()).reshape(ctx.shape), None
+
+
+def linear(x, weight, bias=None, act=None, precision="fp32"):
+    return Linear.apply(x, weight, bias, act, precision)
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return Dropout.apply(x, float(p), next_seed())
+
+
+def concat_cols(*tensors):
+    return ConcatCols.apply(*tensors)

@@ -12,6 +12,8 @@ namespace bbbp {
 void set_error(const char* fmt, ...);
 // cudaGetLastError() after a launch -> BBBP_OK / BBBP_ECUDA (message recorded)
 int launch_status(const char* what);
+// adds n to the launch counter behind bbbp_launch_count() (launch_status itself counts one)
+void note_launches(int n);
 
 inline cudaStream_t as_stream(bbbp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -242,6 +242,7 @@ extern "C" int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* 
   if (st != BBBP_OK || !db) return st;
   conv_bgrad_partial_kernel<<<dim3(Cout, N), 256, 0, s>>>(dpre, part_b, Cout, H * W);
   sum_over_images_kernel<<<(unsigned)ceil_div(per_b, (size_t)256), 256, 0, s>>>(part_b, db, N, per_b);
+  note_launches(1);
   return launch_status("conv3x3 bias grad");
 }
 

@@ -46,6 +46,27 @@ __global__ void __launch_bounds__(128) fusion_softmax_mix_bwd_kernel(const float
   if (lane < n) dscores[(size_t)row * n + lane] = wl * (t - wsum * t);
 }
 
+// ---- plain row softmax over n <= 32 scores (big variant's 2-way modality weights, 20250107_network.py:83) ----------
+__global__ void __launch_bounds__(128) softmax_rows_fwd_kernel(const float* __restrict__ scores, float* __restrict__ w,
+                                                               int rows, int n) {
+  const int row = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float sc = lane < n ? scores[(size_t)row * n + lane] : -INFINITY;
+  const float mx = warp_max(sc);
+  const float e = lane < n ? expf(sc - mx) : 0.0f;
+  const float s = warp_sum(e);
+  if (lane < n) w[(size_t)row * n + lane] = e / s;
+}
+__global__ void __launch_bounds__(128) softmax_rows_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dw,
+                                                               float* __restrict__ dscores, int rows, int n) {
+  const int row = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float wl = lane < n ? w[(size_t)row * n + lane] : 0.0f;
+  const float gl = lane < n ? dw[(size_t)row * n + lane] : 0.0f;
+  const float dot = warp_sum(wl * gl);
+  if (lane < n) dscores[(size_t)row * n + lane] = wl * (gl - dot);
+}
+
 // ---- scaled column mean (big variant, 20250107_network.py:85-96) -------------------------------------------------
 __device__ __forceinline__ float strip_reduce(float v, float (*red)[33]) {
   red[threadIdx.y][threadIdx.x] = v;
@@ -334,6 +355,7 @@ extern "C" int bbbp_scaled_colmean_bwd_f32(const float* dout, int ld_dout, const
   scaled_colmean_bwd_dx_kernel<<<ceil_div(cols, 32), dim3(32, 8), 0, as_stream(stream)>>>(dout, ld_dout, scale, ld_scale, dx,
                                                                                         ldx, rows, cols);
   rowdot_vec_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(dout, ld_dout, colmean, dscale, rows, cols);
+  note_launches(1);
   return launch_status("scaled_colmean_bwd");
 }
 
@@ -433,4 +455,19 @@ extern "C" int bbbp_u8_zscore_f32(const uint8_t* img, float* out, int rows, int 
   if (rows == 0) return BBBP_OK;
   u8_zscore_kernel<<<rows, 256, 0, as_stream(stream)>>>(img, out, n);
   return launch_status("u8_zscore");
+}
+
+extern "C" int bbbp_softmax_rows_fwd_f32(const float* scores, float* w, int rows, int n, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(scores && w && rows >= 0 && n > 0 && n <= 32, "softmax_rows_fwd: bad argument");
+  if (rows == 0) return BBBP_OK;
+  softmax_rows_fwd_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(scores, w, rows, n);
+  return launch_status("softmax_rows_fwd");
+}
+
+extern "C" int bbbp_softmax_rows_bwd_f32(const float* w, const float* dw, float* dscores, int rows, int n,
+                                         bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(w && dw && dscores && rows >= 0 && n > 0 && n <= 32, "softmax_rows_bwd: bad argument");
+  if (rows == 0) return BBBP_OK;
+  softmax_rows_bwd_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(w, dw, dscores, rows, n);
+  return launch_status("softmax_rows_bwd");
 }

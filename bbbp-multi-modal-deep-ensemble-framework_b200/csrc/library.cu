@@ -1,6 +1,7 @@
 // Library-level entry points: ABI version, error string, device check.
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include "common.cuh"
 
 namespace bbbp {
@@ -13,7 +14,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<uint64_t> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
 int launch_status(const char* what) {
+  note_launches(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -24,6 +29,7 @@ int launch_status(const char* what) {
 }  // namespace bbbp
 
 extern "C" int bbbp_abi_version(void) { return BBBP_ABI_VERSION; }
+extern "C" uint64_t bbbp_launch_count(void) { return bbbp::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* bbbp_last_error(void) { return bbbp::g_error; }
 
 extern "C" int bbbp_device_check(void) {

@@ -211,6 +211,7 @@ extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const flo
   layernorm_bwd_param_partial_kernel<<<dim3(LN_PARTS, ceil_div(dim, 128)), 128, 0, st>>>(dy, s, mean, rstd, workspace,
                                                                                          rows, dim);
   layernorm_bwd_param_final_kernel<<<ceil_div(dim, 128), 128, 0, st>>>(workspace, dgamma, dbeta, dim);
+  note_launches(2);
   return launch_status("layernorm_bwd");
 }
 

@@ -1,0 +1,388 @@
+"""Drop-in replacements for the reference's inline ``nn.Module`` classes.
+
+Constructor signatures, ``forward(fingerprint, image)`` and every ``state_dict`` key equal the
+reference's, so ``load_state_dict(torch.load("best_nn_model_maccs.pth"))``, stock ``optim.AdamW``,
+``pickle.dump(model)`` and the ensemble scripts keep working unchanged:
+
+  * transformer-CNN, canonical: Models/multi_input_data_regression_opt_transformer_cnn_20250113.py:48-119
+    (identical class bodies in ..._transformer_cnn.py, ..._20250108.py, Descriptors/..._opt_all.py)
+  * transformer-CNN, big:       Models/multi_input_data_regression_opt_transformer_cnn_opt_20250107_network.py:51-174
+  * transformer-CNN, no fusion: Descriptors/multi_input_data_regression_opt_round_2_transformer_cnn.py:45-102
+  * MLP family:                 Models/..._transformer_cnn_opt.py:52-105, ..._opt_more.py:57-110,
+                                ..._rdkit.py:53-102, ..._morgan.py (== _opt)
+
+The stock ``torch.nn`` sub-modules are kept ONLY as parameter containers (same construction order =>
+same random initial weights under the same seed, same key names).  Their ``forward`` is never called:
+every arithmetic step goes through the sm_100a kernels behind include/bbbp_b200.h.  There is no CPU
+path; calling a model on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import autograd as ag
+
+_DEFAULT_PRECISION = os.environ.get("BBBP_PRECISION", "fp32")
+
+
+def encoder_heads(fingerprint_size: int, start: int | None = None) -> int:
+    """20250113.py:71-73 (start = max(1, F // 8)); 20250107_network.py:112-117 (start = 8)."""
+    nhead = max(1, fingerprint_size // 8) if start is None else start
+    while fingerprint_size % nhead != 0 and nhead > 1:
+        nhead -= 1
+    return nhead
+
+
+def _encoder(fingerprint_size: int, nhead: int, layers: int) -> nn.TransformerEncoder:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # "enable_nested_tensor is True, but ... batch_first was not True"
+        return nn.TransformerEncoder(nn.TransformerEncoderLayer(d_model=fingerprint_size, nhead=nhead), num_layers=layers)
+
+
+def _score_mlp(in_dim: int, hidden: int, out_dim: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(in_dim, hidden), nn.Tanh(), nn.Linear(hidden, out_dim))
+
+
+class _KernelModule(nn.Module):
+    """Shared helpers: every op dispatches to the CUDA library."""
+
+    precision = _DEFAULT_PRECISION  # "fp32" (CUDA-core FMA) | "bf16" (tcgen05 GEMMs, fp32 accumulation)
+
+    def set_precision(self, precision: str):
+        assert precision in ("fp32", "bf16")
+        for m in self.modules():
+            if isinstance(m, _KernelModule):
+                m.precision = precision
+        return self
+
+    def _lin(self, x, layer: nn.Linear, act=None):
+        return ag.linear(x, layer.weight, layer.bias, act, self.precision)
+
+    def _bn(self, x, bn: nn.BatchNorm1d):
+        training = self.training and bn.training
+        use_batch = training or bn.running_mean is None
+        if use_batch and x.shape[0] == 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
+        if training and bn.track_running_stats:
+            bn.num_batches_tracked += 1
+        return ag.BatchNorm.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
+                                  bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+
+    def _drop(self, x, module_or_p):
+        p = module_or_p.p if isinstance(module_or_p, nn.Dropout) else float(module_or_p)
+        return ag.dropout(x, p, self.training)
+
+    @staticmethod
+    def _check_inputs(*tensors):
+        for t in tensors:
+            if not t.is_cuda:
+                raise RuntimeError("bbbp_b200 models run on CUDA (sm_100a) tensors only: there is no CPU fallback; "
+                                   "move the model and its inputs to the GPU")
+            if t.dtype != torch.float32:
+                raise TypeError(f"bbbp_b200 models take float32 inputs, got {t.dtype}")
+
+
+# ---- fusion blocks ---------------------------------------------------------------------------------------------------
+class MultiHeadAttentionFusion(_KernelModule):
+    """20250113.py:48-65: softmax over the head axis; the weights multiply the same concatenated vector."""
+
+    def __init__(self, input_dim, num_heads=4, hidden_dim=128):
+        super().__init__()
+        self.attention_heads = nn.ModuleList(_score_mlp(input_dim, hidden_dim, 1) for _ in range(num_heads))
+        self.softmax = nn.Softmax(dim=1)
+
+    def forward(self, x1, x2):
+        both = ag.concat_cols(x1, x2)
+        scores = [self._lin(self._lin(both, head[0], "tanh"), head[2]) for head in self.attention_heads]
+        return ag.FusionMix.apply(ag.concat_cols(*scores), both)
+
+
+class AttentionFusion(_KernelModule):
+    """_rdkit.py:53-66: Softmax(dim=1) over a width-1 score, i.e. a weight that is identically 1."""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        self.attention = nn.Sequential(nn.Linear(input_dim, 128), nn.Tanh(), nn.Linear(128, 1), nn.Softmax(dim=1))
+
+    def forward(self, x1, x2):
+        both = ag.concat_cols(x1, x2)
+        score = self._lin(self._lin(both, self.attention[0], "tanh"), self.attention[2])
+        return ag.FusionMix.apply(score, both)
+
+
+class MultiModalAttentionFusion(_KernelModule):
+    """20250107_network.py:51-105.  The (B,1,1)*(B,D) broadcast + mean(dim=1) makes each weighted block
+    ``w[i] * mean_over_the_batch(feature)``; ``groups`` > 1 evaluates several reference batches at once."""
+
+    def __init__(self, fingerprint_dim, image_dim, hidden_dim=128):
+        super().__init__()
+        self.fingerprint_attention = _score_mlp(fingerprint_dim, hidden_dim, 1)
+        self.image_attention = _score_mlp(image_dim, hidden_dim, 1)
+        self.cross_modal_attention = _score_mlp(fingerprint_dim + image_dim, hidden_dim, fingerprint_dim)
+        self.softmax = nn.Softmax(dim=1)
+
+    def _mlp(self, x, seq_mod):
+        return self._lin(self._lin(x, seq_mod[0], "tanh"), seq_mod[2])
+
+    def forward(self, fingerprint, image, groups: int = 1):
+        w_fp = self._mlp(fingerprint, self.fingerprint_attention)
+        w_im = self._mlp(image, self.image_attention)
+        cross = self._mlp(ag.concat_cols(fingerprint, image), self.cross_modal_attention)
+        w = ag.SoftmaxRows.apply(ag.concat_cols(w_fp, w_im))
+        seq = fingerprint.shape[0] // groups
+        parts = []
+        for g in range(groups):
+            rows = slice(g * seq, (g + 1) * seq)
+            fp_w = ag.ScaledColmean.apply(fingerprint[rows], w[rows, 0])
+            im_w = ag.ScaledColmean.apply(image[rows], w[rows, 1])
+            parts.append(ag.concat_cols(fp_w, im_w, cross[rows]))
+        return parts[0] if groups == 1 else torch.cat(parts, dim=0)
+
+
+# ---- transformer-CNN family --------------------------------------------------------------------------------------------
+def _conv_stack(channels, image_feature_size, fc_out, dropout):
+    layers, cin = [], 3
+    for cout in channels:
+        layers += [nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1), nn.ReLU(), nn.MaxPool2d(kernel_size=2, stride=2)]
+        cin = cout
+    side = image_feature_size // (2 ** len(channels))
+    layers += [nn.Flatten(), nn.Linear(cin * side * side, fc_out), nn.ReLU()]
+    if dropout:
+        layers.append(nn.Dropout(dropout))
+    return nn.Sequential(*layers)
+
+
+class TransformerCnnModel(_KernelModule):
+    """kind: "canonical" | "big" | "nofusion" (see module docstring for the reference sources)."""
+
+    IMAGE_SIDE = 128  # the reference hard-codes image.view(-1, 3, 128, 128) (20250113.py:114)
+
+    def __init__(self, fingerprint_size, image_feature_size, kind="canonical"):
+        super().__init__()
+        self.kind = kind
+        big = kind == "big"
+        nhead = encoder_heads(fingerprint_size, 8 if big else None)
+        if fingerprint_size % nhead != 0:
+            raise ValueError(f"fingerprint_size={fingerprint_size} must be divisible by nhead={nhead}.")
+        self.fingerprint_transformer = _encoder(fingerprint_size, nhead, 12 if big else 6)
+        width = 512 if big else 128
+        fp_fc = [nn.Linear(fingerprint_size, width), nn.ReLU()]
+        if big:
+            fp_fc.append(nn.Dropout(0.3))
+        self.fingerprint_fc = nn.Sequential(*fp_fc)
+        self.image_cnn = _conv_stack((64, 128, 256) if big else (32, 64), image_feature_size, width, 0.3 if big else 0.0)
+        if kind == "canonical":
+            self.attention_fusion = MultiHeadAttentionFusion(256, num_heads=4)
+        elif big:
+            self.attention_fusion = MultiModalAttentionFusion(512, 512)
+        elif kind != "nofusion":
+            raise ValueError(kind)
+        if big:
+            self.fc = nn.Sequential(nn.Linear(1536, 1024), nn.ReLU(), nn.BatchNorm1d(1024), nn.Linear(1024, 512), nn.ReLU(),
+                                    nn.Dropout(0.3), nn.Linear(512, 256), nn.ReLU(), nn.Linear(256, 128), nn.ReLU(),
+                                    nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1))
+        else:
+            self.fc = nn.Sequential(nn.Linear(256, 256), nn.ReLU(), nn.BatchNorm1d(256), nn.Linear(256, 128), nn.ReLU(),
+                                    nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1))
+
+    # -- encoder ------------------------------------------------------------------------------------------------------
+    def _encoder_layer(self, x, layer: nn.TransformerEncoderLayer, groups: int, seq: int):
+        attn = layer.self_attn
+        heads = attn.num_heads
+        head_dim = x.shape[1] // heads
+        p_attn = float(attn.dropout) if self.training else 0.0
+        qkv = ag.linear(x, attn.in_proj_weight, attn.in_proj_bias, None, self.precision)
+        a = ag.Attention.apply(qkv, groups, seq, heads, head_dim, p_attn, ag.next_seed() if p_attn > 0 else 0)
+        sa = self._drop(self._lin(a, attn.out_proj), layer.dropout1)
+        x = ag.AddLayerNorm.apply(sa, x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+        h = self._drop(self._lin(x, layer.linear1, "relu"), layer.dropout)
+        f = self._drop(self._lin(h, layer.linear2), layer.dropout2)
+        return ag.AddLayerNorm.apply(f, x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+
+    def _head(self, x):
+        mods = list(self.fc)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                act = "relu" if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) else None
+                x = self._lin(x, m, act)
+                i += 2 if act else 1
+            elif isinstance(m, nn.BatchNorm1d):
+                x = self._bn(x, m)
+                i += 1
+            elif isinstance(m, nn.Dropout):
+                x = self._drop(x, m)
+                i += 1
+            else:
+                raise TypeError(m)
+        return x
+
+    def _image_branch(self, image):
+        side = self.IMAGE_SIDE
+        x = image.reshape(-1, 3, side, side)
+        mods = list(self.image_cnn)
+        i = 0
+        while isinstance(mods[i], nn.Conv2d):
+            x = ag.ConvReluPool.apply(x, mods[i].weight, mods[i].bias)
+            i += 3  # Conv2d, ReLU, MaxPool2d
+        x = x.reshape(x.shape[0], -1)          # nn.Flatten: (C, H, W) order, a view
+        x = self._lin(x, mods[i + 1], "relu")
+        if len(mods) > i + 3:
+            x = self._drop(x, mods[i + 3])
+        return x
+
+    def forward_groups(self, fingerprint, image, groups: int = 1):
+        """``groups`` independent reference batches of equal size stacked along dim 0 (attention and the
+        big variant's batch-mean stay inside each batch).  Train-mode BatchNorm would mix
+        the groups, so groups > 1 is for eval mode."""
+        self._check_inputs(fingerprint, image)
+        if groups > 1 and self.training:
+            raise RuntimeError("forward_groups(groups > 1) is an inference path: call model.eval() first")
+        rows = fingerprint.shape[0]
+        if rows % groups:
+            raise ValueError(f"{rows} molecules do not split into {groups} equal reference batches")
+        x = fingerprint if fingerprint.is_contiguous() else fingerprint.contiguous()
+        for layer in self.fingerprint_transformer.layers:
+            x = self._encoder_layer(x, layer, groups, rows // groups)
+        fp = self._lin(x, self.fingerprint_fc[0], "relu")
+        if len(self.fingerprint_fc) > 2:
+            fp = self._drop(fp, self.fingerprint_fc[2])
+        im = self._image_branch(image)
+        if self.kind == "nofusion":
+            fused = ag.concat_cols(fp, im)
+        elif self.kind == "big":
+            fused = self.attention_fusion(fp, im, groups)
+        else:
+            fused = self.attention_fusion(fp, im)
+        return self._head(fused)
+
+    def forward(self, fingerprint, image):
+        return self.forward_groups(fingerprint, image, 1)
+
+    @torch.no_grad()
+    def predict_batches(self, fingerprint, image, batch_size: int, max_rows_per_pass: int = 16384):
+        """Batched inference with the reference's batch semantics (20250113.py:229-237): molecules
+        [b*batch_size, (b+1)*batch_size) form reference batch b; returns (N,) scores.  Full batches are
+        evaluated ``max_rows_per_pass`` molecules at a time, the ragged tail batch on its own."""
+        assert not self.training, "call model.eval() first"
+        n = fingerprint.shape[0]
+        out = torch.empty((n,), device=fingerprint.device, dtype=torch.float32)
+        per_pass = max(1, max_rows_per_pass // batch_size) * batch_size
+        full = (n // batch_size) * batch_size
+        start = 0
+        while start < full:
+            stop = min(full, start + per_pass)
+            y = self.forward_groups(fingerprint[start:stop], image[start:stop], (stop - start) // batch_size)
+            out[start:stop].copy_(y.reshape(-1))
+            start = stop
+        if full < n:
+            out[full:].copy_(self.forward_groups(fingerprint[full:], image[full:], 1).reshape(-1))
+        return out
+
+
+class MixedInputModel(TransformerCnnModel):
+    """The canonical network: ``MixedInputModel(fingerprint_size, image_feature_size)`` (20250113.py:68-119)."""
+
+    def __init__(self, fingerprint_size, image_feature_size):
+        super().__init__(fingerprint_size, image_feature_size, "canonical")
+
+
+class MixedInputModelBig(TransformerCnnModel):
+    """``MixedInputModel`` of ..._opt_20250107_network.py:109-174."""
+
+    def __init__(self, fingerprint_size, image_feature_size):
+        super().__init__(fingerprint_size, image_feature_size, "big")
+
+
+class MixedInputModelNoFusion(TransformerCnnModel):
+    """``MixedInputModel`` of Descriptors/..._round_2_transformer_cnn.py:45-102."""
+
+    def __init__(self, fingerprint_size, image_feature_size):
+        super().__init__(fingerprint_size, image_feature_size, "nofusion")
+
+
+# ---- MLP family ----------------------------------------------------------------------------------------------------------
+class MlpModel(_KernelModule):
+    """kind: "opt" (also _morgan) | "more" | "rdkit"; inputs are PCA-reduced feature vectors."""
+
+    def __init__(self, fingerprint_size, image_feature_size, kind="opt"):
+        super().__init__()
+        self.kind = kind
+        if kind == "more":
+            def branch(n_in):
+                return nn.Sequential(nn.Linear(n_in, 256), nn.ReLU(), nn.BatchNorm1d(256), nn.Dropout(0.3))
+            self.fingerprint_fc, self.image_fc = branch(fingerprint_size), branch(image_feature_size)
+            self.attention_fusion = MultiHeadAttentionFusion(512)
+            self.fc = nn.Sequential(nn.Linear(512, 256), nn.ReLU(), nn.BatchNorm1d(256), nn.Linear(256, 128), nn.ReLU(),
+                                    nn.Linear(128, 1))
+        elif kind in ("opt", "rdkit"):
+            self.fingerprint_fc = nn.Sequential(nn.Linear(fingerprint_size, 128), nn.ReLU())
+            self.image_fc = nn.Sequential(nn.Linear(image_feature_size, 128), nn.ReLU())
+            self.attention_fusion = AttentionFusion(256) if kind == "rdkit" else MultiHeadAttentionFusion(256)
+            self.fc = nn.Sequential(nn.Linear(256, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1))
+        else:
+            raise ValueError(kind)
+
+    def _branch(self, x, seq_mod):
+        x = self._lin(x, seq_mod[0], "relu")
+        if len(seq_mod) > 2:
+            x = self._drop(self._bn(x, seq_mod[2]), seq_mod[3])
+        return x
+
+    def forward(self, fingerprint, image):
+        self._check_inputs(fingerprint, image)
+        fused = self.attention_fusion(self._branch(fingerprint, self.fingerprint_fc), self._branch(image, self.image_fc))
+        return TransformerCnnModel._head(self, fused)
+
+
+class MixedInputModelMLP(MlpModel):
+    """``MixedInputModel`` of Models/..._transformer_cnn_opt.py:72-105 and ..._morgan.py."""
+
+    def __init__(self, fingerprint_size, image_feature_size):
+        super().__init__(fingerprint_size, image_feature_size, "opt")
+
+
+class MixedInputModelMLPMore(MlpModel):
+    """``MixedInputModel`` of Models/..._transformer_cnn_opt_more.py:80-110."""
+
+    def __init__(self, fingerprint_size, image_feature_size):
+        super().__init__(fingerprint_size, image_feature_size, "more")
+
+
+class MixedInputModelMLPRdkit(MlpModel):
+    """``MixedInputModel`` of Models/..._transformer_cnn_rdkit.py:68-102."""
+
+    def __init__(self, fingerprint_size, image_feature_size):
+        super().__init__(fingerprint_size, image_feature_size, "rdkit")
+
+
+VARIANTS = {
+    "tcnn": MixedInputModel, "tcnn_first": MixedInputModel, "tcnn_20250108": MixedInputModel,
+    "tcnn_big": MixedInputModelBig, "tcnn_nofusion": MixedInputModelNoFusion,
+    "mlp": MixedInputModelMLP, "mlp_morgan": MixedInputModelMLP, "mlp_rdkit": MixedInputModelMLPRdkit,
+    "mlp_more": MixedInputModelMLPMore,
+}
+
+
+def build(variant: str, fingerprint_size: int, image_feature_size: int) -> nn.Module:
+    """Variant names follow the reference script each class comes from (see VARIANTS)."""
+    return VARIANTS[variant](fingerprint_size, image_feature_size)
+
+
+class MSELoss(nn.Module):
+    """Drop-in for ``nn.MSELoss()`` (20250113.py:143): fused loss + gradient kernel."""
+
+    def forward(self, pred, target):
+        return ag.MSELoss.apply(pred, target)
+
+
+class BCEWithLogitsLoss(nn.Module):
+    """Extension head for the classification config (no reference NN uses BCE)."""
+
+    def forward(self, logit, target):
+        return ag.BCEWithLogitsLoss.apply(logit, target)

@@ -1,0 +1,384 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see autograd.py).
+
+Each function takes CUDA tensors, allocates outputs/workspaces through torch's caching
+allocator, and enqueues the kernel on torch's current stream.  PyTorch is plumbing only:
+device memory and streams.  Nothing in this file computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import lib, check
+
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+_ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2, 0: 0, 1: 1, 2: 2}
+
+_SM_COUNT = {}
+
+
+def sm_count(device) -> int:
+    idx = torch.device(device).index or 0
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"bbbp_b200: {name} must be a CUDA tensor (this package has no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"bbbp_b200: {name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _KernelTimer:
+    """Optional CUDA-event brackets around named kernels (bench.py's live roofline measurement).
+    Disabled by default: the wrappers then pay one set lookup."""
+
+    def __init__(self):
+        self.names, self.spans = frozenset(), {}
+
+    def enable(self, names):
+        self.names = frozenset(names)
+        self.spans = {n: [] for n in names}
+
+    def disable(self):
+        self.names = frozenset()
+
+    def start(self, name):
+        if name not in self.names:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, name, e0, units):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.spans[name].append((e0, e1, units))
+
+    def collect(self, name):
+        torch.cuda.synchronize()
+        spans = self.spans.get(name, [])
+        return [a.elapsed_time(b) for a, b, _ in spans], [u for _, _, u in spans]
+
+
+KERNEL_TIMER = _KernelTimer()
+
+
+def require_device() -> None:
+    check(lib.bbbp_device_check(), "device_check")
+
+
+# ---- dense ---------------------------------------------------------------------------------------------------------
+def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=None, out=None, accumulate=False, split_k=1):
+    """act(op(a) @ op(b) + bias) with row-major 2-D float32 operands (pitches = tensor strides)."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    Kb, N = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    assert K == Kb, (a.shape, b.shape, trans_a, trans_b)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    ws = None
+    if split_k > 1:
+        ws = torch.empty((split_k * M * N,), device=a.device, dtype=torch.float32)
+    check(lib.bbbp_gemm_f32(int(trans_a), int(trans_b), M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                            out.data_ptr(), out.stride(0), _ptr(bias), _ACT[act], int(accumulate), split_k, _ptr(ws),
+                            0 if ws is None else ws.numel() * 4, _stream()), "gemm_f32")
+    return out
+
+
+def pick_split_k(M: int, N: int, K: int, device, tile_m=64, tile_n=64, min_k=512) -> int:
+    tiles = -(-M // tile_m) * -(-N // tile_n)
+    want = -(-2 * sm_count(device) // tiles)
+    return max(1, min(want, K // min_k))
+
+
+def cast_bf16(x: torch.Tensor, ld: int | None = None) -> torch.Tensor:
+    """(rows, cols) float32 -> (rows, ld) bfloat16 with zero fill of the pad columns; ld multiple of 8."""
+    rows, cols = x.shape
+    if ld is None:
+        ld = -(-cols // 8) * 8
+    out = torch.empty((rows, ld), device=x.device, dtype=torch.bfloat16)
+    check(lib.bbbp_cast_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), ld, rows, cols, ld, _stream()), "cast_bf16")
+    return out
+
+
+def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, out_bf16=False, split_k=1):
+    """act(a16[:, :K] @ w16[:N, :K]^T + bias) (+ residual) on the tcgen05 path.  Returns (f32 | None, bf16 | None)."""
+    M = a16.shape[0]
+    o32 = torch.empty((M, N), device=a16.device, dtype=torch.float32) if out_f32 else None
+    ld16 = -(-N // 8) * 8
+    o16 = torch.zeros((M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
+    ws_bytes = lib.bbbp_gemm_bf16_workspace(M, N, split_k)
+    ws = torch.empty((ws_bytes,), device=a16.device, dtype=torch.uint8) if ws_bytes else None
+    check(lib.bbbp_gemm_bf16(M, N, K, a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), _ptr(bias),
+                             _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(o32), N, _ptr(o16), ld16,
+                             _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
+    return o32, o16
+
+
+# ---- image branch -----------------------------------------------------------------------------------------------------
+def conv3x3(x, w, b, pool=True, want_argmax=False):
+    N, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    if pool:
+        y = torch.empty((N, Cout, H // 2, W // 2), device=x.device, dtype=torch.float32)
+        arg = torch.empty(y.shape, device=x.device, dtype=torch.uint8) if want_argmax else None
+    else:
+        y = torch.empty((N, Cout, H, W), device=x.device, dtype=torch.float32)
+        arg = None
+    name = "conv1" if Cin == 3 else "conv2" if (Cin, Cout) == (32, 64) else "conv"
+    t0 = KERNEL_TIMER.start(name)
+    check(lib.bbbp_conv3x3_f32(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), _ptr(arg), N, Cin, Cout, H, W,
+                               int(pool), _stream()), "conv3x3_f32")
+    KERNEL_TIMER.stop(name, t0, N)
+    return y, arg
+
+
+def relu_pool_bwd(dy, y, argmax, H, W):
+    N, C = y.shape[:2]
+    dpre = torch.empty((N, C, H, W), device=y.device, dtype=torch.float32)
+    check(lib.bbbp_relu_pool_bwd_f32(dy.data_ptr(), y.data_ptr(), argmax.data_ptr(), dpre.data_ptr(), N, C, H, W,
+                                     _stream()), "relu_pool_bwd")
+    return dpre
+
+
+def conv3x3_wgrad(dpre, x, Cout, Cin):
+    N, _, H, W = x.shape
+    dw = torch.empty((Cout, Cin, 3, 3), device=x.device, dtype=torch.float32)
+    db = torch.empty((Cout,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((N * (Cout * Cin * 9 + Cout),), device=x.device, dtype=torch.float32)
+    check(lib.bbbp_conv3x3_wgrad_f32(dpre.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), N, Cin, Cout, H, W,
+                                     ws.data_ptr(), ws.numel() * 4, _stream()), "conv3x3_wgrad")
+    return dw, db
+
+
+def conv3x3_flip_weights(w):
+    Cout, Cin = w.shape[:2]
+    wt = torch.empty((Cin, Cout, 3, 3), device=w.device, dtype=torch.float32)
+    check(lib.bbbp_conv3x3_flip_weights_f32(w.data_ptr(), wt.data_ptr(), Cin, Cout, _stream()), "flip_weights")
+    return wt
+
+
+# ---- attention --------------------------------------------------------------------------------------------------------
+def attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p=0.0, seed=0, want_lse=True):
+    E = heads * head_dim
+    out = torch.empty((groups * seq, E), device=qkv.device, dtype=torch.float32)
+    lse = torch.empty((groups * seq, heads), device=qkv.device, dtype=torch.float32) if want_lse else None
+    check(lib.bbbp_attention_fwd_f32(qkv.data_ptr(), out.data_ptr(), _ptr(lse), groups, seq, heads, head_dim,
+                                     float(dropout_p), int(seed), _stream()), "attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, lse, dout, groups, seq, heads, head_dim, dropout_p=0.0, seed=0):
+    dqkv = torch.empty_like(qkv)
+    check(lib.bbbp_attention_bwd_f32(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+                                     groups, seq, heads, head_dim, float(dropout_p), int(seed), _stream()),
+          "attention_bwd")
+    return dqkv
+
+
+# ---- norms ------------------------------------------------------------------------------------------------------------
+def add_layernorm_fwd(x, res, gamma, beta, eps=1e-5, save=False, bf16_ld=0):
+    rows, dim = x.shape
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if save else None
+    mean = torch.empty((rows,), device=x.device, dtype=torch.float32) if save else None
+    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32) if save else None
+    y16 = torch.empty((rows, bf16_ld), device=x.device, dtype=torch.bfloat16) if bf16_ld else None
+    check(lib.bbbp_add_layernorm_fwd_f32(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                         _ptr(s), _ptr(mean), _ptr(rstd), _ptr(y16), bf16_ld, rows, dim, float(eps),
+                                         _stream()), "add_layernorm_fwd")
+    return y, s, mean, rstd, y16
+
+
+def layernorm_bwd(dy, s, mean, rstd, gamma):
+    rows, dim = s.shape
+    dx = torch.empty_like(s)
+    dg = torch.empty_like(gamma)
+    db = torch.empty_like(gamma)
+    ws = torch.empty((2 * 64 * dim,), device=s.device, dtype=torch.float32)
+    check(lib.bbbp_layernorm_bwd_f32(dy.data_ptr(), s.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                     dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, dim, ws.data_ptr(),
+                                     ws.numel() * 4, _stream()), "layernorm_bwd")
+    return dx, dg, db
+
+
+def batchnorm_fwd(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    rows, C = x.shape
+    y = torch.empty_like(x)
+    sm = torch.empty((C,), device=x.device, dtype=torch.float32) if training else None
+    sr = torch.empty((C,), device=x.device, dtype=torch.float32) if training else None
+    check(lib.bbbp_batchnorm_fwd_f32(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                     running_var.data_ptr(), y.data_ptr(), _ptr(sm), _ptr(sr), rows, C, int(training),
+                                     float(momentum), float(eps), _stream()), "batchnorm_fwd")
+    return y, sm, sr
+
+
+def batchnorm_bwd(dy, x, gamma, save_mean, save_rstd):
+    rows, C = x.shape
+    dx, dg, db = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+    check(lib.bbbp_batchnorm_bwd_f32(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), save_mean.data_ptr(),
+                                     save_rstd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C,
+                                     _stream()), "batchnorm_bwd")
+    return dx, dg, db
+
+
+def batchnorm_eval_bwd(dy, x, gamma, running_mean, running_var, eps=1e-5):
+    rows, C = x.shape
+    dx, dg, db = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+    check(lib.bbbp_batchnorm_eval_bwd_f32(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), running_mean.data_ptr(),
+                                          running_var.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C,
+                                          float(eps), _stream()), "batchnorm_eval_bwd")
+    return dx, dg, db
+
+
+# ---- fusion blocks ----------------------------------------------------------------------------------------------------
+def fusion_softmax_mix_fwd(scores, c, want_w=False):
+    rows, n = scores.shape
+    dim = c.shape[1]
+    out = torch.empty_like(c)
+    w = torch.empty_like(scores) if want_w else None
+    check(lib.bbbp_fusion_softmax_mix_fwd_f32(scores.data_ptr(), c.data_ptr(), out.data_ptr(), _ptr(w), rows, n, dim,
+                                              _stream()), "fusion_softmax_mix_fwd")
+    return out, w
+
+
+def fusion_softmax_mix_bwd(w, c, dout):
+    rows, n = w.shape
+    dim = c.shape[1]
+    dc, ds = torch.empty_like(c), torch.empty_like(w)
+    check(lib.bbbp_fusion_softmax_mix_bwd_f32(w.data_ptr(), c.data_ptr(), dout.data_ptr(), dc.data_ptr(), ds.data_ptr(),
+                                              rows, n, dim, _stream()), "fusion_softmax_mix_bwd")
+    return dc, ds
+
+
+def softmax_rows_fwd(scores):
+    rows, n = scores.shape
+    w = torch.empty_like(scores)
+    check(lib.bbbp_softmax_rows_fwd_f32(scores.data_ptr(), w.data_ptr(), rows, n, _stream()), "softmax_rows_fwd")
+    return w
+
+
+def softmax_rows_bwd(w, dw):
+    rows, n = w.shape
+    ds = torch.empty_like(w)
+    check(lib.bbbp_softmax_rows_bwd_f32(w.data_ptr(), dw.data_ptr(), ds.data_ptr(), rows, n, _stream()),
+          "softmax_rows_bwd")
+    return ds
+
+
+def scaled_colmean_fwd(x, scale):
+    """x (rows, cols) any row pitch; scale: 1-D strided view of length rows."""
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), device=x.device, dtype=torch.float32)
+    cm = torch.empty((cols,), device=x.device, dtype=torch.float32)
+    check(lib.bbbp_scaled_colmean_fwd_f32(x.data_ptr(), x.stride(0), scale.data_ptr(), scale.stride(0), out.data_ptr(),
+                                          cols, cm.data_ptr(), rows, cols, _stream()), "scaled_colmean_fwd")
+    return out, cm
+
+
+def scaled_colmean_bwd(dout, scale, colmean):
+    rows, cols = dout.shape
+    dx = torch.empty((rows, cols), device=dout.device, dtype=torch.float32)
+    dscale = torch.empty((rows,), device=dout.device, dtype=torch.float32)
+    check(lib.bbbp_scaled_colmean_bwd_f32(dout.data_ptr(), dout.stride(0), scale.data_ptr(), scale.stride(0),
+                                          colmean.data_ptr(), dx.data_ptr(), cols, dscale.data_ptr(), rows, cols,
+                                          _stream()), "scaled_colmean_bwd")
+    return dx, dscale
+
+
+# ---- elementwise ------------------------------------------------------------------------------------------------------
+def act_bwd(dy, y, act):
+    rows, cols = y.shape
+    dx = torch.empty((rows, cols), device=y.device, dtype=torch.float32)
+    check(lib.bbbp_act_bwd_f32(dy.data_ptr(), dy.stride(0), y.data_ptr(), y.stride(0), dx.data_ptr(), cols, rows, cols,
+                               _ACT[act], _stream()), "act_bwd")
+    return dx
+
+
+def scale_by_device_scalar(x, scalar):
+    y = torch.empty_like(x)
+    check(lib.bbbp_scale_by_device_scalar_f32(x.data_ptr(), scalar.data_ptr(), y.data_ptr(), x.numel(), _stream()),
+          "scale_by_device_scalar")
+    return y
+
+
+def colsum(x):
+    rows, cols = x.shape
+    out = torch.empty((cols,), device=x.device, dtype=torch.float32)
+    check(lib.bbbp_colsum_f32(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, _stream()), "colsum")
+    return out
+
+
+def copy2d(src, dst):
+    """dst[:, :] = src[:, :] for 2-D views with unit inner stride and arbitrary row pitch."""
+    rows, cols = src.shape
+    assert dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    check(lib.bbbp_copy2d_f32(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, _stream()),
+          "copy2d")
+    return dst
+
+
+def dropout(x, p, seed, offset=0):
+    y = torch.empty_like(x)
+    check(lib.bbbp_dropout_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset), _stream()),
+          "dropout")
+    return y
+
+
+# ---- losses / optimiser --------------------------------------------------------------------------------------------------
+def mse_loss(pred, target, want_grad=True, grad_scale=1.0):
+    n = pred.numel()
+    loss = torch.empty((1,), device=pred.device, dtype=torch.float32)
+    dpred = torch.empty((n,), device=pred.device, dtype=torch.float32) if want_grad else None
+    check(lib.bbbp_mse_loss_f32(pred.data_ptr(), target.data_ptr(), loss.data_ptr(), _ptr(dpred), n, float(grad_scale),
+                                _stream()), "mse_loss")
+    return loss, dpred
+
+
+def bce_logits_loss(logit, target, want_grad=True, grad_scale=1.0):
+    n = logit.numel()
+    loss = torch.empty((1,), device=logit.device, dtype=torch.float32)
+    d = torch.empty((n,), device=logit.device, dtype=torch.float32) if want_grad else None
+    check(lib.bbbp_bce_logits_loss_f32(logit.data_ptr(), target.data_ptr(), loss.data_ptr(), _ptr(d), n,
+                                       float(grad_scale), _stream()), "bce_logits_loss")
+    return loss, d
+
+
+def adamw(ptr_table, sizes, chunk_tensor, chunk_offset, ntensors, nchunks, lr, beta1, beta2, eps, weight_decay, step,
+          grad_scale=1.0):
+    check(lib.bbbp_adamw_f32(ptr_table.data_ptr(), sizes.data_ptr(), chunk_tensor.data_ptr(), chunk_offset.data_ptr(),
+                             ntensors, nchunks, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                             int(step), float(grad_scale), _stream()), "adamw")
+
+
+# ---- input contracts ------------------------------------------------------------------------------------------------------
+def unpack_zscore(packed: torch.Tensor, n_bits: int) -> torch.Tensor:
+    rows, bpr = packed.shape
+    assert packed.dtype == torch.uint8 and packed.is_contiguous()
+    out = torch.empty((rows, n_bits), device=packed.device, dtype=torch.float32)
+    check(lib.bbbp_unpack_zscore_f32(packed.data_ptr(), bpr, out.data_ptr(), n_bits, rows, n_bits, _stream()),
+          "unpack_zscore")
+    return out
+
+
+def u8_zscore(img: torch.Tensor) -> torch.Tensor:
+    rows = img.shape[0]
+    flat = img.reshape(rows, -1)
+    assert flat.dtype == torch.uint8 and flat.is_contiguous()
+    out = torch.empty(flat.shape, device=img.device, dtype=torch.float32)
+    check(lib.bbbp_u8_zscore_f32(flat.data_ptr(), out.data_ptr(), rows, flat.shape[1], _stream()), "u8_zscore")
+    return out

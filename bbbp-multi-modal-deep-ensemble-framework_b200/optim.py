@@ -1,0 +1,73 @@
+"""Fused multi-tensor AdamW: one kernel launch updates every parameter tensor.
+
+Semantics follow ``torch.optim.AdamW`` single-tensor math as the reference configures it
+(``optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)``, 20250113.py:172,191):
+decoupled decay, bias-corrected moments, eps added after the sqrt.  ``lr`` is read from the
+param group at every step, so torch LR schedulers (``CosineAnnealingWarmRestarts`` in
+_transformer_cnn.py:161, ``ReduceLROnPlateau`` in _opt_more.py:162) keep working.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+_CHUNK = 65536
+
+
+class AdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self._tables = {}
+
+    def _table(self, gi, params):
+        """Device tables for one param group: [param | grad | exp_avg | exp_avg_sq] pointers, sizes, chunks."""
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        hit = self._tables.get(gi)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dev = params[0].device
+        ptrs, sizes, chunk_t, chunk_o = [], [], [], []
+        for p in params:
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        for sel in (lambda p: p, lambda p: p.grad, lambda p: self.state[p]["exp_avg"],
+                    lambda p: self.state[p]["exp_avg_sq"]):
+            ptrs += [sel(p).data_ptr() for p in params]
+        for t, p in enumerate(params):
+            n = p.numel()
+            sizes.append(n)
+            for off in range(0, n, _CHUNK):
+                chunk_t.append(t)
+                chunk_o.append(off)
+        tab = (torch.tensor(ptrs, dtype=torch.int64).to(dev), torch.tensor(sizes, dtype=torch.int64).to(dev),
+               torch.tensor(chunk_t, dtype=torch.int32).to(dev), torch.tensor(chunk_o, dtype=torch.int64).to(dev),
+               len(params), len(chunk_t))
+        self._tables[gi] = (key, tab)
+        return tab
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            for p in params:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
+                    raise RuntimeError("bbbp_b200.AdamW needs contiguous float32 CUDA parameters and gradients")
+            group["step"] = group.get("step", 0) + 1
+            ptrs, sizes, chunk_t, chunk_o, nt, nc = self._table(gi, params)
+            b1, b2 = group["betas"]
+            ops.adamw(ptrs, sizes, chunk_t, chunk_o, nt, nc, group["lr"], b1, b2, group["eps"], group["weight_decay"],
+                      group["step"], grad_scale)
+        # the kernel wrote the parameters behind torch's version counters: drop derived bf16 weight copies
+        from .autograd import clear_weight_cache
+        clear_weight_cache()
+        return loss

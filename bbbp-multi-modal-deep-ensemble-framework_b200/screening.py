@@ -1,0 +1,64 @@
+"""Batch-sharded virtual screening across 1/2/4/8 GPUs.
+
+The reference scores molecules batch by batch (20250113.py:229-237) and, because the encoder attends
+across the molecules of a batch, a reference batch is the atomic unit of work: molecules
+[b*Bs, (b+1)*Bs) form batch b no matter how many GPUs take part.  Rank r of R owns a contiguous block
+of whole batches; there is no data-path collective, only one gather of the fp32 scores at the end.
+Results are therefore bit-identical for every R.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def partition_batches(n_molecules: int, batch_size: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Molecule range [start, stop) of ``rank``: batches [floor(r*nb/R), floor((r+1)*nb/R)), where the
+    ragged tail batch (n mod batch_size molecules) is the last batch and so lands on the last rank."""
+    if n_molecules < 0 or batch_size <= 0 or world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError((n_molecules, batch_size, world_size, rank))
+    nb = -(-n_molecules // batch_size)
+    b0 = rank * nb // world_size
+    b1 = (rank + 1) * nb // world_size
+    return min(n_molecules, b0 * batch_size), min(n_molecules, b1 * batch_size)
+
+
+def gather_scores(local: torch.Tensor, n_molecules: int, batch_size: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank score slices into the (n_molecules,) vector (one collective; NCCL over
+    NVLink on GPUs, gloo on CPU tensors in the tests).  Slices are padded to the largest count."""
+    if not (dist.is_available() and dist.is_initialized()):
+        assert local.numel() == n_molecules
+        return local
+    world = dist.get_world_size(group)
+    spans = [partition_batches(n_molecules, batch_size, world, r) for r in range(world)]
+    counts = [b - a for a, b in spans]
+    width = max(max(counts), 1)
+    send = torch.zeros((width,), device=local.device, dtype=local.dtype)
+    send[: local.numel()].copy_(local.reshape(-1))
+    recv = torch.empty((world * width,), device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    out = torch.empty((n_molecules,), device=local.device, dtype=local.dtype)
+    for r, (a, b) in enumerate(spans):
+        out[a:b].copy_(recv[r * width: r * width + (b - a)])
+    return out
+
+
+@torch.no_grad()
+def screen(model, load_molecules, n_molecules: int, batch_size: int = 256, chunk_molecules: int = 8192, group=None,
+           gather: bool = True) -> torch.Tensor:
+    """Score ``n_molecules`` with the reference's batch semantics, sharded by whole batches.
+
+    ``load_molecules(start, stop)`` returns this rank's (fingerprint, image) CUDA float32 tensors for the
+    global molecule range [start, stop) -- always whole reference batches except the global tail.
+    Returns the full (n_molecules,) score vector on every rank (or the local slice if gather=False)."""
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    a, b = partition_batches(n_molecules, batch_size, world, rank)
+    device = next(model.parameters()).device
+    local = torch.empty((b - a,), device=device, dtype=torch.float32)
+    chunk = max(1, chunk_molecules // batch_size) * batch_size
+    for start in range(a, b, chunk):
+        stop = min(b, start + chunk)
+        fp, img = load_molecules(start, stop)
+        local[start - a: stop - a].copy_(model.predict_batches(fp, img, batch_size, max_rows_per_pass=chunk))
+    return gather_scores(local, n_molecules, batch_size, group) if gather else local

@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Throughput bench of the hot path: batched inference of the multi-input transformer-CNN
+(MixedInputModel, MACCS 167-bit + 3x128x128 depiction) with the reference's batch-256 semantics.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1 under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU PyTorch path (oracle port)
+
+One "step" scores ``--groups`` independent reference batches of 256 molecules (default 32 -> 8 192
+molecules; inputs 1.6 GB fp32 per step, far larger than the 126 MB L2, so nothing is cache-resident
+between iterations).  ``value`` times the step with inputs already in HBM; ``e2e`` times the same call
+from pinned HOST buffers including the H2D copy of the step's inputs and the D2H read of its scores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_BITS, IMG = 167, 3 * 128 * 128
+BATCH = 256
+METRIC, UNIT = "molecules/sec multi-input NN inference", "molecules/s"
+# algorithmic work (SURVEY 8d / DESIGN.md): conv2 = 75.50 MMAC per molecule
+CONV2_FLOP_PER_MOL = 2 * 64 * 64 * 64 * 288
+FWD_FLOP_PER_MOL = 207.2e6
+IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = float(rows[0][2])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows):
+                    out["reasons"].append(n)
+            out["samples"] = len(rows)
+        except Exception as e:  # nvidia-smi missing (CPU container)
+            out["error"] = str(e)[:80]
+        finally:
+            if self.path and os.path.exists(self.path):
+                os.unlink(self.path)
+        return out
+
+
+def synthetic_inputs(n, seed, device):
+    """B3DB/ZINC-shaped synthetic molecules: MACCS bits ~ Bernoulli(0.25) with bit 0 = 0, per-molecule
+    z-scored (P1); depictions ~ N(0,1) (a z-scored image, P2).  Generated with torch RNG, outside any timer."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(20250113 + seed)
+    bits = (torch.rand(n, F_BITS, generator=g, device=device) < 0.25).float()
+    bits[:, 0] = 0
+    mean = bits.mean(1, keepdim=True)
+    std = bits.std(1, unbiased=False, keepdim=True).clamp_min(1e-12)
+    fp = ((bits - mean) / std).contiguous()
+    img = torch.randn(n, IMG, generator=g, device=device)
+    return fp, img
+
+
+def cpu_reference_rate(n_batches, threads, warm=1):
+    """The reference's CPU PyTorch path (oracle/nets.py, pinned to the reference classes): eval, no_grad,
+    fp32, inputs resident as contiguous CPU tensors, batch 256.  Returns (mol/s, seconds, molecules)."""
+    import torch
+    from oracle import nets
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = nets.build("tcnn", F_BITS, 128).eval()
+    fp, img = synthetic_inputs(BATCH * max(1, n_batches), 7, "cpu")
+    with torch.no_grad():
+        for _ in range(warm):
+            model(fp[:BATCH], img[:BATCH])
+        t0 = time.perf_counter()
+        for b in range(n_batches):
+            model(fp[b * BATCH:(b + 1) * BATCH], img[b * BATCH:(b + 1) * BATCH])
+        dt = time.perf_counter() - t0
+    return n_batches * BATCH / dt, dt, n_batches * BATCH
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    per_step = 2                                   # bounded sample: 2 reference batches of 256 per step
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_rate(1, threads, warm=0)
+    t_all, n_all = 0.0, 0
+    for _ in range(args.steps):
+        _, dt, n = cpu_reference_rate(per_step, threads, warm=0)
+        t_all += dt
+        n_all += n
+    v = n_all / t_all
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "screen_maccs_b256", "model": "MixedInputModel(167,128) 20250113", "batch": BATCH,
+                       "molecules_per_step": per_step * BATCH},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps x {per_step} batches of {BATCH} molecules, torch {torch.__version__} CPU fp32, "
+                                       "oracle/nets.py (pinned to the reference classes)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=32, help="reference batches of 256 molecules per step")
+    ap.add_argument("--precision", default=os.environ.get("BBBP_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-batches", type=int, default=12, help="bounded CPU-baseline sample (batches of 256)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import bbbp_b200
+    from bbbp_b200 import ops
+    from oracle import nets          # cpu_baseline leg and weight init only (never on the timed GPU path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.require_device()
+
+    torch.manual_seed(0)
+    model = bbbp_b200.MixedInputModel(F_BITS, 128)       # random-init weights of the reference architecture
+    model.to(dev).eval()
+    model.set_precision(args.precision)
+    n = args.groups * BATCH
+    fp, img = synthetic_inputs(n, rank, dev)
+    fp_host = fp.cpu().pin_memory()
+    img_host = img.cpu().pin_memory()
+    scores_host = torch.empty(n, dtype=torch.float32).pin_memory()
+    gathered = torch.empty(world * n, device=dev, dtype=torch.float32) if world > 1 else None
+
+    def step_resident():
+        s = model.predict_batches(fp, img, BATCH, max_rows_per_pass=n)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, s)        # the one collective: score gather over NVLink
+        return s
+
+    def step_e2e():
+        f = fp_host.to(dev, non_blocking=True)
+        i = img_host.to(dev, non_blocking=True)
+        s = model.predict_batches(f, i, BATCH, max_rows_per_pass=n)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, s)
+        scores_host.copy_(s, non_blocking=True)
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        ops.KERNEL_TIMER.enable({"conv2"})
+        l0 = bbbp_b200._lib.lib.bbbp_launch_count()
+        with ClockSampler(local) as clocks:
+            ms = timed(step_resident, args.steps)
+        launches = bbbp_b200._lib.lib.bbbp_launch_count() - l0
+        conv2_ms, conv2_mols = ops.KERNEL_TIMER.collect("conv2")
+        ops.KERNEL_TIMER.disable()
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+
+    total_mols = world * n * args.steps
+    value = total_mols / (ms * 1e-3)
+    e2e = total_mols / (ms_e2e * 1e-3)
+    pk = peaks()
+    roof = None
+    if conv2_ms:
+        per_launch_ms = statistics.mean(conv2_ms)
+        flop = CONV2_FLOP_PER_MOL * statistics.mean(conv2_mols)
+        ach = flop / (per_launch_ms * 1e-3) / 1e12
+        roof = {"kernel": "conv2 (3x3, 32->64, +bias+ReLU+maxpool) implicit GEMM", "bound": "tensor", "achieved": ach,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None,
+                "peak_source": pk["src"] + " bf16_tflops_sustained", "launch_ms": per_launch_ms,
+                "share_of_step": sum(conv2_ms) / ms, "whole_model_tflops": FWD_FLOP_PER_MOL * value / 1e12}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "screen_maccs_b256", "model": "MixedInputModel(167,128) 20250113 (13.46M params)",
+                       "batch": BATCH, "molecules_per_step_per_gpu": n, "input": "fp32 z-scored fingerprint + fp32 CHW image",
+                       "l2_policy": f"inputs {n * IN_BYTES_PER_MOL / 1e6:.0f} MB per step > 126 MB L2", "precision": args.precision},
+            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * (F_BITS + IMG) * 4, "d2h_bytes_per_step": n * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": roof}
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            v, dt, mols = cpu_reference_rate(args.cpu_batches, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{mols} molecules ({args.cpu_batches} batches of {BATCH}) in {dt:.1f} s, torch "
+                                              f"{torch.__version__} CPU fp32, oracle/nets.py restatement of the reference classes"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,9 @@ int bbbp_abi_version(void);
 const char* bbbp_last_error(void);
 /* 0 when the current device is compute capability 10.x, BBBP_EUNSUPPORTED otherwise. */
 int bbbp_device_check(void);
+/* Number of kernels this library has launched in this process (monotonic; bench.py reports the
+ * difference over its timed region as "gpu_launches"). */
+uint64_t bbbp_launch_count(void);
 
 /* ---- dense layers: nn.Linear call sites C:80,92,53-55,99-106; encoder in_proj/out_proj/
  *      linear1/linear2 (torch.nn.TransformerEncoderLayer via C:75-78); PCA transform
@@ -140,6 +143,10 @@ int bbbp_fusion_softmax_mix_fwd_f32(const float* scores, const float* c, float* 
 /* dc[rows, dim] and dscores[rows, n] from dout */
 int bbbp_fusion_softmax_mix_bwd_f32(const float* w, const float* c, const float* dout, float* dc, float* dscores,
                                     int rows, int n, int dim, bbbp_stream_t stream);
+/* w[rows, n] = softmax over the last axis of scores[rows, n], n <= 32 (nn.Softmax(dim=1) of the fusion blocks) */
+int bbbp_softmax_rows_fwd_f32(const float* scores, float* w, int rows, int n, bbbp_stream_t stream);
+/* dscores = w * (dw - sum_h dw_h w_h) */
+int bbbp_softmax_rows_bwd_f32(const float* w, const float* dw, float* dscores, int rows, int n, bbbp_stream_t stream);
 /* out[r, c] = scale[r*ld_scale] * colmean(x)[c]  (the (B,1,1)*(B,D) -> mean(dim=1) broadcast of the big variant);
  * colmean_out[cols] optional. */
 int bbbp_scaled_colmean_fwd_f32(const float* x, int ldx, const float* scale, int ld_scale, float* out, int ld_out,
@@ -182,45 +189,6 @@ int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, float* out,
                            bbbp_stream_t stream);
 /* uint8 depictions (rows x n values) -> x/255 -> per-molecule z-score, fp32 */
 int bbbp_u8_zscore_f32(const uint8_t* img, float* out, int rows, int n, bbbp_stream_t stream);
-
-/* ---- fused batched inference of the canonical transformer-CNN (C:109-119, eval mode) -------------- */
-typedef struct {
-  int32_t fingerprint_size; /* F: 167 (MACCS) or 2048 (Morgan / RDKFingerprint)                         */
-  int32_t heads;            /* encoder heads (C:71-73)                                                   */
-  int32_t layers;           /* 6                                                                         */
-  int32_t ffn;              /* 2048                                                                      */
-  int32_t groups;           /* independent reference batches in this call                               */
-  int32_t seq;              /* molecules per reference batch (attention scope)               */
-  int32_t precision;        /* BBBP_PREC_*                                                               */
-  int32_t reserved;
-} bbbp_tcnn_desc;
-
-/* Parameter pointer table for bbbp_tcnn_forward, fp32 tensors in the reference's state_dict layout.
- * Index = BBBP_P_* ; per encoder layer l the 12 tensors start at BBBP_P_LAYER0 + 12*l. */
-enum {
-  BBBP_L_IN_W = 0, BBBP_L_IN_B, BBBP_L_OUT_W, BBBP_L_OUT_B, BBBP_L_FF1_W, BBBP_L_FF1_B, BBBP_L_FF2_W, BBBP_L_FF2_B,
-  BBBP_L_LN1_G, BBBP_L_LN1_B, BBBP_L_LN2_G, BBBP_L_LN2_B, BBBP_L_COUNT
-};
-enum {
-  BBBP_P_FPFC_W = 0, BBBP_P_FPFC_B, BBBP_P_CONV1_W, BBBP_P_CONV1_B, BBBP_P_CONV2_W, BBBP_P_CONV2_B, BBBP_P_IMGFC_W,
-  BBBP_P_IMGFC_B, BBBP_P_FUS_W1 /* 4 heads x (128,256), contiguous per head: +0..3 */, BBBP_P_FUS_B1 = BBBP_P_FUS_W1 + 4,
-  BBBP_P_FUS_W2 = BBBP_P_FUS_B1 + 4, BBBP_P_FUS_B2 = BBBP_P_FUS_W2 + 4, BBBP_P_FC0_W = BBBP_P_FUS_B2 + 4, BBBP_P_FC0_B,
-  BBBP_P_BN_G, BBBP_P_BN_B, BBBP_P_BN_MEAN, BBBP_P_BN_VAR, BBBP_P_FC3_W, BBBP_P_FC3_B, BBBP_P_FC5_W, BBBP_P_FC5_B,
-  BBBP_P_FC7_W, BBBP_P_FC7_B, BBBP_P_LAYER0
-};
-
-/* Bytes of the derived-weight cache (bf16 copies / re-laid-out conv and fc weights) and of the
- * per-call activation workspace for ``groups*seq`` molecules. */
-size_t bbbp_tcnn_prepared_bytes(const bbbp_tcnn_desc* desc);
-size_t bbbp_tcnn_workspace_bytes(const bbbp_tcnn_desc* desc);
-/* Build the derived-weight cache from the fp32 parameters (call again whenever they change). */
-int bbbp_tcnn_prepare(const bbbp_tcnn_desc* desc, const void* const* params /* host array */, void* prepared,
-                      size_t prepared_bytes, bbbp_stream_t stream);
-/* out[groups*seq] = model(fingerprint[groups*seq, F], image[groups*seq, 3*128*128]) in eval mode.
- * aux_stream (may be NULL) lets the fingerprint branch overlap the image branch. */
-int bbbp_tcnn_forward(const bbbp_tcnn_desc* desc, const void* const* params /* host array */, const void* prepared,
-                      const float* fingerprint, const float* image, float* out, void* workspace,
-                      size_t workspace_bytes, bbbp_stream_t stream, bbbp_stream_t aux_stream);
 
 #ifdef __cplusplus
 }

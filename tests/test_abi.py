@@ -1,0 +1,66 @@
+"""The C-ABI shared library loads and exports every symbol include/bbbp_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import bbbp_b200
+from bbbp_b200 import _lib
+
+
+def test_header_symbols_all_exported():
+    header = open(_lib.HEADER_PATH).read()
+    declared = set(re.findall(r"\b(bbbp_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", " ", header, flags=re.S)))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert len(declared) >= 34
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(raw, name) is not None
+
+
+def test_abi_version_and_no_torch_in_signatures():
+    assert bbbp_b200.ABI_VERSION == 1
+    header = open(_lib.HEADER_PATH).read()
+    code = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    assert "torch" not in code.lower() and "Tensor" not in code and "at::" not in code
+    assert 'extern "C"' in code
+
+
+def test_library_has_no_torch_dependency():
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out
+
+
+def test_argument_validation_reports_through_last_error():
+    # argument checks run before any CUDA call, so they are testable without a device
+    rc = _lib.lib.bbbp_gemm_f32(0, 1, 4, 4, 4, None, 4, None, 4, None, 4, None, 0, 0, 1, None, 0, None)
+    assert rc == -1
+    assert "null operand" in bbbp_b200.last_error()
+    rc = _lib.lib.bbbp_conv3x3_f32(1, 1, None, 1, None, 1, 3, 30, 128, 128, 1, None)
+    assert rc == -1 and "multiple of 32" in bbbp_b200.last_error()
+    rc = _lib.lib.bbbp_gemm_bf16(4, 4, 7, 16, 7, 16, 8, None, None, 0, 16, 4, None, 0, 0, 1, None, 0, None)
+    assert rc == -1 and "multiples of 8" in bbbp_b200.last_error()
+    rc = _lib.lib.bbbp_batchnorm_fwd_f32(1, 1, 1, 1, 1, 1, 1, 1, 1, 8, 1, 0.1, 1e-5, None)
+    assert rc == -1 and "more than 1 value per channel" in bbbp_b200.last_error()
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lib_probe", os.path.join(_lib.PKG_DIR, "_lib.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setattr(os.path, "exists", lambda p, _orig=os.path.exists: False if p.endswith("libbbbp_b200.so") else _orig(p))
+    try:
+        spec.loader.exec_module(mod)
+    except ImportError as e:
+        assert "no CPU or PyTorch fallback" in str(e)
+    else:
+        raise AssertionError("import succeeded without the library")
+
+
+def test_cuda_sources_are_blackwell_native():
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass      # tcgen05.mma
+    assert "UTMALDG" in sass      # TMA tensor loads
+    assert "LDTM" in sass         # tcgen05.ld
+    assert "HGMMA" not in sass

@@ -1,0 +1,133 @@
+"""Host-side logic that needs no GPU: the drop-in module surface (constructor, state_dict ABI, seeded init,
+pickling, checkpoint loading), the batch partitioner and the world_size-2 gloo score gather."""
+import io
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import bbbp_b200
+from bbbp_b200 import partition_batches
+from conftest import load_golden
+from oracle import nets
+
+VARIANT_DIMS = [
+    ("tcnn", 167, 128), ("tcnn_nofusion", 167, 128), ("tcnn_big", 167, 128), ("mlp", 64, 128), ("mlp_morgan", 128, 256),
+    ("mlp_rdkit", 64, 128), ("mlp_more", 64, 128),
+]
+
+
+@pytest.mark.parametrize("variant,fp_dim,img_side", VARIANT_DIMS)
+def test_state_dict_abi_and_seeded_init_match_reference_layout(variant, fp_dim, img_side):
+    torch.manual_seed(5)
+    ours = bbbp_b200.build(variant, fp_dim, img_side)
+    torch.manual_seed(5)
+    ref = nets.build(variant, fp_dim, img_side)       # pinned to the reference classes in test_oracle_pinning
+    a, b = ours.state_dict(), ref.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    ref.load_state_dict(a, strict=True)
+    ours.load_state_dict(b, strict=True)
+
+
+def test_parameter_counts():
+    count = lambda m: sum(p.numel() for p in m.parameters())
+    assert count(bbbp_b200.MixedInputModel(167, 128)) == 13_464_087
+    assert count(bbbp_b200.MixedInputModelBig(167, 128)) == 46_203_559
+    assert count(bbbp_b200.MixedInputModelMLP(64, 128)) == 198_149       # best_nn_model_maccs.pth
+    assert count(bbbp_b200.MixedInputModelMLP(128, 256)) == 222_725      # best_nn_model.pth
+
+
+def test_encoder_head_rule():
+    assert bbbp_b200.encoder_heads(167) == 1          # 167 is prime
+    assert bbbp_b200.encoder_heads(2048) == 256
+    assert bbbp_b200.encoder_heads(167, 8) == 1
+    assert bbbp_b200.encoder_heads(2048, 8) == 8
+    m = bbbp_b200.MixedInputModel(2048 // 8, 128)     # small stand-in: 256 -> 32 heads
+    assert m.fingerprint_transformer.layers[0].self_attn.num_heads == 32
+
+
+@pytest.mark.parametrize("name,fp_dim,img_dim", [("mlp_ckpt_maccs", 64, 128), ("mlp_ckpt_morgan", 128, 256)])
+def test_shipped_checkpoints_load_strict(name, fp_dim, img_dim):
+    g = load_golden(name)
+    state = {k[len("param:"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param:")}
+    model = bbbp_b200.MixedInputModelMLP(fp_dim, img_dim)
+    model.load_state_dict(state, strict=True)
+    buf = io.BytesIO()
+    torch.save(model.state_dict(), buf)               # Models/..._opt.py:179
+    buf.seek(0)
+    again = bbbp_b200.MixedInputModelMLP(fp_dim, img_dim)
+    again.load_state_dict(torch.load(buf), strict=True)
+
+
+def test_whole_model_pickles():
+    model = bbbp_b200.MixedInputModelMLP(64, 128)      # 20250113.py:243 pickles the whole module
+    clone = pickle.loads(pickle.dumps(model))
+    for (k, a), (_, b) in zip(model.state_dict().items(), clone.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_cpu_tensors_are_refused_loudly():
+    model = bbbp_b200.MixedInputModelMLP(64, 128)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.randn(2, 64), torch.randn(2, 128))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.dirname(bbbp_b200.__file__)
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+@pytest.mark.parametrize("n,bs,world", [(0, 256, 4), (1, 256, 8), (1058, 256, 1), (1058, 256, 2), (1058, 256, 8),
+                                        (7807, 32, 4), (10_000_000, 256, 8), (255, 256, 2), (512, 256, 3)])
+def test_partitioner_covers_every_molecule_once_on_batch_boundaries(n, bs, world):
+    spans = [partition_batches(n, bs, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 == b0 and a0 <= a1
+    for a, b in spans:
+        assert a % bs == 0                      # every rank starts on a reference-batch boundary
+        assert b % bs == 0 or b == n            # only the global tail batch is ragged
+    nb = -(-n // bs)
+    sizes = [-(-(b - a) // bs) for a, b in spans]
+    assert sum(sizes) == nb and max(sizes) - min(sizes) <= 1
+
+
+def test_partitioner_rejects_bad_arguments():
+    with pytest.raises(ValueError):
+        partition_batches(10, 0, 1, 0)
+    with pytest.raises(ValueError):
+        partition_batches(10, 4, 2, 2)
+
+
+def _gather_worker(rank, world, port, n, bs, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = partition_batches(n, bs, world, rank)
+        local = torch.arange(a, b, dtype=torch.float32) * 0.5      # "score" of molecule i is i/2
+        full = bbbp_b200.gather_scores(local, n, bs)
+        np.save(os.path.join(out_dir, f"r{rank}.npy"), full.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,bs", [(1058, 256), (600, 32), (3, 8)])
+def test_score_gather_world2_gloo(tmp_path, n, bs):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gather_worker, args=(2, port, n, bs, str(tmp_path)), nprocs=2, join=True)
+    want = np.arange(n, dtype=np.float32) * 0.5
+    for r in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"r{r}.npy"), want)

@@ -1,0 +1,338 @@
+"""Per-kernel parity on the B200: every C-ABI entry point against the oracle for that op.
+
+The reference delegates all arithmetic to stock PyTorch, so the oracle of a single op is the
+torch CPU fp32 functional the reference's module would have dispatched to; the packed-input contracts use
+oracle/preprocess.py.  Integer/bit work must be exact; fp32 kernels are held to 1e-4-class tolerances
+(written at each assert); the bf16 tensor-core GEMM is compared with an fp32 product of the SAME
+bf16-rounded operands, so only accumulation order differs.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    import bbbp_b200
+    return bbbp_b200.ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g) * scale
+
+
+def close(a, b, atol, rtol=0.0, what=""):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape, what)
+    err = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    assert bool((err <= bound).all()), f"{what}: max err {float(err.max()):.3e} (atol {atol}, rtol {rtol})"
+
+
+# ---- fp32 GEMM ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,split", [(1, 1, 1, 1), (5, 167, 167, 1), (37, 501, 167, 1), (256, 2048, 167, 1),
+                                         (33, 128, 65536, 16), (64, 64, 64, 1), (130, 70, 1000, 3)])
+@pytest.mark.parametrize("act", [None, "relu", "tanh"])
+def test_gemm_f32_linear(ops, M, N, K, split, act):
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K)), rnd(N, seed=3)
+    y = ops.gemm_f32(x.cuda(), w.cuda(), trans_b=True, bias=b.cuda(), act=act, split_k=split)
+    ref = F.linear(x.double(), w.double(), b.double())
+    ref = {"relu": torch.relu, "tanh": torch.tanh, None: lambda t: t}[act](ref).float()
+    close(y, ref, atol=2e-5 * max(1.0, math.sqrt(K) / 16), what=f"gemm_f32 {M}x{N}x{K}")
+
+
+def test_gemm_f32_transposes_and_accumulate(ops):
+    a, b = rnd(40, 23, seed=4), rnd(23, 31, seed=5)
+    close(ops.gemm_f32(a.cuda(), b.cuda()), a @ b, 1e-5, what="NN")
+    close(ops.gemm_f32(a.t().contiguous().cuda(), b.cuda(), trans_a=True), a @ b, 1e-5, what="TN")
+    close(ops.gemm_f32(a.cuda(), b.t().contiguous().cuda(), trans_b=True), a @ b, 1e-5, what="NT")
+    c0 = rnd(40, 31, seed=6)
+    c = c0.clone().cuda()
+    ops.gemm_f32(a.cuda(), b.cuda(), out=c, accumulate=True)
+    close(c, c0 + a @ b, 1e-5, what="accumulate")
+
+
+# ---- tcgen05 GEMM -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,split", [
+    (128, 128, 64, 1), (128, 128, 256, 1), (1, 1, 8, 1), (5, 167, 167, 1), (300, 501, 167, 1), (256, 2048, 167, 1),
+    (256, 167, 2048, 1), (37, 64, 128, 1), (33, 128, 65536, 32), (256, 128, 65536, 64), (1000, 40, 512, 2),
+    (129, 129, 65, 1)])
+def test_gemm_bf16_tcgen05(ops, M, N, K, split):
+    x, w, b = rnd(M, K, seed=7), rnd(N, K, seed=8, scale=1 / math.sqrt(K)), rnd(N, seed=9)
+    x16, w16 = ops.cast_bf16(x.cuda()), ops.cast_bf16(w.cuda())
+    assert x16.shape[1] % 8 == 0 and x16.dtype == torch.bfloat16
+    torch.testing.assert_close(x16[:, :K].float().cpu(), x.bfloat16().float(), rtol=0, atol=0)   # RN cast, exact
+    y, _ = ops.gemm_bf16(x16, K, w16, N, bias=b.cuda(), split_k=split)
+    ref = F.linear(x.bfloat16().double(), w.bfloat16().double(), b.double()).float()
+    close(y, ref, atol=2e-5 * max(1.0, math.sqrt(K) / 8), what=f"gemm_bf16 {M}x{N}x{K} split {split}")
+
+
+@pytest.mark.parametrize("act", ["relu", "tanh"])
+def test_gemm_bf16_epilogues(ops, act):
+    M, N, K = 200, 167, 167
+    x, w, b, r = rnd(M, K, seed=10), rnd(N, K, seed=11, scale=0.1), rnd(N, seed=12), rnd(M, N, seed=13)
+    x16, w16 = ops.cast_bf16(x.cuda()), ops.cast_bf16(w.cuda())
+    ref = F.linear(x.bfloat16().double(), w.bfloat16().double(), b.double())
+    ref = (torch.relu(ref) if act == "relu" else torch.tanh(ref)).float()
+    y, y16 = ops.gemm_bf16(x16, K, w16, N, bias=b.cuda(), act=act, out_bf16=True)
+    close(y, ref, 3e-5, what=act)
+    close(y16[:, :N], ref.bfloat16().float(), atol=1e-2, rtol=1e-2, what="bf16 out")
+    y2, _ = ops.gemm_bf16(x16, K, w16, N, bias=b.cuda(), residual=r.cuda(), act=None)
+    close(y2, F.linear(x.bfloat16().double(), w.bfloat16().double(), b.double()).float() + r, 3e-5, what="residual")
+
+
+# ---- convolution block -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 3, 32, 128), (3, 32, 64, 64), (1, 64, 128, 32), (1, 128, 256, 16), (2, 3, 64, 32)])
+def test_conv_relu_pool_forward_backward(ops, N, Cin, Cout, H):
+    x = rnd(N, Cin, H, H, seed=20).requires_grad_()
+    w = rnd(Cout, Cin, 3, 3, seed=21, scale=1 / math.sqrt(9 * Cin)).requires_grad_()
+    b = rnd(Cout, seed=22, scale=0.1).requires_grad_()
+    ref = F.max_pool2d(F.relu(F.conv2d(x, w, b, padding=1)), 2)
+    dy = rnd(*ref.shape, seed=23)
+    ref.backward(dy)
+    xc, wc, bc = x.detach().cuda(), w.detach().cuda(), b.detach().cuda()
+    y, arg = ops.conv3x3(xc, wc, bc, pool=True, want_argmax=True)
+    close(y, ref, 2e-5 * math.sqrt(Cin), what="conv fwd")
+    dpre = ops.relu_pool_bwd(dy.cuda(), y, arg, H, H)
+    dw, db = ops.conv3x3_wgrad(dpre, xc, Cout, Cin)
+    scale = float(w.grad.abs().max())
+    close(dw, w.grad, 2e-4 * max(1.0, scale), what="conv wgrad")
+    close(db, b.grad, 2e-4 * max(1.0, float(b.grad.abs().max())), what="conv bgrad")
+    if Cin % 32 == 0:
+        dx, _ = ops.conv3x3(dpre, ops.conv3x3_flip_weights(wc), None, pool=False)
+        close(dx, x.grad, 1e-4, what="conv dgrad")
+
+
+def test_conv_plain_mode(ops):
+    x, w, b = rnd(1, 32, 32, 32, seed=24), rnd(32, 32, 3, 3, seed=25, scale=0.05), rnd(32, seed=26)
+    y, _ = ops.conv3x3(x.cuda(), w.cuda(), b.cuda(), pool=False)
+    close(y, F.conv2d(x, w, b, padding=1), 5e-5, what="plain conv")
+
+
+# ---- attention across the batch -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("groups,seq,heads,d", [(1, 1, 1, 167), (1, 32, 1, 167), (3, 67, 1, 167), (1, 256, 1, 167),
+                                                (2, 33, 256, 8), (1, 5, 8, 16), (1, 300, 4, 64)])
+def test_attention_forward_backward(ops, groups, seq, heads, d):
+    E = heads * d
+    qkv = rnd(groups * seq, 3 * E, seed=30, scale=0.7).requires_grad_()
+    dout = rnd(groups * seq, E, seed=31)
+    q, k, v = qkv.view(groups, seq, 3, heads, d).permute(2, 0, 3, 1, 4)      # (g, h, s, d)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(groups * seq, E)
+    ref.backward(dout)
+    out, lse = ops.attention_fwd(qkv.detach().cuda(), groups, seq, heads, d)
+    close(out, ref, 2e-5, what="attention fwd")
+    dqkv = ops.attention_bwd(qkv.detach().cuda(), out, lse, dout.cuda(), groups, seq, heads, d)
+    close(dqkv, qkv.grad, 5e-5, what="attention bwd")
+
+
+def test_attention_dropout_is_consistent_between_forward_and_backward(ops):
+    groups, seq, heads, d, p = 1, 64, 2, 32, 0.25
+    E = heads * d
+    qkv = rnd(seq, 3 * E, seed=32).cuda()
+    o1, lse = ops.attention_fwd(qkv, groups, seq, heads, d, p, 1234)
+    o2, _ = ops.attention_fwd(qkv, groups, seq, heads, d, p, 1234)
+    o3, _ = ops.attention_fwd(qkv, groups, seq, heads, d, p, 99)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    # directional derivative check of the dropped attention against a finite difference in float64 is
+    # not available on device; instead check linearity in dout and agreement with p=0 in expectation
+    dout = rnd(seq, E, seed=33).cuda()
+    g1 = ops.attention_bwd(qkv, o1, lse, dout, groups, seq, heads, d, p, 1234)
+    g2 = ops.attention_bwd(qkv, o1, lse, 2 * dout, groups, seq, heads, d, p, 1234)
+    close(g2, 2 * g1, 1e-5, what="linearity")
+    o0, _ = ops.attention_fwd(qkv, groups, seq, heads, d)
+    outs = torch.stack([ops.attention_fwd(qkv, groups, seq, heads, d, p, s)[0] for s in range(200)]).mean(0)
+    assert float((outs - o0).abs().mean()) < 0.05
+
+
+# ---- normalisation ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,dim", [(1, 167), (33, 167), (256, 2048), (7, 8)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_add_layernorm_forward_backward(ops, rows, dim, with_res):
+    x = rnd(rows, dim, seed=40).requires_grad_()
+    r = rnd(rows, dim, seed=41).requires_grad_() if with_res else None
+    g, b = (1 + 0.1 * rnd(dim, seed=42)).requires_grad_(), (0.1 * rnd(dim, seed=43)).requires_grad_()
+    s_ref = x + r if with_res else x
+    ref = F.layer_norm(s_ref, (dim,), g, b, 1e-5)
+    dy = rnd(rows, dim, seed=44)
+    ref.backward(dy)
+    y, s, mean, rstd, y16 = ops.add_layernorm_fwd(x.detach().cuda(), None if r is None else r.detach().cuda(), g.detach().cuda(),
+                                                  b.detach().cuda(), 1e-5, save=True, bf16_ld=-(-dim // 8) * 8)
+    close(y, ref, 1e-5, what="ln fwd")
+    close(y16[:, :dim], ref.bfloat16().float(), atol=1e-6, rtol=1e-2, what="ln bf16 copy")
+    dx, dg, db = ops.layernorm_bwd(dy.cuda(), s, mean, rstd, g.detach().cuda())
+    close(dx, x.grad, 2e-5, what="ln dx")
+    close(dg, g.grad, 1e-4 * max(1, math.sqrt(rows)), what="ln dgamma")
+    close(db, b.grad, 1e-4 * max(1, math.sqrt(rows)), what="ln dbeta")
+
+
+@pytest.mark.parametrize("rows,C", [(2, 256), (32, 256), (300, 1024), (5, 40)])
+def test_batchnorm_train_eval_forward_backward(ops, rows, C):
+    bn = torch.nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.1 * rnd(C, seed=50))
+        bn.bias.copy_(0.1 * rnd(C, seed=51))
+        bn.running_mean.copy_(0.2 * rnd(C, seed=52))
+        bn.running_var.copy_(1 + 0.3 * rnd(C, seed=53).abs())
+    rm, rv = bn.running_mean.clone().cuda(), bn.running_var.clone().cuda()
+    x = rnd(rows, C, seed=54, scale=2.0).requires_grad_()
+    dy = rnd(rows, C, seed=55)
+    bn.train()
+    ref = bn(x)
+    ref.backward(dy)
+    gw, gb = bn.weight.detach().cuda(), bn.bias.detach().cuda()
+    y, sm, sr = ops.batchnorm_fwd(x.detach().cuda(), gw, gb, rm, rv, True)
+    close(y, ref, 2e-5, what="bn train fwd")
+    close(rm, bn.running_mean, 1e-6, what="running mean")
+    close(rv, bn.running_var, 1e-5, what="running var (unbiased)")
+    dx, dg, db = ops.batchnorm_bwd(dy.cuda(), x.detach().cuda(), gw, sm, sr)
+    close(dx, x.grad, 5e-5, what="bn dx")
+    close(dg, bn.weight.grad, 2e-4, what="bn dgamma")
+    close(db, bn.bias.grad, 2e-4, what="bn dbeta")
+    bn.eval()
+    x.grad = None
+    bn.weight.grad = bn.bias.grad = None
+    ref = bn(x)
+    ref.backward(dy)
+    y, _, _ = ops.batchnorm_fwd(x.detach().cuda(), gw, gb, rm, rv, False)
+    close(y, ref, 2e-5, what="bn eval fwd")
+    dx, dg, db = ops.batchnorm_eval_bwd(dy.cuda(), x.detach().cuda(), gw, rm, rv)
+    close(dx, x.grad, 2e-5, what="bn eval dx")
+    close(dg, bn.weight.grad, 2e-4, what="bn eval dgamma")
+
+
+# ---- fusion blocks ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,n,dim", [(1, 4, 256), (37, 4, 256), (300, 4, 512), (9, 1, 256)])
+def test_fusion_softmax_mix(ops, rows, n, dim):
+    sc = rnd(rows, n, seed=60).requires_grad_()
+    c = rnd(rows, dim, seed=61).requires_grad_()
+    w_ref = torch.softmax(sc.unsqueeze(2), dim=1)                     # (rows, n, 1): nn.Softmax(dim=1) over heads
+    ref = (w_ref * c.unsqueeze(1)).sum(dim=1)
+    dout = rnd(rows, dim, seed=62)
+    ref.backward(dout)
+    out, w = ops.fusion_softmax_mix_fwd(sc.detach().cuda(), c.detach().cuda(), want_w=True)
+    close(out, ref, 1e-6, what="mix fwd")       # sum_h w_h * c: <= 1 ulp class from c
+    close(w, w_ref.squeeze(2), 1e-6, what="mix weights")
+    dc, ds = ops.fusion_softmax_mix_bwd(w, c.detach().cuda(), dout.cuda())
+    close(dc, c.grad, 1e-5, what="mix dc")
+    close(ds, sc.grad, 1e-4, what="mix dscores (analytically 0)")
+
+
+def test_softmax_rows_and_scaled_colmean(ops):
+    sc = rnd(19, 2, seed=63).requires_grad_()
+    w_ref = torch.softmax(sc, dim=1)
+    dw = rnd(19, 2, seed=64)
+    w_ref.backward(dw)
+    w = ops.softmax_rows_fwd(sc.detach().cuda())
+    close(w, w_ref, 1e-6, what="softmax rows")
+    close(ops.softmax_rows_bwd(w, dw.cuda()), sc.grad, 1e-6, what="softmax rows bwd")
+    x = rnd(19, 512, seed=65).requires_grad_()
+    s = rnd(19, 2, seed=66).requires_grad_()
+    ref = (s[:, 0:1].unsqueeze(1) * x).mean(dim=1)                    # (B,1,1)*(B,D) -> (B,B,D) -> mean(dim=1)
+    dout = rnd(19, 512, seed=67)
+    ref.backward(dout)
+    sd = s.detach().cuda()
+    out, cm = ops.scaled_colmean_fwd(x.detach().cuda(), sd[:, 0])
+    close(out, ref, 1e-6, what="scaled colmean")
+    dx, dscale = ops.scaled_colmean_bwd(dout.cuda(), sd[:, 0], cm)
+    close(dx, x.grad, 1e-6, what="scaled colmean dx")
+    close(dscale, s.grad[:, 0], 1e-5, what="scaled colmean dscale")
+
+
+# ---- elementwise -------------------------------------------------------------------------------------------------------------
+def test_act_bwd_colsum_copy2d_scale(ops):
+    y = torch.relu(rnd(33, 167, seed=70))
+    dy = rnd(33, 167, seed=71)
+    close(ops.act_bwd(dy.cuda(), y.cuda(), "relu"), dy * (y > 0), 0, what="relu bwd")
+    t = torch.tanh(rnd(33, 167, seed=72))
+    close(ops.act_bwd(dy.cuda(), t.cuda(), "tanh"), dy * (1 - t * t), 1e-7, what="tanh bwd")
+    close(ops.colsum(dy.cuda()), dy.sum(0), 2e-5, what="colsum")
+    big = torch.zeros(33, 400).cuda()
+    ops.copy2d(dy.cuda(), big[:, 100:267])
+    assert torch.equal(big[:, 100:267].cpu(), dy) and float(big[:, :100].abs().sum()) == 0
+    close(ops.scale_by_device_scalar(dy.cuda(), torch.tensor([0.25]).cuda()), dy * 0.25, 0, what="scale")
+
+
+def test_dropout_mask_statistics_and_determinism(ops):
+    x = torch.ones(1 << 20).cuda()
+    y1, y2, y3 = ops.dropout(x, 0.3, 7), ops.dropout(x, 0.3, 7), ops.dropout(x, 0.3, 8)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    vals = torch.unique(y1).cpu()
+    close(vals, torch.tensor([0.0, 1 / 0.7]), 1e-6, what="values")
+    assert abs(float((y1 == 0).float().mean()) - 0.3) < 5e-3
+    assert torch.equal(ops.dropout(x[:1001], 0.0, 7), x[:1001])
+
+
+# ---- losses ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 32, 257, 5000])
+def test_mse_and_bce_losses(ops, n):
+    p = rnd(n, seed=80).requires_grad_()
+    t = rnd(n, seed=81)
+    ref = F.mse_loss(p, t)
+    ref.backward()
+    loss, d = ops.mse_loss(p.detach().cuda(), t.cuda())
+    close(loss.reshape(()), ref, 1e-6, rtol=1e-5, what="mse")
+    close(d, p.grad, 1e-7, rtol=1e-6, what="mse grad")
+    z = (3 * rnd(n, seed=82)).requires_grad_()
+    lab = (rnd(n, seed=83) > 0).float()
+    ref = F.binary_cross_entropy_with_logits(z, lab)      # extension: parity unpinned by the reference
+    ref.backward()
+    loss, d = ops.bce_logits_loss(z.detach().cuda(), lab.cuda())
+    close(loss.reshape(()), ref, 1e-6, rtol=1e-5, what="bce")
+    close(d, z.grad, 1e-7, rtol=1e-5, what="bce grad")
+
+
+# ---- AdamW -------------------------------------------------------------------------------------------------------------------
+def test_fused_adamw_matches_torch_adamw_trajectory(cuda_device):
+    import bbbp_b200
+    shapes = [(128, 167), (501,), (3,), (65536 + 5,), (1,), (64, 32, 3, 3)]
+    ref_p = [torch.nn.Parameter(rnd(*s, seed=90 + i)) for i, s in enumerate(shapes)]
+    our_p = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref_p]
+    ref_opt = torch.optim.AdamW(ref_p, lr=1e-4, weight_decay=1e-5)             # 20250113.py:172
+    our_opt = bbbp_b200.AdamW(our_p, lr=1e-4, weight_decay=1e-5)
+    for step in range(5):
+        for i, (a, b) in enumerate(zip(ref_p, our_p)):
+            g = rnd(*a.shape, seed=1000 * step + i)
+            a.grad, b.grad = g.clone(), g.clone().cuda()
+        if step == 3:
+            for grp in ref_opt.param_groups + our_opt.param_groups:
+                grp["lr"] = 5e-5                                                 # LR schedulers write param_group['lr']
+        ref_opt.step()
+        our_opt.step()
+    for a, b in zip(ref_p, our_p):
+        close(b, a, 1e-7, rtol=1e-6, what="adamw params")
+    for a, b in zip(ref_p, our_p):
+        close(our_opt.state[b]["exp_avg_sq"], ref_opt.state[a]["exp_avg_sq"], 1e-9, rtol=1e-5, what="v")
+
+
+# ---- packed input contracts (bit-exact) ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,n_bits", [(1, 167), (64, 167), (33, 2048), (5, 8), (3, 13)])
+def test_unpack_zscore_bit_exact(ops, rows, n_bits):
+    from oracle import preprocess
+    rng = np.random.default_rng(n_bits + rows)
+    bits = (rng.random((rows, n_bits)) < 0.25).astype(np.uint8)
+    bits[0] = 0                                                  # constant row -> std 0 -> sklearn uses 1
+    if rows > 2:
+        bits[2] = 1
+    packed = preprocess.pack_bits(bits)
+    out = ops.unpack_zscore(torch.from_numpy(packed).cuda(), n_bits).cpu().numpy()
+    want = preprocess.unpack_zscore(packed, n_bits)
+    mixed = (bits.min(axis=1) != bits.max(axis=1))
+    np.testing.assert_array_equal((out > 0)[mixed], bits[mixed] == 1)          # the bits themselves: exact
+    np.testing.assert_array_equal(out, want)                     # floats: same float64 formula, identical rounding
+
+
+def test_u8_image_zscore(ops):
+    from oracle import preprocess
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(3, 3, 128, 128), dtype=np.uint8)
+    img[1] = 255                                                 # blank depiction: std 0
+    out = ops.u8_zscore(torch.from_numpy(img).cuda()).cpu().numpy()
+    want = preprocess.u8_image_zscore(img)
+    np.testing.assert_allclose(out, want, rtol=0, atol=2e-6)     # fp64 statistics on both sides; final cast 1 ulp
