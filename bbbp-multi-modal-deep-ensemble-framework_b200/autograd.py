@@ -5,6 +5,7 @@ because every op of the forward registers its hand-written backward kernels here
 from __future__ import annotations
 
 import itertools
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -29,23 +30,33 @@ def contig(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-# bf16 copies of weights for the tcgen05 GEMMs, refreshed when the parameter is updated in place
+# bf16 copies of weights for the tcgen05 GEMMs, keyed by the identity of the parameter object (a weak reference
+# evicts the entry when the parameter dies, so a recycled device address can never alias a stale copy).  An entry
+# is refreshed when the storage moves, torch's version counter moves (load_state_dict, stock optimizers), or a bbbp
+# kernel rewrote parameters behind torch's back (fused AdamW bumps the epoch).
+_weight_epoch = 0
 _W16_CACHE: dict = {}
 
 
+def derived_weight(w: torch.Tensor, tag: str, make):
+    """Cached re-layout / down-cast of parameter ``w`` (``make(w_detached)`` builds it)."""
+    key = (w.data_ptr(), w._version, _weight_epoch)
+    ident = (id(w), tag)
+    hit = _W16_CACHE.get(ident)
+    if hit is not None and hit[1] == key and hit[0]() is w:
+        return hit[2]
+    val = make(w.detach())
+    _W16_CACHE[ident] = (weakref.ref(w, lambda _r, ident=ident: _W16_CACHE.pop(ident, None)), key, val)
+    return val
+
+
 def weight_bf16(w: torch.Tensor) -> torch.Tensor:
-    key = (w.data_ptr(), tuple(w.shape))
-    hit = _W16_CACHE.get(key)
-    if hit is not None and hit[0] == w._version:
-        return hit[1]
-    w2 = w.detach().reshape(w.shape[0], -1)
-    w16 = ops.cast_bf16(w2)
-    _W16_CACHE[key] = (w._version, w16)
-    return w16
+    return derived_weight(w, "bf16", lambda d: ops.cast_bf16(d.reshape(d.shape[0], -1)))
 
 
 def clear_weight_cache() -> None:
-    _W16_CACHE.clear()
+    global _weight_epoch
+    _weight_epoch += 1
 
 
 class Linear(Function):
@@ -58,11 +69,9 @@ class Linear(Function):
         N = weight.shape[0]
         if precision == "bf16":
             a16 = ops.cast_bf16(x)
-            split = ops.pick_split_k(M, N, K, x.device, 128, 128, 1024)
-            y, _ = ops.gemm_bf16(a16, K, weight_bf16(weight), N, bias=bias, act=act, split_k=split)
+            y, _ = ops.gemm_bf16(a16, K, weight_bf16(weight), N, bias=bias, act=act, split_k=ops.fixed_split_k(K))
         else:
-            split = ops.pick_split_k(M, N, K, x.device)
-            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=split)
+            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=ops.fixed_split_k(K))
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if act else None)
@@ -77,7 +86,7 @@ class Linear(Function):
         N = weight.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm_f32(dpre, weight, split_k=ops.pick_split_k(M, K, N, x.device))
+            dx = ops.gemm_f32(dpre, weight, split_k=ops.fixed_split_k(N))
         if ctx.needs_input_grad[1]:
             dw = ops.gemm_f32(dpre, x, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -1,0 +1,368 @@
+// tcgen05 implicit-GEMM 3x3 convolution with the bias + ReLU + 2x2 max-pool epilogue fused in, bf16 operands,
+// fp32 accumulation in TMEM.  Replaces nn.Conv2d(3,32,3,p1)+ReLU+MaxPool2d(2) and nn.Conv2d(32,64,3,p1)+ReLU+
+// MaxPool2d(2) of the reference's image branch (20250113.py:85-90) on the inference path; conv2 is 73 % of the
+// network's FLOPs.
+//
+// Data layout: activations are NHWC bf16 with C = 8*KC (conv1: 3 real channels zero-padded to 8; conv2: 32).
+// One CTA tile = 128 POOLED output pixels (8 wide x 16 high) x COUT channels; the four members of every 2x2 pooling
+// window are four separate TMEM accumulators (same lane = same pooled pixel), so pooling is a per-thread max in the
+// epilogue and the pre-pool activation never exists outside TMEM.
+//
+// A operand without im2col: the (16+2) x (32+2) input halo of the tile is staged ONCE in shared memory in the
+// no-swizzle K-major core-matrix layout  [kc][x parity][y][x/2][8 channels = 16 B].  For window member (dy,dx) and
+// filter tap (kh,kw), GEMM row m = (ph,pw) reads input pixel (2ph+dy+kh, 2pw+dx+kw) of the halo: consecutive pw are
+// consecutive 16-byte core-matrix rows, consecutive ph are 2 halo rows apart (= the descriptor's stride byte offset),
+// and a K=16 step pairs two 8-channel chunks through the leading byte offset.  So all 9 taps x 4 window members are
+// just different START ADDRESSES into the same staged halo -- the tile is read from L2 once, not 9 times.
+//
+// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quadrant = warp), warps 4-7 producers (cp.async 16-byte
+// chunks with zero fill = the conv's zero padding), warp 8 TMEM allocation + single-thread MMA issue.  Persistent
+// over tiles: 3-stage halo ring (full/empty mbarriers) and a double-buffered accumulator (acc_full/acc_empty), so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace bbbp {
+namespace conv {
+using namespace sm100;
+
+constexpr int TILE_PW = 8, TILE_PH = 16;       // pooled tile
+constexpr int HALO_W = 2 * TILE_PW + 2;        // 18
+constexpr int HALO_H = 2 * TILE_PH + 2;        // 34
+constexpr int XH = HALO_W / 2;                 // 9 halo columns per parity
+constexpr int ROW_B = XH * 16;                 // 144 bytes per (parity, y) row
+constexpr int PAR_B = HALO_H * ROW_B;          // 4896
+constexpr int KC_B = 2 * PAR_B;                // 9792 bytes per 8-channel chunk plane
+constexpr int STAGES = 3;
+constexpr int EPI_THREADS = 128, PROD_THREADS = 128, THREADS = 288;
+
+template <int KC, int COUT>
+struct Cfg {
+  static constexpr int A_BYTES = KC * KC_B;
+  static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // MMAs (K=16) per window member
+  static constexpr int W_BYTES = KC == 1 ? 2 * 5 * 2 * COUT * 16 : 9 * KC * COUT * 16;
+  static constexpr int ACC_COLS = 4 * COUT;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 128 + STAGES * A_BYTES + W_BYTES + COUT * 4 + BAR_BYTES;
+};
+
+__host__ __device__ inline int halo_offset(int dy, int dx, int tap) {
+  const int kh = tap / 3, kw = tap % 3, s = dx + kw;
+  return (s & 1) * PAR_B + (dy + kh) * ROW_B + (s >> 1) * 16;
+}
+// conv1 (one 8-channel chunk per pixel): a K=16 MMA step covers TWO taps, the second reached through the leading
+// byte offset.  Pair i = taps (2i, 2i+1); the 9th tap is paired with tap 7 under zero weights.  The descriptor
+// offset must be positive, so the pair is ordered by halo address, which depends on dx only.
+__host__ __device__ inline void conv1_pair(int dx, int i, int& first, int& second, int& zero_slot) {
+  const bool pad = 2 * i + 1 >= 9;
+  const int t0 = 2 * i, t1 = pad ? 7 : 2 * i + 1;
+  if (halo_offset(0, dx, t1) > halo_offset(0, dx, t0)) {
+    first = t0, second = t1, zero_slot = pad ? 1 : -1;
+  } else {
+    first = t1, second = t0, zero_slot = pad ? 0 : -1;
+  }
+}
+
+template <int KC, int COUT>
+__device__ __forceinline__ void mma_operands(int q, int i, uint32_t& a_off, uint32_t& a_lbo, uint32_t& b_off) {
+  const int dy = q >> 1, dx = q & 1;
+  if constexpr (KC == 1) {
+    int first, second, z;
+    conv1_pair(dx, i, first, second, z);
+    const int oa = halo_offset(dy, dx, first), ob = halo_offset(dy, dx, second);
+    a_off = oa;
+    a_lbo = ob - oa;
+    b_off = (dx * 5 + i) * (2 * COUT * 16);
+  } else {
+    const int tap = i / (KC / 2), j = i % (KC / 2);
+    a_off = (2 * j) * KC_B + halo_offset(dy, dx, tap);
+    a_lbo = KC_B;
+    b_off = (tap * KC + 2 * j) * (COUT * 16);
+  }
+}
+
+template <int KC, int COUT>
+__global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat16* __restrict__ src,
+                                                               const uint4* __restrict__ wprep,
+                                                               const float* __restrict__ bias,
+                                                               __nv_bfloat16* __restrict__ dst, int n_img, int H,
+                                                               int W, int swap_desc) {
+  using C = Cfg<KC, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sA = base;
+  uint8_t* sW = sA + STAGES * C::A_BYTES;
+  float* sBias = reinterpret_cast<float*>(sW + C::W_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBias + COUT);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int tiles_x = (W / 2) / TILE_PW, tiles_y = (H / 2) / TILE_PH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int num_tiles = n_img * tiles_per_img;
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  // ---- one-time setup: weights + bias to smem, barriers, TMEM -----------------------------------------------------
+  for (int i = threadIdx.x; i < C::W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wprep[i];
+  for (int i = threadIdx.x; i < COUT; i += THREADS) sBias[i] = bias[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], PROD_THREADS);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  fence_proxy_async_smem();  // the weight stores above are generic-proxy writes read by tcgen05.mma (async proxy)
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ===== producers: stage the halo of each tile ====================================================================
+    const int ptid = threadIdx.x - 4 * 32;
+    constexpr int CHUNKS = HALO_H * HALO_W * KC;
+    const size_t pix_bytes = (size_t)KC * 16;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      const int n = t / tiles_per_img, r = t % tiles_per_img;
+      const int y0 = 2 * (r / tiles_x) * TILE_PH - 1, x0 = 2 * (r % tiles_x) * TILE_PW - 1;
+      const int s = i % STAGES;
+      mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+      const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * pix_bytes;
+      for (int c = ptid; c < CHUNKS; c += PROD_THREADS) {
+        const int kc = c % KC, p = c / KC;
+        const int X = p % HALO_W, Y = p / HALO_W;
+        const int y = y0 + Y, x = x0 + X;
+        const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+        const uint8_t* g = img + ((size_t)(ok ? y : 0) * W + (ok ? x : 0)) * pix_bytes + kc * 16;
+        cp_async_16(stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16, g, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (i > 0) {
+        cp_async_wait<1>();  // tile i-1 of this thread has landed
+        fence_proxy_async_smem();
+        mbar_arrive(&full[(i - 1) % STAGES]);
+      }
+    }
+    if (my_tiles > 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[(my_tiles - 1) % STAGES]);
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer ==================================================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+      const uint32_t w_addr = smem_u32(sW);
+      const uint32_t a_sbo = 2 * ROW_B, b_sbo = 128, b_lbo = COUT * 16;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % STAGES, b = i & 1;
+        mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&full[s], (i / STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t d = tmem_base + b * C::ACC_COLS + q * COUT;
+#pragma unroll 1
+          for (int m = 0; m < C::NMMA; ++m) {
+            uint32_t a_off, a_lbo, b_off;
+            mma_operands<KC, COUT>(q, m, a_off, a_lbo, b_off);
+            const uint64_t ad = swap_desc ? make_smem_desc(a_addr + a_off, a_sbo, a_lbo, kLayoutNone)
+                                          : make_smem_desc(a_addr + a_off, a_lbo, a_sbo, kLayoutNone);
+            const uint64_t bd = swap_desc ? make_smem_desc(w_addr + b_off, b_sbo, b_lbo, kLayoutNone)
+                                          : make_smem_desc(w_addr + b_off, b_lbo, b_sbo, kLayoutNone);
+            umma_bf16(d, ad, bd, idesc, m != 0);
+          }
+        }
+        umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
+        umma_commit(&acc_full[b]);   // accumulators of this tile complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: max over the pooling window, + bias, ReLU, bf16, NHWC store ==========================================
+    const int m = threadIdx.x;  // pooled pixel within the tile == TMEM lane
+    const int PH = H / 2, PW = W / 2;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      const int n = t / tiles_per_img, r = t % tiles_per_img;
+      const int ph = (r / tiles_x) * TILE_PH + (m >> 3), pw = (r % tiles_x) * TILE_PW + (m & 7);
+      const int b = i & 1;
+      mbar_wait(&acc_full[b], (i >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + b * C::ACC_COLS;
+      uint4* out = reinterpret_cast<uint4*>(dst + (((size_t)n * PH + ph) * PW + pw) * COUT);
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        tmem_ld_32x16(taddr + c0, r0);
+        tmem_ld_32x16(taddr + COUT + c0, r1);
+        tmem_ld_32x16(taddr + 2 * COUT + c0, r2);
+        tmem_ld_32x16(taddr + 3 * COUT + c0, r3);
+        tmem_ld_wait();
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          float v0 = fmaxf(fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])),
+                           fmaxf(__uint_as_float(r2[j]), __uint_as_float(r3[j])));
+          float v1 = fmaxf(fmaxf(__uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1])),
+                           fmaxf(__uint_as_float(r2[j + 1]), __uint_as_float(r3[j + 1])));
+          v0 = fmaxf(v0 + sBias[c0 + j], 0.0f);
+          v1 = fmaxf(v1 + sBias[c0 + j + 1], 0.0f);
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          packed[j / 2] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        out[c0 / 8] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        out[c0 / 8 + 1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[b]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- weight / input re-layout (prepare-time and per-call helpers) --------------------------------------------------
+// conv2-style (KC >= 2): wp[tap][kc][n][8] = w[n][kc*8 + c][kh][kw]
+__global__ void prep_weights_kc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
+  const int KC = Cin / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * KC * Cout * 8) return;
+  const int c = i % 8, n = (i / 8) % Cout, kc = (i / (8 * Cout)) % KC, tap = i / (8 * Cout * KC);
+  wp[i] = __float2bfloat16(w[((size_t)n * Cin + kc * 8 + c) * 9 + tap]);
+}
+// conv1-style (Cin <= 8, one chunk): wp[dx][pair][chunk][n][8]
+__global__ void prep_weights_c8_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * 5 * 2 * Cout * 8) return;
+  const int c = i % 8, n = (i / 8) % Cout, chunk = (i / (8 * Cout)) % 2, pair = (i / (16 * Cout)) % 5, dx = i / (80 * Cout);
+  int first, second, zero_slot;
+  conv1_pair(dx, pair, first, second, zero_slot);
+  const int tap = chunk == 0 ? first : second;
+  const bool zero = chunk == zero_slot || c >= Cin;
+  wp[i] = __float2bfloat16(zero ? 0.0f : w[((size_t)n * Cin + c) * 9 + tap]);
+}
+// fp32 NCHW image (C <= 8 planes) -> bf16 NHWC with 8 channels per pixel (zero padded): one 16-byte store per pixel
+__global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ img, uint4* __restrict__ out,
+                                                              int C, int HW, size_t total_pixels) {
+  const size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= total_pixels) return;
+  const size_t n = p / HW, hw = p % HW;
+  const float* s = img + n * (size_t)C * HW + hw;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = c < C ? s[(size_t)c * HW] : 0.0f;
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) h[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+  out[p] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                      *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+}
+// Linear weight over a flattened (C,H,W) activation -> the same weight over the (H,W,C) flattening, bf16
+__global__ void fc_weight_to_hwc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int HW,
+                                        size_t total) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t K = (size_t)C * HW;
+  const size_t o = i / K, k = i % K;
+  const size_t hw = k / C, c = k % C;
+  out[i] = __float2bfloat16(w[o * K + c * HW + hw]);
+}
+
+template <int KC, int COUT>
+int launch(const void* x, const void* wprep, const float* bias, void* y, int N, int H, int W, cudaStream_t stream) {
+  using C = Cfg<KC, COUT>;
+  static int sms = 0;
+  static bool attr = false;
+  static int swap_desc = 0;
+  if (!attr) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    const char* e = getenv("BBBP_CONV_SWAP_DESC");
+    swap_desc = e && e[0] == '1';
+    attr = true;
+  }
+  const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
+  const int per_sm = (C::TMEM_COLS <= 256 && C::SMEM_BYTES <= 100 * 1024) ? 2 : 1;
+  const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
+  conv3x3_umma_kernel<KC, COUT><<<grid, THREADS, C::SMEM_BYTES, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W,
+      swap_desc);
+  return launch_status("conv3x3_relu_pool_bf16");
+}
+
+}  // namespace conv
+}  // namespace bbbp
+
+using namespace bbbp;
+
+extern "C" size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout) {
+  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16;
+  return (size_t)9 * (Cin / 8) * Cout * 16;
+}
+
+extern "C" int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(w && wprep, "conv3x3_prepare: null operand");
+  BBBP_CHECK_ARG((Cin == 3 && Cout == 32) || (Cin == 32 && Cout == 64),
+                 "conv3x3_prepare: only (3->32) and (32->64) are built for the tcgen05 path, got %d->%d", Cin, Cout);
+  const int total = (int)(bbbp_conv3x3_prepared_bytes(Cin, Cout) / 2);
+  if (Cin <= 8)
+    conv::prep_weights_c8_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(wprep), Cin, Cout);
+  else
+    conv::prep_weights_kc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(wprep), Cin, Cout);
+  return launch_status("conv3x3_prepare");
+}
+
+extern "C" int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep, const float* bias, void* y_nhwc, int N,
+                                           int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x_nhwc && wprep && bias && y_nhwc, "conv3x3_relu_pool_bf16: null operand");
+  BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
+                 "conv3x3_relu_pool_bf16: H=%d must be a multiple of 32 and W=%d of 16", H, W);
+  BBBP_CHECK_ARG(((uintptr_t)x_nhwc % 16) == 0 && ((uintptr_t)y_nhwc % 16) == 0 && ((uintptr_t)wprep % 16) == 0,
+                 "conv3x3_relu_pool_bf16: operands must be 16-byte aligned");
+  if (N == 0) return BBBP_OK;
+  cudaStream_t s = as_stream(stream);
+  if (Cin_pad == 8 && Cout == 32) return conv::launch<1, 32>(x_nhwc, wprep, bias, y_nhwc, N, H, W, s);
+  if (Cin_pad == 32 && Cout == 64) return conv::launch<4, 64>(x_nhwc, wprep, bias, y_nhwc, N, H, W, s);
+  set_error("conv3x3_relu_pool_bf16: unsupported channels %d->%d (built: 8->32, 32->64)", Cin_pad, Cout);
+  return BBBP_EUNSUPPORTED;
+}
+
+extern "C" int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W,
+                                        bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img_nchw && out_nhwc8 && N >= 0 && C >= 1 && C <= 8 && H > 0 && W > 0, "image_to_nhwc8: bad argument");
+  const size_t total = (size_t)N * H * W;
+  if (total == 0) return BBBP_OK;
+  conv::image_to_nhwc8_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
+      img_nchw, static_cast<uint4*>(out_nhwc8), C, H * W, total);
+  return launch_status("image_to_nhwc8");
+}
+
+extern "C" int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, int HW, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(w && out_bf16 && rows > 0 && C > 0 && HW > 0, "fc_weight_to_hwc: bad argument");
+  const size_t total = (size_t)rows * C * HW;
+  conv::fc_weight_to_hwc_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(out_bf16), C, HW, total);
+  return launch_status("fc_weight_to_hwc");
+}

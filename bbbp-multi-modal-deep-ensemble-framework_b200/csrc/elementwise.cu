@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ pr
 constexpr int ADAMW_CHUNK = 65536;
 __global__ void __launch_bounds__(256) adamw_kernel(void* const* __restrict__ ptrs, const int64_t* __restrict__ sizes,
                                                     const int32_t* __restrict__ chunk_tensor,
-                                                    const int64_t* __restrict__ chunk_offset, int ntensors, float lr,
-                                                    float beta1, float beta2, float eps, float decay_mul, float step_size,
-                                                    float bc2_sqrt, float grad_scale) {
+                                                    const int64_t* __restrict__ chunk_offset, int ntensors,
+                                                    float one_minus_beta1, float beta2, float one_minus_beta2, float eps,
+                                                    float decay_mul, float step_size, float bc2_sqrt, float grad_scale) {
   const int t = chunk_tensor[blockIdx.x];
   const int64_t off = chunk_offset[blockIdx.x];
   float* __restrict__ p = static_cast<float*>(ptrs[t]) + off;
@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(void* const* __restrict__ pt
   auto update = [&](float& pp, float gg, float& mm, float& vv) {
     gg *= grad_scale;
     pp *= decay_mul;
-    mm = mm + (gg - mm) * (1.0f - beta1);
-    vv = vv * beta2 + (1.0f - beta2) * gg * gg;
+    mm = mm + (gg - mm) * one_minus_beta1;            // exp_avg.lerp_(grad, 1 - beta1)
+    vv = vv * beta2 + one_minus_beta2 * gg * gg;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     const float denom = sqrtf(vv) / bc2_sqrt + eps;
     pp = pp - step_size * (mm / denom);
   };
@@ -427,17 +427,21 @@ extern "C" int bbbp_bce_logits_loss_f32(const float* logit, const float* target,
 }
 
 extern "C" int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor,
-                              const int64_t* chunk_offset, int ntensors, int nchunks, float lr, float beta1, float beta2,
-                              float eps, float weight_decay, int step, float grad_scale, bbbp_stream_t stream) {
+                              const int64_t* chunk_offset, int ntensors, int nchunks, double lr, double beta1,
+                              double beta2, double eps, double weight_decay, int step, float grad_scale,
+                              bbbp_stream_t stream) {
   BBBP_CHECK_ARG(ptrs && sizes && chunk_tensor && chunk_offset && ntensors > 0 && nchunks > 0 && step >= 1,
                  "adamw: bad argument");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
+  // hyper-parameters arrive as doubles (Python floats) so every derived scalar is formed exactly as torch forms it
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
   const float bc2_sqrt = (float)sqrt(bc2);
-  const float decay_mul = (float)(1.0 - (double)lr * (double)weight_decay);
-  adamw_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(ptrs, sizes, chunk_tensor, chunk_offset, ntensors, lr, beta1, beta2,
-                                                       eps, decay_mul, step_size, bc2_sqrt, grad_scale);
+  const float decay_mul = (float)(1.0 - lr * weight_decay);
+  // torch forms 1 - beta in double before narrowing; 1.0f - (float)beta would be off by ~1e-5 relative
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
+  adamw_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(ptrs, sizes, chunk_tensor, chunk_offset, ntensors, omb1, (float)beta2,
+                                                       omb2, (float)eps, decay_mul, step_size, bc2_sqrt, grad_scale);
   return launch_status("adamw");
 }
 

@@ -224,8 +224,11 @@ class TransformerCnnModel(_KernelModule):
 
     def _image_branch(self, image):
         side = self.IMAGE_SIDE
-        x = image.reshape(-1, 3, side, side)
         mods = list(self.image_cnn)
+        if (self.precision == "bf16" and self.kind != "big" and side == 128
+                and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.image_cnn.parameters()))):
+            return self._image_branch_tensor_core(image, mods)
+        x = image.reshape(-1, 3, side, side)
         i = 0
         while isinstance(mods[i], nn.Conv2d):
             x = ag.ConvReluPool.apply(x, mods[i].weight, mods[i].bias)
@@ -235,6 +238,32 @@ class TransformerCnnModel(_KernelModule):
         if len(mods) > i + 3:
             x = self._drop(x, mods[i + 3])
         return x
+
+    tensor_core_chunk = 0   # images per pass of the tcgen05 image branch (0 = all at once)
+
+    def _image_branch_tensor_core(self, image, mods):
+        """Inference path: fp32 CHW image -> bf16 NHWC8 -> tcgen05 conv1 -> tcgen05 conv2 (each with bias + ReLU +
+        max-pool in the TMEM epilogue) -> tcgen05 split-K GEMM against the (H,W,C)-re-laid fc weight.  No
+        activation leaves the chip in fp32 and the flatten is free (NHWC rows ARE the fc's K-major A operand)."""
+        from . import ops
+        conv1, conv2, fc = mods[0], mods[3], mods[7]
+        w1 = ag.derived_weight(conv1.weight, "conv_umma", ops.conv3x3_prepare_bf16)
+        w2 = ag.derived_weight(conv2.weight, "conv_umma", ops.conv3x3_prepare_bf16)
+        wfc = ag.derived_weight(fc.weight, "hwc_bf16", lambda w: ops.fc_weight_to_hwc_bf16(w, 64, 32 * 32))
+        img = image if image.is_contiguous() else image.contiguous()
+        n = img.numel() // (3 * 128 * 128)
+        img = img.reshape(n, 3 * 128 * 128)
+        chunk = self.tensor_core_chunk or n
+        outs = []
+        for a in range(0, n, chunk):
+            x = ops.image_to_nhwc8_bf16(img[a:a + chunk])
+            y1 = ops.conv3x3_relu_pool_bf16(x, w1, conv1.bias, 32)
+            y2 = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64)
+            flat = y2.view(y2.shape[0], 65536)
+            o, _ = ops.gemm_bf16(flat, 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
+                                 split_k=ops.fixed_split_k(65536))
+            outs.append(o)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def forward_groups(self, fingerprint, image, groups: int = 1):
         """``groups`` independent reference batches of equal size stacked along dim 0 (attention and the

@@ -99,10 +99,11 @@ def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=None, out=None, 
     return out
 
 
-def pick_split_k(M: int, N: int, K: int, device, tile_m=64, tile_n=64, min_k=512) -> int:
-    tiles = -(-M // tile_m) * -(-N // tile_n)
-    want = -(-2 * sm_count(device) // tiles)
-    return max(1, min(want, K // min_k))
+def fixed_split_k(K: int) -> int:
+    """Split-K factor as a function of K ONLY.  Each output row then sees the same reduction order whatever the
+    number of rows in the call, so a molecule's score does not depend on how many reference batches share a launch
+    or on how batches are sharded over GPUs (bit-identical 1/2/4/8-GPU screening)."""
+    return 1 if K < 8192 else min(32, K // 2048)
 
 
 def cast_bf16(x: torch.Tensor, ld: int | None = None) -> torch.Tensor:
@@ -170,6 +171,40 @@ def conv3x3_flip_weights(w):
     wt = torch.empty((Cin, Cout, 3, 3), device=w.device, dtype=torch.float32)
     check(lib.bbbp_conv3x3_flip_weights_f32(w.data_ptr(), wt.data_ptr(), Cin, Cout, _stream()), "flip_weights")
     return wt
+
+
+# ---- tcgen05 image branch (inference) ---------------------------------------------------------------------------------
+def conv3x3_prepare_bf16(w: torch.Tensor) -> torch.Tensor:
+    Cout, Cin = w.shape[:2]
+    n = lib.bbbp_conv3x3_prepared_bytes(Cin, Cout)
+    wp = torch.empty((n,), device=w.device, dtype=torch.uint8)
+    check(lib.bbbp_conv3x3_prepare_bf16(w.data_ptr(), wp.data_ptr(), Cin, Cout, _stream()), "conv3x3_prepare_bf16")
+    return wp
+
+
+def image_to_nhwc8_bf16(img: torch.Tensor, C=3, H=128, W=128) -> torch.Tensor:
+    N = img.numel() // (C * H * W)
+    out = torch.empty((N, H, W, 8), device=img.device, dtype=torch.bfloat16)
+    check(lib.bbbp_image_to_nhwc8_bf16(img.data_ptr(), out.data_ptr(), N, C, H, W, _stream()), "image_to_nhwc8")
+    return out
+
+
+def conv3x3_relu_pool_bf16(x_nhwc: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, Cout: int) -> torch.Tensor:
+    N, H, W, Cin_pad = x_nhwc.shape
+    y = torch.empty((N, H // 2, W // 2, Cout), device=x_nhwc.device, dtype=torch.bfloat16)
+    name = "conv1" if Cin_pad == 8 else "conv2"
+    t0 = KERNEL_TIMER.start(name)
+    check(lib.bbbp_conv3x3_relu_pool_bf16(x_nhwc.data_ptr(), wprep.data_ptr(), bias.data_ptr(), y.data_ptr(), N, Cin_pad,
+                                          Cout, H, W, _stream()), "conv3x3_relu_pool_bf16")
+    KERNEL_TIMER.stop(name, t0, N)
+    return y
+
+
+def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int) -> torch.Tensor:
+    rows = w.shape[0]
+    out = torch.empty((rows, C * HW), device=w.device, dtype=torch.bfloat16)
+    check(lib.bbbp_fc_weight_to_hwc_bf16(w.data_ptr(), out.data_ptr(), rows, C, HW, _stream()), "fc_weight_to_hwc")
+    return out
 
 
 # ---- attention --------------------------------------------------------------------------------------------------------

@@ -95,6 +95,22 @@ int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* dw, float* 
 /* w_t[Cin,Cout,3,3] = spatially flipped, channel-transposed w[Cout,Cin,3,3] (weights of the data-gradient conv) */
 int bbbp_conv3x3_flip_weights_f32(const float* w, float* w_t, int Cin, int Cout, bbbp_stream_t stream);
 
+/* tcgen05 inference path of the same block: NHWC bf16 activations with 8*k channels per pixel, implicit GEMM with the
+ * halo tile staged once in shared memory, bias + ReLU + 2x2 max-pool fused into the TMEM epilogue (conv_umma.cu).
+ * Built for the reference's two layers: (Cin 3 -> padded 8, Cout 32) and (Cin 32, Cout 64). */
+size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout);
+/* w[Cout,Cin,3,3] fp32 -> the kernel's bf16 shared-memory weight image (call again whenever w changes) */
+int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream);
+/* y[N,H/2,W/2,Cout] = maxpool2(relu(conv3x3(x[N,H,W,Cin_pad]) + bias)), bf16 NHWC in and out; H % 32 == 0, W % 16 == 0 */
+int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep, const float* bias, void* y_nhwc, int N,
+                                int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream);
+/* fp32 NCHW image with C <= 8 planes (the reference's (B,3*128*128) input viewed as (B,3,128,128), 20250113.py:114)
+ * -> bf16 NHWC with 8 channels per pixel, channels >= C zero */
+int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W, bbbp_stream_t stream);
+/* out[o][(hw)*C + c] = bf16(w[o][c*HW + hw]): nn.Linear weight over nn.Flatten's (C,H,W) order re-laid for an NHWC
+ * activation (20250113.py:91-92) */
+int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, int HW, bbbp_stream_t stream);
+
 /* ---- encoder self-attention across the molecules of a reference batch: the (B,1,F)
  *      input of C:110-111 is read by nn.TransformerEncoder as seq_len = B, batch = 1.  ``groups``
  *      independent reference batches of ``seq`` molecules each are processed in one launch. ------ */
@@ -178,9 +194,10 @@ int bbbp_bce_logits_loss_f32(const float* logit, const float* target, float* los
                              float grad_scale, bbbp_stream_t stream);
 /* torch.optim.AdamW semantics, one launch for all tensors.  ptrs is a DEVICE array of 4*ntensors pointers
  * laid out [param | grad | exp_avg | exp_avg_sq] and sizes a DEVICE array of ntensors element counts;
- * chunk_tensor / chunk_offset (DEVICE, nchunks entries) enumerate 64Ki-element chunks. step is 1-based. */
+ * chunk_tensor / chunk_offset (DEVICE, nchunks entries) enumerate 64Ki-element chunks. step is 1-based.
+ * Hyper-parameters are doubles so that 1-beta, lr/bias_correction etc. round exactly as torch's do. */
 int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor, const int64_t* chunk_offset,
-                   int ntensors, int nchunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int ntensors, int nchunks, double lr, double beta1, double beta2, double eps, double weight_decay,
                    int step, float grad_scale, bbbp_stream_t stream);
 
 /* ---- input contracts P1/P2 (extensions; oracle = oracle/preprocess.py) --------------------------- */
