@@ -173,9 +173,9 @@ def test_one_train_step_elementwise_vs_oracle(cuda_device, variant, fp_dim, batc
     our_opt.step()
     for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
         gk = grads[k]
-        solid = gk.abs() > 1e-3 * gk.abs().max()
-        if not bool(solid.any()):
+        if float(gk.abs().max()) < 1e-7:                  # noise-only gradient: Adam's step there is noise too
             continue
+        solid = gk.abs() > 1e-3 * gk.abs().max()
         moved = (q.detach() - before[k])[solid]
         assert float(moved.abs().max()) > 1e-5            # AdamW moved the reference by ~lr there
         d = (p.detach().cpu() - q.detach())[solid].abs().max()
