@@ -21,6 +21,7 @@
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "umma.cuh"
+#include <utility>
 
 namespace bbbp {
 namespace conv {
@@ -47,39 +48,58 @@ struct Cfg {
   static constexpr int SMEM_BYTES = 128 + STAGES * A_BYTES + W_BYTES + COUT * 4 + BAR_BYTES;
 };
 
-__host__ __device__ inline int halo_offset(int dy, int dx, int tap) {
+__host__ __device__ constexpr int halo_offset(int dy, int dx, int tap) {
   const int kh = tap / 3, kw = tap % 3, s = dx + kw;
   return (s & 1) * PAR_B + (dy + kh) * ROW_B + (s >> 1) * 16;
 }
 // conv1 (one 8-channel chunk per pixel): a K=16 MMA step covers TWO taps, the second reached through the leading
 // byte offset.  Pair i = taps (2i, 2i+1); the 9th tap is paired with tap 7 under zero weights.  The descriptor
 // offset must be positive, so the pair is ordered by halo address, which depends on dx only.
-__host__ __device__ inline void conv1_pair(int dx, int i, int& first, int& second, int& zero_slot) {
+struct TapPair {
+  int first, second, zero_slot;  // zero_slot: which K chunk carries zero weights (-1 none)
+};
+__host__ __device__ constexpr TapPair conv1_pair(int dx, int i) {
   const bool pad = 2 * i + 1 >= 9;
   const int t0 = 2 * i, t1 = pad ? 7 : 2 * i + 1;
-  if (halo_offset(0, dx, t1) > halo_offset(0, dx, t0)) {
-    first = t0, second = t1, zero_slot = pad ? 1 : -1;
-  } else {
-    first = t1, second = t0, zero_slot = pad ? 0 : -1;
-  }
+  if (halo_offset(0, dx, t1) > halo_offset(0, dx, t0)) return TapPair{t0, t1, pad ? 1 : -1};
+  return TapPair{t1, t0, pad ? 0 : -1};
 }
 
+struct MmaOp {
+  uint32_t a_off, a_lbo, b_off;
+};
+// Operands of MMA number m (0 .. NMMA-1) of window member q = 2*dy + dx: byte offsets into the staged halo / the
+// shared-memory weight image.  constexpr: the issue loop is fully unrolled and every descriptor is an immediate.
 template <int KC, int COUT>
-__device__ __forceinline__ void mma_operands(int q, int i, uint32_t& a_off, uint32_t& a_lbo, uint32_t& b_off) {
+__host__ __device__ constexpr MmaOp mma_op(int q, int m) {
   const int dy = q >> 1, dx = q & 1;
-  if constexpr (KC == 1) {
-    int first, second, z;
-    conv1_pair(dx, i, first, second, z);
-    const int oa = halo_offset(dy, dx, first), ob = halo_offset(dy, dx, second);
-    a_off = oa;
-    a_lbo = ob - oa;
-    b_off = (dx * 5 + i) * (2 * COUT * 16);
-  } else {
-    const int tap = i / (KC / 2), j = i % (KC / 2);
-    a_off = (2 * j) * KC_B + halo_offset(dy, dx, tap);
-    a_lbo = KC_B;
-    b_off = (tap * KC + 2 * j) * (COUT * 16);
+  if (KC == 1) {
+    const TapPair p = conv1_pair(dx, m);
+    const int oa = halo_offset(dy, dx, p.first), ob = halo_offset(dy, dx, p.second);
+    return MmaOp{(uint32_t)oa, (uint32_t)(ob - oa), (uint32_t)((dx * 5 + m) * (2 * COUT * 16))};
   }
+  const int tap = m / (KC / 2 > 0 ? KC / 2 : 1), j = m % (KC / 2 > 0 ? KC / 2 : 1);
+  return MmaOp{(uint32_t)((2 * j) * KC_B + halo_offset(dy, dx, tap)), (uint32_t)KC_B,
+               (uint32_t)((tap * KC + 2 * j) * (COUT * 16))};
+}
+
+// descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46) | no swizzle
+template <int KC, int COUT, int I>
+__device__ __forceinline__ void issue_one(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc) {
+  using C = Cfg<KC, COUT>;
+  constexpr int q = I / C::NMMA, m = I % C::NMMA;
+  constexpr MmaOp op = mma_op<KC, COUT>(q, m);
+  constexpr uint32_t a_lo_c = (op.a_off >> 4) | ((op.a_lbo >> 4) << 16);
+  constexpr uint32_t b_lo_c = (op.b_off >> 4) | (((COUT * 16) >> 4) << 16);
+  constexpr uint64_t a_hi = (uint64_t)(((2 * ROW_B) >> 4) | (1u << 14)) << 32;
+  constexpr uint64_t b_hi = (uint64_t)((128 >> 4) | (1u << 14)) << 32;
+  constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+  umma_bf16(tmem_acc + q * COUT, a_hi | (a_lo + a_lo_c), b_hi | (w_lo + b_lo_c), idesc, m != 0);
+}
+template <int KC, int COUT, int... I>
+__device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc,
+                                           std::integer_sequence<int, I...>) {
+  (issue_one<KC, COUT, I>(a_lo, w_lo, tmem_acc), ...);
 }
 
 template <int KC, int COUT>
@@ -87,7 +107,7 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
                                                                const uint4* __restrict__ wprep,
                                                                const float* __restrict__ bias,
                                                                __nv_bfloat16* __restrict__ dst, int n_img, int H,
-                                                               int W, int swap_desc) {
+                                                               int W) {
   using C = Cfg<KC, COUT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -130,8 +150,11 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
   if (warp >= 4 && warp < 8) {
     // ===== producers: stage the halo of each tile ====================================================================
     const int ptid = threadIdx.x - 4 * 32;
-    constexpr int CHUNKS = HALO_H * HALO_W * KC;
-    const size_t pix_bytes = (size_t)KC * 16;
+    constexpr int ROWC = HALO_W * KC;                  // 16-byte chunks per halo row
+    constexpr int CHUNKS = HALO_H * ROWC;
+    constexpr int STEP_Y = PROD_THREADS / ROWC, STEP_J = PROD_THREADS % ROWC;
+    constexpr int PIX_B = KC * 16;
+    const int Yi = ptid / ROWC, ji = ptid % ROWC;      // first chunk of this thread: the same for every tile
     for (int i = 0; i < my_tiles; ++i) {
       const int t = blockIdx.x + i * gridDim.x;
       const int n = t / tiles_per_img, r = t % tiles_per_img;
@@ -139,14 +162,21 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
       const int s = i % STAGES;
       mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
       const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
-      const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * pix_bytes;
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * PIX_B;
+      int Y = Yi, j = ji;
+#pragma unroll 4
       for (int c = ptid; c < CHUNKS; c += PROD_THREADS) {
-        const int kc = c % KC, p = c / KC;
-        const int X = p % HALO_W, Y = p / HALO_W;
+        const int X = j / KC, kc = j % KC;
         const int y = y0 + Y, x = x0 + X;
         const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-        const uint8_t* g = img + ((size_t)(ok ? y : 0) * W + (ok ? x : 0)) * pix_bytes + kc * 16;
-        cp_async_16(stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16, g, ok ? 16u : 0u);
+        const int goff = ok ? (y * W + x) * PIX_B + kc * 16 : 0;
+        cp_async_16(stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16, img + goff, ok ? 16u : 0u);
+        j += STEP_J;
+        Y += STEP_Y;
+        if (j >= ROWC) {
+          j -= ROWC;
+          ++Y;
+        }
       }
       cp_async_commit();
       if (i > 0) {
@@ -163,29 +193,14 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
   } else if (warp == 8) {
     // ===== MMA issuer ==================================================================================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
-      const uint32_t w_addr = smem_u32(sW);
-      const uint32_t a_sbo = 2 * ROW_B, b_sbo = 128, b_lbo = COUT * 16;
+      const uint32_t w_lo = smem_u32(sW) >> 4;
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % STAGES, b = i & 1;
         mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
         mbar_wait(&full[s], (i / STAGES) & 1);
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES);
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t d = tmem_base + b * C::ACC_COLS + q * COUT;
-#pragma unroll 1
-          for (int m = 0; m < C::NMMA; ++m) {
-            uint32_t a_off, a_lbo, b_off;
-            mma_operands<KC, COUT>(q, m, a_off, a_lbo, b_off);
-            const uint64_t ad = swap_desc ? make_smem_desc(a_addr + a_off, a_sbo, a_lbo, kLayoutNone)
-                                          : make_smem_desc(a_addr + a_off, a_lbo, a_sbo, kLayoutNone);
-            const uint64_t bd = swap_desc ? make_smem_desc(w_addr + b_off, b_sbo, b_lbo, kLayoutNone)
-                                          : make_smem_desc(w_addr + b_off, b_lbo, b_sbo, kLayoutNone);
-            umma_bf16(d, ad, bd, idesc, m != 0);
-          }
-        }
+        issue_tile<KC, COUT>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+                             std::make_integer_sequence<int, 4 * C::NMMA>{});
         umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
         umma_commit(&acc_full[b]);   // accumulators of this tile complete
       }
@@ -253,10 +268,9 @@ __global__ void prep_weights_c8_kernel(const float* __restrict__ w, __nv_bfloat1
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * 5 * 2 * Cout * 8) return;
   const int c = i % 8, n = (i / 8) % Cout, chunk = (i / (8 * Cout)) % 2, pair = (i / (16 * Cout)) % 5, dx = i / (80 * Cout);
-  int first, second, zero_slot;
-  conv1_pair(dx, pair, first, second, zero_slot);
-  const int tap = chunk == 0 ? first : second;
-  const bool zero = chunk == zero_slot || c >= Cin;
+  const TapPair tp = conv1_pair(dx, pair);
+  const int tap = chunk == 0 ? tp.first : tp.second;
+  const bool zero = chunk == tp.zero_slot || c >= Cin;
   wp[i] = __float2bfloat16(zero ? 0.0f : w[((size_t)n * Cin + c) * 9 + tap]);
 }
 // fp32 NCHW image (C <= 8 planes) -> bf16 NHWC with 8 channels per pixel (zero padded): one 16-byte store per pixel
@@ -291,22 +305,18 @@ int launch(const void* x, const void* wprep, const float* bias, void* y, int N, 
   using C = Cfg<KC, COUT>;
   static int sms = 0;
   static bool attr = false;
-  static int swap_desc = 0;
   if (!attr) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    const char* e = getenv("BBBP_CONV_SWAP_DESC");
-    swap_desc = e && e[0] == '1';
     attr = true;
   }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
   const int per_sm = (C::TMEM_COLS <= 256 && C::SMEM_BYTES <= 100 * 1024) ? 2 : 1;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
   conv3x3_umma_kernel<KC, COUT><<<grid, THREADS, C::SMEM_BYTES, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W,
-      swap_desc);
+      static_cast<const __nv_bfloat16*>(x), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W);
   return launch_status("conv3x3_relu_pool_bf16");
 }
 

@@ -1,14 +1,16 @@
-// tcgen05 / TMEM / TMA GEMM for every nn.Linear on the path (bf16 operands, fp32 accumulation in TMEM):
-//   out = act(A[M,K] * W[N,K]^T + bias) (+ residual)
-// Call sites replaced: encoder in_proj / out_proj / linear1 / linear2 (torch.nn.TransformerEncoderLayer via
-// 20250113.py:75-78), fingerprint_fc :80, image_cnn Linear(65536,128) :92, fusion heads :53-55, head fc :99-106,
-// PCA transform (_opt.py:30-33).
+// tcgen05 / TMEM / TMA GEMM for every nn.Linear on the path and for the two attention contractions
+// (bf16 operands, fp32 accumulation in TMEM):
+//   out[b] = act(A[b][M,K] * W[b][N,K]^T + bias) (+ residual[b])                      (linear epilogue)
+//   P[b]   = softmax_rows(scale * A[b] * W[b]^T)  as bf16                               (attention-score epilogue)
+// Call sites replaced: encoder in_proj / out_proj / linear1 / linear2 and the softmax(QK^T/sqrt(d)) V products inside
+// nn.MultiheadAttention (torch.nn.TransformerEncoderLayer via 20250113.py:75-78, 110-111), fingerprint_fc :80,
+// image_cnn Linear(65536,128) :92, fusion heads :53-55, head fc :99-106, PCA transform (_opt.py:30-33).
 //
-// One CTA computes one 128 x BN output tile over a K range (split-K over blockIdx.z):
-//   warp 0   TMA producer   cp.async.bulk.tensor 2-D, 128B-swizzled 128x64 / BNx64 bf16 boxes, STAGES-deep mbarrier ring
+// One CTA computes one 128 x BN output tile of one batch entry over a K range (blockIdx.z = batch * splits + split):
+//   warp 0   TMA producer   cp.async.bulk.tensor 3-D {K, rows, batch}, 128B-swizzled 128x64 / BNx64 bf16 boxes, mbarrier ring
 //   warp 1   MMA issuer     one elected thread: tcgen05.mma.cta_group::1.kind::f16 M=128 N=BN K=16, accumulators in TMEM
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual -> global (fp32 and/or bf16)
+//   warps 4-7 epilogue      tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual (or row softmax) -> global
 // K tails and M/N tails are covered by TMA out-of-bounds zero fill; nothing has to be padded in HBM except the row
 // pitch (multiple of 8 elements).
 #include "common.cuh"
@@ -30,23 +32,29 @@ tensormap_encode_fn get_tensormap_encoder() {
   return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                      uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+// bf16 [batches][rows][cols] with row pitch ld and batch pitch batch_stride (elements); box = box_rows x box_cols x 1
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t batches,
+                      uint64_t batch_stride, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
   tensormap_encode_fn enc = get_tensormap_encoder();
   if (!enc) return BBBP_ECUDA;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t dims[3] = {cols, rows, batches};
+  cuuint64_t strides[2] = {ld * 2, (batches > 1 ? batch_stride : rows * ld) * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, base,
-              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu batches=%llu stride=%llu box=%ux%u",
+              (int)r, base, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld,
+              (unsigned long long)batches, (unsigned long long)batch_stride, box_rows, box_cols);
     return BBBP_ECUDA;
   }
   return BBBP_OK;
+}
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  return make_tmap_bf16_3d(map, base, rows, cols, ld, 1, 0, box_rows, box_cols, swizzle);
 }
 
 namespace gemm {
@@ -54,25 +62,47 @@ using namespace sm100;
 
 constexpr int BM = 128, BK = 64;
 constexpr int THREADS = 256;
+enum { EPI_LINEAR = 0, EPI_SOFTMAX = 1 };
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int STAGES = BN == 64 ? 4 : 3;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // tiles | full[STAGES] empty[STAGES] accum | tmem slot ; +1024 for manual alignment of the tile area
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
 };
 
-template <int BN>
+struct Params {
+  int M, N, total_kb, kb_per_split, splits;
+  const float* bias;
+  const float* residual;
+  int ld_res;
+  long long res_bs;
+  float* out;
+  int ld_out;
+  long long out_bs;
+  __nv_bfloat16* out16;
+  int ld_out16;
+  long long out16_bs;
+  int act;
+  float* partial;
+  int M_pad, N_pad;
+  float scale;  // EPI_SOFTMAX: logits are scale * (A W^T)
+};
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmB, int M, int N,
-                                                            int total_kb, int kb_per_split,
-                                                            const float* __restrict__ bias,
-                                                            const float* __restrict__ residual, int ld_res,
-                                                            float* __restrict__ out, int ld_out,
-                                                            __nv_bfloat16* __restrict__ out16, int ld_out16, int act,
-                                                            float* __restrict__ partial, int M_pad, int N_pad) {
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const __grid_constant__ Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,8 +115,9 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int num_kb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
+  const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int kb_begin = split * p.kb_per_split;
+  const int num_kb = min(p.total_kb, kb_begin + p.kb_per_split) - kb_begin;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -113,8 +144,8 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
         const uint32_t ph = (i / C::STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
-        tma_load_2d(&tmA, &full[s], sA + s * C::A_BYTES, (kb_begin + i) * BK, m0);
-        tma_load_2d(&tmB, &full[s], sB + s * C::B_BYTES, (kb_begin + i) * BK, n0);
+        tma_load_3d(&tmA, &full[s], sA + s * C::A_BYTES, (kb_begin + i) * BK, m0, batch);
+        tma_load_3d(&tmB, &full[s], sB + s * C::B_BYTES, (kb_begin + i) * BK, n0, batch);
       }
     }
     __syncwarp();
@@ -145,28 +176,118 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
     tc_fence_after_sync();
     const int row = m0 + q * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if constexpr (EPI == EPI_SOFTMAX) {
+      // one thread owns one full row of logits (N <= BN): three passes over its TMEM lane
+      const int N = p.N;
+      float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(taddr + c * 32, r);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (partial) {
-        float4* dst = reinterpret_cast<float4*>(partial + ((size_t)blockIdx.z * M_pad + row) * N_pad + col0);
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
-      } else if (row < M) {
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+      const float sl2 = p.scale * 1.4426950408889634f;  // exp(scale*(x-mx)) = exp2(sl2*(x-mx))
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < N) {
-            float v = __uint_as_float(r[j]) + (bias ? __ldg(bias + col) : 0.0f);
-            v = apply_act(v, act);
-            if (residual) v += residual[(size_t)row * ld_res + col];
-            if (out) out[(size_t)row * ld_out + col] = v;
-            if (out16) out16[(size_t)row * ld_out16 + col] = __float2bfloat16(v);
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < N) sum += exp2f((__uint_as_float(r[j]) - mx) * sl2);
+      }
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* dst = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= p.ld_out16) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);   // .sync.aligned: the whole warp loads, only valid rows store
+        tmem_ld_wait();
+        if (row < p.M) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float v0 = c * 32 + j < N ? exp2f((__uint_as_float(r[j]) - mx) * sl2) * inv : 0.0f;
+            const float v1 = c * 32 + j + 1 < N ? exp2f((__uint_as_float(r[j + 1]) - mx) * sl2) * inv : 0.0f;
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            pk[j / 2] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          // ld_out16 is a multiple of 8: write whole 16-byte groups, zero in the pad columns
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (c * 32 + g * 8 < p.ld_out16)
+              reinterpret_cast<uint4*>(dst + c * 32)[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+    } else {
+      const bool vec32 = p.out && (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.out_bs % 4 == 0);
+      const bool vec16 = p.out16 && (p.ld_out16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out16) & 15) == 0) && (p.out16_bs % 8 == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (!p.partial && col0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (p.partial) {
+          float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M_pad + row) * p.N_pad + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+        } else if (row < p.M) {
+          float v[32];
+          const float* res = p.residual ? p.residual + (size_t)batch * p.res_bs + (size_t)row * p.ld_res : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            float t = __uint_as_float(r[j]);
+            if (col < p.N) {
+              t += p.bias ? __ldg(p.bias + col) : 0.0f;
+              t = apply_act(t, p.act);
+              if (res) t += res[col];
+            } else {
+              t = 0.0f;
+            }
+            v[j] = t;
+          }
+          if (p.out) {
+            float* o = p.out + (size_t)batch * p.out_bs + (size_t)row * p.ld_out + col0;
+            if (vec32 && col0 + 32 <= p.ld_out) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col0 + 4 * j < p.ld_out) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = v[j];
+            }
+          }
+          if (p.out16) {
+            __nv_bfloat16* o = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16 + col0;
+            if (vec16 && col0 + 32 <= p.ld_out16) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
+                  pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                reinterpret_cast<uint4*>(o)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.ld_out16) o[j] = __float2bfloat16(v[j]);  // pad columns [N, ld) get zeros
+            }
           }
         }
       }
@@ -199,36 +320,70 @@ __global__ void __launch_bounds__(256) splitk_finish_bf16_kernel(const float* __
   if (out16) out16[(size_t)m * ld_out16 + n] = __float2bfloat16(v);
 }
 
-template <int BN>
-int launch(int M, int N, int K, const void* A, int lda, const void* W, int ldw, const float* bias, const float* residual,
-           int ld_res, float* out, int ld_out, void* out16, int ld_out16, int act, int split_k, float* partial,
-           cudaStream_t stream) {
+struct Problem {
+  int M, N, K, batches;
+  const void* A;
+  int lda;
+  long long a_bs;
+  const void* W;
+  int ldw;
+  long long w_bs;
+  Params p;
+};
+
+template <int BN, int EPI>
+int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap tmA, tmB;
-  int st = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  int st = make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
+                             (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != BBBP_OK) return st;
-  st = make_tmap_bf16_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  st = make_tmap_bf16_3d(&tmB, pr.W, (uint64_t)pr.N, (uint64_t)pr.K, (uint64_t)pr.ldw, (uint64_t)pr.batches,
+                         (uint64_t)pr.w_bs, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != BBBP_OK) return st;
-  const int total_kb = ceil_div(K, BK);
-  int kb_per_split = ceil_div(total_kb, split_k);
-  split_k = ceil_div(total_kb, kb_per_split);
-  const int M_pad = ceil_div(M, 128) * 128, N_pad = ceil_div(N, 128) * 128;
+  Params p = pr.p;
+  p.M = pr.M;
+  p.N = pr.N;
+  p.total_kb = ceil_div(pr.K, BK);
+  p.kb_per_split = ceil_div(p.total_kb, split_k);
+  p.splits = ceil_div(p.total_kb, p.kb_per_split);
+  p.M_pad = ceil_div(pr.M, 128) * 128;
+  p.N_pad = ceil_div(pr.N, 128) * 128;
+  if (p.splits <= 1) p.partial = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), split_k);
-  gemm_bf16_kernel<BN><<<grid, THREADS, C::SMEM_BYTES, stream>>>(
-      tmA, tmB, M, N, total_kb, kb_per_split, bias, residual, ld_res, out, ld_out,
-      reinterpret_cast<__nv_bfloat16*>(out16), ld_out16, act, split_k > 1 ? partial : nullptr, M_pad, N_pad);
+  dim3 grid(ceil_div(pr.N, BN), ceil_div(pr.M, BM), pr.batches * p.splits);
+  gemm_bf16_kernel<BN, EPI><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
   st = launch_status("gemm_bf16");
-  if (st != BBBP_OK || split_k <= 1) return st;
-  const size_t total = (size_t)M * N;
+  if (st != BBBP_OK || p.splits <= 1) return st;
+  const size_t total = (size_t)pr.M * pr.N;
   splitk_finish_bf16_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, stream>>>(
-      partial, split_k, M, N, M_pad, N_pad, bias, residual, ld_res, out, ld_out, reinterpret_cast<__nv_bfloat16*>(out16),
-      ld_out16, act);
+      p.partial, p.splits, pr.M, pr.N, p.M_pad, p.N_pad, p.bias, p.residual, p.ld_res, p.out, p.ld_out, p.out16, p.ld_out16,
+      p.act);
   return launch_status("gemm_bf16 split-k finish");
+}
+
+// batched [batches][rows][cols] bf16 -> [batches][cols][rows] bf16 (V -> V^T for the P V product), 32x32 smem tiles
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld_src,
+                                                             long long src_bs, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                             long long dst_bs, int rows, int cols) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const __nv_bfloat16* s = src + (size_t)b * src_bs;
+  __nv_bfloat16* d = dst + (size_t)b * dst_bs;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? s[(size_t)r * ld_src + c] : __float2bfloat16(0.0f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < ld_dst) d[(size_t)c * ld_dst + r] = tile[threadIdx.x][i];  // rows >= `rows` carry zeros
+  }
 }
 
 }  // namespace gemm
@@ -240,16 +395,35 @@ extern "C" size_t bbbp_gemm_bf16_workspace(int M, int N, int split_k) {
   return (size_t)split_k * M_pad * N_pad * sizeof(float);
 }
 
+static int check_operands(const char* who, int M, int N, int K, const void* A, int lda, const void* W, int ldw) {
+  using namespace bbbp;
+  if (M < 0 || N < 0 || K <= 0) {
+    set_error("%s: bad dimension M=%d N=%d K=%d", who, M, N, K);
+    return BBBP_EINVAL;
+  }
+  if (!A || !W) {
+    set_error("%s: null operand", who);
+    return BBBP_EINVAL;
+  }
+  if (lda < K || ldw < K || lda % 8 || ldw % 8) {
+    set_error("%s: lda=%d ldw=%d must be >= K=%d and multiples of 8", who, lda, ldw, K);
+    return BBBP_EINVAL;
+  }
+  if (((uintptr_t)A % 16) || ((uintptr_t)W % 16)) {
+    set_error("%s: operands must be 16-byte aligned", who);
+    return BBBP_EINVAL;
+  }
+  return BBBP_OK;
+}
+
 extern "C" int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, const void* W_bf16, int ldw,
                               const float* bias, const float* residual, int ld_res, float* out_f32, int ld_out,
                               void* out_bf16, int ld_out16, int act, int split_k, void* workspace,
                               size_t workspace_bytes, bbbp_stream_t stream) {
   using namespace bbbp;
-  BBBP_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_bf16: bad dimension M=%d N=%d K=%d", M, N, K);
-  BBBP_CHECK_ARG(A_bf16 && W_bf16, "gemm_bf16: null operand");
+  int st = check_operands("gemm_bf16", M, N, K, A_bf16, lda, W_bf16, ldw);
+  if (st != BBBP_OK) return st;
   BBBP_CHECK_ARG(out_f32 || out_bf16, "gemm_bf16: no output given");
-  BBBP_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: lda=%d ldw=%d must be >= K=%d and multiples of 8", lda, ldw, K);
-  BBBP_CHECK_ARG(((uintptr_t)A_bf16 % 16) == 0 && ((uintptr_t)W_bf16 % 16) == 0, "gemm_bf16: operands must be 16-byte aligned");
   BBBP_CHECK_ARG(!residual || ld_res >= N, "gemm_bf16: ld_res < N");
   BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out_bf16 || ld_out16 >= N), "gemm_bf16: output pitch < N");
   if (M == 0 || N == 0) return BBBP_OK;
@@ -264,10 +438,68 @@ extern "C" int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, 
       return BBBP_EWORKSPACE;
     }
   }
+  gemm::Problem pr{};
+  pr.M = M, pr.N = N, pr.K = K, pr.batches = 1;
+  pr.A = A_bf16, pr.lda = lda, pr.W = W_bf16, pr.ldw = ldw;
+  pr.p.bias = bias, pr.p.residual = residual, pr.p.ld_res = ld_res;
+  pr.p.out = out_f32, pr.p.ld_out = ld_out;
+  pr.p.out16 = static_cast<__nv_bfloat16*>(out_bf16), pr.p.ld_out16 = ld_out16;
+  pr.p.act = act, pr.p.partial = static_cast<float*>(workspace);
   cudaStream_t s = as_stream(stream);
-  if (N <= 64)
-    return gemm::launch<64>(M, N, K, A_bf16, lda, W_bf16, ldw, bias, residual, ld_res, out_f32, ld_out, out_bf16, ld_out16,
-                            act, split_k, static_cast<float*>(workspace), s);
-  return gemm::launch<128>(M, N, K, A_bf16, lda, W_bf16, ldw, bias, residual, ld_res, out_f32, ld_out, out_bf16, ld_out16,
-                           act, split_k, static_cast<float*>(workspace), s);
+  if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, split_k, s);
+  if (N >= 512 && split_k == 1) return gemm::launch<256, gemm::EPI_LINEAR>(pr, split_k, s);
+  return gemm::launch<128, gemm::EPI_LINEAR>(pr, split_k, s);
+}
+
+extern "C" int bbbp_gemm_bf16_batched(int batches, int M, int N, int K, const void* A_bf16, int lda, long long a_batch_stride,
+                                      const void* W_bf16, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
+                                      long long out_batch_stride, void* out_bf16, int ld_out16,
+                                      long long out16_batch_stride, bbbp_stream_t stream) {
+  using namespace bbbp;
+  int st = check_operands("gemm_bf16_batched", M, N, K, A_bf16, lda, W_bf16, ldw);
+  if (st != BBBP_OK) return st;
+  BBBP_CHECK_ARG(batches >= 0 && batches <= 65535, "gemm_bf16_batched: batches=%d out of range", batches);
+  BBBP_CHECK_ARG(a_batch_stride % 8 == 0 && w_batch_stride % 8 == 0, "gemm_bf16_batched: batch strides must be multiples of 8");
+  BBBP_CHECK_ARG(out_f32 || out_bf16, "gemm_bf16_batched: no output given");
+  BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out_bf16 || ld_out16 >= N), "gemm_bf16_batched: output pitch < N");
+  if (M == 0 || N == 0 || batches == 0) return BBBP_OK;
+  gemm::Problem pr{};
+  pr.M = M, pr.N = N, pr.K = K, pr.batches = batches;
+  pr.A = A_bf16, pr.lda = lda, pr.a_bs = a_batch_stride, pr.W = W_bf16, pr.ldw = ldw, pr.w_bs = w_batch_stride;
+  pr.p.out = out_f32, pr.p.ld_out = ld_out, pr.p.out_bs = out_batch_stride;
+  pr.p.out16 = static_cast<__nv_bfloat16*>(out_bf16), pr.p.ld_out16 = ld_out16, pr.p.out16_bs = out16_batch_stride;
+  cudaStream_t s = as_stream(stream);
+  if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, 1, s);
+  return gemm::launch<128, gemm::EPI_LINEAR>(pr, 1, s);
+}
+
+extern "C" int bbbp_attention_scores_softmax_bf16(int groups, int seq, int head_dim, const void* q_bf16, int ldq,
+                                                  const void* k_bf16, int ldk, long long group_stride, float scale,
+                                                  void* p_bf16, int ldp, bbbp_stream_t stream) {
+  using namespace bbbp;
+  int st = check_operands("attention_scores_softmax", seq, seq, head_dim, q_bf16, ldq, k_bf16, ldk);
+  if (st != BBBP_OK) return st;
+  BBBP_CHECK_ARG(seq <= 256, "attention_scores_softmax: seq=%d > 256 (one CTA must own a full row of scores)", seq);
+  BBBP_CHECK_ARG(groups >= 0 && groups <= 65535 && group_stride % 8 == 0, "attention_scores_softmax: bad groups/stride");
+  BBBP_CHECK_ARG(p_bf16 && ldp >= seq && ldp % 8 == 0 && ldp <= 256, "attention_scores_softmax: ldp=%d must be a multiple of 8 in [seq, 256]", ldp);
+  if (groups == 0 || seq == 0) return BBBP_OK;
+  gemm::Problem pr{};
+  pr.M = seq, pr.N = seq, pr.K = head_dim, pr.batches = groups;
+  pr.A = q_bf16, pr.lda = ldq, pr.a_bs = group_stride, pr.W = k_bf16, pr.ldw = ldk, pr.w_bs = group_stride;
+  pr.p.out16 = static_cast<__nv_bfloat16*>(p_bf16), pr.p.ld_out16 = ldp, pr.p.out16_bs = (long long)seq * ldp;
+  pr.p.scale = scale;
+  return gemm::launch<256, gemm::EPI_SOFTMAX>(pr, 1, as_stream(stream));
+}
+
+extern "C" int bbbp_transpose_bf16(int batches, int rows, int cols, const void* src, int ld_src, long long src_batch_stride,
+                                   void* dst, int ld_dst, long long dst_batch_stride, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(src && dst && batches >= 0 && batches <= 65535 && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= rows,
+                 "transpose_bf16: bad argument");
+  if (batches == 0) return BBBP_OK;
+  dim3 grid(ceil_div(cols, 32), ceil_div(ld_dst, 32), batches);
+  gemm::transpose_bf16_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), ld_src, src_batch_stride, static_cast<__nv_bfloat16*>(dst), ld_dst,
+      dst_batch_stride, rows, cols);
+  return launch_status("transpose_bf16");
 }

@@ -203,6 +203,56 @@ class TransformerCnnModel(_KernelModule):
         f = self._drop(self._lin(h, layer.linear2), layer.dropout2)
         return ag.AddLayerNorm.apply(f, x, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
 
+    # -- encoder, inference fast path: every contraction on tcgen05, activations stay bf16 between GEMMs -----------------
+    def _encoder_tensor_core_ok(self, seq: int) -> bool:
+        attn = self.fingerprint_transformer.layers[0].self_attn
+        return (self.precision == "bf16" and not self.training and attn.num_heads == 1 and seq <= 256
+                and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.fingerprint_transformer.parameters())))
+
+    def _encoder_tensor_core(self, x, groups: int, seq: int):
+        """6 x [in_proj GEMM -> (QK^T + row softmax) GEMM -> V transpose -> PV GEMM -> out_proj GEMM (+residual) -> LN
+        -> FFN1 GEMM (+ReLU, bf16 out) -> FFN2 GEMM (+residual) -> LN], then fingerprint_fc.  9 launches per layer."""
+        from . import ops
+        F_ = x.shape[1]
+        Fq = -(-F_ // 8) * 8                          # q | k | v each start on a 16-byte boundary
+        rows = x.shape[0]
+        x32 = x
+        x16 = ops.cast_bf16(x32, ld=Fq)
+
+        def padded_in_proj(w):                       # (3F, F) -> bf16 (3*Fq, Fq), zero rows/cols in the pads
+            out = torch.zeros((3 * Fq, Fq), device=w.device, dtype=torch.bfloat16)
+            for part in range(3):
+                ops.cast_bf16(w[part * F_:(part + 1) * F_], out=out[part * Fq: part * Fq + F_])
+            return out
+
+        def padded_in_bias(b):
+            out = torch.zeros((1, 3 * Fq), device=b.device, dtype=torch.float32)
+            for part in range(3):
+                ops.copy2d(b[part * F_:(part + 1) * F_].reshape(1, F_), out[:, part * Fq: part * Fq + F_])
+            return out.reshape(-1)
+
+        for layer in self.fingerprint_transformer.layers:
+            attn = layer.self_attn
+            w_in = ag.derived_weight(attn.in_proj_weight, "qkv_pad16", padded_in_proj)
+            b_in = ag.derived_weight(attn.in_proj_bias, "qkv_pad", padded_in_bias)
+            _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True)
+            p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5)
+            ldp = p16.shape[1]
+            vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
+            _, a16 = ops.gemm_bf16_batched(groups, seq, F_, seq, p16, ldp, seq * ldp, vt, ldp, F_ * ldp, ld_out16=Fq)
+            s32, _ = ops.gemm_bf16(a16, F_, ag.weight_bf16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32)
+            x32, _, _, _, x16 = ops.add_layernorm_fwd(s32, None, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps,
+                                                      bf16_ld=Fq)
+            _, h16 = ops.gemm_bf16(x16, F_, ag.weight_bf16(layer.linear1.weight), layer.linear1.out_features,
+                                   bias=layer.linear1.bias, act="relu", out_f32=False, out_bf16=True)
+            f32, _ = ops.gemm_bf16(h16, layer.linear1.out_features, ag.weight_bf16(layer.linear2.weight), F_,
+                                   bias=layer.linear2.bias, residual=x32)
+            x32, _, _, _, x16 = ops.add_layernorm_fwd(f32, None, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
+                                                      bf16_ld=Fq)
+        fc = self.fingerprint_fc[0]
+        out, _ = ops.gemm_bf16(x16, F_, ag.weight_bf16(fc.weight), fc.out_features, bias=fc.bias, act="relu")
+        return out
+
     def _head(self, x):
         mods = list(self.fc)
         i = 0
@@ -276,9 +326,12 @@ class TransformerCnnModel(_KernelModule):
         if rows % groups:
             raise ValueError(f"{rows} molecules do not split into {groups} equal reference batches")
         x = fingerprint if fingerprint.is_contiguous() else fingerprint.contiguous()
-        for layer in self.fingerprint_transformer.layers:
-            x = self._encoder_layer(x, layer, groups, rows // groups)
-        fp = self._lin(x, self.fingerprint_fc[0], "relu")
+        if self._encoder_tensor_core_ok(rows // groups):
+            fp = self._encoder_tensor_core(x, groups, rows // groups)
+        else:
+            for layer in self.fingerprint_transformer.layers:
+                x = self._encoder_layer(x, layer, groups, rows // groups)
+            fp = self._lin(x, self.fingerprint_fc[0], "relu")
         if len(self.fingerprint_fc) > 2:
             fp = self._drop(fp, self.fingerprint_fc[2])
         im = self._image_branch(image)

@@ -106,28 +106,67 @@ def fixed_split_k(K: int) -> int:
     return 1 if K < 8192 else min(32, K // 2048)
 
 
-def cast_bf16(x: torch.Tensor, ld: int | None = None) -> torch.Tensor:
-    """(rows, cols) float32 -> (rows, ld) bfloat16 with zero fill of the pad columns; ld multiple of 8."""
+def cast_bf16(x: torch.Tensor, ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(rows, cols) float32 -> (rows, ld) bfloat16 with zero fill of the pad columns; ld multiple of 8.
+    ``out`` may be a pitched 2-D bf16 view (its row stride is the destination pitch)."""
     rows, cols = x.shape
-    if ld is None:
-        ld = -(-cols // 8) * 8
-    out = torch.empty((rows, ld), device=x.device, dtype=torch.bfloat16)
-    check(lib.bbbp_cast_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), ld, rows, cols, ld, _stream()), "cast_bf16")
+    if out is None:
+        if ld is None:
+            ld = -(-cols // 8) * 8
+        out = torch.empty((rows, ld), device=x.device, dtype=torch.bfloat16)
+        pad_to, pitch = ld, ld
+    else:
+        pad_to, pitch = out.shape[1], out.stride(0)
+    check(lib.bbbp_cast_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), pitch, rows, cols, pad_to, _stream()), "cast_bf16")
     return out
 
 
-def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, out_bf16=False, split_k=1):
-    """act(a16[:, :K] @ w16[:N, :K]^T + bias) (+ residual) on the tcgen05 path.  Returns (f32 | None, bf16 | None)."""
+def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, out_bf16=False, split_k=1,
+              ld_out=None, ld_out16=None):
+    """act(a16[:, :K] @ w16[:N, :K]^T + bias) (+ residual) on the tcgen05 path.  Returns (f32 | None, bf16 | None);
+    outputs are (M, ld) buffers whose first N columns are the result (bf16 pad columns are zero)."""
     M = a16.shape[0]
-    o32 = torch.empty((M, N), device=a16.device, dtype=torch.float32) if out_f32 else None
-    ld16 = -(-N // 8) * 8
-    o16 = torch.zeros((M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
+    ld_out = N if ld_out is None else ld_out
+    ld16 = -(-N // 8) * 8 if ld_out16 is None else ld_out16
+    o32 = torch.empty((M, ld_out), device=a16.device, dtype=torch.float32) if out_f32 else None
+    o16 = torch.empty((M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
     ws_bytes = lib.bbbp_gemm_bf16_workspace(M, N, split_k)
     ws = torch.empty((ws_bytes,), device=a16.device, dtype=torch.uint8) if ws_bytes else None
+    if o16 is not None and ws_bytes and ld16 > N:
+        o16[:, N:].zero_()          # the split-K finish kernel writes only the N result columns
     check(lib.bbbp_gemm_bf16(M, N, K, a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), _ptr(bias),
-                             _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(o32), N, _ptr(o16), ld16,
-                             _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
+                             _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(o32), ld_out, _ptr(o16),
+                             ld16, _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
     return o32, o16
+
+
+def gemm_bf16_batched(batches, M, N, K, a16, lda, a_bs, w16, ldw, w_bs, out_bf16=True, out_f32=False, ld_out16=None):
+    """out[b] = A[b] @ W[b]^T for b < batches; outputs are (batches*M, ld) with batch b at rows [b*M, (b+1)*M)."""
+    ld16 = -(-N // 8) * 8 if ld_out16 is None else ld_out16
+    o32 = torch.empty((batches * M, N), device=a16.device, dtype=torch.float32) if out_f32 else None
+    o16 = torch.empty((batches * M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
+    check(lib.bbbp_gemm_bf16_batched(batches, M, N, K, a16.data_ptr(), lda, a_bs, w16.data_ptr(), ldw, w_bs, _ptr(o32), N,
+                                     M * N, _ptr(o16), ld16, M * ld16, _stream()), "gemm_bf16_batched")
+    return o32, o16
+
+
+def attention_scores_softmax_bf16(q16, k16, ld, groups, seq, head_dim, scale):
+    """softmax(scale * Q K^T) per group as bf16 (groups*seq, ldp); q16 / k16 are views into the packed qkv buffer."""
+    ldp = -(-seq // 8) * 8
+    p = torch.empty((groups * seq, ldp), device=q16.device, dtype=torch.bfloat16)
+    t0 = KERNEL_TIMER.start("attn_scores")
+    check(lib.bbbp_attention_scores_softmax_bf16(groups, seq, head_dim, q16.data_ptr(), ld, k16.data_ptr(), ld, seq * ld,
+                                                 float(scale), p.data_ptr(), ldp, _stream()), "attention_scores_softmax")
+    KERNEL_TIMER.stop("attn_scores", t0, groups * seq)
+    return p
+
+
+def transpose_bf16(src, batches, rows, cols, ld_src, src_bs, ld_dst):
+    """(batches, rows, cols) pitched bf16 -> (batches, cols, ld_dst) with zero fill of columns >= rows."""
+    dst = torch.empty((batches, cols, ld_dst), device=src.device, dtype=torch.bfloat16)
+    check(lib.bbbp_transpose_bf16(batches, rows, cols, src.data_ptr(), ld_src, src_bs, dst.data_ptr(), ld_dst, cols * ld_dst,
+                                  _stream()), "transpose_bf16")
+    return dst
 
 
 # ---- image branch -----------------------------------------------------------------------------------------------------

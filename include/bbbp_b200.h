@@ -77,6 +77,23 @@ int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, const void*
                    const float* residual, int ld_res, float* out_f32, int ld_out, void* out_bf16, int ld_out16,
                    int act, int split_k, void* workspace, size_t workspace_bytes, bbbp_stream_t stream);
 
+/* Batched form (blockIdx.z = batch): out[b] = A[b][M,K] * W[b][N,K]^T, no bias/activation; batch strides in elements
+ * (multiples of 8 for the operands).  Used for the attention P V product with W = V^T. */
+int bbbp_gemm_bf16_batched(int batches, int M, int N, int K, const void* A_bf16, int lda, long long a_batch_stride,
+                           const void* W_bf16, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
+                           long long out_batch_stride, void* out_bf16, int ld_out16, long long out16_batch_stride,
+                           bbbp_stream_t stream);
+/* Attention scores with the row softmax in the TMEM epilogue (single head, seq <= 256: one CTA owns whole rows):
+ * P[g] = softmax_rows(scale * Q[g] K[g]^T) as bf16 [groups][seq][ldp], pad columns [seq, ldp) zero.
+ * q/k: bf16, row pitches ldq/ldk, group g starts group_stride elements after group g-1 (nn.MultiheadAttention's
+ * scaled_dot_product_attention over S = the reference batch). */
+int bbbp_attention_scores_softmax_bf16(int groups, int seq, int head_dim, const void* q_bf16, int ldq, const void* k_bf16,
+                                       int ldk, long long group_stride, float scale, void* p_bf16, int ldp,
+                                       bbbp_stream_t stream);
+/* dst[b][c][r] = src[b][r][c] (bf16); rows r in [rows, ld_dst) of dst are zero filled */
+int bbbp_transpose_bf16(int batches, int rows, int cols, const void* src, int ld_src, long long src_batch_stride, void* dst,
+                        int ld_dst, long long dst_batch_stride, bbbp_stream_t stream);
+
 /* ---- image branch: nn.Conv2d(k3,s1,p1) + ReLU + MaxPool2d(2) C:85-90 (and 20250107_network.py:133-141) */
 
 /* y[N,Cout,H/2,W/2] = maxpool2(relu(conv3x3(x[N,Cin,H,W], w[Cout,Cin,3,3]) + b)), NCHW fp32, CUDA cores.

@@ -389,3 +389,41 @@ def test_fc_weight_relayout_is_exact(ops):
     out = ops.fc_weight_to_hwc_bf16(w.cuda(), 64, 16)
     want = w.view(8, 64, 16).permute(0, 2, 1).reshape(8, -1).bfloat16()
     assert torch.equal(out.cpu(), want)
+
+
+# ---- tensor-core attention pieces: (QK^T + row softmax) epilogue, V transpose, batched P V -------------------------------
+@pytest.mark.parametrize("groups,seq,d", [(1, 256, 167), (3, 67, 167), (2, 1, 167), (5, 32, 64), (1, 200, 8)])
+def test_attention_tcgen05_pipeline(ops, groups, seq, d):
+    dq = -(-d // 8) * 8
+    rows = groups * seq
+    qkv = rnd(rows, 3, d, seed=110, scale=0.8)
+    packed = torch.zeros(rows, 3 * dq)
+    for part in range(3):
+        packed[:, part * dq: part * dq + d] = qkv[:, part]
+    qkv16 = packed.bfloat16().cuda()
+    q, k, v = (qkv[:, i].bfloat16().double().view(groups, seq, d) for i in range(3))
+    p_ref = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(d), dim=-1)
+    p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, dq:], 3 * dq, groups, seq, d, d ** -0.5)
+    ldp = p16.shape[1]
+    assert ldp % 8 == 0 and ldp >= seq
+    close(p16[:, :seq], p_ref.reshape(rows, seq).float(), atol=2e-3, rtol=1e-2, what="softmax(QK^T)")
+    assert float(p16[:, seq:].float().abs().sum()) == 0.0
+    vt = ops.transpose_bf16(qkv16[:, 2 * dq:], groups, seq, d, 3 * dq, seq * 3 * dq, ldp)
+    assert torch.equal(vt[:, :, :seq].cpu(), qkv[:, 2].bfloat16().view(groups, seq, d).transpose(1, 2))
+    assert float(vt[:, :, seq:].float().abs().sum()) == 0.0
+    _, o16 = ops.gemm_bf16_batched(groups, seq, d, seq, p16, ldp, seq * ldp, vt, ldp, d * ldp, ld_out16=dq)
+    o_ref = (p16[:, :seq].float().cpu().double().view(groups, seq, seq) @ v).reshape(rows, d).float()
+    close(o16[:, :d], o_ref, atol=2e-3, rtol=1e-2, what="P V")
+    close(o16[:, :d], (p_ref @ v).reshape(rows, d).float(), atol=1e-2, rtol=2e-2, what="attention end to end")
+
+
+def test_gemm_bf16_padded_outputs(ops):
+    M, N, K = 300, 167, 167
+    x, w, b = rnd(M, K, seed=111), rnd(N, K, seed=112, scale=0.1), rnd(N, seed=113)
+    x16, w16 = ops.cast_bf16(x.cuda()), ops.cast_bf16(w.cuda())
+    ref = F.linear(x.bfloat16().double(), w.bfloat16().double(), b.double()).float()
+    o32, o16 = ops.gemm_bf16(x16, K, w16, N, bias=b.cuda(), out_bf16=True, ld_out=168, ld_out16=176)
+    assert o32.shape == (M, 168) and o16.shape == (M, 176)
+    close(o32[:, :N], ref, 3e-5, what="padded fp32 out")
+    close(o16[:, :N], ref, atol=1e-2, rtol=1e-2, what="padded bf16 out")
+    assert float(o16[:, N:].float().abs().sum()) == 0.0
