@@ -15,8 +15,9 @@
 // and a K=16 step pairs two 8-channel chunks through the leading byte offset.  So all 9 taps x 4 window members are
 // just different START ADDRESSES into the same staged halo -- the tile is read from L2 once, not 9 times.
 //
-// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quadrant = warp), warps 4-7 producers (cp.async 16-byte
-// chunks with zero fill = the conv's zero padding), warp 8 TMEM allocation + single-thread MMA issue.  Persistent
+// Warp roles (416 threads): warps 0-7 epilogue (TMEM lane quadrant = warp % 4, channel half = warp / 4), warps 8-11
+// producers (cp.async 16-byte chunks with zero fill = the conv's zero padding), warp 12 TMEM allocation +
+// single-thread MMA issue.  Persistent
 // over tiles: 3-stage halo ring (full/empty mbarriers) and a double-buffered accumulator (acc_full/acc_empty), so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
@@ -32,13 +33,20 @@ constexpr int HALO_W = 2 * TILE_PW + 2;        // 18
 constexpr int HALO_H = 2 * TILE_PH + 2;        // 34
 constexpr int XH = HALO_W / 2;                 // 9 halo columns per parity
 constexpr int ROW_B = XH * 16;                 // 144 bytes per (parity, y) row
-constexpr int PAR_B = HALO_H * ROW_B;          // 4896
-constexpr int KC_B = 2 * PAR_B;                // 9792 bytes per 8-channel chunk plane
+// plane pitches carry a few pad bytes so that the producers' 16-byte cp.async stores of one quarter-warp
+// (x parity alternates, then the 8-channel chunk index) land in eight different 16-byte bank groups
+constexpr int PAR_B = HALO_H * ROW_B + 32;     // 4928 = 64 (mod 128)
+constexpr int KC_B = 2 * PAR_B + 16;           // 9872 = 16 (mod 128) bytes per 8-channel chunk plane
 constexpr int STAGES = 3;
-constexpr int EPI_THREADS = 128, PROD_THREADS = 128, THREADS = 288;
+constexpr int PROD_THREADS = 128;
 
 template <int KC, int COUT>
 struct Cfg {
+  // conv2's epilogue (64 channels) gets two warps per TMEM lane quadrant; conv1's (32 channels) one, which also keeps
+  // its CTA small enough for two CTAs per SM
+  static constexpr int EPI_WARPS = COUT >= 64 ? 8 : 4;
+  static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 32;
+  static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + 4;
   static constexpr int A_BYTES = KC * KC_B;
   static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // MMAs (K=16) per window member
   static constexpr int W_BYTES = KC == 1 ? 2 * 5 * 2 * COUT * 16 : 9 * KC * COUT * 16;
@@ -103,12 +111,13 @@ __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_
 }
 
 template <int KC, int COUT>
-__global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat16* __restrict__ src,
+__global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(const __nv_bfloat16* __restrict__ src,
                                                                const uint4* __restrict__ wprep,
                                                                const float* __restrict__ bias,
                                                                __nv_bfloat16* __restrict__ dst, int n_img, int H,
                                                                int W) {
   using C = Cfg<KC, COUT>;
+  constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sA = base;
@@ -140,16 +149,16 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, C::TMEM_COLS);
   fence_proxy_async_smem();  // the weight stores above are generic-proxy writes read by tcgen05.mma (async proxy)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // ===== producers: stage the halo of each tile ====================================================================
-    const int ptid = threadIdx.x - 4 * 32;
+    const int ptid = threadIdx.x - PROD_WARP0 * 32;
     constexpr int ROWC = HALO_W * KC;                  // 16-byte chunks per halo row
     constexpr int CHUNKS = HALO_H * ROWC;
     constexpr int STEP_Y = PROD_THREADS / ROWC, STEP_J = PROD_THREADS % ROWC;
@@ -190,7 +199,7 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
       fence_proxy_async_smem();
       mbar_arrive(&full[(my_tiles - 1) % STAGES]);
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===== MMA issuer ==================================================================================================
     if (lane == 0) {
       const uint32_t w_lo = smem_u32(sW) >> 4;
@@ -208,8 +217,13 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
     __syncwarp();
   } else {
     // ===== epilogue: max over the pooling window, + bias, ReLU, bf16, NHWC store ==========================================
-    const int m = threadIdx.x;  // pooled pixel within the tile == TMEM lane
+    // 8 warps: warp % 4 is the TMEM lane quadrant it may read (32 pooled pixels), warp / 4 the half of the channels.
+    // One warp per scheduler runs this mostly-serial code, so two warps per quadrant halve the epilogue's latency and
+    // keep it hidden behind the next tile's MMAs.
+    const int quad = warp & 3, half = warp >> 2;
+    const int m = quad * 32 + lane;  // pooled pixel within the tile == TMEM lane
     const int PH = H / 2, PW = W / 2;
+    constexpr int CH = COUT / (C::EPI_WARPS / 4);  // channels per epilogue warp
     for (int i = 0; i < my_tiles; ++i) {
       const int t = blockIdx.x + i * gridDim.x;
       const int n = t / tiles_per_img, r = t % tiles_per_img;
@@ -217,10 +231,10 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
       const int b = i & 1;
       mbar_wait(&acc_full[b], (i >> 1) & 1);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + b * C::ACC_COLS;
-      uint4* out = reinterpret_cast<uint4*>(dst + (((size_t)n * PH + ph) * PW + pw) * COUT);
-#pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
+      uint4* out = reinterpret_cast<uint4*>(dst + (((size_t)n * PH + ph) * PW + pw) * COUT + half * CH);
+#pragma unroll
+      for (int c0 = 0; c0 < CH; c0 += 16) {
         uint32_t r0[16], r1[16], r2[16], r3[16];
         tmem_ld_32x16(taddr + c0, r0);
         tmem_ld_32x16(taddr + COUT + c0, r1);
@@ -229,15 +243,20 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
         tmem_ld_wait();
         uint32_t packed[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float v0 = fmaxf(fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])),
-                           fmaxf(__uint_as_float(r2[j]), __uint_as_float(r3[j])));
-          float v1 = fmaxf(fmaxf(__uint_as_float(r0[j + 1]), __uint_as_float(r1[j + 1])),
-                           fmaxf(__uint_as_float(r2[j + 1]), __uint_as_float(r3[j + 1])));
-          v0 = fmaxf(v0 + sBias[c0 + j], 0.0f);
-          v1 = fmaxf(v1 + sBias[c0 + j + 1], 0.0f);
-          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          packed[j / 2] = *reinterpret_cast<uint32_t*>(&h);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sBias + half * CH + c0 + j);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int k = 0; k < 4; k += 2) {
+            float v0 = fmaxf(fmaxf(__uint_as_float(r0[j + k]), __uint_as_float(r1[j + k])),
+                             fmaxf(__uint_as_float(r2[j + k]), __uint_as_float(r3[j + k])));
+            float v1 = fmaxf(fmaxf(__uint_as_float(r0[j + k + 1]), __uint_as_float(r1[j + k + 1])),
+                             fmaxf(__uint_as_float(r2[j + k + 1]), __uint_as_float(r3[j + k + 1])));
+            v0 = fmaxf(v0 + bb[k], 0.0f);
+            v1 = fmaxf(v1 + bb[k + 1], 0.0f);
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            packed[(j + k) / 2] = *reinterpret_cast<uint32_t*>(&h);
+          }
         }
         out[c0 / 8] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         out[c0 / 8 + 1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const __nv_bfloat
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
@@ -315,7 +334,7 @@ int launch(const void* x, const void* wprep, const float* bias, void* y, int N, 
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
   const int per_sm = (C::TMEM_COLS <= 256 && C::SMEM_BYTES <= 100 * 1024) ? 2 : 1;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
-  conv3x3_umma_kernel<KC, COUT><<<grid, THREADS, C::SMEM_BYTES, stream>>>(
+  conv3x3_umma_kernel<KC, COUT><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W);
   return launch_status("conv3x3_relu_pool_bf16");
 }

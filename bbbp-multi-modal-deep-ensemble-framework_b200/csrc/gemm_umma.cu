@@ -70,7 +70,7 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // tiles | full[STAGES] empty[STAGES] accum | tmem slot ; +1024 for manual alignment of the tile area
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 16 + BN * 4;
 };
 
 struct Params {
@@ -112,9 +112,11 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
   uint64_t* empty = full + C::STAGES;
   uint64_t* accum = empty + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* sBias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // bias of this CTA's columns
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  for (int i = threadIdx.x; i < BN; i += THREADS) sBias[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
   const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int kb_begin = split * p.kb_per_split;
   const int num_kb = min(p.total_kb, kb_begin + p.kb_per_split) - kb_begin;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
           if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
       }
       const float sl2 = p.scale * 1.4426950408889634f;  // exp(scale*(x-mx)) = exp2(sl2*(x-mx))
+      const float off = mx * sl2;
       float sum = 0.0f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < N) sum += exp2f((__uint_as_float(r[j]) - mx) * sl2);
+          if (c * 32 + j < N) sum += exp2f(fmaf(__uint_as_float(r[j]), sl2, -off));
       }
       const float inv = 1.0f / sum;
       __nv_bfloat16* dst = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16;
@@ -208,14 +211,14 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
       for (int c = 0; c < BN / 32; ++c) {
         if (c * 32 >= p.ld_out16) break;
         uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);   // .sync.aligned: the whole warp loads, only valid rows store
+        tmem_ld_32x32(taddr + c * 32, r);  // .sync.aligned: the whole warp loads, only valid rows store
         tmem_ld_wait();
         if (row < p.M) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float v0 = c * 32 + j < N ? exp2f((__uint_as_float(r[j]) - mx) * sl2) * inv : 0.0f;
-            const float v1 = c * 32 + j + 1 < N ? exp2f((__uint_as_float(r[j + 1]) - mx) * sl2) * inv : 0.0f;
+            const float v0 = c * 32 + j < N ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -off)) * inv : 0.0f;
+            const float v1 = c * 32 + j + 1 < N ? exp2f(fmaf(__uint_as_float(r[j + 1]), sl2, -off)) * inv : 0.0f;
             __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
             pk[j / 2] = *reinterpret_cast<uint32_t*>(&h);
           }
@@ -227,12 +230,17 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
         }
       }
     } else {
-      const bool vec32 = p.out && (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.out_bs % 4 == 0);
-      const bool vec16 = p.out16 && (p.ld_out16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out16) & 15) == 0) && (p.out16_bs % 8 == 0);
+      // Every runtime switch (activation, residual, which outputs, vector eligibility) is resolved ONCE PER 32-column
+      // chunk, never per element: with one epilogue warp per scheduler the per-element instruction count is what the
+      // epilogue costs.  Thread = output row; it owns 32 consecutive columns per chunk (128 B fp32 / 64 B bf16).
+      const bool al32 = p.out && p.ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_bs % 4 == 0;
+      const bool al16 = p.out16 && p.ld_out16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0 && p.out16_bs % 8 == 0;
+      const bool alres = p.residual && p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && p.res_bs % 4 == 0;
+      const float4* bias4 = reinterpret_cast<const float4*>(sBias);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
-        if (!p.partial && col0 >= p.N) break;
+        if (!p.partial && col0 >= max(p.N, p.out16 ? p.ld_out16 : 0)) break;
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
@@ -242,52 +250,73 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
           for (int j = 0; j < 8; ++j)
             dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                  __uint_as_float(r[4 * j + 3]));
-        } else if (row < p.M) {
-          float v[32];
-          const float* res = p.residual ? p.residual + (size_t)batch * p.res_bs + (size_t)row * p.ld_res : nullptr;
+          continue;
+        }
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float t = __uint_as_float(r[j]);
-            if (col < p.N) {
-              t += p.bias ? __ldg(p.bias + col) : 0.0f;
-              t = apply_act(t, p.act);
-              if (res) t += res[col];
-            } else {
-              t = 0.0f;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = bias4[c * 8 + j];  // zero where there is no bias or the column is >= N
+          v[4 * j] = __uint_as_float(r[4 * j]) + b.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        }
+        if (p.act == BBBP_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act == BBBP_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        }
+        if (row >= p.M) continue;
+        const int nvalid = p.N - col0;  // columns of this chunk that belong to the result (may be <= 0 in the bf16 pad)
+        if (p.residual) {
+          const float* res = p.residual + (size_t)batch * p.res_bs + (size_t)row * p.ld_res + col0;
+          if (alres && col0 + 32 <= p.ld_res) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = reinterpret_cast<const float4*>(res)[j];
+              v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
             }
-            v[j] = t;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += res[j];
           }
-          if (p.out) {
-            float* o = p.out + (size_t)batch * p.out_bs + (size_t)row * p.ld_out + col0;
-            if (vec32 && col0 + 32 <= p.ld_out) {
+        }
+        if (nvalid < 32) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (col0 + 4 * j < p.ld_out) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
+          for (int j = 0; j < 32; ++j)
+            if (j >= nvalid) v[j] = 0.0f;  // pad columns carry zeros
+        }
+        if (p.out) {
+          float* o = p.out + (size_t)batch * p.out_bs + (size_t)row * p.ld_out + col0;
+          if (al32 && col0 + 32 <= p.ld_out) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = v[j];
-            }
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) o[j] = v[j];
           }
-          if (p.out16) {
-            __nv_bfloat16* o = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16 + col0;
-            if (vec16 && col0 + 32 <= p.ld_out16) {
+        }
+        if (p.out16) {
+          __nv_bfloat16* o = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16 + col0;
+          if (al16 && col0 + 32 <= p.ld_out16) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t pk[4];
+            for (int g = 0; g < 4; ++g) {
+              uint32_t pk[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
-                  pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                reinterpret_cast<uint4*>(o)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.ld_out16) o[j] = __float2bfloat16(v[j]);  // pad columns [N, ld) get zeros
+              reinterpret_cast<uint4*>(o)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.ld_out16) o[j] = __float2bfloat16(v[j]);
           }
         }
       }

@@ -103,7 +103,7 @@ def fixed_split_k(K: int) -> int:
     """Split-K factor as a function of K ONLY.  Each output row then sees the same reduction order whatever the
     number of rows in the call, so a molecule's score does not depend on how many reference batches share a launch
     or on how batches are sharded over GPUs (bit-identical 1/2/4/8-GPU screening)."""
-    return 1 if K < 8192 else min(32, K // 2048)
+    return 1 if K < 8192 else min(8, K // 2048)
 
 
 def cast_bf16(x: torch.Tensor, ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
