@@ -110,13 +110,23 @@ __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_
   (issue_one<KC, COUT, I>(a_lo, w_lo, tmem_acc), ...);
 }
 
-template <int KC, int COUT>
-__global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(const __nv_bfloat16* __restrict__ src,
+enum { SRC_NHWC_BF16 = 0, SRC_CHW_F32 = 1, SRC_CHW_U8 = 2 };
+
+// SRC selects what the producers read: NHWC bf16 activations (cp.async), or -- first layer only -- the reference's
+// own input contract, planar fp32 CHW (20250113.py:114), or raw uint8 CHW depictions normalised on the fly with a
+// per-image (mean, 1/std) pair (ToTensor + per-molecule StandardScaler, Descriptors/..._preprocess_maccs_opt.py:52-67,
+// 121-124).  In both planar cases the 3 channels are packed to one 16-byte bf16 chunk per pixel in registers, so the
+// NHWC8 image never exists in HBM.
+template <int KC, int COUT, int SRC>
+__global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(const void* __restrict__ src_any,
+                                                               const float2* __restrict__ stats,
                                                                const uint4* __restrict__ wprep,
                                                                const float* __restrict__ bias,
                                                                __nv_bfloat16* __restrict__ dst, int n_img, int H,
                                                                int W) {
   using C = Cfg<KC, COUT>;
+  static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
+  const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_any);
   constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -164,40 +174,123 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
     constexpr int STEP_Y = PROD_THREADS / ROWC, STEP_J = PROD_THREADS % ROWC;
     constexpr int PIX_B = KC * 16;
     const int Yi = ptid / ROWC, ji = ptid % ROWC;      // first chunk of this thread: the same for every tile
-    for (int i = 0; i < my_tiles; ++i) {
-      const int t = blockIdx.x + i * gridDim.x;
-      const int n = t / tiles_per_img, r = t % tiles_per_img;
-      const int y0 = 2 * (r / tiles_x) * TILE_PH - 1, x0 = 2 * (r % tiles_x) * TILE_PW - 1;
-      const int s = i % STAGES;
-      mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
-      const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
-      const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * PIX_B;
-      int Y = Yi, j = ji;
-#pragma unroll 4
-      for (int c = ptid; c < CHUNKS; c += PROD_THREADS) {
-        const int X = j / KC, kc = j % KC;
-        const int y = y0 + Y, x = x0 + X;
-        const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-        const int goff = ok ? (y * W + x) * PIX_B + kc * 16 : 0;
-        cp_async_16(stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16, img + goff, ok ? 16u : 0u);
-        j += STEP_J;
-        Y += STEP_Y;
-        if (j >= ROWC) {
-          j -= ROWC;
-          ++Y;
+    if constexpr (SRC == SRC_NHWC_BF16) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int t = blockIdx.x + i * gridDim.x;
+        const int n = t / tiles_per_img, r = t % tiles_per_img;
+        const int y0 = 2 * (r / tiles_x) * TILE_PH - 1, x0 = 2 * (r % tiles_x) * TILE_PW - 1;
+        const int s = i % STAGES;
+        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * PIX_B;
+        int Y = Yi, j = ji;
+  #pragma unroll 4
+        for (int c = ptid; c < CHUNKS; c += PROD_THREADS) {
+          const int X = j / KC, kc = j % KC;
+          const int y = y0 + Y, x = x0 + X;
+          const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+          const int goff = ok ? (y * W + x) * PIX_B + kc * 16 : 0;
+          cp_async_16(stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16, img + goff, ok ? 16u : 0u);
+          j += STEP_J;
+          Y += STEP_Y;
+          if (j >= ROWC) {
+            j -= ROWC;
+            ++Y;
+          }
+        }
+        cp_async_commit();
+        if (i > 0) {
+          cp_async_wait<1>();  // tile i-1 of this thread has landed
+          fence_proxy_async_smem();
+          mbar_arrive(&full[(i - 1) % STAGES]);
         }
       }
-      cp_async_commit();
-      if (i > 0) {
-        cp_async_wait<1>();  // tile i-1 of this thread has landed
+      if (my_tiles > 0) {
+        cp_async_wait<0>();
         fence_proxy_async_smem();
-        mbar_arrive(&full[(i - 1) % STAGES]);
+        mbar_arrive(&full[(my_tiles - 1) % STAGES]);
       }
-    }
-    if (my_tiles > 0) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(&full[(my_tiles - 1) % STAGES]);
+    } else {
+      // planar source: each thread owns up to PPT halo pixels of every tile; the loads of tile i+1 are issued into a
+      // second register set before tile i is converted and stored, so two tiles of global loads are always in flight
+      constexpr int NPIX = HALO_H * HALO_W, PPT = (NPIX + PROD_THREADS - 1) / PROD_THREADS, CH = 3;
+      const int HW = H * W;
+      auto tile_origin = [&](int i, int& n, int& y0, int& x0) {
+        const int t = blockIdx.x + i * gridDim.x;
+        n = t / tiles_per_img;
+        const int r = t % tiles_per_img;
+        y0 = 2 * (r / tiles_x) * TILE_PH - 1;
+        x0 = 2 * (r % tiles_x) * TILE_PW - 1;
+      };
+      auto load_tile = [&](int i, float (&v)[PPT][CH], uint32_t& okmask) {
+        int n, y0, x0;
+        tile_origin(i, n, y0, x0);
+        okmask = 0;
+        int Y = Yi, X = ji;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const int y = y0 + Y, x = x0 + X;
+          const bool ok = (ptid + k * PROD_THREADS < NPIX) && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+          okmask |= (uint32_t)ok << k;
+          const size_t off = (size_t)n * CH * HW + (ok ? y * W + x : 0);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if constexpr (SRC == SRC_CHW_F32)
+              v[k][c] = ok ? __ldg(static_cast<const float*>(src_any) + off + (size_t)c * HW) : 0.0f;
+            else
+              v[k][c] = ok ? (float)__ldg(static_cast<const uint8_t*>(src_any) + off + (size_t)c * HW) : 0.0f;
+          }
+          X += STEP_J;
+          Y += STEP_Y;
+          if (X >= ROWC) {
+            X -= ROWC;
+            ++Y;
+          }
+        }
+      };
+      float cur[PPT][CH], nxt[PPT][CH];
+      uint32_t cur_ok = 0, nxt_ok = 0;
+      if (my_tiles > 0) load_tile(0, cur, cur_ok);
+      for (int i = 0; i < my_tiles; ++i) {
+        if (i + 1 < my_tiles) load_tile(i + 1, nxt, nxt_ok);
+        float mean = 0.0f, rstd = 1.0f;
+        if constexpr (SRC == SRC_CHW_U8) {
+          const float2 st = __ldg(stats + (blockIdx.x + i * gridDim.x) / tiles_per_img);
+          mean = st.x, rstd = st.y;
+        }
+        const int s = i % STAGES;
+        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        uint8_t* stage = sA + s * C::A_BYTES;
+        int Y = Yi, X = ji;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          if (ptid + k * PROD_THREADS < NPIX) {
+            float a = cur[k][0], b = cur[k][1], c = cur[k][2];
+            if constexpr (SRC == SRC_CHW_U8) {
+              const bool ok = (cur_ok >> k) & 1;   // zero padding applies to the NORMALISED image
+              a = ok ? (a / 255.0f - mean) * rstd : 0.0f;
+              b = ok ? (b / 255.0f - mean) * rstd : 0.0f;
+              c = ok ? (c / 255.0f - mean) * rstd : 0.0f;
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, 0.0f);
+            *reinterpret_cast<uint4*>(stage + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16) =
+                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), 0u, 0u);
+          }
+          X += STEP_J;
+          Y += STEP_Y;
+          if (X >= ROWC) {
+            X -= ROWC;
+            ++Y;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[s]);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+#pragma unroll
+          for (int c = 0; c < CH; ++c) cur[k][c] = nxt[k][c];
+        cur_ok = nxt_ok;
+      }
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer ==================================================================================================
@@ -319,8 +412,57 @@ __global__ void fc_weight_to_hwc_kernel(const float* __restrict__ w, __nv_bfloat
   out[i] = __float2bfloat16(w[o * K + c * HW + hw]);
 }
 
-template <int KC, int COUT>
-int launch(const void* x, const void* wprep, const float* bias, void* y, int N, int H, int W, cudaStream_t stream) {
+// per-image mean and 1/std of x/255 over all C*H*W values, fp64 accumulation (sklearn StandardScaler on one molecule's
+// pixel column; std 0 -> 1), narrowed to fp32
+__global__ void __launch_bounds__(256) u8_image_stats_kernel(const uint8_t* __restrict__ img, float2* __restrict__ stats,
+                                                              int n) {
+  __shared__ double red_s[8], red_q[8];
+  const uint8_t* src = img + (size_t)blockIdx.x * n;
+  // integer sums are exact: sum(u) < 2^32, sum(u^2) < 2^40 for n <= 2^24
+  unsigned long long su = 0, sq = 0;
+  for (int i = threadIdx.x * 16; i < n; i += 256 * 16) {
+    if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0)) {
+      const uint4 w = *reinterpret_cast<const uint4*>(src + i);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const unsigned u = (ws[k] >> (8 * b)) & 255u;
+          su += u;
+          sq += u * u;
+        }
+    } else {
+      for (int k = i; k < min(n, i + 16); ++k) {
+        const unsigned u = src[k];
+        su += u;
+        sq += u * u;
+      }
+    }
+  }
+  double ds = (double)su, dq = (double)sq;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if (threadIdx.x % 32 == 0) red_s[threadIdx.x / 32] = ds, red_q[threadIdx.x / 32] = dq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int i = 0; i < 8; ++i) S += red_s[i], Q += red_q[i];
+    const double mean = S / 255.0 / n;
+    double var = Q / (255.0 * 255.0) / n - mean * mean;
+    if (var < 0) var = 0;
+    double sd = sqrt(var);
+    if (sd == 0.0) sd = 1.0;
+    stats[blockIdx.x] = make_float2((float)mean, (float)(1.0 / sd));
+  }
+}
+
+template <int KC, int COUT, int SRC>
+int launch(const void* x, const float* stats, const void* wprep, const float* bias, void* y, int N, int H, int W,
+           cudaStream_t stream) {
   using C = Cfg<KC, COUT>;
   static int sms = 0;
   static bool attr = false;
@@ -328,14 +470,14 @@ int launch(const void* x, const void* wprep, const float* bias, void* y, int N, 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     attr = true;
   }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
   const int per_sm = (C::TMEM_COLS <= 256 && C::SMEM_BYTES <= 100 * 1024) ? 2 : 1;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
-  conv3x3_umma_kernel<KC, COUT><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W);
+  conv3x3_umma_kernel<KC, COUT, SRC><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
+      x, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W);
   return launch_status("conv3x3_relu_pool_bf16");
 }
 
@@ -372,8 +514,8 @@ extern "C" int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep
                  "conv3x3_relu_pool_bf16: operands must be 16-byte aligned");
   if (N == 0) return BBBP_OK;
   cudaStream_t s = as_stream(stream);
-  if (Cin_pad == 8 && Cout == 32) return conv::launch<1, 32>(x_nhwc, wprep, bias, y_nhwc, N, H, W, s);
-  if (Cin_pad == 32 && Cout == 64) return conv::launch<4, 64>(x_nhwc, wprep, bias, y_nhwc, N, H, W, s);
+  if (Cin_pad == 8 && Cout == 32) return conv::launch<1, 32, conv::SRC_NHWC_BF16>(x_nhwc, nullptr, wprep, bias, y_nhwc, N, H, W, s);
+  if (Cin_pad == 32 && Cout == 64) return conv::launch<4, 64, conv::SRC_NHWC_BF16>(x_nhwc, nullptr, wprep, bias, y_nhwc, N, H, W, s);
   set_error("conv3x3_relu_pool_bf16: unsupported channels %d->%d (built: 8->32, 32->64)", Cin_pad, Cout);
   return BBBP_EUNSUPPORTED;
 }
@@ -394,4 +536,23 @@ extern "C" int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int ro
   conv::fc_weight_to_hwc_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
       w, static_cast<__nv_bfloat16*>(out_bf16), C, HW, total);
   return launch_status("fc_weight_to_hwc");
+}
+
+extern "C" int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img && stats && rows >= 0 && n > 0 && n <= (1 << 24), "u8_image_stats: bad argument");
+  if (rows == 0) return BBBP_OK;
+  conv::u8_image_stats_kernel<<<rows, 256, 0, as_stream(stream)>>>(img, reinterpret_cast<float2*>(stats), n);
+  return launch_status("u8_image_stats");
+}
+
+extern "C" int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
+                                          const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img_chw && wprep && bias && y_nhwc, "conv1_from_image: null operand");
+  BBBP_CHECK_ARG(!img_is_u8 || stats, "conv1_from_image: uint8 input needs the per-image (mean, 1/std) table");
+  BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
+                 "conv1_from_image: H=%d must be a multiple of 32 and W=%d of 16", H, W);
+  if (N == 0) return BBBP_OK;
+  cudaStream_t s = as_stream(stream);
+  if (img_is_u8) return conv::launch<1, 32, conv::SRC_CHW_U8>(img_chw, stats, wprep, bias, y_nhwc, N, H, W, s);
+  return conv::launch<1, 32, conv::SRC_CHW_F32>(img_chw, nullptr, wprep, bias, y_nhwc, N, H, W, s);
 }

@@ -292,9 +292,10 @@ class TransformerCnnModel(_KernelModule):
     tensor_core_chunk = 0   # images per pass of the tcgen05 image branch (0 = all at once)
 
     def _image_branch_tensor_core(self, image, mods):
-        """Inference path: fp32 CHW image -> bf16 NHWC8 -> tcgen05 conv1 -> tcgen05 conv2 (each with bias + ReLU +
-        max-pool in the TMEM epilogue) -> tcgen05 split-K GEMM against the (H,W,C)-re-laid fc weight.  No
-        activation leaves the chip in fp32 and the flatten is free (NHWC rows ARE the fc's K-major A operand)."""
+        """Inference path: planar CHW image (fp32 standardised, or raw uint8 normalised in the producer) -> tcgen05
+        conv1 -> tcgen05 conv2 (each with bias + ReLU + max-pool in the TMEM epilogue) -> tcgen05 split-K GEMM against
+        the (H,W,C)-re-laid fc weight.  No activation leaves the chip in fp32 and the flatten is free (NHWC rows ARE
+        the fc's K-major A operand)."""
         from . import ops
         conv1, conv2, fc = mods[0], mods[3], mods[7]
         w1 = ag.derived_weight(conv1.weight, "conv_umma", ops.conv3x3_prepare_bf16)
@@ -306,8 +307,9 @@ class TransformerCnnModel(_KernelModule):
         chunk = self.tensor_core_chunk or n
         outs = []
         for a in range(0, n, chunk):
-            x = ops.image_to_nhwc8_bf16(img[a:a + chunk])
-            y1 = ops.conv3x3_relu_pool_bf16(x, w1, conv1.bias, 32)
+            part = img[a:a + chunk]
+            stats = ops.u8_image_stats(part) if part.dtype == torch.uint8 else None
+            y1 = ops.conv1_from_image_bf16(part, w1, conv1.bias, stats)
             y2 = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64)
             flat = y2.view(y2.shape[0], 65536)
             o, _ = ops.gemm_bf16(flat, 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
@@ -319,7 +321,17 @@ class TransformerCnnModel(_KernelModule):
         """``groups`` independent reference batches of equal size stacked along dim 0 (attention and the
         big variant's batch-mean stay inside each batch).  Train-mode BatchNorm would mix
         the groups, so groups > 1 is for eval mode."""
-        self._check_inputs(fingerprint, image)
+        self._check_inputs(fingerprint)
+        if image.dtype == torch.uint8:
+            # raw depictions (extension of contract P2): the tcgen05 image branch normalises them in its producer;
+            # every other path gets the exact ToTensor + per-molecule z-score first
+            if not image.is_cuda:
+                raise RuntimeError("bbbp_b200 models run on CUDA (sm_100a) tensors only: there is no CPU fallback")
+            if not (self.precision == "bf16" and self.kind != "big" and not torch.is_grad_enabled()):
+                from . import ops
+                image = ops.u8_zscore(image.reshape(fingerprint.shape[0], -1).contiguous())
+        else:
+            self._check_inputs(image)
         if groups > 1 and self.training:
             raise RuntimeError("forward_groups(groups > 1) is an inference path: call model.eval() first")
         rows = fingerprint.shape[0]
@@ -345,6 +357,16 @@ class TransformerCnnModel(_KernelModule):
 
     def forward(self, fingerprint, image):
         return self.forward_groups(fingerprint, image, 1)
+
+    @torch.no_grad()
+    def predict_batches_packed(self, packed_bits, image_u8, batch_size: int, max_rows_per_pass: int = 16384):
+        """Screening entry point on the compact input formats (SURVEY cfg4): fingerprints as little-endian packed bits
+        (B, ceil(F/8)) uint8 and depictions as raw uint8 (B, 3, 128, 128).  Unpack + per-molecule z-score and the image
+        normalisation run on the device, reproducing the reference's preprocessing formulas (oracle/preprocess.py)."""
+        from . import ops
+        n_bits = self.fingerprint_transformer.layers[0].self_attn.embed_dim
+        fp = ops.unpack_zscore(packed_bits.contiguous(), n_bits)
+        return self.predict_batches(fp, image_u8, batch_size, max_rows_per_pass)
 
     @torch.no_grad()
     def predict_batches(self, fingerprint, image, batch_size: int, max_rows_per_pass: int = 16384):

@@ -239,6 +239,28 @@ def conv3x3_relu_pool_bf16(x_nhwc: torch.Tensor, wprep: torch.Tensor, bias: torc
     return y
 
 
+def u8_image_stats(img_u8: torch.Tensor) -> torch.Tensor:
+    rows = img_u8.shape[0]
+    flat = img_u8.reshape(rows, -1)
+    assert flat.dtype == torch.uint8 and flat.is_contiguous()
+    stats = torch.empty((rows, 2), device=img_u8.device, dtype=torch.float32)
+    check(lib.bbbp_u8_image_stats_f32(flat.data_ptr(), stats.data_ptr(), rows, flat.shape[1], _stream()), "u8_image_stats")
+    return stats
+
+
+def conv1_from_image_bf16(img: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, stats=None, H=128, W=128):
+    """conv1 + ReLU + pool straight from the planar (N, 3, H, W) input: fp32 (standardised) or uint8 (+ stats)."""
+    N = img.numel() // (3 * H * W)
+    y = torch.empty((N, H // 2, W // 2, 32), device=img.device, dtype=torch.bfloat16)
+    is_u8 = img.dtype == torch.uint8
+    assert is_u8 or img.dtype == torch.float32
+    t0 = KERNEL_TIMER.start("conv1")
+    check(lib.bbbp_conv1_from_image_bf16(img.data_ptr(), int(is_u8), _ptr(stats), wprep.data_ptr(), bias.data_ptr(),
+                                         y.data_ptr(), N, H, W, _stream()), "conv1_from_image_bf16")
+    KERNEL_TIMER.stop("conv1", t0, N)
+    return y
+
+
 def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int) -> torch.Tensor:
     rows = w.shape[0]
     out = torch.empty((rows, C * HW), device=w.device, dtype=torch.bfloat16)

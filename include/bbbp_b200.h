@@ -121,6 +121,14 @@ int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bb
 /* y[N,H/2,W/2,Cout] = maxpool2(relu(conv3x3(x[N,H,W,Cin_pad]) + bias)), bf16 NHWC in and out; H % 32 == 0, W % 16 == 0 */
 int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep, const float* bias, void* y_nhwc, int N,
                                 int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream);
+/* First layer straight from the reference's input contract: img_chw is (N, 3, H, W) planar, either fp32 (already
+ * standardised, contract P2) or -- img_is_u8 != 0 -- raw uint8 depictions normalised on the fly as
+ * (u/255 - mean) * rstd with stats[n] = {mean, rstd} from bbbp_u8_image_stats_f32 (ToTensor + per-molecule z-score).
+ * The producers pack 3 channels to one bf16 chunk per pixel in registers; output as bbbp_conv3x3_relu_pool_bf16. */
+int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
+                               const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream);
+/* stats[r] = {mean, 1/std} of img[r, 0:n] / 255 (population std, 0 -> 1), exact integer sums, fp64 finish */
+int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, bbbp_stream_t stream);
 /* fp32 NCHW image with C <= 8 planes (the reference's (B,3*128*128) input viewed as (B,3,128,128), 20250113.py:114)
  * -> bf16 NHWC with 8 channels per pixel, channels >= C zero */
 int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W, bbbp_stream_t stream);

@@ -427,3 +427,35 @@ def test_gemm_bf16_padded_outputs(ops):
     close(o32[:, :N], ref, 3e-5, what="padded fp32 out")
     close(o16[:, :N], ref, atol=1e-2, rtol=1e-2, what="padded bf16 out")
     assert float(o16[:, N:].float().abs().sum()) == 0.0
+
+
+# ---- first layer straight from the planar input contract (fp32 CHW, or raw uint8 + per-image statistics) -------------
+@pytest.mark.parametrize("N", [1, 5, 33])
+def test_conv1_tcgen05_from_planar_fp32(ops, N):
+    img = rnd(N, 3, 128, 128, seed=120)
+    w, b = rnd(32, 3, 3, 3, seed=121, scale=0.2), rnd(32, seed=122, scale=0.1)
+    wp = ops.conv3x3_prepare_bf16(w.cuda())
+    y = ops.conv1_from_image_bf16(img.cuda(), wp, b.cuda())
+    via_nhwc8 = ops.conv3x3_relu_pool_bf16(ops.image_to_nhwc8_bf16(img.cuda()), wp, b.cuda(), 32)
+    assert torch.equal(y, via_nhwc8), "the fused producer must stage exactly what the NHWC8 pre-pass stages"
+    close(y, _conv_ref_bf16(img, w, b).permute(0, 2, 3, 1), atol=2e-3, rtol=1e-2, what="conv1 from fp32 planes")
+
+
+@pytest.mark.parametrize("N", [1, 4, 19])
+def test_conv1_tcgen05_from_uint8_with_stats(ops, N):
+    from oracle import preprocess
+    rng = np.random.default_rng(N)
+    img = rng.integers(0, 256, size=(N, 3, 128, 128), dtype=np.uint8)
+    img[0, :, 10:100, 20:90] = 255                                   # mostly-white depiction
+    if N > 1:
+        img[1] = 255                                                 # blank depiction: std 0 -> 1, all zeros
+    w, b = rnd(32, 3, 3, 3, seed=123, scale=0.2), rnd(32, seed=124, scale=0.1)
+    dev = torch.from_numpy(img).cuda()
+    stats = ops.u8_image_stats(dev)
+    x = img.reshape(N, -1).astype(np.float64) / 255.0
+    sd = x.std(axis=1)
+    want = np.stack([x.mean(axis=1), 1.0 / np.where(sd == 0, 1.0, sd)], axis=1)
+    np.testing.assert_allclose(stats.cpu().numpy(), want, rtol=2e-6, atol=1e-7)
+    y = ops.conv1_from_image_bf16(dev, ops.conv3x3_prepare_bf16(w.cuda()), b.cuda(), stats)
+    z = torch.from_numpy(preprocess.u8_image_zscore(img)).view(N, 3, 128, 128)      # the reference's preprocessing
+    close(y, _conv_ref_bf16(z, w, b).permute(0, 2, 3, 1), atol=2e-2, rtol=2e-2, what="conv1 from uint8")

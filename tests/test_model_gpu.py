@@ -254,3 +254,30 @@ def test_dropout_active_in_train_mode(cuda_device):
     assert not torch.equal(a, b)
     a.sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ours.parameters())
+
+
+def test_screening_on_packed_bits_and_uint8_depictions(cuda_device):
+    """Extension of the input contracts (SURVEY cfg4; parity unpinned by reference code): packed MACCS bits + raw
+    uint8 depictions through the tcgen05 path == the oracle net fed with the reference's preprocessing of the same
+    molecules (oracle/preprocess.py), within the bf16 tolerance; and the fp32 path within 1e-3."""
+    from oracle import preprocess
+    ref, ours = make_pair("tcnn", 167, 128, 6, cuda_device)
+    ref.eval(), ours.eval()
+    rng = np.random.default_rng(1)
+    n, bs = 70, 32
+    bits = (rng.random((n, 167)) < 0.25).astype(np.uint8)
+    bits[:, 0] = 0
+    img = np.full((n, 3, 128, 128), 255, dtype=np.uint8)
+    strokes = rng.random((n, 1, 128, 128)) < 0.06
+    img[np.broadcast_to(strokes, img.shape)] = rng.integers(0, 200, size=int(strokes.sum()) * 3, dtype=np.uint8)
+    packed = preprocess.pack_bits(bits)
+    fp = torch.from_numpy(preprocess.unpack_zscore(packed, 167))
+    im = torch.from_numpy(preprocess.u8_image_zscore(img))
+    with torch.no_grad():
+        want = torch.cat([ref(fp[i:i + bs], im[i:i + bs]).reshape(-1) for i in range(0, n, bs)])
+    p_dev, i_dev = torch.from_numpy(packed).cuda(), torch.from_numpy(img).cuda()
+    got32 = ours.predict_batches_packed(p_dev, i_dev, bs).cpu()
+    assert float((got32 - want).abs().max()) <= 1e-3
+    ours.set_precision("bf16")
+    got16 = ours.predict_batches_packed(p_dev, i_dev, bs).cpu()
+    assert float((got16 - want).abs().max()) <= BF16_TOL
