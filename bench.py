@@ -44,49 +44,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (every ~5 ms; the
+    timed region of a default run is only tens of milliseconds, too short for `nvidia-smi -lms 200`)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.samples, self.reasons, self.thread, self.stop, self.err = index, [], 0, None, False, None
+        self.max_mhz, self.power = None, []
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: match by PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                    h = hi
+            h = h or pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.reasons |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                time.sleep(0.004)
+        except Exception as e:  # no NVML (CPU container)
+            self.err = str(e)[:100]
 
     def __enter__(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        time.sleep(0.05)       # let the first sample land before the timed region starts
         return self
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        self.thread.join(timeout=2)
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        try:
-            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = [float(r[1]) for r in rows]
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = float(rows[0][2])
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for i, n in enumerate(names):
-                if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows):
-                    out["reasons"].append(n)
-            out["samples"] = len(rows)
-        except Exception as e:  # nvidia-smi missing (CPU container)
-            out["error"] = str(e)[:80]
-        finally:
-            if self.path and os.path.exists(self.path):
-                os.unlink(self.path)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": [n for n, bit in self.BAD.items() if self.reasons & bit], "samples": len(self.samples),
+               "power_w_max": max(self.power) if self.power else None}
+        if self.err:
+            out["error"] = self.err
         return out
 
 
