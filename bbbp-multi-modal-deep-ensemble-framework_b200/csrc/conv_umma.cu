@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
       if (my_tiles > 0) load_tile(0, cur, cur_ok);
       for (int i = 0; i < my_tiles; ++i) {
         if (i + 1 < my_tiles) load_tile(i + 1, nxt, nxt_ok);
-        float mean = 0.0f, rstd = 1.0f;
+        float scale = 1.0f, shift = 0.0f;   // (u/255 - mean) * rstd == u * scale + shift
         if constexpr (SRC == SRC_CHW_U8) {
           const float2 st = __ldg(stats + (blockIdx.x + i * gridDim.x) / tiles_per_img);
-          mean = st.x, rstd = st.y;
+          scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
         }
         const int s = i % STAGES;
         mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
             float a = cur[k][0], b = cur[k][1], c = cur[k][2];
             if constexpr (SRC == SRC_CHW_U8) {
               const bool ok = (cur_ok >> k) & 1;   // zero padding applies to the NORMALISED image
-              a = ok ? (a / 255.0f - mean) * rstd : 0.0f;
-              b = ok ? (b / 255.0f - mean) * rstd : 0.0f;
-              c = ok ? (c / 255.0f - mean) * rstd : 0.0f;
+              a = ok ? fmaf(a, scale, shift) : 0.0f;
+              b = ok ? fmaf(b, scale, shift) : 0.0f;
+              c = ok ? fmaf(c, scale, shift) : 0.0f;
             }
             __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, 0.0f);
             *reinterpret_cast<uint4*>(stage + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16) =

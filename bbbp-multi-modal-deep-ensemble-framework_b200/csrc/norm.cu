@@ -143,6 +143,19 @@ __global__ void __launch_bounds__(256) batchnorm_fwd_kernel(const float* __restr
   for (int r = threadIdx.y; r < rows; r += 8) y[(size_t)r * C + c] = (x[(size_t)r * C + c] - mean) * rstd * g + b;
 }
 
+// eval-mode forward over many rows: purely elementwise, so parallelise over rows as well (the strip kernel above has
+// only channels/32 blocks, far too few when a screening pass normalises thousands of molecules)
+__global__ void __launch_bounds__(256) batchnorm_eval_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta,
+                                                                 const float* __restrict__ rmean,
+                                                                 const float* __restrict__ rvar, float* __restrict__ y,
+                                                                 size_t total, int C, float eps) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % C;
+  y[i] = (x[i] - rmean[c]) * rsqrtf(rvar[c] + eps) * gamma[c] + beta[c];
+}
+
 // training != 0: batch-statistics backward; else running statistics are constants
 __global__ void __launch_bounds__(256) batchnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
@@ -223,6 +236,12 @@ extern "C" int bbbp_batchnorm_fwd_f32(const float* x, const float* gamma, const 
                  "batchnorm_fwd: bad argument");
   BBBP_CHECK_ARG(!training || (save_mean && save_rstd), "batchnorm_fwd: training needs save_mean/save_rstd");
   BBBP_CHECK_ARG(!training || rows > 1, "batchnorm_fwd: Expected more than 1 value per channel when training");
+  if (!training && rows >= 64) {
+    const size_t total = (size_t)rows * channels;
+    batchnorm_eval_fwd_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
+        x, gamma, beta, running_mean, running_var, y, total, channels, eps);
+    return launch_status("batchnorm_fwd (eval)");
+  }
   batchnorm_fwd_kernel<<<ceil_div(channels, 32), dim3(32, 8), 0, as_stream(stream)>>>(
       x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, rows, channels, training, momentum, eps);
   return launch_status("batchnorm_fwd");

@@ -50,40 +50,51 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.samples, self.reasons, self.thread, self.stop, self.err = index, [], 0, None, False, None
-        self.max_mhz, self.power = None, []
-
-    def _run(self):
-        try:
+        self.max_mhz, self.power, self.nvml, self.h = None, [], None, None
+        try:                       # NVML start-up costs ~100 ms: do it here, before any timed region
             import pynvml
-            pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may renumber devices: match by PCI bus id of the torch device
             import torch
-            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
-            h = None
+            pynvml.nvmlInit()
+            bus = torch.cuda.get_device_properties(index).pci_bus_id   # CUDA_VISIBLE_DEVICES may renumber devices
             for i in range(pynvml.nvmlDeviceGetCount()):
                 hi = pynvml.nvmlDeviceGetHandleByIndex(i)
                 if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
-                    h = hi
-            h = h or pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    self.h = hi
+            self.h = self.h or pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception as e:     # no NVML (CPU container)
+            self.err = str(e)[:100]
+
+    def _sample(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.reasons |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+
+    def _run(self):
+        try:
             while not self.stop:
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                self.reasons |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                time.sleep(0.004)
-        except Exception as e:  # no NVML (CPU container)
+                self._sample()
+                time.sleep(0.003)
+        except Exception as e:
             self.err = str(e)[:100]
 
     def __enter__(self):
         import threading
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
-        time.sleep(0.05)       # let the first sample land before the timed region starts
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.thread.join(timeout=2)
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+            try:
+                self._sample()         # one more sample while the last step's kernels are still draining
+            except Exception:
+                pass
 
     def summary(self):
         out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -127,6 +138,53 @@ def cpu_reference_rate(n_batches, threads, warm=1):
     return n_batches * BATCH / dt, dt, n_batches * BATCH
 
 
+def train_step_ms(torch, bbbp_b200, nets, dev, with_cpu=True):
+    """Secondary figure of BASELINE.json's metric ("train step ms"): fwd + bwd + AdamW of the same network with the
+    reference's settings (20250113.py:172,187-191: batch 32, AdamW lr 1e-4 wd 1e-5, MSE), fp32 kernels, dropout off
+    (the reference's dominant regime).  CUDA events, 3 warm-ups, inputs resident."""
+    out = {"precision": "fp32", "optimizer": "bbbp_b200.AdamW (one fused launch)", "loss": "bbbp_b200.MSELoss"}
+    torch.manual_seed(0)
+    model = bbbp_b200.MixedInputModel(F_BITS, 128).to(dev)
+    nets.zero_dropout(model)
+    model.train()
+    opt = bbbp_b200.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+    crit = bbbp_b200.MSELoss()
+    for batch in (32, 256):
+        fp, img = synthetic_inputs(batch, 3, dev)
+        y = torch.randn(batch, device=dev) * 0.75 - 0.1
+
+        def step():
+            opt.zero_grad()
+            loss = crit(model(fp, img).squeeze(), y)
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"ms_batch{batch}"] = e0.elapsed_time(e1) / 10
+    if with_cpu:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        ref = nets.zero_dropout(nets.build("tcnn", F_BITS, 128)).train()
+        ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-5)
+        fp, img = synthetic_inputs(32, 3, "cpu")
+        y = torch.randn(32) * 0.75 - 0.1
+        nets.train_step(ref, ropt, fp, img, y)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            nets.train_step(ref, ropt, fp, img, y)
+        out["cpu_ms_batch32"] = (time.perf_counter() - t0) / 3 * 1e3
+        out["cpu_cores"] = threads
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -165,6 +223,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("BBBP_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-batches", type=int, default=12, help="bounded CPU-baseline sample (batches of 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -296,6 +355,8 @@ def main():
                                   "d2h_bytes_per_step": n * 4, "ms_per_step": ms_e2e32 / args.steps,
                                   "api": "model.predict_batches(fp32 fingerprint, fp32 image) from pinned host buffers"},
             "roofline": roof}
+    if world == 1 and not args.no_train:
+        line["train_step"] = train_step_ms(torch, bbbp_b200, nets, dev, with_cpu=not args.no_cpu_baseline)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
