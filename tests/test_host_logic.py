@@ -131,3 +131,31 @@ def test_score_gather_world2_gloo(tmp_path, n, bs):
     want = np.arange(n, dtype=np.float32) * 0.5
     for r in range(2):
         np.testing.assert_array_equal(np.load(tmp_path / f"r{r}.npy"), want)
+
+
+def _avg_grad_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+        params[0].grad = torch.full((5, 3), float(rank + 1))
+        params[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+        bbbp_b200.average_gradients(params)          # params[2] has no gradient: skipped
+        np.save(os.path.join(out_dir, f"g{rank}.npy"), torch.cat([params[0].grad.reshape(-1), params[1].grad]).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_averaging_world2_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_avg_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    want = np.concatenate([np.full(15, 1.5, dtype=np.float32), np.arange(7, dtype=np.float32) * 1.5])
+    for r in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"g{r}.npy"), want)

@@ -281,3 +281,39 @@ def test_screening_on_packed_bits_and_uint8_depictions(cuda_device):
     ours.set_precision("bf16")
     got16 = ours.predict_batches_packed(p_dev, i_dev, bs).cpu()
     assert float((got16 - want).abs().max()) <= BF16_TOL
+
+
+def test_pca_projection_matches_shipped_pca(cuda_device):
+    """P16: maccs_pca.pkl (the reference's fitted PCA, 167 -> 30) applied on the device == sklearn's transform."""
+    import bbbp_b200
+    g = load_golden("maccs_pca")
+    y = bbbp_b200.pca_transform(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["mean"]).cuda(),
+                                torch.from_numpy(g["components"]).cuda())
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=0, atol=2e-5)
+    big = torch.randn(37, 49152, generator=torch.Generator().manual_seed(0))
+    comp = torch.randn(16, 49152, generator=torch.Generator().manual_seed(1)) / 200
+    mu = big.mean(0)
+    want = (big.double() - mu.double()) @ comp.double().T
+    got = bbbp_b200.pca_transform(big.cuda(), mu.cuda(), comp.cuda()).cpu().double()
+    assert float((got - want).abs().max()) <= 2e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sharded_screening_is_bit_identical_for_any_rank_count(cuda_device, precision):
+    """ranks own whole reference batches, so the concatenation of the per-rank score slices must equal
+    the 1-GPU result bit for bit for R in {1, 2, 4, 8} (ranks emulated one after the other on one device)."""
+    import bbbp_b200
+    _, ours = make_pair("tcnn", 167, 128, 3, cuda_device)
+    ours.eval().set_precision(precision)
+    n, bs = 1058, 32
+    g = torch.Generator().manual_seed(8)
+    fp, img = torch.randn(n, 167, generator=g).cuda(), torch.randn(n, IMG, generator=g).cuda()
+    whole = ours.predict_batches(fp, img, bs)
+    for world in (2, 4, 8):
+        parts = []
+        for rank in range(world):
+            a, b = bbbp_b200.partition_batches(n, bs, world, rank)
+            parts.append(ours.predict_batches(fp[a:b], img[a:b], bs, max_rows_per_pass=bs * (1 + rank)))
+        assert torch.equal(torch.cat(parts), whole), f"world {world}"
+    loader = lambda a, b: (fp[a:b], img[a:b])
+    assert torch.equal(bbbp_b200.screen(ours, loader, n, batch_size=bs, chunk_molecules=200), whole)
