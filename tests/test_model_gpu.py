@@ -317,3 +317,25 @@ def test_sharded_screening_is_bit_identical_for_any_rank_count(cuda_device, prec
         assert torch.equal(torch.cat(parts), whole), f"world {world}"
     loader = lambda a, b: (fp[a:b], img[a:b])
     assert torch.equal(bbbp_b200.screen(ours, loader, n, batch_size=bs, chunk_molecules=200), whole)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_equals_eager_and_tracks_weight_updates(cuda_device, precision):
+    _, ours = make_pair("tcnn", 167, 128, 9, cuda_device)
+    ours.eval().set_precision(precision)
+    fp, img, _ = seeded_inputs(12, 32, 167, IMG)
+    fp, img = fp.cuda(), img.cuda()
+    with torch.no_grad():
+        ours.use_cuda_graphs = False
+        eager = ours(fp, img)
+        ours.use_cuda_graphs = True
+        first = ours(fp, img)                 # captures
+        second = ours(fp * 1.0, img * 1.0)    # replays with fresh input tensors
+        assert ours._graphs and len(ours._graphs) == 1
+        assert torch.equal(first, eager) and torch.equal(second, eager)
+        other = ours(fp[:7].contiguous(), img[:7].contiguous())      # another shape: its own graph
+        assert other.shape == (7, 1) and len(ours._graphs) == 2
+        with torch.no_grad():
+            ours.fc[7].bias.add_(0.5)                                  # a weight update must invalidate the graph
+        moved = ours(fp, img)
+        assert torch.allclose(moved, eager + 0.5, atol=1e-6)
