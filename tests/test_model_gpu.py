@@ -339,3 +339,22 @@ def test_cuda_graph_replay_equals_eager_and_tracks_weight_updates(cuda_device, p
             ours.fc[7].bias.add_(0.5)                                  # a weight update must invalidate the graph
         moved = ours(fp, img)
         assert torch.allclose(moved, eager + 0.5, atol=1e-6)
+
+
+def test_predict_from_host_overlapped_pipeline(cuda_device):
+    _, ours = make_pair("tcnn", 167, 128, 3, cuda_device)
+    ours.eval().set_precision("bf16")
+    n, bs = 300, 32
+    g = torch.Generator().manual_seed(4)
+    fp, img = torch.randn(n, 167, generator=g).pin_memory(), torch.randn(n, IMG, generator=g).pin_memory()
+    want = ours.predict_batches(fp.cuda(), img.cuda(), bs).cpu()
+    got = ours.predict_from_host(fp, img, bs, chunk_molecules=64)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    rng = np.random.default_rng(2)
+    packed = torch.from_numpy(rng.integers(0, 256, size=(n, 21), dtype=np.uint8)).pin_memory()
+    img8 = torch.from_numpy(rng.integers(0, 256, size=(n, 3, 128, 128), dtype=np.uint8)).pin_memory()
+    want = ours.predict_batches_packed(packed.cuda(), img8.cuda(), bs).cpu()
+    got = ours.predict_from_host(packed, img8, bs, chunk_molecules=96, packed=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
