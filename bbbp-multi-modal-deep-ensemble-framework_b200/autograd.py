@@ -71,7 +71,7 @@ class Linear(Function):
             a16 = ops.cast_bf16(x)
             y, _ = ops.gemm_bf16(a16, K, weight_bf16(weight), N, bias=bias, act=act, split_k=ops.fixed_split_k(K))
         else:
-            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=ops.fixed_split_k(K))
+            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=ops.fixed_split_k_f32(K))
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if act else None)
@@ -86,9 +86,9 @@ class Linear(Function):
         N = weight.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm_f32(dpre, weight, split_k=ops.fixed_split_k(N))
+            dx = ops.gemm_f32(dpre, weight, split_k=ops.tile_split_k(M, K, N, x.device))
         if ctx.needs_input_grad[1]:
-            dw = ops.gemm_f32(dpre, x, trans_a=True)
+            dw = ops.gemm_f32(dpre, x, trans_a=True, split_k=ops.tile_split_k(N, K, M, x.device))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dpre)
         return dx, dw, db, None, None

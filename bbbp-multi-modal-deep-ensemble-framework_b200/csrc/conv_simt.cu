@@ -108,21 +108,25 @@ __global__ void relu_pool_bwd_kernel(const float* __restrict__ dy, const float* 
   o[W + 1] = a == 3 ? g : 0.0f;
 }
 
-// per-image partial weight gradient: block = (ci tile of 16, co tile of 16, image); thread = (co, ci), 9 taps
+// partial weight gradient: block = (ci tile of 16 x band of image rows, co tile of 16, image); thread = (co, ci), 9 taps.
+// The image is cut into `bands` horizontal bands so that small batches still fill the GPU; partials are summed by
+// sum_over_images_kernel in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) conv3x3_wgrad_partial_kernel(const float* __restrict__ dpre,
                                                                     const float* __restrict__ x,
                                                                     float* __restrict__ part, int Cin, int Cout, int H,
-                                                                    int W) {
+                                                                    int W, int bands) {
   __shared__ float ds[16][256];
   __shared__ float xs[16][18][18];
   const int tid = threadIdx.x;
-  const int ci0 = blockIdx.x * 16, co0 = blockIdx.y * 16, n = blockIdx.z;
+  const int band = blockIdx.x % bands;
+  const int ci0 = (blockIdx.x / bands) * 16, co0 = blockIdx.y * 16, n = blockIdx.z;
+  const int rows_per_band = H / bands;
   const int ci_l = tid % 16, co_l = tid / 16;
   float acc[9] = {};
   const float* xn = x + (size_t)n * Cin * H * W;
   const float* dn = dpre + (size_t)n * Cout * H * W;
   const int nci = min(16, Cin - ci0);
-  for (int ty0 = 0; ty0 < H; ty0 += 16)
+  for (int ty0 = band * rows_per_band; ty0 < (band + 1) * rows_per_band; ty0 += 16)
     for (int tx0 = 0; tx0 < W; tx0 += 16) {
       for (int i = tid; i < 16 * 256; i += 256) {
         int co = i / 256, p = i % 256;
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_partial_kernel(const float*
       __syncthreads();
     }
   if (ci_l < nci) {
-    float* o = part + (((size_t)n * Cout + co0 + co_l) * Cin + ci0 + ci_l) * 9;
+    float* o = part + ((((size_t)n * bands + band) * Cout + co0 + co_l) * Cin + ci0 + ci_l) * 9;
 #pragma unroll
     for (int t = 0; t < 9; ++t) o[t] = acc[t];
   }
@@ -225,19 +229,20 @@ extern "C" int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* 
   BBBP_CHECK_ARG(Cout % 16 == 0 && H % 16 == 0 && W % 16 == 0, "conv3x3_wgrad: Cout/H/W must be multiples of 16");
   BBBP_CHECK_ARG(N > 0 && N <= 65535, "conv3x3_wgrad: N=%d out of range", N);
   size_t per_w = (size_t)Cout * Cin * 9, per_b = Cout;
-  size_t need = (size_t)N * (per_w + per_b) * sizeof(float);
+  const int bands = (H % 128 == 0) ? 8 : (H % 64 == 0) ? 4 : (H % 32 == 0) ? 2 : 1;   // each band is a multiple of 16 rows
+  size_t need = (size_t)N * (bands * per_w + per_b) * sizeof(float);
   if (!workspace || workspace_bytes < need) {
     set_error("conv3x3_wgrad: needs %zu workspace bytes, got %zu", need, workspace_bytes);
     return BBBP_EWORKSPACE;
   }
   cudaStream_t s = as_stream(stream);
   float* part_w = workspace;
-  float* part_b = workspace + (size_t)N * per_w;
-  dim3 grid(ceil_div(Cin, 16), Cout / 16, N);
-  conv3x3_wgrad_partial_kernel<<<grid, 256, 0, s>>>(dpre, x, part_w, Cin, Cout, H, W);
+  float* part_b = workspace + (size_t)N * bands * per_w;
+  dim3 grid(ceil_div(Cin, 16) * bands, Cout / 16, N);
+  conv3x3_wgrad_partial_kernel<<<grid, 256, 0, s>>>(dpre, x, part_w, Cin, Cout, H, W, bands);
   int st = launch_status("conv3x3_wgrad partial");
   if (st != BBBP_OK) return st;
-  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)256), 256, 0, s>>>(part_w, dw, N, per_w);
+  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)256), 256, 0, s>>>(part_w, dw, N * bands, per_w);
   st = launch_status("conv3x3_wgrad reduce");
   if (st != BBBP_OK || !db) return st;
   conv_bgrad_partial_kernel<<<dim3(Cout, N), 256, 0, s>>>(dpre, part_b, Cout, H * W);

@@ -106,6 +106,17 @@ def fixed_split_k(K: int) -> int:
     return 1 if K < 8192 else min(8, K // 2048)
 
 
+def fixed_split_k_f32(K: int) -> int:
+    """Same contract for the CUDA-core fp32 GEMM (64-wide tiles, used at small batch where tiles are few)."""
+    return 1 if K < 1024 else min(64, K // 256)
+
+
+def tile_split_k(M: int, N: int, K: int, device) -> int:
+    """Backward GEMMs carry no bit-identity contract: split K until the grid fills the GPU."""
+    tiles = -(-M // 64) * -(-N // 64)
+    return max(1, min(-(-2 * sm_count(device) // tiles), K // 128))
+
+
 def cast_bf16(x: torch.Tensor, ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """(rows, cols) float32 -> (rows, ld) bfloat16 with zero fill of the pad columns; ld multiple of 8.
     ``out`` may be a pitched 2-D bf16 view (its row stride is the destination pitch)."""
@@ -199,7 +210,7 @@ def conv3x3_wgrad(dpre, x, Cout, Cin):
     N, _, H, W = x.shape
     dw = torch.empty((Cout, Cin, 3, 3), device=x.device, dtype=torch.float32)
     db = torch.empty((Cout,), device=x.device, dtype=torch.float32)
-    ws = torch.empty((N * (Cout * Cin * 9 + Cout),), device=x.device, dtype=torch.float32)
+    ws = torch.empty((N * (8 * Cout * Cin * 9 + Cout),), device=x.device, dtype=torch.float32)
     check(lib.bbbp_conv3x3_wgrad_f32(dpre.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), N, Cin, Cout, H, W,
                                      ws.data_ptr(), ws.numel() * 4, _stream()), "conv3x3_wgrad")
     return dw, db

@@ -29,4 +29,4 @@ def pca_transform(x: torch.Tensor, mean: torch.Tensor, components: torch.Tensor)
     comp = components if components.is_contiguous() else components.contiguous()
     shift = ops.gemm_f32(mean.reshape(1, -1).contiguous(), comp, trans_b=True)          # (1, k) = mean @ C^T
     neg = ops.scale_by_device_scalar(shift.reshape(-1), torch.full((1,), -1.0, device=x.device))
-    return ops.gemm_f32(x, comp, trans_b=True, bias=neg, split_k=ops.fixed_split_k(x.shape[1]))
+    return ops.gemm_f32(x, comp, trans_b=True, bias=neg, split_k=ops.fixed_split_k_f32(x.shape[1]))

@@ -106,7 +106,7 @@ int bbbp_conv3x3_f32(const float* x, const float* w, const float* b, float* y, u
 int bbbp_relu_pool_bwd_f32(const float* dy, const float* y, const uint8_t* argmax, float* dpre, int N, int C, int H,
                            int W, bbbp_stream_t stream);
 /* dw[Cout,Cin,3,3] and db[Cout] from dpre[N,Cout,H,W] and x[N,Cin,H,W]; deterministic two-pass.
- * workspace: N * (Cout*Cin*9 + Cout) floats. */
+ * workspace: N * (8*Cout*Cin*9 + Cout) floats (partials per image and per band of image rows). */
 int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* dw, float* db, int N, int Cin, int Cout, int H,
                            int W, float* workspace, size_t workspace_bytes, bbbp_stream_t stream);
 /* w_t[Cin,Cout,3,3] = spatially flipped, channel-transposed w[Cout,Cin,3,3] (weights of the data-gradient conv) */
