@@ -48,12 +48,17 @@ struct Cfg {
   static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 32;
   static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + 4;
   static constexpr int A_BYTES = KC * KC_B;
-  static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // MMAs (K=16) per window member
+  static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // K=16 steps per window member
+  // instructions per tile: conv1 issues one N=COUT MMA per (member, step); conv2 pairs the two members of a pooling
+  // row that read the SAME halo view (dx=0 with tap kw+1, dx=1 with tap kw) into one N=2*COUT MMA: 24 per K-chunk pair
+  static constexpr int NISSUE = KC == 1 ? 4 * NMMA : 24 * (KC / 2);
   static constexpr int W_BYTES = KC == 1 ? 2 * 5 * 2 * COUT * 16 : 9 * KC * COUT * 16;
   static constexpr int ACC_COLS = 4 * COUT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = 128 + STAGES * A_BYTES + W_BYTES + COUT * 4 + BAR_BYTES;
+  static constexpr int OUT_ROW_B = COUT * 2;            // bytes of one pooled pixel (= the TMA store's swizzle span)
+  static constexpr int OUT_BYTES = 128 * OUT_ROW_B;     // one output tile: 128 pooled pixels x COUT bf16
+  static constexpr int SMEM_BYTES = 1024 + 2 * OUT_BYTES + STAGES * A_BYTES + W_BYTES + COUT * 4 + BAR_BYTES;
 };
 
 __host__ __device__ constexpr int halo_offset(int dy, int dx, int tap) {
@@ -74,35 +79,48 @@ __host__ __device__ constexpr TapPair conv1_pair(int dx, int i) {
 }
 
 struct MmaOp {
-  uint32_t a_off, a_lbo, b_off;
+  uint32_t a_off, a_lbo, b_off, b_lbo, d_col, n, accumulate;
 };
-// Operands of MMA number m (0 .. NMMA-1) of window member q = 2*dy + dx: byte offsets into the staged halo / the
-// shared-memory weight image.  constexpr: the issue loop is fully unrolled and every descriptor is an immediate.
+// Operands of the I-th MMA of a tile: byte offsets into the staged halo / the shared-memory weight image, the
+// accumulator column, the instruction's N and its accumulate flag.  constexpr: the issue loop is fully unrolled and
+// every descriptor is an immediate.
 template <int KC, int COUT>
-__host__ __device__ constexpr MmaOp mma_op(int q, int m) {
-  const int dy = q >> 1, dx = q & 1;
+__host__ __device__ constexpr MmaOp mma_op(int I) {
   if (KC == 1) {
+    // conv1: member q = 2*dy + dx, step m covers the tap pair (2m, 2m+1) through the leading byte offset
+    const int q = I / 5, m = I % 5, dy = q >> 1, dx = q & 1;
     const TapPair p = conv1_pair(dx, m);
     const int oa = halo_offset(dy, dx, p.first), ob = halo_offset(dy, dx, p.second);
-    return MmaOp{(uint32_t)oa, (uint32_t)(ob - oa), (uint32_t)((dx * 5 + m) * (2 * COUT * 16))};
+    return MmaOp{(uint32_t)oa, (uint32_t)(ob - oa), (uint32_t)((dx * 5 + m) * (2 * COUT * 16)), (uint32_t)(COUT * 16),
+                 (uint32_t)(q * COUT), (uint32_t)COUT, (uint32_t)(m != 0)};
   }
-  const int tap = m / (KC / 2 > 0 ? KC / 2 : 1), j = m % (KC / 2 > 0 ? KC / 2 : 1);
-  return MmaOp{(uint32_t)((2 * j) * KC_B + halo_offset(dy, dx, tap)), (uint32_t)KC_B,
-               (uint32_t)((tap * KC + 2 * j) * (COUT * 16))};
+  // conv2: K-chunk pair j, pooling row dy, then 12 (kh, sx) halo views; sx = dx + kw is the view's x shift.
+  // sx = 1, 2: both members of the row use this view (dx=0 with kw=sx, dx=1 with kw=sx-1): one N = 2*COUT MMA whose
+  // B rows are the two taps' weights, adjacent in the [kc][8 - tap][cout] weight image.  sx = 0 / 3: one member only.
+  // The first view of every row is a paired one with accumulate = 0, so it initialises both accumulators.
+  const int j = I / 24, rem = I % 24, dy = rem / 12, e = rem % 12;
+  const int kh = e < 4 ? 0 : (e - 4) / 4 + 1;
+  const int order0[4] = {1, 2, 0, 3};
+  const int sx = e < 4 ? order0[e] : (e - 4) % 4;
+  const bool paired = sx == 1 || sx == 2;
+  const int dx = sx == 3 ? 1 : 0;                     // member that owns columns d_col (the left one when paired)
+  const int tap = kh * 3 + (sx == 3 ? 2 : sx);        // tap of that member: kw = sx - dx
+  const int a_off = (2 * j) * KC_B + (sx & 1) * PAR_B + (dy + kh) * ROW_B + (sx >> 1) * 16;
+  const int b_off = ((2 * j) * 9 + (8 - tap)) * (COUT * 16);
+  return MmaOp{(uint32_t)a_off, (uint32_t)KC_B, (uint32_t)b_off, (uint32_t)(9 * COUT * 16), (uint32_t)((2 * dy + dx) * COUT),
+               (uint32_t)(paired ? 2 * COUT : COUT), (uint32_t)!(j == 0 && e == 0)};
 }
 
 // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46) | no swizzle
 template <int KC, int COUT, int I>
 __device__ __forceinline__ void issue_one(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc) {
-  using C = Cfg<KC, COUT>;
-  constexpr int q = I / C::NMMA, m = I % C::NMMA;
-  constexpr MmaOp op = mma_op<KC, COUT>(q, m);
+  constexpr MmaOp op = mma_op<KC, COUT>(I);
   constexpr uint32_t a_lo_c = (op.a_off >> 4) | ((op.a_lbo >> 4) << 16);
-  constexpr uint32_t b_lo_c = (op.b_off >> 4) | (((COUT * 16) >> 4) << 16);
+  constexpr uint32_t b_lo_c = (op.b_off >> 4) | ((op.b_lbo >> 4) << 16);
   constexpr uint64_t a_hi = (uint64_t)(((2 * ROW_B) >> 4) | (1u << 14)) << 32;
   constexpr uint64_t b_hi = (uint64_t)((128 >> 4) | (1u << 14)) << 32;
-  constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
-  umma_bf16(tmem_acc + q * COUT, a_hi | (a_lo + a_lo_c), b_hi | (w_lo + b_lo_c), idesc, m != 0);
+  constexpr uint32_t idesc = make_idesc_bf16(128, op.n);
+  umma_bf16(tmem_acc + op.d_col, a_hi | (a_lo + a_lo_c), b_hi | (w_lo + b_lo_c), idesc, op.accumulate != 0);
 }
 template <int KC, int COUT, int... I>
 __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc,
@@ -122,15 +140,16 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
                                                                const float2* __restrict__ stats,
                                                                const uint4* __restrict__ wprep,
                                                                const float* __restrict__ bias,
-                                                               __nv_bfloat16* __restrict__ dst, int n_img, int H,
-                                                               int W) {
+                                                               const __grid_constant__ CUtensorMap tmOut, int n_img,
+                                                               int H, int W) {
   using C = Cfg<KC, COUT>;
   static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
   const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_any);
   constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* sA = base;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sOut = base;                     // 2 swizzled output tiles (1024-byte aligned) for the TMA stores
+  uint8_t* sA = sOut + 2 * C::OUT_BYTES;
   uint8_t* sW = sA + STAGES * C::A_BYTES;
   float* sBias = reinterpret_cast<float*>(sW + C::W_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sBias + COUT);
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
         mbar_wait(&full[s], (i / STAGES) & 1);
         tc_fence_after_sync();
         issue_tile<KC, COUT>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
-                             std::make_integer_sequence<int, 4 * C::NMMA>{});
+                             std::make_integer_sequence<int, C::NISSUE>{});
         umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
         umma_commit(&acc_full[b]);   // accumulators of this tile complete
       }
@@ -314,18 +333,27 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
     // One warp per scheduler runs this mostly-serial code, so two warps per quadrant halve the epilogue's latency and
     // keep it hidden behind the next tile's MMAs.
     const int quad = warp & 3, half = warp >> 2;
-    const int m = quad * 32 + lane;  // pooled pixel within the tile == TMEM lane
-    const int PH = H / 2, PW = W / 2;
+    const int m = quad * 32 + lane;  // pooled pixel within the tile == TMEM lane == row of the output tile
+    const int PH = H / 2;
     constexpr int CH = COUT / (C::EPI_WARPS / 4);  // channels per epilogue warp
+    // The tile is written to shared memory in the TMA store's swizzled layout (row = pixel, 16-byte chunk j of row r
+    // at position j ^ swz(r)): conflict-free 16-byte stores here, and ONE bulk tensor store per tile instead of 32
+    // scattered 16-byte global stores per warp instruction (which cost the L1 data pipe 32 wavefronts each -- the
+    // pipe this kernel is bound by).
+    constexpr int SWZ_SHIFT = C::OUT_ROW_B == 128 ? 0 : 1, SWZ_MASK = C::OUT_ROW_B / 16 - 1;
+    const int swz = (m >> SWZ_SHIFT) & SWZ_MASK;
+    const bool issuer = warp == 0 && lane == 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int t = blockIdx.x + i * gridDim.x;
       const int n = t / tiles_per_img, r = t % tiles_per_img;
-      const int ph = (r / tiles_x) * TILE_PH + (m >> 3), pw = (r % tiles_x) * TILE_PW + (m & 7);
       const int b = i & 1;
+      uint8_t* otile = sOut + b * C::OUT_BYTES;
+      if (issuer) bulk_store_wait_read<1>();   // the store of tile i-2 has finished reading this buffer
+      named_bar_sync(1, EPI_THREADS);
       mbar_wait(&acc_full[b], (i >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
-      uint4* out = reinterpret_cast<uint4*>(dst + (((size_t)n * PH + ph) * PW + pw) * COUT + half * CH);
+      uint8_t* orow = otile + m * C::OUT_ROW_B;
 #pragma unroll
       for (int c0 = 0; c0 < CH; c0 += 16) {
         uint32_t r0[16], r1[16], r2[16], r3[16];
@@ -351,12 +379,20 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
             packed[(j + k) / 2] = *reinterpret_cast<uint32_t*>(&h);
           }
         }
-        out[c0 / 8] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        out[c0 / 8 + 1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        const int chunk = (half * CH + c0) / 8;
+        *reinterpret_cast<uint4*>(orow + ((chunk ^ swz) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(orow + (((chunk + 1) ^ swz) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
       tc_fence_before_sync();
-      mbar_arrive(&acc_empty[b]);
+      mbar_arrive(&acc_empty[b]);   // TMEM reads done: the MMA warp may start the tile after next
+      fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA (async proxy)
+      named_bar_sync(2, EPI_THREADS);
+      if (issuer) {
+        tma_store_3d(&tmOut, otile, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
+        bulk_store_commit();
+      }
     }
+    if (issuer) bulk_store_wait_all();   // shared memory must outlive the last store's reads
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -367,13 +403,14 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
 }
 
 // ---- weight / input re-layout (prepare-time and per-call helpers) --------------------------------------------------
-// conv2-style (KC >= 2): wp[tap][kc][n][8] = w[n][kc*8 + c][kh][kw]
+// conv2-style (KC >= 2): wp[kc][8 - tap][n][8] = w[n][kc*8 + c][kh][kw]; taps are stored in REVERSE order so that the
+// weights of taps (kh, kw) and (kh, kw-1) -- the two B halves of a paired MMA -- are adjacent 64-row blocks
 __global__ void prep_weights_kc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
   const int KC = Cin / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * KC * Cout * 8) return;
-  const int c = i % 8, n = (i / 8) % Cout, kc = (i / (8 * Cout)) % KC, tap = i / (8 * Cout * KC);
-  wp[i] = __float2bfloat16(w[((size_t)n * Cin + kc * 8 + c) * 9 + tap]);
+  const int c = i % 8, n = (i / 8) % Cout, u = (i / (8 * Cout)) % 9, kc = i / (8 * Cout * 9);
+  wp[i] = __float2bfloat16(w[((size_t)n * Cin + kc * 8 + c) * 9 + (8 - u)]);
 }
 // conv1-style (Cin <= 8, one chunk): wp[dx][pair][chunk][n][8]
 __global__ void prep_weights_c8_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
@@ -473,11 +510,29 @@ int launch(const void* x, const float* stats, const void* wprep, const float* bi
     cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     attr = true;
   }
+  // NHWC output as a 3-D tensor {COUT, PW, N*PH}; one box = one tile (COUT x 8 x 16), swizzle span = one pixel row
+  CUtensorMap tmOut;
+  {
+    tensormap_encode_fn enc = get_tensormap_encoder();
+    if (!enc) return BBBP_ECUDA;
+    const int PH = H / 2, PW = W / 2;
+    cuuint64_t dims[3] = {(cuuint64_t)COUT, (cuuint64_t)PW, (cuuint64_t)N * PH};
+    cuuint64_t strides[2] = {(cuuint64_t)COUT * 2, (cuuint64_t)PW * COUT * 2};
+    cuuint32_t box[3] = {(cuuint32_t)COUT, TILE_PW, TILE_PH};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     COUT * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv3x3_relu_pool_bf16: cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
+      return BBBP_ECUDA;
+    }
+  }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
   const int per_sm = (C::TMEM_COLS <= 256 && C::SMEM_BYTES <= 100 * 1024) ? 2 : 1;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
   conv3x3_umma_kernel<KC, COUT, SRC><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
-      x, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, static_cast<__nv_bfloat16*>(y), N, H, W);
+      x, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, tmOut, N, H, W);
   return launch_status("conv3x3_relu_pool_bf16");
 }
 
