@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <utility>
+#include <type_traits>
 
 namespace bbbp {
 namespace conv {
@@ -38,15 +39,20 @@ constexpr int ROW_B = XH * 16;                 // 144 bytes per (parity, y) row
 constexpr int PAR_B = HALO_H * ROW_B + 32;     // 4928 = 64 (mod 128)
 constexpr int KC_B = 2 * PAR_B + 16;           // 9872 = 16 (mod 128) bytes per 8-channel chunk plane
 constexpr int STAGES = 3;
-constexpr int PROD_THREADS = 128;
 
-template <int KC, int COUT>
+template <int KC, int COUT, int SRC = 0>
 struct Cfg {
   // conv2's epilogue (64 channels) gets two warps per TMEM lane quadrant; conv1's (32 channels) one, which also keeps
   // its CTA small enough for two CTAs per SM
   static constexpr int EPI_WARPS = COUT >= 64 ? 8 : 4;
+  // the producers are latency-bound (global loads / cp.async behind a shared-memory pipe the tensor core keeps busy):
+  // eight warps halve the per-thread chunk count
+  // (measured: conv2 1.21 -> 1.14 ms).  conv1 keeps four: with eight, two CTAs per SM need a 72-register cap that spills
+  // in the epilogue and costs more than the producers gain.
+  static constexpr int PROD_WARPS = KC == 1 ? 4 : 8, PROD_THREADS = PROD_WARPS * 32;
   static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 32;
-  static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + 4;
+  static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS;
+  static constexpr int MIN_CTAS = KC == 1 ? 2 : 1;
   static constexpr int A_BYTES = KC * KC_B;
   static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // K=16 steps per window member
   // instructions per tile: conv1 issues one N=COUT MMA per (member, step); conv2 pairs the two members of a pooling
@@ -130,22 +136,30 @@ __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_
 
 enum { SRC_NHWC_BF16 = 0, SRC_CHW_F32 = 1, SRC_CHW_U8 = 2 };
 
+// Optional cycle probe (bbbp_debug_conv_probe): when set, CTA 0 accumulates clock64() deltas of its role loops into
+// probe[0..15]: MMA thread {wait acc_empty, wait full, issue}, epilogue thread 0 {wait acc_full, tmem+math+sts, barriers+
+// store}, producer thread 0 {wait empty, fill}.  One predictable branch per tile when unset.
+__device__ unsigned long long* g_conv_probe = nullptr;
+#define PROBE_T0() const long long _t0 = probe ? clock64() : 0
+#define PROBE_ADD(slot, t0) do { if (probe) { const long long _n = clock64(); probe[slot] += (unsigned long long)(_n - (t0)); (t0) = _n; } } while (0)
+
 // SRC selects what the producers read: NHWC bf16 activations (cp.async), or -- first layer only -- the reference's
 // own input contract, planar fp32 CHW (20250113.py:114), or raw uint8 CHW depictions normalised on the fly with a
 // per-image (mean, 1/std) pair (ToTensor + per-molecule StandardScaler, Descriptors/..._preprocess_maccs_opt.py:52-67,
 // 121-124).  In both planar cases the 3 channels are packed to one 16-byte bf16 chunk per pixel in registers, so the
 // NHWC8 image never exists in HBM.
 template <int KC, int COUT, int SRC>
-__global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(const void* __restrict__ src_any,
+__global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC>::MIN_CTAS) conv3x3_umma_kernel(const void* __restrict__ src_any,
                                                                const float2* __restrict__ stats,
                                                                const uint4* __restrict__ wprep,
                                                                const float* __restrict__ bias,
                                                                const __grid_constant__ CUtensorMap tmOut, int n_img,
                                                                int H, int W) {
-  using C = Cfg<KC, COUT>;
+  using C = Cfg<KC, COUT, SRC>;
   static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
   const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_any);
   constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
+  constexpr int PROD_THREADS = C::PROD_THREADS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sOut = base;                     // 2 swizzled output tiles (1024-byte aligned) for the TMA stores
@@ -184,6 +198,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  unsigned long long* probe = (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == PROD_WARP0 || warp == MMA_WARP)) ? g_conv_probe : nullptr;
 
   if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // ===== producers: stage the halo of each tile ====================================================================
@@ -199,7 +214,9 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
         const int n = t / tiles_per_img, r = t % tiles_per_img;
         const int y0 = 2 * (r / tiles_x) * TILE_PH - 1, x0 = 2 * (r % tiles_x) * TILE_PW - 1;
         const int s = i % STAGES;
+        long long tp = probe ? clock64() : 0;
         mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        PROBE_ADD(8, tp);
         const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
         const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * PIX_B;
         int Y = Yi, j = ji;
@@ -218,11 +235,13 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
           }
         }
         cp_async_commit();
+        PROBE_ADD(9, tp);
         if (i > 0) {
           cp_async_wait<1>();  // tile i-1 of this thread has landed
           fence_proxy_async_smem();
           mbar_arrive(&full[(i - 1) % STAGES]);
         }
+        PROBE_ADD(10, tp);
       }
       if (my_tiles > 0) {
         cp_async_wait<0>();
@@ -230,10 +249,21 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
         mbar_arrive(&full[(my_tiles - 1) % STAGES]);
       }
     } else {
-      // planar source: each thread owns up to PPT halo pixels of every tile; the loads of tile i+1 are issued into a
-      // second register set before tile i is converted and stored, so two tiles of global loads are always in flight
-      constexpr int NPIX = HALO_H * HALO_W, PPT = (NPIX + PROD_THREADS - 1) / PROD_THREADS, CH = 3;
+      // planar source.  The halo row [x0, x0+18) with x0 = 16*tx - 1 is covered by six ALIGNED groups of four pixels
+      // starting at 16*tx - 4: one 128-bit (fp32) or 32-bit (uint8) load per plane fetches a whole group, and because
+      // W % 16 == 0 a group is either completely inside the image or completely outside (zero padding).  A task is
+      // (halo row Y, group g): 204 tasks per tile, TPT per thread; the loads of tile i+1 are issued into a second
+      // register set before tile i is converted and stored (loop unrolled by two, no register copies).
+      constexpr int NTASK = HALO_H * 6, TPT = (NTASK + PROD_THREADS - 1) / PROD_THREADS, CH = 3;
+      using Vec = typename std::conditional<SRC == SRC_CHW_F32, float4, uint32_t>::type;
       const int HW = H * W;
+      int tY[TPT], tG[TPT];
+#pragma unroll
+      for (int k = 0; k < TPT; ++k) {
+        const int task = ptid + k * PROD_THREADS;
+        tY[k] = task / 6;
+        tG[k] = task % 6;
+      }
       auto tile_origin = [&](int i, int& n, int& y0, int& x0) {
         const int t = blockIdx.x + i * gridDim.x;
         n = t / tiles_per_img;
@@ -241,74 +271,79 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
         y0 = 2 * (r / tiles_x) * TILE_PH - 1;
         x0 = 2 * (r % tiles_x) * TILE_PW - 1;
       };
-      auto load_tile = [&](int i, float (&v)[PPT][CH], uint32_t& okmask) {
+      auto load_tile = [&](int i, Vec (&v)[TPT][CH], uint32_t& okmask) {
         int n, y0, x0;
         tile_origin(i, n, y0, x0);
         okmask = 0;
-        int Y = Yi, X = ji;
 #pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-          const int y = y0 + Y, x = x0 + X;
-          const bool ok = (ptid + k * PROD_THREADS < NPIX) && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+        for (int k = 0; k < TPT; ++k) {
+          const int y = y0 + tY[k], x = x0 - 3 + 4 * tG[k];
+          const bool ok = (ptid + k * PROD_THREADS < NTASK) && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
           okmask |= (uint32_t)ok << k;
           const size_t off = (size_t)n * CH * HW + (ok ? y * W + x : 0);
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
-            if constexpr (SRC == SRC_CHW_F32)
-              v[k][c] = ok ? __ldg(static_cast<const float*>(src_any) + off + (size_t)c * HW) : 0.0f;
-            else
-              v[k][c] = ok ? (float)__ldg(static_cast<const uint8_t*>(src_any) + off + (size_t)c * HW) : 0.0f;
-          }
-          X += STEP_J;
-          Y += STEP_Y;
-          if (X >= ROWC) {
-            X -= ROWC;
-            ++Y;
+            if constexpr (SRC == SRC_CHW_F32) {
+              v[k][c] = ok ? __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(src_any) + off + (size_t)c * HW))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              v[k][c] = ok ? __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(src_any) + off + (size_t)c * HW))
+                           : 0u;
+            }
           }
         }
       };
-      float cur[PPT][CH], nxt[PPT][CH];
-      uint32_t cur_ok = 0, nxt_ok = 0;
-      if (my_tiles > 0) load_tile(0, cur, cur_ok);
-      for (int i = 0; i < my_tiles; ++i) {
-        if (i + 1 < my_tiles) load_tile(i + 1, nxt, nxt_ok);
+      auto store_tile = [&](int i, const Vec (&v)[TPT][CH], uint32_t okmask) {
         float scale = 1.0f, shift = 0.0f;   // (u/255 - mean) * rstd == u * scale + shift
         if constexpr (SRC == SRC_CHW_U8) {
           const float2 st = __ldg(stats + (blockIdx.x + i * gridDim.x) / tiles_per_img);
           scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
         }
         const int s = i % STAGES;
+        long long tp = probe ? clock64() : 0;
         mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        PROBE_ADD(8, tp);
         uint8_t* stage = sA + s * C::A_BYTES;
-        int Y = Yi, X = ji;
 #pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-          if (ptid + k * PROD_THREADS < NPIX) {
-            float a = cur[k][0], b = cur[k][1], c = cur[k][2];
-            if constexpr (SRC == SRC_CHW_U8) {
-              const bool ok = (cur_ok >> k) & 1;   // zero padding applies to the NORMALISED image
-              a = ok ? fmaf(a, scale, shift) : 0.0f;
-              b = ok ? fmaf(b, scale, shift) : 0.0f;
-              c = ok ? fmaf(c, scale, shift) : 0.0f;
+        for (int k = 0; k < TPT; ++k) {
+          if (ptid + k * PROD_THREADS < NTASK) {
+            const bool ok = (okmask >> k) & 1;
+            float px[4][CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              if constexpr (SRC == SRC_CHW_F32) {
+                px[0][c] = v[k][c].x, px[1][c] = v[k][c].y, px[2][c] = v[k][c].z, px[3][c] = v[k][c].w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)   // zero padding applies to the NORMALISED image
+                  px[e][c] = ok ? fmaf((float)((v[k][c] >> (8 * e)) & 255u), scale, shift) : 0.0f;
+              }
             }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, 0.0f);
-            *reinterpret_cast<uint4*>(stage + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16) =
-                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), 0u, 0u);
-          }
-          X += STEP_J;
-          Y += STEP_Y;
-          if (X >= ROWC) {
-            X -= ROWC;
-            ++Y;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int X = 4 * tG[k] + e - 3;   // halo column of this pixel; groups 0 and 5 keep one pixel each
+              if (X >= 0 && X < HALO_W) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(px[e][0], px[e][1]), h1 = __floats2bfloat162_rn(px[e][2], 0.0f);
+                *reinterpret_cast<uint4*>(stage + (X & 1) * PAR_B + tY[k] * ROW_B + (X >> 1) * 16) =
+                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), 0u, 0u);
+              }
+            }
           }
         }
         fence_proxy_async_smem();
         mbar_arrive(&full[s]);
-#pragma unroll
-        for (int k = 0; k < PPT; ++k)
-#pragma unroll
-          for (int c = 0; c < CH; ++c) cur[k][c] = nxt[k][c];
-        cur_ok = nxt_ok;
+        PROBE_ADD(10, tp);
+      };
+      Vec bufA[TPT][CH], bufB[TPT][CH];
+      uint32_t okA = 0, okB = 0;
+      if (my_tiles > 0) load_tile(0, bufA, okA);
+      for (int i = 0; i < my_tiles; i += 2) {
+        if (i + 1 < my_tiles) load_tile(i + 1, bufB, okB);
+        store_tile(i, bufA, okA);
+        if (i + 1 < my_tiles) {
+          if (i + 2 < my_tiles) load_tile(i + 2, bufA, okA);
+          store_tile(i + 1, bufB, okB);
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -317,13 +352,18 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
       const uint32_t w_lo = smem_u32(sW) >> 4;
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % STAGES, b = i & 1;
+        long long tp = probe ? clock64() : 0;
         mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
+        PROBE_ADD(0, tp);
         mbar_wait(&full[s], (i / STAGES) & 1);
+        PROBE_ADD(1, tp);
         tc_fence_after_sync();
         issue_tile<KC, COUT>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
                              std::make_integer_sequence<int, C::NISSUE>{});
         umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
         umma_commit(&acc_full[b]);   // accumulators of this tile complete
+        PROBE_ADD(2, tp);
+        if (probe) probe[3] += 1;
       }
     }
     __syncwarp();
@@ -348,9 +388,12 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
       const int n = t / tiles_per_img, r = t % tiles_per_img;
       const int b = i & 1;
       uint8_t* otile = sOut + b * C::OUT_BYTES;
+      long long tp = probe ? clock64() : 0;
       if (issuer) bulk_store_wait_read<1>();   // the store of tile i-2 has finished reading this buffer
       named_bar_sync(1, EPI_THREADS);
+      PROBE_ADD(6, tp);
       mbar_wait(&acc_full[b], (i >> 1) & 1);
+      PROBE_ADD(4, tp);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
       uint8_t* orow = otile + m * C::OUT_ROW_B;
@@ -385,12 +428,14 @@ __global__ void __launch_bounds__(Cfg<KC, COUT>::THREADS) conv3x3_umma_kernel(co
       }
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[b]);   // TMEM reads done: the MMA warp may start the tile after next
+      PROBE_ADD(5, tp);
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA (async proxy)
       named_bar_sync(2, EPI_THREADS);
       if (issuer) {
         tma_store_3d(&tmOut, otile, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
         bulk_store_commit();
       }
+      PROBE_ADD(7, tp);
     }
     if (issuer) bulk_store_wait_all();   // shared memory must outlive the last store's reads
   }
@@ -500,7 +545,7 @@ __global__ void __launch_bounds__(256) u8_image_stats_kernel(const uint8_t* __re
 template <int KC, int COUT, int SRC>
 int launch(const void* x, const float* stats, const void* wprep, const float* bias, void* y, int N, int H, int W,
            cudaStream_t stream) {
-  using C = Cfg<KC, COUT>;
+  using C = Cfg<KC, COUT, SRC>;
   static int sms = 0;
   static bool attr = false;
   if (!attr) {
@@ -610,4 +655,15 @@ extern "C" int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, co
   cudaStream_t s = as_stream(stream);
   if (img_is_u8) return conv::launch<1, 32, conv::SRC_CHW_U8>(img_chw, stats, wprep, bias, y_nhwc, N, H, W, s);
   return conv::launch<1, 32, conv::SRC_CHW_F32>(img_chw, nullptr, wprep, bias, y_nhwc, N, H, W, s);
+}
+
+// debug: probe = device array of 16 uint64 counters (zero it first), or NULL to switch the probe off
+extern "C" int bbbp_debug_conv_probe(void* probe) {
+  unsigned long long* p = static_cast<unsigned long long*>(probe);
+  cudaError_t e = cudaMemcpyToSymbol(conv::g_conv_probe, &p, sizeof(p));
+  if (e != cudaSuccess) {
+    set_error("debug_conv_probe: %s", cudaGetErrorString(e));
+    return BBBP_ECUDA;
+  }
+  return BBBP_OK;
 }

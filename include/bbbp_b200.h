@@ -129,6 +129,9 @@ int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* 
                                const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream);
 /* stats[r] = {mean, 1/std} of img[r, 0:n] / 255 (population std, 0 -> 1), exact integer sums, fp64 finish */
 int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, bbbp_stream_t stream);
+/* Diagnostics: probe = DEVICE array of 16 uint64 cycle counters that CTA 0 of the tcgen05 conv kernels accumulates
+ * per pipeline role (see conv_umma.cu), or NULL to switch the probe off (default). */
+int bbbp_debug_conv_probe(void* probe);
 /* fp32 NCHW image with C <= 8 planes (the reference's (B,3*128*128) input viewed as (B,3,128,128), 20250113.py:114)
  * -> bf16 NHWC with 8 channels per pixel, channels >= C zero */
 int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W, bbbp_stream_t stream);
