@@ -415,6 +415,50 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
   }
 }
 
+// Row softmax of fp32 logits -> bf16 probabilities for attention scopes wider than one CTA tile (S > 256):
+// p[r, c] = softmax_c(scale * s[r, c]); one block per row, three passes (max, sum, write) of 128-bit loads.
+__global__ void __launch_bounds__(256) softmax_rows_scaled_bf16_kernel(const float* __restrict__ s, size_t ld_s,
+                                                                       __nv_bfloat16* __restrict__ p, size_t ld_p, int cols,
+                                                                       float scale) {
+  __shared__ float red[8];
+  const float* row = s + (size_t)blockIdx.x * ld_s;
+  __nv_bfloat16* out = p + (size_t)blockIdx.x * ld_p;
+  const int n4 = cols / 4;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(row)[i];
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < cols; i += 256) mx = fmaxf(mx, row[i]);
+  mx = warp_max(mx);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  const float sl2 = scale * 1.4426950408889634f, off = mx * sl2;
+  float sum = 0.0f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(row)[i];
+    sum += exp2f(fmaf(v.x, sl2, -off)) + exp2f(fmaf(v.y, sl2, -off)) + exp2f(fmaf(v.z, sl2, -off)) + exp2f(fmaf(v.w, sl2, -off));
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < cols; i += 256) sum += exp2f(fmaf(row[i], sl2, -off));
+  sum = warp_sum(sum);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < (int)ld_p / 2; i += 256) {   // ld_p is a multiple of 8: bf16 pairs, zeros in the pad
+    const int c = 2 * i;
+    const float a = c < cols ? exp2f(fmaf(row[c], sl2, -off)) * inv : 0.0f;
+    const float b = c + 1 < cols ? exp2f(fmaf(row[c + 1], sl2, -off)) * inv : 0.0f;
+    reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
+  }
+}
+
 }  // namespace gemm
 }  // namespace bbbp
 
@@ -531,4 +575,18 @@ extern "C" int bbbp_transpose_bf16(int batches, int rows, int cols, const void* 
       static_cast<const __nv_bfloat16*>(src), ld_src, src_batch_stride, static_cast<__nv_bfloat16*>(dst), ld_dst,
       dst_batch_stride, rows, cols);
   return launch_status("transpose_bf16");
+}
+
+extern "C" int bbbp_softmax_rows_scaled_bf16(const float* scores, long long ld_scores, void* p_bf16, long long ld_p,
+                                             long long rows, int cols, float scale, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(scores && p_bf16 && rows >= 0 && cols > 0, "softmax_rows_scaled: bad argument");
+  BBBP_CHECK_ARG(ld_scores >= cols && ld_scores % 4 == 0 && ((uintptr_t)scores % 16) == 0,
+                 "softmax_rows_scaled: ld_scores must be >= cols and a multiple of 4, base 16-byte aligned");
+  BBBP_CHECK_ARG(ld_p >= cols && ld_p % 8 == 0, "softmax_rows_scaled: ld_p must be >= cols and a multiple of 8");
+  BBBP_CHECK_ARG(rows <= 0x7fffffffLL, "softmax_rows_scaled: too many rows");
+  if (rows == 0) return BBBP_OK;
+  gemm::softmax_rows_scaled_bf16_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+      scores, (size_t)ld_scores, static_cast<__nv_bfloat16*>(p_bf16), (size_t)ld_p, cols, scale);
+  return launch_status("softmax_rows_scaled_bf16");
 }

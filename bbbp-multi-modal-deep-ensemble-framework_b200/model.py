@@ -206,7 +206,7 @@ class TransformerCnnModel(_KernelModule):
     # -- encoder, inference fast path: every contraction on tcgen05, activations stay bf16 between GEMMs -----------------
     def _encoder_tensor_core_ok(self, seq: int) -> bool:
         attn = self.fingerprint_transformer.layers[0].self_attn
-        return (self.precision == "bf16" and not self.training and attn.num_heads == 1 and seq <= 256
+        return (self.precision == "bf16" and not self.training and attn.num_heads == 1
                 and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.fingerprint_transformer.parameters())))
 
     def _encoder_tensor_core(self, x, groups: int, seq: int):

@@ -151,18 +151,37 @@ def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, 
     return o32, o16
 
 
-def gemm_bf16_batched(batches, M, N, K, a16, lda, a_bs, w16, ldw, w_bs, out_bf16=True, out_f32=False, ld_out16=None):
+def gemm_bf16_batched(batches, M, N, K, a16, lda, a_bs, w16, ldw, w_bs, out_bf16=True, out_f32=False, ld_out16=None,
+                      ld_out=None):
     """out[b] = A[b] @ W[b]^T for b < batches; outputs are (batches*M, ld) with batch b at rows [b*M, (b+1)*M)."""
     ld16 = -(-N // 8) * 8 if ld_out16 is None else ld_out16
-    o32 = torch.empty((batches * M, N), device=a16.device, dtype=torch.float32) if out_f32 else None
+    ld32 = N if ld_out is None else ld_out
+    o32 = torch.empty((batches * M, ld32), device=a16.device, dtype=torch.float32) if out_f32 else None
     o16 = torch.empty((batches * M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
-    check(lib.bbbp_gemm_bf16_batched(batches, M, N, K, a16.data_ptr(), lda, a_bs, w16.data_ptr(), ldw, w_bs, _ptr(o32), N,
-                                     M * N, _ptr(o16), ld16, M * ld16, _stream()), "gemm_bf16_batched")
+    check(lib.bbbp_gemm_bf16_batched(batches, M, N, K, a16.data_ptr(), lda, a_bs, w16.data_ptr(), ldw, w_bs, _ptr(o32), ld32,
+                                     M * ld32, _ptr(o16), ld16, M * ld16, _stream()), "gemm_bf16_batched")
     return o32, o16
 
 
+def softmax_rows_scaled_bf16(scores: torch.Tensor, cols: int, scale: float) -> torch.Tensor:
+    """(rows, ld) fp32 logits -> (rows, ceil8(cols)) bf16 softmax(scale * logits) with zero pad columns."""
+    rows = scores.shape[0]
+    ldp = -(-cols // 8) * 8
+    p = torch.empty((rows, ldp), device=scores.device, dtype=torch.bfloat16)
+    check(lib.bbbp_softmax_rows_scaled_bf16(scores.data_ptr(), scores.stride(0), p.data_ptr(), ldp, rows, cols, float(scale),
+                                            _stream()), "softmax_rows_scaled_bf16")
+    return p
+
+
 def attention_scores_softmax_bf16(q16, k16, ld, groups, seq, head_dim, scale):
-    """softmax(scale * Q K^T) per group as bf16 (groups*seq, ldp); q16 / k16 are views into the packed qkv buffer."""
+    """softmax(scale * Q K^T) per group as bf16 (groups*seq, ldp); q16 / k16 are views into the packed qkv buffer.
+    seq <= 256: one GEMM with the softmax in its TMEM epilogue.  Wider scopes: batched GEMM to fp32 logits, then a
+    row-softmax kernel (the S x S logits are materialised: 4*S*S bytes per group)."""
+    if seq > 256:
+        ld_s = -(-seq // 4) * 4
+        s32, _ = gemm_bf16_batched(groups, seq, seq, head_dim, q16, ld, seq * ld, k16, ld, seq * ld, out_bf16=False,
+                                   out_f32=True, ld_out=ld_s)
+        return softmax_rows_scaled_bf16(s32, seq, scale)
     ldp = -(-seq // 8) * 8
     p = torch.empty((groups * seq, ldp), device=q16.device, dtype=torch.bfloat16)
     t0 = KERNEL_TIMER.start("attn_scores")

@@ -90,6 +90,10 @@ int bbbp_gemm_bf16_batched(int batches, int M, int N, int K, const void* A_bf16,
 int bbbp_attention_scores_softmax_bf16(int groups, int seq, int head_dim, const void* q_bf16, int ldq, const void* k_bf16,
                                        int ldk, long long group_stride, float scale, void* p_bf16, int ldp,
                                        bbbp_stream_t stream);
+/* Wide attention scopes (seq > 256): p[r, 0:cols) = softmax(scale * scores[r, 0:cols)) as bf16, pad columns zero.
+ * scores come from bbbp_gemm_bf16_batched (fp32 out); one block per row. */
+int bbbp_softmax_rows_scaled_bf16(const float* scores, long long ld_scores, void* p_bf16, long long ld_p, long long rows,
+                                  int cols, float scale, bbbp_stream_t stream);
 /* dst[b][c][r] = src[b][r][c] (bf16); rows r in [rows, ld_dst) of dst are zero filled */
 int bbbp_transpose_bf16(int batches, int rows, int cols, const void* src, int ld_src, long long src_batch_stride, void* dst,
                         int ld_dst, long long dst_batch_stride, bbbp_stream_t stream);

@@ -392,7 +392,8 @@ def test_fc_weight_relayout_is_exact(ops):
 
 
 # ---- tensor-core attention pieces: (QK^T + row softmax) epilogue, V transpose, batched P V -------------------------------
-@pytest.mark.parametrize("groups,seq,d", [(1, 256, 167), (3, 67, 167), (2, 1, 167), (5, 32, 64), (1, 200, 8)])
+@pytest.mark.parametrize("groups,seq,d", [(1, 256, 167), (3, 67, 167), (2, 1, 167), (5, 32, 64), (1, 200, 8), (2, 300, 167),
+                                          (1, 1030, 167)])
 def test_attention_tcgen05_pipeline(ops, groups, seq, d):
     dq = -(-d // 8) * 8
     rows = groups * seq

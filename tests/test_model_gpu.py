@@ -358,3 +358,18 @@ def test_predict_from_host_overlapped_pipeline(cuda_device):
     got = ours.predict_from_host(packed, img8, bs, chunk_molecules=96, packed=True)
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+
+
+def test_bf16_mode_with_attention_scope_wider_than_one_tile(cuda_device):
+    """B = 600 molecules in ONE reference batch (S = 600 > 256): logits are materialised, softmaxed row-wise and fed
+    to the batched P V GEMM -- still all tensor-core contractions."""
+    ref, ours = make_pair("tcnn", 167, 128, 5, cuda_device)
+    ref.eval(), ours.eval()
+    fp, img, _ = seeded_inputs(21, 600, 167, IMG)
+    with torch.no_grad():
+        want = ref(fp, img)
+        got32 = ours(fp.cuda(), img.cuda()).cpu()
+        ours.set_precision("bf16")
+        got16 = ours(fp.cuda(), img.cuda()).cpu()
+    assert float((got32 - want).abs().max()) <= 1e-3
+    assert float((got16 - want).abs().max()) <= BF16_TOL
