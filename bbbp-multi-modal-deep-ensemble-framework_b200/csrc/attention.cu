@@ -280,6 +280,57 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dkv_kernel(const
   }
 }
 
+// Many small heads (Morgan / RDKit-2048: 256 heads of dimension 8, 20250113.py:71-73): one block per (group, head),
+// one thread per query.  K and V of the head (seq x D each) live in shared memory and every thread walks all keys with
+// its query row in registers: score reads are warp broadcasts, no cross-lane traffic, exact two-pass softmax.
+template <int D>
+__global__ void __launch_bounds__(256) attention_small_head_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                       float* __restrict__ lse, int seq, int heads) {
+  extern __shared__ float smem[];
+  float* Ks = smem;
+  float* Vs = smem + (size_t)seq * D;
+  const int h = blockIdx.x, g = blockIdx.y;
+  const int E = heads * D, ldq = 3 * E;
+  const size_t row0 = (size_t)g * seq;
+  for (int i = threadIdx.x; i < seq * D; i += blockDim.x) {
+    const int j = i / D, dd = i % D;
+    const float* src = qkv + (row0 + j) * ldq + h * D + dd;
+    Ks[i] = src[E];
+    Vs[i] = src[2 * E];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)D);
+  for (int qi = threadIdx.x; qi < seq; qi += blockDim.x) {
+    float q[D], o[D];
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) {
+      q[dd] = qkv[(row0 + qi) * ldq + h * D + dd] * scale;
+      o[dd] = 0.0f;
+    }
+    float m = -INFINITY;
+    for (int j = 0; j < seq; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) s = fmaf(q[dd], Ks[j * D + dd], s);
+      m = fmaxf(m, s);
+    }
+    float l = 0.0f;
+    for (int j = 0; j < seq; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) s = fmaf(q[dd], Ks[j * D + dd], s);
+      const float p = __expf(s - m);
+      l += p;
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) o[dd] = fmaf(p, Vs[j * D + dd], o[dd]);
+    }
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) out[(row0 + qi) * E + h * D + dd] = o[dd] * inv;
+    if (lse) lse[(row0 + qi) * heads + h] = m + __logf(l);
+  }
+}
+
 static int attention_args_ok(const char* who, int groups, int seq, int heads, int d) {
   if (groups < 0 || seq <= 0 || heads <= 0 || d <= 0 || d > 32 * MAX_DT) {
     set_error("%s: groups=%d seq=%d heads=%d head_dim=%d unsupported (head_dim <= %d)", who, groups, seq, heads, d,
@@ -302,6 +353,19 @@ extern "C" int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, 
   BBBP_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f, "attention_fwd: dropout_p must be in [0,1)");
   if (!attention_args_ok("attention_fwd", groups, seq, heads, head_dim)) return BBBP_EINVAL;
   if (groups == 0) return BBBP_OK;
+  if (dropout_p == 0.0f && (head_dim == 8 || head_dim == 16) && (size_t)seq * head_dim * 8 <= 160 * 1024) {
+    const size_t sm = (size_t)seq * head_dim * 2 * sizeof(float);
+    const int threads = seq >= 256 ? 256 : (seq + 31) / 32 * 32;
+    dim3 grid(heads, groups);
+    if (head_dim == 8) {
+      cudaFuncSetAttribute(attention_small_head_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      attention_small_head_fwd_kernel<8><<<grid, threads, sm, as_stream(stream)>>>(qkv, out, lse, seq, heads);
+    } else {
+      cudaFuncSetAttribute(attention_small_head_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      attention_small_head_fwd_kernel<16><<<grid, threads, sm, as_stream(stream)>>>(qkv, out, lse, seq, heads);
+    }
+    return launch_status("attention_fwd (small heads)");
+  }
   const int ld = head_dim | 1;
   const int qpb = 16;
   size_t smem = (size_t)(2 * KT + ATT_WARPS) * ld * sizeof(float);
