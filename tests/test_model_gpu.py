@@ -373,3 +373,44 @@ def test_bf16_mode_with_attention_scope_wider_than_one_tile(cuda_device):
         got16 = ours(fp.cuda(), img.cuda()).cpu()
     assert float((got32 - want).abs().max()) <= 1e-3
     assert float((got16 - want).abs().max()) <= BF16_TOL
+
+
+def test_bf16_mode_dataset_level_error(cuda_device):
+    """BASELINE configs[0] shape in tensor-core mode: 1 058 molecules, batch 256.  Stated bf16 tolerance is 2e-2; on
+    this seeded set the observed maximum is 3.6e-4, so the fp32/TF32 bound of north_star (1e-3) holds as well."""
+    ref, ours = make_pair("tcnn", 167, 128, 0, cuda_device)
+    ref.eval(), ours.eval().set_precision("bf16")
+    n, bs = 1058, 256
+    g = torch.Generator().manual_seed(5)
+    bits = (torch.rand(n, 167, generator=g) < 0.25).float()
+    bits[:, 0] = 0
+    fp = (bits - bits.mean(1, keepdim=True)) / bits.std(1, unbiased=False, keepdim=True)
+    img = torch.randn(n, IMG, generator=g)
+    with torch.no_grad():
+        want = torch.cat([ref(fp[i:i + bs], img[i:i + bs]).reshape(-1) for i in range(0, n, bs)])
+        got = ours.predict_batches(fp.cuda(), img.cuda(), bs).cpu()
+    assert float((got - want).abs().max()) <= 1e-3
+
+
+def test_mixed_precision_training_tracks_fp32(cuda_device):
+    """BASELINE configs[1]: fwd + bwd + AdamW with tensor-core (bf16-operand) linear layers in the forward pass versus
+    the all-fp32 run, same data and initial weights: the loss trajectories must agree to 1 % over 6 steps."""
+    import bbbp_b200
+    losses = {}
+    for prec in ("fp32", "bf16"):
+        _, model = make_pair("tcnn", 167, 128, 2, cuda_device)
+        nets.zero_dropout(model)
+        model.train().set_precision(prec)
+        opt = bbbp_b200.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+        crit = bbbp_b200.MSELoss()
+        out = []
+        for step in range(6):
+            fp, img, y = seeded_inputs(700 + step, 32, 167, IMG)
+            opt.zero_grad()
+            loss = crit(model(fp.cuda(), img.cuda()).squeeze(), y.cuda())
+            loss.backward()
+            opt.step()
+            out.append(float(loss.detach()))
+        losses[prec] = out
+    np.testing.assert_allclose(losses["bf16"], losses["fp32"], rtol=1e-2)
+    assert losses["fp32"][-1] < losses["fp32"][0] * 1.5      # sanity: finite, not diverging
