@@ -38,12 +38,13 @@ constexpr int ROW_B = XH * 16;                 // 144 bytes per (parity, y) row
 // (x parity alternates, then the 8-channel chunk index) land in eight different 16-byte bank groups
 constexpr int PAR_B = HALO_H * ROW_B + 32;     // 4928 = 64 (mod 128)
 constexpr int KC_B = 2 * PAR_B + 16;           // 9872 = 16 (mod 128) bytes per 8-channel chunk plane
-constexpr int STAGES = 3;
 
 template <int KC, int COUT, int SRC = 0>
 struct Cfg {
   // conv2's epilogue (64 channels) gets two warps per TMEM lane quadrant; conv1's (32 channels) one, which also keeps
   // its CTA small enough for two CTAs per SM
+  static constexpr bool PACK4 = SRC != 0;
+  static constexpr int STAGES = 3;                      // halo ring depth
   static constexpr int EPI_WARPS = COUT >= 64 ? 8 : 4;
   // the producers are latency-bound (global loads / cp.async behind a shared-memory pipe the tensor core keeps busy):
   // eight warps halve the per-thread chunk count
@@ -52,13 +53,20 @@ struct Cfg {
   static constexpr int PROD_WARPS = KC == 1 ? 4 : 8, PROD_THREADS = PROD_WARPS * 32;
   static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 32;
   static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS;
+  // the first layer runs two small CTAs per SM (measured: one CTA with 8 + 8 + 1 warps and a 6-deep ring is slower,
+  // 1.65 ms vs 1.42 ms per 8 192 images)
   static constexpr int MIN_CTAS = KC == 1 ? 2 : 1;
   static constexpr int A_BYTES = KC * KC_B;
   static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // K=16 steps per window member
   // instructions per tile: conv1 issues one N=COUT MMA per (member, step); conv2 pairs the two members of a pooling
   // row that read the SAME halo view (dx=0 with tap kw+1, dx=1 with tap kw) into one N=2*COUT MMA: 24 per K-chunk pair
-  static constexpr int NISSUE = KC == 1 ? 4 * NMMA : 24 * (KC / 2);
-  static constexpr int W_BYTES = KC == 1 ? 2 * 5 * 2 * COUT * 16 : 9 * KC * COUT * 16;
+  // PACK4 (planar first-layer sources): 4 channels (8 bytes) per pixel, two pixels per 16-byte chunk, so one K=16 MMA
+  // covers a whole kernel ROW (kw = 0..2 and a zero-weight dummy): 3 MMAs per window member instead of 5, i.e. 40 %
+  // fewer shared-memory operand wavefronts on the first layer, which is bound by exactly those.
+  static constexpr int NISSUE = PACK4 ? 12 : KC == 1 ? 4 * NMMA : 24 * (KC / 2);
+  static constexpr int W8_BYTES = 2 * 5 * 2 * COUT * 16;                  // conv1 weight image for the NHWC8 source
+  static constexpr int W_BYTES = PACK4 ? 3 * 2 * COUT * 16 : KC == 1 ? W8_BYTES : 9 * KC * COUT * 16;
+  static constexpr int W_OFFSET = PACK4 ? W8_BYTES : 0;                   // the prepared blob holds both conv1 images
   static constexpr int ACC_COLS = 4 * COUT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -90,11 +98,20 @@ struct MmaOp {
 // Operands of the I-th MMA of a tile: byte offsets into the staged halo / the shared-memory weight image, the
 // accumulator column, the instruction's N and its accumulate flag.  constexpr: the issue loop is fully unrolled and
 // every descriptor is an immediate.
-template <int KC, int COUT>
+template <int KC, int COUT, bool PACK4>
 __host__ __device__ constexpr MmaOp mma_op(int I) {
+  if (PACK4) {
+    // member q = 2*dy + dx reads copy dx of the halo (chunk j = pixels 2j+dx, 2j+dx+1); kernel row kh is one MMA:
+    // K chunk 0 = pixels (X, X+1), chunk 1 = (X+2, X+3) with X = 2*pw + dx, i.e. kw = 0..3 (kw = 3 has zero weights)
+    // issue order: kernel row outermost, the four members innermost -- consecutive MMAs then accumulate into DIFFERENT
+    // TMEM accumulators and pipeline in the tensor core instead of serialising on the accumulator dependency
+    const int q = I % 4, kh = I / 4, dy = q >> 1, dx = q & 1;
+    return MmaOp{(uint32_t)(dx * PAR_B + (dy + kh) * ROW_B), 16u, (uint32_t)(kh * (2 * COUT * 16)), (uint32_t)(COUT * 16),
+                 (uint32_t)(q * COUT), (uint32_t)COUT, (uint32_t)(kh != 0)};
+  }
   if (KC == 1) {
     // conv1: member q = 2*dy + dx, step m covers the tap pair (2m, 2m+1) through the leading byte offset
-    const int q = I / 5, m = I % 5, dy = q >> 1, dx = q & 1;
+    const int q = I % 4, m = I / 4, dy = q >> 1, dx = q & 1;   // members innermost (independent accumulators back to back)
     const TapPair p = conv1_pair(dx, m);
     const int oa = halo_offset(dy, dx, p.first), ob = halo_offset(dy, dx, p.second);
     return MmaOp{(uint32_t)oa, (uint32_t)(ob - oa), (uint32_t)((dx * 5 + m) * (2 * COUT * 16)), (uint32_t)(COUT * 16),
@@ -104,7 +121,9 @@ __host__ __device__ constexpr MmaOp mma_op(int I) {
   // sx = 1, 2: both members of the row use this view (dx=0 with kw=sx, dx=1 with kw=sx-1): one N = 2*COUT MMA whose
   // B rows are the two taps' weights, adjacent in the [kc][8 - tap][cout] weight image.  sx = 0 / 3: one member only.
   // The first view of every row is a paired one with accumulate = 0, so it initialises both accumulators.
-  const int j = I / 24, rem = I % 24, dy = rem / 12, e = rem % 12;
+  // issue order: K-chunk pair, view, then the pooling row innermost, so back-to-back MMAs alternate between the two
+  // rows' accumulators (independent) instead of chaining on one accumulator
+  const int j = I / 24, rem = I % 24, dy = rem % 2, e = rem / 2;
   const int kh = e < 4 ? 0 : (e - 4) / 4 + 1;
   const int order0[4] = {1, 2, 0, 3};
   const int sx = e < 4 ? order0[e] : (e - 4) % 4;
@@ -118,9 +137,9 @@ __host__ __device__ constexpr MmaOp mma_op(int I) {
 }
 
 // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46) | no swizzle
-template <int KC, int COUT, int I>
+template <int KC, int COUT, bool PACK4, int I>
 __device__ __forceinline__ void issue_one(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc) {
-  constexpr MmaOp op = mma_op<KC, COUT>(I);
+  constexpr MmaOp op = mma_op<KC, COUT, PACK4>(I);
   constexpr uint32_t a_lo_c = (op.a_off >> 4) | ((op.a_lbo >> 4) << 16);
   constexpr uint32_t b_lo_c = (op.b_off >> 4) | ((op.b_lbo >> 4) << 16);
   constexpr uint64_t a_hi = (uint64_t)(((2 * ROW_B) >> 4) | (1u << 14)) << 32;
@@ -128,10 +147,10 @@ __device__ __forceinline__ void issue_one(uint32_t a_lo, uint32_t w_lo, uint32_t
   constexpr uint32_t idesc = make_idesc_bf16(128, op.n);
   umma_bf16(tmem_acc + op.d_col, a_hi | (a_lo + a_lo_c), b_hi | (w_lo + b_lo_c), idesc, op.accumulate != 0);
 }
-template <int KC, int COUT, int... I>
+template <int KC, int COUT, bool PACK4, int... I>
 __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc,
                                            std::integer_sequence<int, I...>) {
-  (issue_one<KC, COUT, I>(a_lo, w_lo, tmem_acc), ...);
+  (issue_one<KC, COUT, PACK4, I>(a_lo, w_lo, tmem_acc), ...);
 }
 
 enum { SRC_NHWC_BF16 = 0, SRC_CHW_F32 = 1, SRC_CHW_U8 = 2 };
@@ -159,7 +178,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
   static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
   const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_any);
   constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
-  constexpr int PROD_THREADS = C::PROD_THREADS;
+  constexpr int PROD_THREADS = C::PROD_THREADS, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sOut = base;                     // 2 swizzled output tiles (1024-byte aligned) for the TMA stores
@@ -179,7 +198,9 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // ---- one-time setup: weights + bias to smem, barriers, TMEM -----------------------------------------------------
-  for (int i = threadIdx.x; i < C::W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wprep[i];
+  for (int i = threadIdx.x; i < C::W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wprep[C::W_OFFSET / 16 + i];
+  if constexpr (C::PACK4)   // pixel 18 of copy 1 is read under zero weights and never written: keep it finite
+    for (int i = threadIdx.x; i < STAGES * C::A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < COUT; i += THREADS) sBias[i] = bias[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -324,8 +345,11 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
               const int X = 4 * tG[k] + e - 3;   // halo column of this pixel; groups 0 and 5 keep one pixel each
               if (X >= 0 && X < HALO_W) {
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(px[e][0], px[e][1]), h1 = __floats2bfloat162_rn(px[e][2], 0.0f);
-                *reinterpret_cast<uint4*>(stage + (X & 1) * PAR_B + tY[k] * ROW_B + (X >> 1) * 16) =
-                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), 0u, 0u);
+                const uint2 pix = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                uint8_t* row = stage + tY[k] * ROW_B;
+                // copy 0: chunk j = pixels (2j, 2j+1); copy 1: chunk j = pixels (2j+1, 2j+2)
+                *reinterpret_cast<uint2*>(row + X * 8) = pix;
+                if (X >= 1) *reinterpret_cast<uint2*>(row + PAR_B + (X - 1) * 8) = pix;
               }
             }
           }
@@ -348,25 +372,27 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer ==================================================================================================
-    if (lane == 0) {
-      const uint32_t w_lo = smem_u32(sW) >> 4;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int s = i % STAGES, b = i & 1;
-        long long tp = probe ? clock64() : 0;
-        mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
-        PROBE_ADD(0, tp);
-        mbar_wait(&full[s], (i / STAGES) & 1);
-        PROBE_ADD(1, tp);
-        tc_fence_after_sync();
-        issue_tile<KC, COUT>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
-                             std::make_integer_sequence<int, C::NISSUE>{});
+    // The whole warp runs this loop (warp-uniform control flow, descriptor arithmetic on the uniform datapath); one
+    // elected lane issues the MMAs and the commits.
+    const uint32_t w_lo = smem_u32(sW) >> 4;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % STAGES, b = i & 1;
+      long long tp = probe ? clock64() : 0;
+      mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
+      PROBE_ADD(0, tp);
+      mbar_wait(&full[s], (i / STAGES) & 1);
+      PROBE_ADD(1, tp);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
+        issue_tile<KC, COUT, C::PACK4>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+                                       std::make_integer_sequence<int, C::NISSUE>{});
         umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
         umma_commit(&acc_full[b]);   // accumulators of this tile complete
-        PROBE_ADD(2, tp);
-        if (probe) probe[3] += 1;
       }
+      __syncwarp();
+      PROBE_ADD(2, tp);
+      if (probe) probe[3] += 1;
     }
-    __syncwarp();
   } else {
     // ===== epilogue: max over the pooling window, + bias, ReLU, bf16, NHWC store ==========================================
     // 8 warps: warp % 4 is the TMEM lane quadrant it may read (32 pooled pixels), warp / 4 the half of the channels.
@@ -466,6 +492,14 @@ __global__ void prep_weights_c8_kernel(const float* __restrict__ w, __nv_bfloat1
   const int tap = chunk == 0 ? tp.first : tp.second;
   const bool zero = chunk == tp.zero_slot || c >= Cin;
   wp[i] = __float2bfloat16(zero ? 0.0f : w[((size_t)n * Cin + c) * 9 + tap]);
+}
+// PACK4 image (planar sources): wp[kh][chunk][n][8], K index k = chunk*8 + e = kw*4 + c, zero for kw = 3 or c >= Cin
+__global__ void prep_weights_pack4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * 2 * Cout * 8) return;
+  const int e = i % 8, n = (i / 8) % Cout, chunk = (i / (8 * Cout)) % 2, kh = i / (16 * Cout);
+  const int k = chunk * 8 + e, kw = k / 4, c = k % 4;
+  wp[i] = __float2bfloat16((kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f);
 }
 // fp32 NCHW image (C <= 8 planes) -> bf16 NHWC with 8 channels per pixel (zero padded): one 16-byte store per pixel
 __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ img, uint4* __restrict__ out,
@@ -574,7 +608,7 @@ int launch(const void* x, const float* stats, const void* wprep, const float* bi
     }
   }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
-  const int per_sm = (C::TMEM_COLS <= 256 && C::SMEM_BYTES <= 100 * 1024) ? 2 : 1;
+  const int per_sm = C::MIN_CTAS;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
   conv3x3_umma_kernel<KC, COUT, SRC><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
       x, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, tmOut, N, H, W);
@@ -587,7 +621,7 @@ int launch(const void* x, const float* stats, const void* wprep, const float* bi
 using namespace bbbp;
 
 extern "C" size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout) {
-  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16;
+  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)3 * 2 * Cout * 16;   // NHWC8 image | PACK4 image
   return (size_t)9 * (Cin / 8) * Cout * 16;
 }
 
@@ -596,10 +630,14 @@ extern "C" int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, i
   BBBP_CHECK_ARG((Cin == 3 && Cout == 32) || (Cin == 32 && Cout == 64),
                  "conv3x3_prepare: only (3->32) and (32->64) are built for the tcgen05 path, got %d->%d", Cin, Cout);
   const int total = (int)(bbbp_conv3x3_prepared_bytes(Cin, Cout) / 2);
-  if (Cin <= 8)
-    conv::prep_weights_c8_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
-        w, static_cast<__nv_bfloat16*>(wprep), Cin, Cout);
-  else
+  if (Cin <= 8) {
+    const int n8 = 2 * 5 * 2 * Cout * 8, n4 = 3 * 2 * Cout * 8;
+    conv::prep_weights_c8_kernel<<<ceil_div(n8, 256), 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wprep),
+                                                                                 Cin, Cout);
+    conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(wprep) + n8, Cin, Cout);
+    note_launches(1);
+  } else
     conv::prep_weights_kc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
         w, static_cast<__nv_bfloat16*>(wprep), Cin, Cout);
   return launch_status("conv3x3_prepare");

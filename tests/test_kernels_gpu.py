@@ -438,7 +438,8 @@ def test_conv1_tcgen05_from_planar_fp32(ops, N):
     wp = ops.conv3x3_prepare_bf16(w.cuda())
     y = ops.conv1_from_image_bf16(img.cuda(), wp, b.cuda())
     via_nhwc8 = ops.conv3x3_relu_pool_bf16(ops.image_to_nhwc8_bf16(img.cuda()), wp, b.cuda(), 32)
-    assert torch.equal(y, via_nhwc8), "the fused producer must stage exactly what the NHWC8 pre-pass stages"
+    # same operands, different K grouping (4 channels x 4 taps per MMA instead of 8 channels x 2 taps): bf16-rounding level
+    close(y, via_nhwc8.float(), atol=2e-3, rtol=1e-2, what="planar vs NHWC8 first layer")
     close(y, _conv_ref_bf16(img, w, b).permute(0, 2, 3, 1), atol=2e-3, rtol=1e-2, what="conv1 from fp32 planes")
 
 
