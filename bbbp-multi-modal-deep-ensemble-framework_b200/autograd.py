@@ -74,7 +74,6 @@ class Linear(Function):
             y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=ops.fixed_split_k_f32(K))
         ctx.act = act
         ctx.has_bias = bias is not None
-        ctx.precision = precision
         ctx.save_for_backward(x, weight, y if act else None)
         return y
 
@@ -86,23 +85,6 @@ class Linear(Function):
         M, K = x.shape
         N = weight.shape[0]
         dx = dw = db = None
-        if ctx.precision == "bf16" and M >= 8:
-            # mixed-precision training: both gradient contractions on the tensor cores (bf16 operands, fp32 accumulate)
-            #   dx[M,K] = dpre[M,N] . W[N,K]      -> A = dpre (K-major in N), W operand = W^T [K, N]
-            #   dW[N,K] = dpre^T[N,M] . x[M,K]    -> A = dpre^T [N, M],       W operand = x^T [K, M]
-            d16 = ops.cast_bf16(dpre)
-            if ctx.needs_input_grad[0]:
-                wt16 = derived_weight(weight, "bf16_T", lambda w: ops.transpose_bf16(
-                    ops.cast_bf16(w.reshape(w.shape[0], -1)), 1, N, K, -(-K // 8) * 8, 0, -(-N // 8) * 8)[0])
-                dx, _ = ops.gemm_bf16(d16, N, wt16, K, split_k=1)
-            if ctx.needs_input_grad[1]:
-                ldm = -(-M // 8) * 8
-                d16t = ops.transpose_bf16(d16, 1, M, N, d16.stride(0), 0, ldm)[0]
-                x16t = ops.transpose_bf16(ops.cast_bf16(x), 1, M, K, -(-K // 8) * 8, 0, ldm)[0]
-                dw, _ = ops.gemm_bf16(d16t, M, x16t, K, split_k=1)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = ops.colsum(dpre)
-            return dx, dw, db, None, None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm_f32(dpre, weight, split_k=ops.tile_split_k(M, K, N, x.device))
         if ctx.needs_input_grad[1]:

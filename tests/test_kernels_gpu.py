@@ -461,23 +461,3 @@ def test_conv1_tcgen05_from_uint8_with_stats(ops, N):
     y = ops.conv1_from_image_bf16(dev, ops.conv3x3_prepare_bf16(w.cuda()), b.cuda(), stats)
     z = torch.from_numpy(preprocess.u8_image_zscore(img)).view(N, 3, 128, 128)      # the reference's preprocessing
     close(y, _conv_ref_bf16(z, w, b).permute(0, 2, 3, 1), atol=2e-2, rtol=2e-2, what="conv1 from uint8")
-
-
-def test_linear_backward_on_tensor_cores(cuda_device):
-    """Mixed-precision training: dX and dW of a Linear through the tcgen05 GEMM (bf16 operands) vs autograd in fp64."""
-    from bbbp_b200 import autograd as ag
-    for (M, K, N, act) in [(32, 167, 2048, "relu"), (32, 65536, 128, "relu"), (256, 2048, 167, None), (9, 256, 1, None)]:
-        x = rnd(M, K, seed=130).requires_grad_()
-        w = rnd(N, K, seed=131, scale=1 / math.sqrt(K)).requires_grad_()
-        b = rnd(N, seed=132, scale=0.1).requires_grad_()
-        ref = F.linear(x.double(), w.double(), b.double())
-        ref = torch.relu(ref) if act else ref
-        dy = rnd(M, N, seed=133)
-        ref.backward(dy.double())
-        xc, wc, bc = (t.detach().cuda().requires_grad_() for t in (x, w, b))
-        y = ag.linear(xc, wc, bc, act, "bf16")
-        y.backward(dy.cuda())
-        for name, got, want in [("dx", xc.grad, x.grad), ("dw", wc.grad, w.grad), ("db", bc.grad, b.grad)]:
-            scale = float(want.abs().max()) + 1e-6
-            err = float((got.cpu() - want).abs().max())
-            assert err <= 2e-2 * scale, f"{name} {M}x{K}x{N}: {err} vs scale {scale}"
