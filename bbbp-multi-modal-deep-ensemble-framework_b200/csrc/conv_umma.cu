@@ -50,7 +50,7 @@ struct Cfg {
   // eight warps halve the per-thread chunk count
   // (measured: conv2 1.21 -> 1.14 ms).  conv1 keeps four: with eight, two CTAs per SM need a 72-register cap that spills
   // in the epilogue and costs more than the producers gain.
-  static constexpr int PROD_WARPS = KC == 1 ? 4 : 8, PROD_THREADS = PROD_WARPS * 32;
+  static constexpr int PROD_WARPS = (KC == 1 && !PACK4) ? 4 : 8, PROD_THREADS = PROD_WARPS * 32;
   static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 32;
   static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS;
   // the first layer runs two small CTAs per SM (measured: one CTA with 8 + 8 + 1 warps and a 6-deep ring is slower,
@@ -423,17 +423,27 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
       uint8_t* orow = otile + m * C::OUT_ROW_B;
+      // CS channels per step (CS/8 output chunks): 4*CS live accumulator registers.  The first layer uses 8 so that its
+      // variants fit the register cap of two CTAs per SM with eight producer warps; conv2 (no cap) uses 16.
+      constexpr int CS = COUT >= 64 ? 16 : 8;
 #pragma unroll
-      for (int c0 = 0; c0 < CH; c0 += 16) {
-        uint32_t r0[16], r1[16], r2[16], r3[16];
-        tmem_ld_32x16(taddr + c0, r0);
-        tmem_ld_32x16(taddr + COUT + c0, r1);
-        tmem_ld_32x16(taddr + 2 * COUT + c0, r2);
-        tmem_ld_32x16(taddr + 3 * COUT + c0, r3);
+      for (int c0 = 0; c0 < CH; c0 += CS) {
+        uint32_t r0[CS], r1[CS], r2[CS], r3[CS];
+        if constexpr (CS == 16) {
+          tmem_ld_32x16(taddr + c0, r0);
+          tmem_ld_32x16(taddr + COUT + c0, r1);
+          tmem_ld_32x16(taddr + 2 * COUT + c0, r2);
+          tmem_ld_32x16(taddr + 3 * COUT + c0, r3);
+        } else {
+          tmem_ld_32x8(taddr + c0, r0);
+          tmem_ld_32x8(taddr + COUT + c0, r1);
+          tmem_ld_32x8(taddr + 2 * COUT + c0, r2);
+          tmem_ld_32x8(taddr + 3 * COUT + c0, r3);
+        }
         tmem_ld_wait();
-        uint32_t packed[8];
+        uint32_t packed[CS / 2];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < CS; j += 4) {
           const float4 bv = *reinterpret_cast<const float4*>(sBias + half * CH + c0 + j);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
@@ -449,8 +459,10 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
           }
         }
         const int chunk = (half * CH + c0) / 8;
-        *reinterpret_cast<uint4*>(orow + ((chunk ^ swz) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(orow + (((chunk + 1) ^ swz) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+#pragma unroll
+        for (int g = 0; g < CS / 8; ++g)
+          *reinterpret_cast<uint4*>(orow + (((chunk + g) ^ swz) << 4)) =
+              make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
       }
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[b]);   // TMEM reads done: the MMA warp may start the tile after next

@@ -138,6 +138,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers: 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 // ---- cp.async (LDGSTS): 16-byte global -> shared copies with zero fill when src_bytes == 0 ---------------------
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
