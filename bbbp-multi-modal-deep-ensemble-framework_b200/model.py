@@ -514,62 +514,6 @@ class TransformerCnnModel(_KernelModule):
         return out_host
 
     @torch.no_grad()
-    def predict_batches_packed(self, packed_bits, image_u8, batch_size: int, max_rows_per_pass: int = 16384):
-        """Screening entry point on the compact input formats (SURVEY cfg4): fingerprints as little-endian packed bits
-        (B, ceil(F/8)) uint8 and depictions as raw uint8 (B, 3, 128, 128).  Unpack + per-molecule z-score and the image
-        normalisation run on the device, reproducing the reference's preprocessing formulas (oracle/preprocess.py)."""
-        from . import ops
-        n_bits = self.fingerprint_transformer.layers[0].self_attn.embed_dim
-        fp = ops.unpack_zscore(packed_bits.contiguous(), n_bits)
-        return self.predict_batches(fp, image_u8, batch_size, max_rows_per_pass)
-
-    @torch.no_grad()
-    def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int = 2048,
-                          packed: bool = False, out_host: torch.Tensor | None = None):
-        """End-to-end scoring of HOST-resident molecules (pinned tensors recommended): the host->device copy of chunk
-        c+1 runs on a second stream while chunk c is being scored, so a pass costs max(copy, compute) instead of their
-        sum.  ``packed`` selects the compact formats of predict_batches_packed.  Chunks are whole reference batches, so
-        scores are identical to predict_batches on the same data.  Returns the (N,) scores on the host."""
-        assert not self.training, "call model.eval() first"
-        dev = next(self.parameters()).device
-        n = fingerprint_host.shape[0]
-        chunk = max(1, chunk_molecules // batch_size) * batch_size
-        scores = torch.empty((n,), device=dev, dtype=torch.float32)
-        compute = torch.cuda.current_stream(dev)
-        copier = torch.cuda.Stream(dev)
-        bufs, ready, freed = [None, None], [None, None], [None, None]
-        spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
-
-        def stage(i):
-            a, b = spans[i]
-            slot = i % 2
-            with torch.cuda.stream(copier):
-                if freed[slot] is not None:
-                    copier.wait_event(freed[slot])        # the compute stream is done with this slot's old contents
-                bufs[slot] = (fingerprint_host[a:b].to(dev, non_blocking=True), image_host[a:b].to(dev, non_blocking=True))
-                ready[slot] = torch.cuda.Event()
-                ready[slot].record(copier)
-
-        if spans:
-            stage(0)
-        for i, (a, b) in enumerate(spans):
-            if i + 1 < len(spans):
-                stage(i + 1)
-            slot = i % 2
-            compute.wait_event(ready[slot])
-            fp, img = bufs[slot]
-            fp.record_stream(compute)
-            img.record_stream(compute)
-            part = (self.predict_batches_packed if packed else self.predict_batches)(fp, img, batch_size, max_rows_per_pass=chunk)
-            scores[a:b].copy_(part)
-            freed[slot] = torch.cuda.Event()
-            freed[slot].record(compute)
-        if out_host is None:
-            out_host = torch.empty((n,), dtype=torch.float32, pin_memory=True)
-        out_host.copy_(scores, non_blocking=True)
-        return out_host
-
-    @torch.no_grad()
     def predict_batches(self, fingerprint, image, batch_size: int, max_rows_per_pass: int = 16384):
         """Batched inference with the reference's batch semantics (20250113.py:229-237): molecules
         [b*batch_size, (b+1)*batch_size) form reference batch b; returns (N,) scores.  Full batches are
