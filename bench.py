@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=32, help="reference batches of 256 molecules per step")
     ap.add_argument("--precision", default=os.environ.get("BBBP_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--cpu-batches", type=int, default=12, help="bounded CPU-baseline sample (batches of 256)")
+    ap.add_argument("--cpu-batches", type=int, default=48, help="bounded CPU-baseline sample (batches of 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement")
     args = ap.parse_args()
