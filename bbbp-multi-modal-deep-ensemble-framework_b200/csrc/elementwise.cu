@@ -162,6 +162,23 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int ld_src, __nv
   dst[(size_t)r * ld_dst + c] = __float2bfloat16(c < cols ? src[(size_t)r * ld_src + c] : 0.0f);
 }
 
+// ---- row gather: dst[r, :] = src[idx[r], :] (device-resident batch feeder, replaces MixedDataset.__getitem__ + collate) ----
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                                          float* __restrict__ dst, int rows, size_t cols) {
+  const int r = blockIdx.y;
+  const float* s = src + (size_t)idx[r] * cols;
+  float* d = dst + (size_t)r * cols;
+  const size_t n4 = cols / 4;
+  const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+  if (vec) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+      reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
+    for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cols; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cols; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+  }
+}
+
 // ---- Philox-4x32-10 dropout -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -474,4 +491,14 @@ extern "C" int bbbp_softmax_rows_bwd_f32(const float* w, const float* dw, float*
   if (rows == 0) return BBBP_OK;
   softmax_rows_bwd_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(w, dw, dscores, rows, n);
   return launch_status("softmax_rows_bwd");
+}
+
+extern "C" int bbbp_gather_rows_f32(const float* src, const int64_t* idx, float* dst, int rows, long long cols,
+                                    bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(src && idx && dst && rows >= 0 && cols > 0, "gather_rows: bad argument");
+  if (rows == 0) return BBBP_OK;
+  BBBP_CHECK_ARG(rows <= 65535, "gather_rows: at most 65535 rows per call");
+  const unsigned bx = (unsigned)ceil_div((size_t)cols, (size_t)(256 * 16));
+  gather_rows_kernel<<<dim3(bx < 1 ? 1 : bx, rows), 256, 0, as_stream(stream)>>>(src, idx, dst, rows, (size_t)cols);
+  return launch_status("gather_rows");
 }

@@ -458,6 +458,14 @@ def copy2d(src, dst):
     return dst
 
 
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """dst[r] = src[idx[r]] for a 2-D float32 table and a device int64 index vector."""
+    rows, cols = idx.numel(), src.shape[1]
+    dst = torch.empty((rows, cols), device=src.device, dtype=torch.float32)
+    check(lib.bbbp_gather_rows_f32(src.data_ptr(), idx.data_ptr(), dst.data_ptr(), rows, cols, _stream()), "gather_rows")
+    return dst
+
+
 def dropout(x, p, seed, offset=0):
     y = torch.empty_like(x)
     check(lib.bbbp_dropout_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset), _stream()),

@@ -159,3 +159,34 @@ def test_gradient_averaging_world2_gloo(tmp_path):
     want = np.concatenate([np.full(15, 1.5, dtype=np.float32), np.arange(7, dtype=np.float32) * 1.5])
     for r in range(2):
         np.testing.assert_array_equal(np.load(tmp_path / f"g{r}.npy"), want)
+
+
+def test_device_batch_feeder_reproduces_dataloader_order():
+    """same batches, same order as the reference's MixedDataset + DataLoader(shuffle=True) under the same
+    torch seed, for several epochs (the DataLoader draws one seed per epoch from the global generator)."""
+    from torch.utils.data import DataLoader, Dataset
+    n, bs = 77, 32
+    fps = np.arange(n * 5, dtype=np.float64).reshape(n, 5)
+    imgs = np.arange(n * 12, dtype=np.float32).reshape(n, 12) * 0.5
+    ys = np.arange(n, dtype=np.float64) * 0.25
+
+    class MixedDataset(Dataset):          # the reference's dataset shape (20250113.py:31-45), re-stated for the test
+        def __len__(self):
+            return n
+
+        def __getitem__(self, i):
+            return (torch.tensor(fps[i], dtype=torch.float32), torch.tensor(imgs[i], dtype=torch.float32),
+                    torch.tensor(ys[i], dtype=torch.float32))
+
+    torch.manual_seed(42)
+    want = [[tuple(t.clone() for t in batch) for batch in DataLoader(MixedDataset(), batch_size=bs, shuffle=True)] for _ in range(3)]
+    torch.manual_seed(42)
+    feeder = bbbp_b200.DeviceBatchFeeder(fps, imgs, ys, batch_size=bs, shuffle=True, device="cpu")
+    assert len(feeder) == 3
+    for epoch in range(3):
+        got = list(feeder)
+        assert len(got) == len(want[epoch])
+        for (a, b, c), (x, y, z) in zip(got, want[epoch]):
+            assert torch.equal(a, x) and torch.equal(b, y) and torch.equal(c, z)
+    plain = list(bbbp_b200.DeviceBatchFeeder(fps, imgs, ys, batch_size=bs, shuffle=False, device="cpu"))
+    assert torch.equal(plain[-1][2], torch.tensor(ys[64:], dtype=torch.float32))

@@ -461,3 +461,19 @@ def test_conv1_tcgen05_from_uint8_with_stats(ops, N):
     y = ops.conv1_from_image_bf16(dev, ops.conv3x3_prepare_bf16(w.cuda()), b.cuda(), stats)
     z = torch.from_numpy(preprocess.u8_image_zscore(img)).view(N, 3, 128, 128)      # the reference's preprocessing
     close(y, _conv_ref_bf16(z, w, b).permute(0, 2, 3, 1), atol=2e-2, rtol=2e-2, what="conv1 from uint8")
+
+
+def test_gather_rows_and_device_feeder(ops):
+    import bbbp_b200
+    src = rnd(50, 49152, seed=140)
+    idx = torch.tensor([3, 3, 49, 0, 17], dtype=torch.int64)
+    assert torch.equal(ops.gather_rows(src.cuda(), idx.cuda()).cpu(), src[idx])
+    odd = rnd(9, 167, seed=141)
+    assert torch.equal(ops.gather_rows(odd.cuda(), idx[:3].cuda() % 9).cpu(), odd[idx[:3] % 9])
+    y = torch.arange(50, dtype=torch.float32)
+    torch.manual_seed(7)
+    cpu = list(bbbp_b200.DeviceBatchFeeder(odd.repeat(6, 1)[:50], src, y, batch_size=16, shuffle=True, device="cpu"))
+    torch.manual_seed(7)
+    gpu = list(bbbp_b200.DeviceBatchFeeder(odd.repeat(6, 1)[:50], src, y, batch_size=16, shuffle=True, device="cuda"))
+    for (a, b, c), (x, yy, z) in zip(gpu, cpu):
+        assert torch.equal(a.cpu(), x) and torch.equal(b.cpu(), yy) and torch.equal(c.cpu(), z)
