@@ -459,11 +459,12 @@ class TransformerCnnModel(_KernelModule):
 
     @torch.no_grad()
     def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int = 2048,
-                          packed: bool = False, out_host: torch.Tensor | None = None):
+                          packed: bool = False, out_host: torch.Tensor | None = None, return_device: bool = False):
         """End-to-end scoring of HOST-resident molecules (pinned tensors recommended): the host->device copy of chunk
         c+1 runs on a second stream while chunk c is being scored, so a pass costs max(copy, compute) instead of their
         sum.  ``packed`` selects the compact formats of predict_batches_packed.  Chunks are whole reference batches, so
-        scores are identical to predict_batches on the same data.  Returns the (N,) scores on the host."""
+        scores are identical to predict_batches on the same data.  Returns the (N,) scores on the host (and, with
+        ``return_device``, also the device copy, e.g. for a cross-rank gather)."""
         assert not self.training, "call model.eval() first"
         dev = next(self.parameters()).device
         n = fingerprint_host.shape[0]
@@ -511,7 +512,7 @@ class TransformerCnnModel(_KernelModule):
         if out_host is None:
             out_host = torch.empty((n,), dtype=torch.float32, pin_memory=True)
         out_host.copy_(scores, non_blocking=True)
-        return out_host
+        return (out_host, scores) if return_device else out_host
 
     @torch.no_grad()
     def predict_batches(self, fingerprint, image, batch_size: int, max_rows_per_pass: int = 16384):

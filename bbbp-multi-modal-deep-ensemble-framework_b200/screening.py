@@ -75,9 +75,12 @@ def average_gradients(parameters, group=None) -> None:
     grads = [p.grad for p in parameters if p.grad is not None]
     if not grads or world == 1:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(world)
+    flat = torch.cat([g.reshape(-1) for g in grads])         # flat fp32 gradient buffer (layout only)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)     # the 1/R lives inside the NCCL reduction
+    else:                                                             # gloo (CPU tests) has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
     off = 0
     for g in grads:
         n = g.numel()

@@ -266,7 +266,6 @@ def main():
     img8_host[strokes.expand(-1, 3, -1, -1)] = 40
     img8_host = img8_host.pin_memory()
     gathered = torch.empty(world * n, device=dev, dtype=torch.float32) if world > 1 else None
-    scores_dev_dummy = torch.zeros(n, device=dev, dtype=torch.float32)   # e2e leg: the gather's payload size is what matters
 
     def step_resident():
         s = model.predict_batches(fp, img, BATCH, max_rows_per_pass=n)
@@ -285,9 +284,10 @@ def main():
 
     def step_e2e_compact():
         # the user-facing host API: chunked H2D on a copy stream overlapped with scoring, D2H of the scores
-        model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=2048, packed=True, out_host=scores_host)
+        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=2048, packed=True, out_host=scores_host,
+                                       return_device=True)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, scores_dev_dummy)
+            dist.all_gather_into_tensor(gathered, s)
 
     def barrier():
         if world > 1:
