@@ -10,12 +10,13 @@ constexpr int LN_WARPS = 4;
 __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ sum_out, float* __restrict__ mean_out,
-    float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y16, int ld16, int rows, int dim, float eps) {
+    float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y16, int ld16, int rows, int dim, float eps, int ld_x,
+    int ld_res, int ld_y) {
   const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  const float* xr = x + (size_t)row * dim;
-  const float* rr = res ? res + (size_t)row * dim : nullptr;
+  const float* xr = x + (size_t)row * ld_x;
+  const float* rr = res ? res + (size_t)row * ld_res : nullptr;
   float s = 0.0f;
   for (int i = lane; i < dim; i += 32) s += xr[i] + (rr ? rr[i] : 0.0f);
   const float mean = warp_sum(s) / dim;
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(
   for (int i = lane; i < dim; i += 32) {
     float t = xr[i] + (rr ? rr[i] : 0.0f);
     float o = (t - mean) * rstd * gamma[i] + beta[i];
-    y[(size_t)row * dim + i] = o;
+    y[(size_t)row * ld_y + i] = o;
     if (sum_out) sum_out[(size_t)row * dim + i] = t;
     if (y16) y16[(size_t)row * ld16 + i] = __float2bfloat16(o);
   }
@@ -204,8 +205,23 @@ extern "C" int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, cons
   BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd: ld_bf16 < dim");
   if (rows == 0) return BBBP_OK;
   add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
-      x, res, gamma, beta, y, sum_out, mean, rstd, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf16, rows, dim, eps);
+      x, res, gamma, beta, y, sum_out, mean, rstd, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf16, rows, dim, eps, dim, dim,
+      dim);
   return launch_status("add_layernorm_fwd");
+}
+
+extern "C" int bbbp_add_layernorm_fwd_pitched_f32(const float* x, int ld_x, const float* res, int ld_res, const float* gamma,
+                                                  const float* beta, float* y, int ld_y, void* y_bf16, int ld_bf16, int rows,
+                                                  int dim, float eps, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(x && gamma && beta && y && rows >= 0 && dim > 0 && ld_x >= dim && ld_y >= dim && (!res || ld_res >= dim),
+                 "add_layernorm_fwd_pitched: bad argument");
+  BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd_pitched: ld_bf16 < dim");
+  if (rows == 0) return BBBP_OK;
+  add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
+      x, res, gamma, beta, y, nullptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf16, rows, dim, eps, ld_x,
+      ld_res, ld_y);
+  return launch_status("add_layernorm_fwd_pitched");
 }
 
 extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const float* mean, const float* rstd,

@@ -247,8 +247,14 @@ class TransformerCnnModel(_KernelModule):
         F_ = x.shape[1]
         Fq = -(-F_ // 8) * 8                          # q | k | v each start on a 16-byte boundary
         rows = x.shape[0]
-        x32 = x
-        x16 = ops.cast_bf16(x32, ld=Fq)
+        # fp32 activations keep pitch Fq (a multiple of 4 floats) so the GEMM epilogues read residuals and write outputs
+        # with 128-bit accesses even though F = 167 is prime
+        if Fq != F_:
+            x32 = torch.empty((rows, Fq), device=x.device, dtype=torch.float32)
+            ops.copy2d(x, x32[:, :F_])
+        else:
+            x32 = x
+        x16 = ops.cast_bf16(x, ld=Fq)
 
         def padded_in_proj(w):                       # (3F, F) -> bf16 (3*Fq, Fq), zero rows/cols in the pads
             out = torch.zeros((3 * Fq, Fq), device=w.device, dtype=torch.bfloat16)
@@ -271,15 +277,16 @@ class TransformerCnnModel(_KernelModule):
             ldp = p16.shape[1]
             vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
             _, a16 = ops.gemm_bf16_batched(groups, seq, F_, seq, p16, ldp, seq * ldp, vt, ldp, F_ * ldp, ld_out16=Fq)
-            s32, _ = ops.gemm_bf16(a16, F_, ag.weight_bf16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32)
-            x32, _, _, _, x16 = ops.add_layernorm_fwd(s32, None, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps,
-                                                      bf16_ld=Fq)
+            s32, _ = ops.gemm_bf16(a16, F_, ag.weight_bf16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32,
+                                   ld_out=Fq)
+            x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,
+                                                 bf16_ld=Fq)
             _, h16 = ops.gemm_bf16(x16, F_, ag.weight_bf16(layer.linear1.weight), layer.linear1.out_features,
                                    bias=layer.linear1.bias, act="relu", out_f32=False, out_bf16=True)
             f32, _ = ops.gemm_bf16(h16, layer.linear1.out_features, ag.weight_bf16(layer.linear2.weight), F_,
-                                   bias=layer.linear2.bias, residual=x32)
-            x32, _, _, _, x16 = ops.add_layernorm_fwd(f32, None, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
-                                                      bf16_ld=Fq)
+                                   bias=layer.linear2.bias, residual=x32, ld_out=Fq)
+            x32, x16 = ops.layernorm_fwd_pitched(f32, F_, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, ld_y=Fq,
+                                                 bf16_ld=Fq)
         fc = self.fingerprint_fc[0]
         out, _ = ops.gemm_bf16(x16, F_, ag.weight_bf16(fc.weight), fc.out_features, bias=fc.bias, act="relu")
         return out

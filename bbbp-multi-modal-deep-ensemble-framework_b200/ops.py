@@ -330,6 +330,18 @@ def add_layernorm_fwd(x, res, gamma, beta, eps=1e-5, save=False, bf16_ld=0):
     return y, s, mean, rstd, y16
 
 
+def layernorm_fwd_pitched(x, dim, gamma, beta, eps=1e-5, ld_y=None, bf16_ld=0):
+    """LN over the first ``dim`` columns of a pitched (rows, ld) buffer -> (rows, ld_y) fp32 [+ (rows, bf16_ld) bf16]."""
+    rows = x.shape[0]
+    ld_y = dim if ld_y is None else ld_y
+    y = torch.empty((rows, ld_y), device=x.device, dtype=torch.float32)
+    y16 = torch.empty((rows, bf16_ld), device=x.device, dtype=torch.bfloat16) if bf16_ld else None
+    check(lib.bbbp_add_layernorm_fwd_pitched_f32(x.data_ptr(), x.stride(0), None, 0, gamma.data_ptr(), beta.data_ptr(),
+                                                 y.data_ptr(), ld_y, _ptr(y16), bf16_ld, rows, dim, float(eps), _stream()),
+          "add_layernorm_fwd_pitched")
+    return y, y16
+
+
 def layernorm_bwd(dy, s, mean, rstd, gamma):
     rows, dim = s.shape
     dx = torch.empty_like(s)

@@ -164,6 +164,11 @@ int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse,
 int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y,
                                float* sum_out, float* mean, float* rstd, void* y_bf16, int ld_bf16, int rows,
                                int dim, float eps, bbbp_stream_t stream);
+/* Inference form with independent row pitches (elements) for x, res and y, so activations can keep a 16-byte-aligned
+ * pitch when dim is not a multiple of 4 (F = 167): y = LN(x + res)*gamma + beta, optional bf16 copy. */
+int bbbp_add_layernorm_fwd_pitched_f32(const float* x, int ld_x, const float* res, int ld_res, const float* gamma,
+                                       const float* beta, float* y, int ld_y, void* y_bf16, int ld_bf16, int rows, int dim,
+                                       float eps, bbbp_stream_t stream);
 /* dx (= gradient wrt s, which is also the gradient of both x and res), dgamma[dim], dbeta[dim].
  * workspace: 2 * 64 * dim floats. */
 int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
