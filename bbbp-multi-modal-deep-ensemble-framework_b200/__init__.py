@@ -11,6 +11,7 @@ from .model import (  # noqa: F401
     MixedInputModelMLPRdkit, MixedInputModelNoFusion, MlpModel, MSELoss, MultiHeadAttentionFusion,
     MultiModalAttentionFusion, TransformerCnnModel, VARIANTS, build, encoder_heads)
 from .optim import AdamW  # noqa: F401
+from .train import GraphedTrainStep  # noqa: F401
 from .feeder import DeviceBatchFeeder  # noqa: F401
 from .screening import average_gradients, gather_scores, partition_batches, screen  # noqa: F401
 from .preprocess import pca_transform, unpack_zscore, u8_image_zscore  # noqa: F401
@@ -19,5 +20,5 @@ __all__ = [
     "MixedInputModel", "MixedInputModelBig", "MixedInputModelNoFusion", "MixedInputModelMLP", "MixedInputModelMLPMore",
     "MixedInputModelMLPRdkit", "MultiHeadAttentionFusion", "AttentionFusion", "MultiModalAttentionFusion", "MSELoss",
     "BCEWithLogitsLoss", "AdamW", "build", "VARIANTS", "ops", "partition_batches", "gather_scores", "screen",
-    "average_gradients", "DeviceBatchFeeder", "pca_transform", "unpack_zscore", "u8_image_zscore",
+    "average_gradients", "DeviceBatchFeeder", "GraphedTrainStep", "pca_transform", "unpack_zscore", "u8_image_zscore",
 ]

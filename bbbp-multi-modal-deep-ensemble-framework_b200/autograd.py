@@ -20,6 +20,29 @@ def next_seed() -> int:
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
+# While a training step is being captured into a CUDA graph (train.GraphedTrainStep) this holds a device int64[1]:
+# the dropout kernels add its CURRENT value to their (baked) host seed each time they run, so every replay draws new masks.
+_seed_dev = None
+
+
+def set_seed_tensor(t):
+    global _seed_dev
+    prev, _seed_dev = _seed_dev, t
+    return prev
+
+
+# Also set during capture: a second stream for the parameter-gradient products (dW, db).  They are leaves of the
+# backward dependency chain -- nothing but the optimizer consumes them -- so forking them keeps only the dX chain on the
+# captured graph's critical path.  GraphedTrainStep joins the stream before the optimizer node.
+_wgrad_stream = None
+
+
+def set_wgrad_stream(s):
+    global _wgrad_stream
+    prev, _wgrad_stream = _wgrad_stream, s
+    return prev
+
+
 def contig(t: torch.Tensor) -> torch.Tensor:
     """Contiguous float32 copy of a 2-D strided view through the copy2d kernel (no torch arithmetic)."""
     if t.is_contiguous():
@@ -71,7 +94,11 @@ class Linear(Function):
             a16 = ops.cast_bf16(x)
             y, _ = ops.gemm_bf16(a16, K, weight_bf16(weight), N, bias=bias, act=act, split_k=ops.fixed_split_k(K))
         else:
-            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act, split_k=ops.fixed_split_k_f32(K))
+            # inference keeps a K-only split (bit-identical scores however batches are grouped); a training forward
+            # has no such contract and takes the latency mode (one-shot kernel at M <= 32)
+            training = any(ctx.needs_input_grad[:3])       # all False under torch.no_grad()
+            y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act,
+                             split_k=0 if training else ops.fixed_split_k_f32(K))
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if act else None)
@@ -86,11 +113,17 @@ class Linear(Function):
         N = weight.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm_f32(dpre, weight, split_k=ops.tile_split_k(M, K, N, x.device))
-        if ctx.needs_input_grad[1]:
-            dw = ops.gemm_f32(dpre, x, trans_a=True, split_k=ops.tile_split_k(N, K, M, x.device))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(dpre)
+            dx = ops.gemm_f32(dpre, weight, split_k=0)
+        side = _wgrad_stream if torch.cuda.is_current_stream_capturing() else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            dpre.record_stream(side)
+            x.record_stream(side)
+        with torch.cuda.stream(side):       # stream(None) is a no-op
+            if ctx.needs_input_grad[1]:
+                dw = ops.gemm_f32(dpre, x, trans_a=True, split_k=0)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = ops.colsum(dpre)
         return dx, dw, db, None, None
 
 
@@ -125,8 +158,10 @@ class Attention(Function):
     @staticmethod
     def forward(ctx, qkv, groups, seq, heads, head_dim, dropout_p, seed):
         qkv = contig(qkv)
-        out, lse = ops.attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p, seed, want_lse=qkv.requires_grad)
-        ctx.cfg = (groups, seq, heads, head_dim, dropout_p, seed)
+        seed_dev = _seed_dev if dropout_p > 0 else None
+        out, lse = ops.attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p, seed, want_lse=qkv.requires_grad,
+                                     seed_dev=seed_dev)
+        ctx.cfg = (groups, seq, heads, head_dim, dropout_p, seed, seed_dev)
         ctx.save_for_backward(qkv, out, lse)
         return out
 
@@ -233,12 +268,12 @@ class ScaledColmean(Function):
 class Dropout(Function):
     @staticmethod
     def forward(ctx, x, p, seed):
-        ctx.p, ctx.seed = p, seed
-        return ops.dropout(x if x.is_contiguous() else x.contiguous(), p, seed)
+        ctx.p, ctx.seed, ctx.seed_dev = p, seed, _seed_dev
+        return ops.dropout(x if x.is_contiguous() else x.contiguous(), p, seed, seed_dev=_seed_dev)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.dropout(dy if dy.is_contiguous() else dy.contiguous(), ctx.p, ctx.seed), None, None
+        return ops.dropout(dy if dy.is_contiguous() else dy.contiguous(), ctx.p, ctx.seed, seed_dev=ctx.seed_dev), None, None
 
 
 class ConcatCols(Function):

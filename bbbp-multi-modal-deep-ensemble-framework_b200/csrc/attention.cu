@@ -36,7 +36,9 @@ __device__ __forceinline__ float keep_scale(float p, float inv_keep, uint64_t se
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const float* __restrict__ qkv,
                                                                        float* __restrict__ out, float* __restrict__ lse,
                                                                        int seq, int heads, int d, int q_per_block,
-                                                                       float drop_p, uint64_t seed) {
+                                                                       float drop_p, uint64_t seed,
+                                                                       const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   extern __shared__ float smem[];
   const int ld = d | 1;  // odd pitch: conflict-free row-per-lane reads
   float* Ks = smem;
@@ -113,7 +115,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dq_kernel(const 
                                                                           const float* __restrict__ dout,
                                                                           float* __restrict__ dqkv, int seq, int heads,
                                                                           int d, int q_per_block, float drop_p,
-                                                                          uint64_t seed) {
+                                                                          uint64_t seed,
+                                                                          const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   const float inv_keep = 1.0f / (1.0f - drop_p);
   extern __shared__ float smem[];
   const int ld = d | 1;
@@ -192,7 +196,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dkv_kernel(const
                                                                            const float* __restrict__ dout,
                                                                            float* __restrict__ dqkv, int seq, int heads,
                                                                            int d, int k_per_block, float drop_p,
-                                                                           uint64_t seed) {
+                                                                           uint64_t seed,
+                                                                           const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   const float inv_keep = 1.0f / (1.0f - drop_p);
   extern __shared__ float smem[];
   const int ld = d | 1;
@@ -331,6 +337,139 @@ __global__ void __launch_bounds__(256) attention_small_head_fwd_kernel(const flo
   }
 }
 
+
+// ---- short attention scopes (seq <= 32: one reference training batch) ---------------------------------------------
+// One CTA per (group, head) holds Q, K, V (and dO) of the whole scope in shared memory, one WARP per row: forward is
+// scores -> softmax -> PV in one launch, backward produces dQ, dK and dV in one launch.  The streaming kernels above
+// need 2 + 8 + 8 CTAs of 4 warps for this shape and re-stage K/V per query block; here every product is a 32 x 32 x d
+// block and the whole scope is fetched with one round of cp.async.
+constexpr int SS = 32;          // maximum scope = warps per CTA
+
+// smem: Q[SS][ld] | K[SS][ld] | V[SS][ld] | P[SS][SS+1]
+__global__ void __launch_bounds__(SS * 32) attention_short_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                      float* __restrict__ lse, int seq, int heads, int d,
+                                                                      float drop_p, uint64_t seed,
+                                                                      const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
+  extern __shared__ float smem[];
+  const int ld = d | 1;
+  float* Qs = smem;
+  float* Ks = Qs + SS * ld;
+  float* Vs = Ks + SS * ld;
+  float* Ps = Vs + SS * ld;
+  const int qi = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int h = blockIdx.x, g = blockIdx.y;
+  const int E = heads * d, ldq = 3 * E;
+  const size_t row0 = (size_t)g * seq;
+  const float scale = rsqrtf((float)d);
+  const float inv_keep = 1.0f / (1.0f - drop_p);
+  for (int i = threadIdx.x; i < SS * d; i += SS * 32) {
+    const int j = i / d, dd = i - j * d;
+    const bool ok = j < seq;
+    const float* src = ok ? qkv + (row0 + j) * ldq + h * d + dd : qkv;
+    cp_async_f32(Qs + j * ld + dd, src, ok);
+    cp_async_f32(Ks + j * ld + dd, src + (ok ? E : 0), ok);
+    cp_async_f32(Vs + j * ld + dd, src + (ok ? 2 * E : 0), ok);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (qi >= seq) return;                       // warp-uniform; no block barrier below
+  float s = 0.0f;
+  for (int dd = 0; dd < d; ++dd) s = fmaf(Qs[qi * ld + dd], Ks[lane * ld + dd], s);
+  s = lane < seq ? s * scale : -INFINITY;
+  const float m = warp_max(s);
+  const float p = __expf(s - m);
+  const float l = warp_sum(p);
+  // dropout acts on the normalised probabilities: the normaliser l keeps every key
+  Ps[qi * (SS + 1) + lane] = p * keep_scale(drop_p, inv_keep, seed, row0 + qi, row0 + lane, h) / l;
+  if (lse && lane == 0) lse[(row0 + qi) * heads + h] = m + __logf(l);
+  __syncwarp();
+  for (int dd = lane; dd < d; dd += 32) {
+    float o = 0.0f;
+    for (int j = 0; j < seq; ++j) o = fmaf(Ps[qi * (SS + 1) + j], Vs[j * ld + dd], o);
+    out[(row0 + qi) * E + h * d + dd] = o;
+  }
+}
+
+// smem: Q[SS][ld] | K | V | dO | P[SS][SS+1] (kept probabilities) | dS[SS][SS+1]
+__global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const float* __restrict__ qkv,
+                                                                      const float* __restrict__ out,
+                                                                      const float* __restrict__ lse,
+                                                                      const float* __restrict__ dout, float* __restrict__ dqkv,
+                                                                      int seq, int heads, int d, float drop_p, uint64_t seed,
+                                                                      const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
+  extern __shared__ float smem[];
+  const int ld = d | 1;
+  float* Qs = smem;
+  float* Ks = Qs + SS * ld;
+  float* Vs = Ks + SS * ld;
+  float* dOs = Vs + SS * ld;
+  float* Ps = dOs + SS * ld;
+  float* dSs = Ps + SS * (SS + 1);
+  const int row = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int h = blockIdx.x, g = blockIdx.y;
+  const int E = heads * d, ldq = 3 * E;
+  const size_t row0 = (size_t)g * seq;
+  const float scale = rsqrtf((float)d);
+  const float inv_keep = 1.0f / (1.0f - drop_p);
+  for (int i = threadIdx.x; i < SS * d; i += SS * 32) {
+    const int j = i / d, dd = i - j * d;
+    const bool ok = j < seq;
+    const float* src = ok ? qkv + (row0 + j) * ldq + h * d + dd : qkv;
+    cp_async_f32(Qs + j * ld + dd, src, ok);
+    cp_async_f32(Ks + j * ld + dd, src + (ok ? E : 0), ok);
+    cp_async_f32(Vs + j * ld + dd, src + (ok ? 2 * E : 0), ok);
+    cp_async_f32(dOs + j * ld + dd, ok ? dout + (row0 + j) * E + h * d + dd : dout, ok);
+  }
+  // D_i = <dO_i, O_i> straight from global memory while the copies fly
+  float D = 0.0f, L = 0.0f;
+  if (row < seq) {
+    for (int dd = lane; dd < d; dd += 32)
+      D = fmaf(dout[(row0 + row) * E + h * d + dd], out[(row0 + row) * E + h * d + dd], D);
+    D = warp_sum(D);
+    L = lse[(row0 + row) * heads + h];
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  {  // P and dS of query `row` (lane = key)
+    float s = 0.0f, dp = 0.0f;
+    for (int dd = 0; dd < d; ++dd) {
+      s = fmaf(Qs[row * ld + dd], Ks[lane * ld + dd], s);
+      dp = fmaf(dOs[row * ld + dd], Vs[lane * ld + dd], dp);
+    }
+    const float p = (row < seq && lane < seq) ? __expf(s * scale - L) : 0.0f;
+    const float keep = keep_scale(drop_p, inv_keep, seed, row0 + row, row0 + lane, h);
+    Ps[row * (SS + 1) + lane] = p * keep;
+    dSs[row * (SS + 1) + lane] = p * (dp * keep - D);
+  }
+  __syncthreads();
+  if (row >= seq) return;
+  // dQ_i = scale * sum_j dS_ij K_j ; dK_j = scale * sum_i dS_ij Q_i ; dV_j = sum_i P_ij dO_i
+  for (int dd = lane; dd < d; dd += 32) {
+    float dq = 0.0f, dk = 0.0f, dv = 0.0f;
+    for (int j = 0; j < seq; ++j) {
+      dq = fmaf(dSs[row * (SS + 1) + j], Ks[j * ld + dd], dq);
+      dk = fmaf(dSs[j * (SS + 1) + row], Qs[j * ld + dd], dk);
+      dv = fmaf(Ps[j * (SS + 1) + row], dOs[j * ld + dd], dv);
+    }
+    float* dst = dqkv + (row0 + row) * ldq + h * d + dd;
+    dst[0] = dq * scale;
+    dst[E] = dk * scale;
+    dst[2 * E] = dv;
+  }
+}
+
+static size_t short_fwd_smem(int d) { return ((size_t)3 * SS * (d | 1) + SS * (SS + 1)) * sizeof(float); }
+static size_t short_bwd_smem(int d) { return ((size_t)4 * SS * (d | 1) + 2 * SS * (SS + 1)) * sizeof(float); }
+
+// Query (or key) rows per CTA: 16 (four passes of the CTA's four warps over one staged K/V tile stream) when that
+// already fills the GPU, otherwise 4 (one pass) -- a reference training batch (seq 32, one head) is 2 CTAs at 16 rows
+// per CTA and the kernel is pure latency.
+static int rows_per_block(int groups, int seq, int heads) {
+  return (long long)ceil_div(seq, 16) * heads * groups >= 2 * 148 ? 16 : ATT_WARPS;
+}
+
 static int attention_args_ok(const char* who, int groups, int seq, int heads, int d) {
   if (groups < 0 || seq <= 0 || heads <= 0 || d <= 0 || d > 32 * MAX_DT) {
     set_error("%s: groups=%d seq=%d heads=%d head_dim=%d unsupported (head_dim <= %d)", who, groups, seq, heads, d,
@@ -347,7 +486,8 @@ static int attention_args_ok(const char* who, int groups, int seq, int heads, in
 }  // namespace bbbp
 
 extern "C" int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, int groups, int seq, int heads,
-                                      int head_dim, float dropout_p, uint64_t seed, bbbp_stream_t stream) {
+                                      int head_dim, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                                      bbbp_stream_t stream) {
   using namespace bbbp;
   BBBP_CHECK_ARG(qkv && out, "attention_fwd: null operand");
   BBBP_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f, "attention_fwd: dropout_p must be in [0,1)");
@@ -366,35 +506,49 @@ extern "C" int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, 
     }
     return launch_status("attention_fwd (small heads)");
   }
+  if (seq <= SS && (long long)groups * heads <= 4096 && short_fwd_smem(head_dim) <= 200 * 1024) {
+    const size_t sm = short_fwd_smem(head_dim);
+    cudaFuncSetAttribute(attention_short_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attention_short_fwd_kernel<<<dim3(heads, groups), SS * 32, sm, as_stream(stream)>>>(qkv, out, lse, seq, heads, head_dim,
+                                                                                             dropout_p, seed, seed_dev);
+    return launch_status("attention_fwd (short scope)");
+  }
   const int ld = head_dim | 1;
-  const int qpb = 16;
+  const int qpb = rows_per_block(groups, seq, heads);
   size_t smem = (size_t)(2 * KT + ATT_WARPS) * ld * sizeof(float);
   cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(seq, qpb), heads, groups);
   attention_fwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(qkv, out, lse, seq, heads, head_dim, qpb,
-                                                                          dropout_p, seed);
+                                                                          dropout_p, seed, seed_dev);
   return launch_status("attention_fwd");
 }
 
 extern "C" int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout,
                                       float* dqkv, int groups, int seq, int heads, int head_dim, float dropout_p,
-                                      uint64_t seed, bbbp_stream_t stream) {
+                                      uint64_t seed, const uint64_t* seed_dev, bbbp_stream_t stream) {
   using namespace bbbp;
   BBBP_CHECK_ARG(qkv && out && lse && dout && dqkv, "attention_bwd: null operand");
   if (!attention_args_ok("attention_bwd", groups, seq, heads, head_dim)) return BBBP_EINVAL;
   if (groups == 0) return BBBP_OK;
+  if (seq <= SS && (long long)groups * heads <= 4096 && short_bwd_smem(head_dim) <= 200 * 1024) {
+    const size_t sm = short_bwd_smem(head_dim);
+    cudaFuncSetAttribute(attention_short_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attention_short_bwd_kernel<<<dim3(heads, groups), SS * 32, sm, as_stream(stream)>>>(
+        qkv, out, lse, dout, dqkv, seq, heads, head_dim, dropout_p, seed, seed_dev);
+    return launch_status("attention_bwd (short scope)");
+  }
   const int ld = head_dim | 1;
-  const int per_block = 16;
+  const int per_block = rows_per_block(groups, seq, heads);
   dim3 grid(ceil_div(seq, per_block), heads, groups);
   size_t smem_q = (size_t)(2 * KT + 2 * ATT_WARPS) * ld * sizeof(float);
   cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
   attention_bwd_dq_kernel<<<grid, ATT_WARPS * 32, smem_q, as_stream(stream)>>>(qkv, out, lse, dout, dqkv, seq, heads,
-                                                                               head_dim, per_block, dropout_p, seed);
+                                                                               head_dim, per_block, dropout_p, seed, seed_dev);
   int st = launch_status("attention_bwd dq");
   if (st != BBBP_OK) return st;
   size_t smem_kv = ((size_t)(2 * KT + 2 * ATT_WARPS) * ld + 2 * KT) * sizeof(float);
   cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
   attention_bwd_dkv_kernel<<<grid, ATT_WARPS * 32, smem_kv, as_stream(stream)>>>(qkv, out, lse, dout, dqkv, seq, heads,
-                                                                                 head_dim, per_block, dropout_p, seed);
+                                                                                 head_dim, per_block, dropout_p, seed, seed_dev);
   return launch_status("attention_bwd dkv");
 }

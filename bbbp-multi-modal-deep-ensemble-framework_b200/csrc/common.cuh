@@ -33,6 +33,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 4-byte asynchronous global -> shared copy (zero fill when !valid): lets a thread keep dozens of scalar loads in
+// flight without holding them in registers.  Pair with cp_async_wait_all() + a barrier.
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src, bool valid) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int src_bytes = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == BBBP_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == BBBP_ACT_TANH) return tanhf(v);

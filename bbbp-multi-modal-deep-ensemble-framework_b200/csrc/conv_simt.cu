@@ -108,52 +108,101 @@ __global__ void relu_pool_bwd_kernel(const float* __restrict__ dy, const float* 
   o[W + 1] = a == 3 ? g : 0.0f;
 }
 
-// partial weight gradient: block = (ci tile of 16 x band of image rows, co tile of 16, image); thread = (co, ci), 9 taps.
-// The image is cut into `bands` horizontal bands so that small batches still fill the GPU; partials are summed by
-// sum_over_images_kernel in a fixed order (deterministic).
-__global__ void __launch_bounds__(256) conv3x3_wgrad_partial_kernel(const float* __restrict__ dpre,
-                                                                    const float* __restrict__ x,
-                                                                    float* __restrict__ part, int Cin, int Cout, int H,
-                                                                    int W, int bands) {
-  __shared__ float ds[16][256];
-  __shared__ float xs[16][18][18];
+// Partial weight gradient, register tiled.  A CTA owns one 8-row strip of the image (band), a tile of COT*16 output
+// channels and a tile of CI_T input channels, and walks images z, z+gridDim.z, ...  Thread (cog, lane): lane -> (ci,
+// row slice), cog -> COT consecutive output channels; it keeps COT x 9 accumulators and slides a 3x3 input window along
+// each row, so a pixel costs 3 + COT shared-memory loads for 9*COT FMAs (the previous kernel: 10 loads for 9 FMAs, and
+// 13 of its 16 ci lanes idle on the 3-channel first layer, which the SLICES split over rows now fills).
+// Partials [z][band][slice][Cout][Cin][9] are summed by sum_over_images_kernel in a fixed order (deterministic).
+constexpr int WG_ROWS = 8, WG_COLS = 16;
+template <int CI_T, int SLICES, int COT>
+__global__ void __launch_bounds__(256) conv3x3_wgrad_tiled_kernel(const float* __restrict__ dpre, const float* __restrict__ x,
+                                                                  float* __restrict__ part, int N, int Cin, int Cout, int H,
+                                                                  int W) {
+  static_assert(CI_T * SLICES == 16 && WG_ROWS % SLICES == 0, "lane split");
+  constexpr int CO_TILE = 16 * COT, XS_PITCH = (WG_ROWS + 2) * (WG_COLS + 2) + 1;   // odd: conflict-free across ci
+  constexpr int ROWS_PER_SLICE = WG_ROWS / SLICES;
+  __shared__ float ds[CO_TILE][WG_ROWS * WG_COLS];
+  __shared__ float xs[CI_T * XS_PITCH];
   const int tid = threadIdx.x;
-  const int band = blockIdx.x % bands;
-  const int ci0 = (blockIdx.x / bands) * 16, co0 = blockIdx.y * 16, n = blockIdx.z;
-  const int rows_per_band = H / bands;
-  const int ci_l = tid % 16, co_l = tid / 16;
-  float acc[9] = {};
-  const float* xn = x + (size_t)n * Cin * H * W;
-  const float* dn = dpre + (size_t)n * Cout * H * W;
-  const int nci = min(16, Cin - ci0);
-  for (int ty0 = band * rows_per_band; ty0 < (band + 1) * rows_per_band; ty0 += 16)
-    for (int tx0 = 0; tx0 < W; tx0 += 16) {
-      for (int i = tid; i < 16 * 256; i += 256) {
-        int co = i / 256, p = i % 256;
-        ds[co][p] = dn[((size_t)(co0 + co) * H + ty0 + p / 16) * W + tx0 + p % 16];
+  const int bands = H / WG_ROWS;
+  const int band = blockIdx.x % bands, ci0 = (blockIdx.x / bands) * CI_T, co0 = blockIdx.y * CO_TILE;
+  const int lane16 = tid % 16, cog = tid / 16;
+  const int ci_l = lane16 % CI_T, slice = lane16 / CI_T;
+  const int nci = min(CI_T, Cin - ci0);
+  const int ty0 = band * WG_ROWS;
+  float acc[COT][9];
+#pragma unroll
+  for (int j = 0; j < COT; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[j][t] = 0.0f;
+
+  for (int n = blockIdx.z; n < N; n += gridDim.z) {
+    const float* xn = x + (size_t)n * Cin * H * W;
+    const float* dn = dpre + (size_t)n * Cout * H * W;
+    for (int tx0 = 0; tx0 < W; tx0 += WG_COLS) {
+      for (int i = tid; i < CO_TILE * WG_ROWS * WG_COLS; i += 256) {
+        const int co = i / (WG_ROWS * WG_COLS), p = i % (WG_ROWS * WG_COLS);
+        ds[co][p] = dn[((size_t)(co0 + co) * H + ty0 + p / WG_COLS) * W + tx0 + p % WG_COLS];
       }
-      for (int i = tid; i < 16 * 324; i += 256) {
-        int ci = i / 324, r = (i % 324) / 18, c = i % 18;
-        int gy = ty0 + r - 1, gx = tx0 + c - 1;
-        xs[ci][r][c] =
+      for (int i = tid; i < CI_T * (WG_ROWS + 2) * (WG_COLS + 2); i += 256) {
+        const int ci = i / ((WG_ROWS + 2) * (WG_COLS + 2)), rc = i % ((WG_ROWS + 2) * (WG_COLS + 2));
+        const int gy = ty0 + rc / (WG_COLS + 2) - 1, gx = tx0 + rc % (WG_COLS + 2) - 1;
+        xs[ci * XS_PITCH + rc] =
             (ci < nci && gy >= 0 && gy < H && gx >= 0 && gx < W) ? xn[((size_t)(ci0 + ci) * H + gy) * W + gx] : 0.0f;
       }
       __syncthreads();
-      for (int p = 0; p < 256; ++p) {
-        const float d = ds[co_l][p];
-        const int py = p / 16, px = p % 16;
+      const float* xc = xs + ci_l * XS_PITCH;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+      for (int rr = 0; rr < ROWS_PER_SLICE; ++rr) {
+        const int py = slice * ROWS_PER_SLICE + rr;
+        const float* r0 = xc + py * (WG_COLS + 2);           // input rows py-1, py, py+1 in tile coordinates (+1 halo)
+        const float* r1 = r0 + (WG_COLS + 2);
+        const float* r2 = r1 + (WG_COLS + 2);
+        float w00 = r0[0], w01 = r0[1], w10 = r1[0], w11 = r1[1], w20 = r2[0], w21 = r2[1];
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf(d, xs[ci_l][py + kh][px + kw], acc[kh * 3 + kw]);
+        for (int px = 0; px < WG_COLS; ++px) {
+          const float w02 = r0[px + 2], w12 = r1[px + 2], w22 = r2[px + 2];
+#pragma unroll
+          for (int j = 0; j < COT; ++j) {
+            const float d = ds[cog * COT + j][py * WG_COLS + px];
+            acc[j][0] = fmaf(d, w00, acc[j][0]);
+            acc[j][1] = fmaf(d, w01, acc[j][1]);
+            acc[j][2] = fmaf(d, w02, acc[j][2]);
+            acc[j][3] = fmaf(d, w10, acc[j][3]);
+            acc[j][4] = fmaf(d, w11, acc[j][4]);
+            acc[j][5] = fmaf(d, w12, acc[j][5]);
+            acc[j][6] = fmaf(d, w20, acc[j][6]);
+            acc[j][7] = fmaf(d, w21, acc[j][7]);
+            acc[j][8] = fmaf(d, w22, acc[j][8]);
+          }
+          w00 = w01; w01 = w02; w10 = w11; w11 = w12; w20 = w21; w21 = w22;
+        }
       }
       __syncthreads();
     }
-  if (ci_l < nci) {
-    float* o = part + ((((size_t)n * bands + band) * Cout + co0 + co_l) * Cin + ci0 + ci_l) * 9;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) o[t] = acc[t];
   }
+  if (ci_l < nci) {
+    const size_t per_w = (size_t)Cout * Cin * 9;
+    float* base = part + (((size_t)blockIdx.z * bands + band) * SLICES + slice) * per_w;
+#pragma unroll
+    for (int j = 0; j < COT; ++j) {
+      float* o = base + ((size_t)(co0 + cog * COT + j) * Cin + ci0 + ci_l) * 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) o[t] = acc[j][t];
+    }
+  }
+}
+
+struct WgradPlan { int ci_t, slices, cot, zn, bands; };
+static WgradPlan wgrad_plan(int N, int Cin, int Cout, int H) {
+  WgradPlan p;
+  p.ci_t = Cin <= 4 ? 4 : Cin <= 8 ? 8 : 16;
+  p.slices = 16 / p.ci_t;
+  p.cot = Cout % 64 == 0 ? 4 : Cout % 32 == 0 ? 2 : 1;
+  p.zn = N < 32 ? N : 32;
+  p.bands = H / WG_ROWS;
+  return p;
 }
 
 // bias-gradient partial: block = (co, n) -> part_b[n][co] = sum over the plane, fixed reduction tree
@@ -222,27 +271,45 @@ extern "C" int bbbp_relu_pool_bwd_f32(const float* dy, const float* y, const uin
   return launch_status("relu_pool_bwd");
 }
 
+extern "C" size_t bbbp_conv3x3_wgrad_workspace(int N, int Cin, int Cout, int H, int W) {
+  using namespace bbbp;
+  (void)W;
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0) return 0;
+  const WgradPlan p = wgrad_plan(N, Cin, Cout, H);
+  return ((size_t)p.zn * p.bands * p.slices * Cout * Cin * 9 + (size_t)N * Cout) * sizeof(float);
+}
+
 extern "C" int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* dw, float* db, int N, int Cin, int Cout,
                                       int H, int W, float* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
   using namespace bbbp;
   BBBP_CHECK_ARG(dpre && x && dw, "conv3x3_wgrad: null operand");
   BBBP_CHECK_ARG(Cout % 16 == 0 && H % 16 == 0 && W % 16 == 0, "conv3x3_wgrad: Cout/H/W must be multiples of 16");
   BBBP_CHECK_ARG(N > 0 && N <= 65535, "conv3x3_wgrad: N=%d out of range", N);
-  size_t per_w = (size_t)Cout * Cin * 9, per_b = Cout;
-  const int bands = (H % 128 == 0) ? 8 : (H % 64 == 0) ? 4 : (H % 32 == 0) ? 2 : 1;   // each band is a multiple of 16 rows
-  size_t need = (size_t)N * (bands * per_w + per_b) * sizeof(float);
+  const WgradPlan p = wgrad_plan(N, Cin, Cout, H);
+  const size_t per_w = (size_t)Cout * Cin * 9, per_b = Cout;
+  const size_t n_part = (size_t)p.zn * p.bands * p.slices;
+  const size_t need = bbbp_conv3x3_wgrad_workspace(N, Cin, Cout, H, W);
   if (!workspace || workspace_bytes < need) {
     set_error("conv3x3_wgrad: needs %zu workspace bytes, got %zu", need, workspace_bytes);
     return BBBP_EWORKSPACE;
   }
   cudaStream_t s = as_stream(stream);
   float* part_w = workspace;
-  float* part_b = workspace + (size_t)N * bands * per_w;
-  dim3 grid(ceil_div(Cin, 16) * bands, Cout / 16, N);
-  conv3x3_wgrad_partial_kernel<<<grid, 256, 0, s>>>(dpre, x, part_w, Cin, Cout, H, W, bands);
+  float* part_b = workspace + n_part * per_w;
+  const dim3 grid(ceil_div(Cin, p.ci_t) * p.bands, Cout / (16 * p.cot), p.zn);
+#define BBBP_WGRAD(CI, SL, CT) \
+  conv3x3_wgrad_tiled_kernel<CI, SL, CT><<<grid, 256, 0, s>>>(dpre, x, part_w, N, Cin, Cout, H, W)
+  if (p.cot == 4) {
+    if (p.ci_t == 4) BBBP_WGRAD(4, 4, 4); else if (p.ci_t == 8) BBBP_WGRAD(8, 2, 4); else BBBP_WGRAD(16, 1, 4);
+  } else if (p.cot == 2) {
+    if (p.ci_t == 4) BBBP_WGRAD(4, 4, 2); else if (p.ci_t == 8) BBBP_WGRAD(8, 2, 2); else BBBP_WGRAD(16, 1, 2);
+  } else {
+    if (p.ci_t == 4) BBBP_WGRAD(4, 4, 1); else if (p.ci_t == 8) BBBP_WGRAD(8, 2, 1); else BBBP_WGRAD(16, 1, 1);
+  }
+#undef BBBP_WGRAD
   int st = launch_status("conv3x3_wgrad partial");
   if (st != BBBP_OK) return st;
-  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)256), 256, 0, s>>>(part_w, dw, N * bands, per_w);
+  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)256), 256, 0, s>>>(part_w, dw, (int)n_part, per_w);
   st = launch_status("conv3x3_wgrad reduce");
   if (st != BBBP_OK || !db) return st;
   conv_bgrad_partial_kernel<<<dim3(Cout, N), 256, 0, s>>>(dpre, part_b, Cout, H * W);

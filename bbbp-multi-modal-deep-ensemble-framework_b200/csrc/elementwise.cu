@@ -2,6 +2,7 @@
 // dropout, losses, fused multi-tensor AdamW, and the packed-input contracts.  All single pass, coalesced,
 // warp-shuffle reductions, deterministic (no floating-point atomics anywhere).
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace bbbp {
@@ -194,9 +195,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, float p, float inv_keep,
-                               uint64_t seed, uint64_t offset) {
+                               uint64_t seed, uint64_t offset, const uint64_t* __restrict__ seed_dev) {
   size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // one Philox block = 4 elements
   if (q * 4 >= n) return;
+  if (seed_dev) seed += *seed_dev;  // graph replay: the per-step part of the seed lives in device memory
   uint64_t ctr = q + offset;
   uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -241,11 +243,18 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ pr
 
 // ---- fused multi-tensor AdamW (torch.optim.AdamW single-tensor semantics, 20250113.py:172,191) -------------------
 constexpr int ADAMW_CHUNK = 65536;
+struct AdamwHyper { float v[8]; };  // bbbp_adamw_hyper() layout
+
+// ONE kernel behind both entry points, so an eager step and a graph replay round identically: the eight per-step
+// scalars come either by value (bbbp_adamw_f32) or from device memory when the kernel runs (bbbp_adamw_dev_f32).
 __global__ void __launch_bounds__(256) adamw_kernel(void* const* __restrict__ ptrs, const int64_t* __restrict__ sizes,
                                                     const int32_t* __restrict__ chunk_tensor,
                                                     const int64_t* __restrict__ chunk_offset, int ntensors,
-                                                    float one_minus_beta1, float beta2, float one_minus_beta2, float eps,
-                                                    float decay_mul, float step_size, float bc2_sqrt, float grad_scale) {
+                                                    AdamwHyper by_value, const float* __restrict__ hyper_dev) {
+  const float one_minus_beta1 = hyper_dev ? hyper_dev[0] : by_value.v[0], beta2 = hyper_dev ? hyper_dev[1] : by_value.v[1],
+              one_minus_beta2 = hyper_dev ? hyper_dev[2] : by_value.v[2], eps = hyper_dev ? hyper_dev[3] : by_value.v[3],
+              decay_mul = hyper_dev ? hyper_dev[4] : by_value.v[4], step_size = hyper_dev ? hyper_dev[5] : by_value.v[5],
+              bc2_sqrt = hyper_dev ? hyper_dev[6] : by_value.v[6], grad_scale = hyper_dev ? hyper_dev[7] : by_value.v[7];
   const int t = chunk_tensor[blockIdx.x];
   const int64_t off = chunk_offset[blockIdx.x];
   float* __restrict__ p = static_cast<float*>(ptrs[t]) + off;
@@ -420,12 +429,12 @@ extern "C" int bbbp_cast_bf16(const float* src, int ld_src, void* dst_bf16, int 
 }
 
 extern "C" int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset,
-                                bbbp_stream_t stream) {
+                                const uint64_t* seed_dev, bbbp_stream_t stream) {
   BBBP_CHECK_ARG(x && y && p >= 0.0f && p < 1.0f, "dropout: p must be in [0,1)");
   if (n == 0) return BBBP_OK;
   size_t quads = ceil_div(n, (size_t)4);
   dropout_kernel<<<(unsigned)ceil_div(quads, (size_t)256), 256, 0, as_stream(stream)>>>(x, y, n, p, 1.0f / (1.0f - p), seed,
-                                                                                         offset);
+                                                                                         offset, seed_dev);
   return launch_status("dropout");
 }
 
@@ -443,23 +452,60 @@ extern "C" int bbbp_bce_logits_loss_f32(const float* logit, const float* target,
   return launch_status("bce_logits_loss");
 }
 
+namespace bbbp {
+struct SmallBlob { uint32_t w[16]; };
+__global__ void store_small_kernel(SmallBlob blob, uint8_t* __restrict__ dst, int n_bytes) {
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(blob.w);
+  if ((int)threadIdx.x < n_bytes) dst[threadIdx.x] = src[threadIdx.x];
+}
+}  // namespace bbbp
+
+extern "C" int bbbp_store_small(const void* host_src, int n_bytes, void* dst_dev, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(host_src && dst_dev && n_bytes > 0 && n_bytes <= 64, "store_small: 1..64 bytes");
+  SmallBlob blob = {};
+  memcpy(blob.w, host_src, (size_t)n_bytes);
+  store_small_kernel<<<1, 64, 0, as_stream(stream)>>>(blob, static_cast<uint8_t*>(dst_dev), n_bytes);
+  return launch_status("store_small");
+}
+
+extern "C" int bbbp_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                                float grad_scale, float* h) {
+  BBBP_CHECK_ARG(h && step >= 1, "adamw_hyper: bad argument");
+  // hyper-parameters arrive as doubles (Python floats) so every derived scalar is formed exactly as torch forms it
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  // torch forms 1 - beta in double before narrowing; 1.0f - (float)beta would be off by ~1e-5 relative
+  h[0] = (float)(1.0 - beta1);
+  h[1] = (float)beta2;
+  h[2] = (float)(1.0 - beta2);
+  h[3] = (float)eps;
+  h[4] = (float)(1.0 - lr * weight_decay);
+  h[5] = (float)(lr / bc1);
+  h[6] = (float)sqrt(bc2);
+  h[7] = grad_scale;
+  return BBBP_OK;
+}
+
 extern "C" int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor,
                               const int64_t* chunk_offset, int ntensors, int nchunks, double lr, double beta1,
                               double beta2, double eps, double weight_decay, int step, float grad_scale,
                               bbbp_stream_t stream) {
   BBBP_CHECK_ARG(ptrs && sizes && chunk_tensor && chunk_offset && ntensors > 0 && nchunks > 0 && step >= 1,
                  "adamw: bad argument");
-  // hyper-parameters arrive as doubles (Python floats) so every derived scalar is formed exactly as torch forms it
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
-  const float step_size = (float)(lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
-  const float decay_mul = (float)(1.0 - lr * weight_decay);
-  // torch forms 1 - beta in double before narrowing; 1.0f - (float)beta would be off by ~1e-5 relative
-  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
-  adamw_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(ptrs, sizes, chunk_tensor, chunk_offset, ntensors, omb1, (float)beta2,
-                                                       omb2, (float)eps, decay_mul, step_size, bc2_sqrt, grad_scale);
+  AdamwHyper h;
+  bbbp_adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, grad_scale, h.v);
+  adamw_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(ptrs, sizes, chunk_tensor, chunk_offset, ntensors, h, nullptr);
   return launch_status("adamw");
+}
+
+extern "C" int bbbp_adamw_dev_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor,
+                                  const int64_t* chunk_offset, int ntensors, int nchunks, const float* hyper_dev,
+                                  bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(ptrs && sizes && chunk_tensor && chunk_offset && ntensors > 0 && nchunks > 0 && hyper_dev,
+                 "adamw_dev: bad argument");
+  adamw_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(ptrs, sizes, chunk_tensor, chunk_offset, ntensors, AdamwHyper{}, hyper_dev);
+  return launch_status("adamw_dev");
 }
 
 extern "C" int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, float* out, int ld_out, int rows,

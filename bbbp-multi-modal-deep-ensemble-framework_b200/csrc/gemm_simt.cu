@@ -88,7 +88,102 @@ __global__ void splitk_finish_kernel(const float* __restrict__ partial, int spli
   *dst = accumulate ? (*dst + v) : v;
 }
 
+// ---- few output rows (M <= 32: one reference training batch) -------------------------------------------------------
+// The tiled kernel above walks K in 16-wide steps with two block barriers each; at M = 32 its grid is a handful of CTAs
+// and every step is a full global-load round trip, so a 32 x 167 x 2048 product is ~130 dependent round trips.  Here a
+// CTA owns a 32 x 32 output tile and a K slab of up to 256: it issues ALL of the slab's loads at once (one round trip),
+// then multiplies out of shared memory.  K slabs are spread over blockIdx.y and summed by splitk_finish_kernel.
+constexpr int SK_M = 32, SK_TN = 32, SK_KC = 256, SK_PITCH = 34;
+
+__global__ void __launch_bounds__(256) gemm_f32_skinny_kernel(int M, int N, int K, const float* __restrict__ A, long sAm,
+                                                              long sAk, const float* __restrict__ B, long sBk, long sBn,
+                                                              float* __restrict__ C, int ldc, const float* __restrict__ bias,
+                                                              int act, int accumulate, float* __restrict__ partial) {
+  extern __shared__ float sk_smem[];
+  float* As = sk_smem;                       // [kc][SK_PITCH], m fast
+  float* Bs = sk_smem + SK_KC * SK_PITCH;    // [kc][SK_PITCH], n fast
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * SK_TN;
+  const int kbeg = blockIdx.y * SK_KC;
+  const int kc = min(SK_KC, K - kbeg);
+  const int total = SK_M * kc;
+  // every load of the slab is issued before anything waits (cp.async, zero fill outside the matrix); src pointers of
+  // masked elements are clamped to the matrix base so no out-of-range address is ever formed
+  if (sAk == 1) {
+    for (int i = tid; i < total; i += 256) {
+      const int m = i / kc, k = i - m * kc;
+      const bool ok = m < M;
+      cp_async_f32(As + k * SK_PITCH + m, ok ? A + m * sAm + kbeg + k : A, ok);
+    }
+  } else {
+    for (int i = tid; i < total; i += 256) {
+      const int k = i / SK_M, m = i % SK_M;
+      const bool ok = m < M;
+      cp_async_f32(As + k * SK_PITCH + m, ok ? A + m * sAm + (kbeg + k) * sAk : A, ok);
+    }
+  }
+  if (sBk == 1) {
+    for (int i = tid; i < total; i += 256) {
+      const int n = i / kc, k = i - n * kc;
+      const bool ok = n0 + n < N;
+      cp_async_f32(Bs + k * SK_PITCH + n, ok ? B + (n0 + n) * sBn + kbeg + k : B, ok);
+    }
+  } else {
+    for (int i = tid; i < total; i += 256) {
+      const int k = i / SK_TN, n = i % SK_TN;
+      const bool ok = n0 + n < N;
+      cp_async_f32(Bs + k * SK_PITCH + n, ok ? B + (kbeg + k) * sBk + (n0 + n) * sBn : B, ok);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int tx = tid % 16, ty = tid / 16;    // 2 x 2 outputs per thread: rows 2ty.., cols 2tx..
+  float a00 = 0.0f, a01 = 0.0f, a10 = 0.0f, a11 = 0.0f;
+#pragma unroll 8
+  for (int k = 0; k < kc; ++k) {
+    const float2 a = *reinterpret_cast<const float2*>(As + k * SK_PITCH + 2 * ty);
+    const float2 b = *reinterpret_cast<const float2*>(Bs + k * SK_PITCH + 2 * tx);
+    a00 = fmaf(a.x, b.x, a00);
+    a01 = fmaf(a.x, b.y, a01);
+    a10 = fmaf(a.y, b.x, a10);
+    a11 = fmaf(a.y, b.y, a11);
+  }
+  const float acc[2][2] = {{a00, a01}, {a10, a11}};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int gm = 2 * ty + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int gn = n0 + 2 * tx + j;
+      if (gn >= N) continue;
+      if (partial) {
+        partial[((size_t)blockIdx.y * M + gm) * N + gn] = acc[i][j];
+      } else {
+        float v = apply_act(acc[i][j] + (bias ? bias[gn] : 0.0f), act);
+        float* dst = C + (size_t)gm * ldc + gn;
+        *dst = accumulate ? (*dst + v) : v;
+      }
+    }
+  }
+}
+
 }  // namespace bbbp
+
+extern "C" size_t bbbp_gemm_f32_auto_workspace(int M, int N, int K) {
+  using namespace bbbp;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (M <= SK_M) {
+    const int slabs = ceil_div(K, SK_KC);
+    return slabs > 1 ? (size_t)slabs * M * N * sizeof(float) : 0;
+  }
+  // the tiled kernel: split K until ~2 CTAs per SM exist
+  const long tiles = (long)ceil_div(M, TM) * ceil_div(N, TN);
+  long split = ceil_div(2L * 148, tiles);
+  if (split > K / 128) split = K / 128;
+  if (split < 1) split = 1;
+  return split > 1 ? (size_t)split * M * N * sizeof(float) : 0;
+}
 
 extern "C" int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
                              int ldb, float* C, int ldc, const float* bias, int act, int accumulate, int split_k,
@@ -97,6 +192,35 @@ extern "C" int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const 
   BBBP_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_f32: negative dimension");
   BBBP_CHECK_ARG(A && B && C, "gemm_f32: null operand");
   if (M == 0 || N == 0) return BBBP_OK;
+  if (split_k == 0 && K > 0) {
+    // latency mode (training path): the library picks the kernel and the K partition from (M, N, K)
+    const size_t need = bbbp_gemm_f32_auto_workspace(M, N, K);
+    if (need && (!workspace || workspace_bytes < need)) {
+      set_error("gemm_f32: auto mode needs %zu workspace bytes, got %zu", need, workspace_bytes);
+      return BBBP_EWORKSPACE;
+    }
+    if (M <= SK_M) {
+      const long sAm = transA ? 1 : lda, sAk = transA ? lda : 1;
+      const long sBk = transB ? 1 : ldb, sBn = transB ? ldb : 1;
+      const int slabs = ceil_div(K, SK_KC);
+      float* partial = slabs > 1 ? workspace : nullptr;
+      const size_t smem = (size_t)2 * SK_KC * SK_PITCH * sizeof(float);
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(gemm_f32_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+      }
+      gemm_f32_skinny_kernel<<<dim3(ceil_div(N, SK_TN), slabs), 256, smem, as_stream(stream)>>>(
+          M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, bias, act, accumulate, partial);
+      int st = launch_status("gemm_f32 (skinny)");
+      if (st != BBBP_OK || !partial) return st;
+      const size_t total = (size_t)M * N;
+      splitk_finish_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(partial, slabs, M, N, C, ldc,
+                                                                                                 bias, act, accumulate);
+      return launch_status("gemm_f32 split-k finish");
+    }
+    split_k = need ? (int)(need / ((size_t)M * N * sizeof(float))) : 1;
+  }
   if (split_k < 1) split_k = 1;
   if (split_k > K) split_k = K > 0 ? K : 1;
   long sAm = transA ? 1 : lda, sAk = transA ? lda : 1;

@@ -95,6 +95,49 @@ __global__ void layernorm_bwd_param_final_kernel(const float* __restrict__ part,
   dbeta[col] = db;
 }
 
+// Few rows (a reference training batch is 32 molecules): ONE launch.  Blocks [0, row_blocks) compute dx exactly as
+// layernorm_bwd_dx_kernel does; the remaining blocks own 128 columns each and walk all rows for dgamma / dbeta.
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_small_kernel(const float* __restrict__ dy,
+                                                                            const float* __restrict__ s,
+                                                                            const float* __restrict__ mean,
+                                                                            const float* __restrict__ rstd,
+                                                                            const float* __restrict__ gamma,
+                                                                            float* __restrict__ dx, float* __restrict__ dgamma,
+                                                                            float* __restrict__ dbeta, int rows, int dim,
+                                                                            int row_blocks) {
+  if ((int)blockIdx.x < row_blocks) {
+    const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float mu = mean[row], rs = rstd[row];
+    const float* dyr = dy + (size_t)row * dim;
+    const float* sr = s + (size_t)row * dim;
+    float c1 = 0.0f, c2 = 0.0f;
+    for (int i = lane; i < dim; i += 32) {
+      float g = dyr[i] * gamma[i];
+      c1 += g;
+      c2 = fmaf(g, (sr[i] - mu) * rs, c2);
+    }
+    c1 = warp_sum(c1) / dim;
+    c2 = warp_sum(c2) / dim;
+    for (int i = lane; i < dim; i += 32) {
+      float g = dyr[i] * gamma[i];
+      dx[(size_t)row * dim + i] = rs * (g - c1 - (sr[i] - mu) * rs * c2);
+    }
+    return;
+  }
+  const int col = (blockIdx.x - row_blocks) * (LN_WARPS * 32) + threadIdx.x;
+  if (col >= dim) return;
+  float dg = 0.0f, db = 0.0f;
+  for (int r = 0; r < rows; ++r) {
+    float d = dy[(size_t)r * dim + col];
+    dg = fmaf(d, (s[(size_t)r * dim + col] - mean[r]) * rstd[r], dg);
+    db += d;
+  }
+  dgamma[col] = dg;
+  dbeta[col] = db;
+}
+
 // ---- BatchNorm1d: block = 32 channels x 8 row lanes -------------------------------------------------------------
 __device__ __forceinline__ float bn_col_reduce(float v, float (*red)[33]) {
   red[threadIdx.y][threadIdx.x] = v;
@@ -236,6 +279,12 @@ extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const flo
     return BBBP_EWORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
+  if (rows <= 256) {
+    const int row_blocks = ceil_div(rows, LN_WARPS);
+    layernorm_bwd_small_kernel<<<row_blocks + ceil_div(dim, LN_WARPS * 32), LN_WARPS * 32, 0, st>>>(
+        dy, s, mean, rstd, gamma, dx, dgamma, dbeta, rows, dim, row_blocks);
+    return launch_status("layernorm_bwd (small)");
+  }
   layernorm_bwd_dx_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, st>>>(dy, s, mean, rstd, gamma, dx, rows, dim);
   layernorm_bwd_param_partial_kernel<<<dim3(LN_PARTS, ceil_div(dim, 128)), 128, 0, st>>>(dy, s, mean, rstd, workspace,
                                                                                          rows, dim);

@@ -355,6 +355,9 @@ class TransformerCnnModel(_KernelModule):
             outs.append(o)
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
+    fork_image_branch = False   # set by train.GraphedTrainStep while it captures
+    _side_stream = None
+
     # -- CUDA-graph replay for small inference calls -------------------------------------------------------------------
     # A reference-sized call (batch 32..256) is ~80 kernel launches of a few microseconds each: launch-bound.  In eval
     # mode under no_grad the whole forward for a given (rows, groups, dtypes, precision, weight version) is captured
@@ -434,6 +437,17 @@ class TransformerCnnModel(_KernelModule):
         if rows % groups:
             raise ValueError(f"{rows} molecules do not split into {groups} equal reference batches")
         x = fingerprint if fingerprint.is_contiguous() else fingerprint.contiguous()
+        side = None
+        if self.fork_image_branch and torch.cuda.is_current_stream_capturing():
+            # the conv branch does not depend on the encoder: fork it so the captured graph has two parallel branches
+            cur = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(fingerprint.device)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                im = self._image_branch(image)
+            im.record_stream(cur)
         if self._encoder_tensor_core_ok(rows // groups):
             fp = self._encoder_tensor_core(x, groups, rows // groups)
         else:
@@ -442,7 +456,10 @@ class TransformerCnnModel(_KernelModule):
             fp = self._lin(x, self.fingerprint_fc[0], "relu")
         if len(self.fingerprint_fc) > 2:
             fp = self._drop(fp, self.fingerprint_fc[2])
-        im = self._image_branch(image)
+        if side is not None:
+            cur.wait_stream(side)
+        else:
+            im = self._image_branch(image)
         if self.kind == "nofusion":
             fused = ag.concat_cols(fp, im)
         elif self.kind == "big":

@@ -93,6 +93,10 @@ def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, act=None, out=None, 
     ws = None
     if split_k > 1:
         ws = torch.empty((split_k * M * N,), device=a.device, dtype=torch.float32)
+    elif split_k == 0:          # latency mode (training): kernel and K partition chosen by the library
+        need = lib.bbbp_gemm_f32_auto_workspace(M, N, K)
+        if need:
+            ws = torch.empty((need // 4,), device=a.device, dtype=torch.float32)
     check(lib.bbbp_gemm_f32(int(trans_a), int(trans_b), M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
                             out.data_ptr(), out.stride(0), _ptr(bias), _ACT[act], int(accumulate), split_k, _ptr(ws),
                             0 if ws is None else ws.numel() * 4, _stream()), "gemm_f32")
@@ -229,7 +233,7 @@ def conv3x3_wgrad(dpre, x, Cout, Cin):
     N, _, H, W = x.shape
     dw = torch.empty((Cout, Cin, 3, 3), device=x.device, dtype=torch.float32)
     db = torch.empty((Cout,), device=x.device, dtype=torch.float32)
-    ws = torch.empty((N * (8 * Cout * Cin * 9 + Cout),), device=x.device, dtype=torch.float32)
+    ws = torch.empty((lib.bbbp_conv3x3_wgrad_workspace(N, Cin, Cout, H, W) // 4,), device=x.device, dtype=torch.float32)
     check(lib.bbbp_conv3x3_wgrad_f32(dpre.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), N, Cin, Cout, H, W,
                                      ws.data_ptr(), ws.numel() * 4, _stream()), "conv3x3_wgrad")
     return dw, db
@@ -299,20 +303,20 @@ def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int) -> torch.Tensor:
 
 
 # ---- attention --------------------------------------------------------------------------------------------------------
-def attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p=0.0, seed=0, want_lse=True):
+def attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p=0.0, seed=0, want_lse=True, seed_dev=None):
     E = heads * head_dim
     out = torch.empty((groups * seq, E), device=qkv.device, dtype=torch.float32)
     lse = torch.empty((groups * seq, heads), device=qkv.device, dtype=torch.float32) if want_lse else None
     check(lib.bbbp_attention_fwd_f32(qkv.data_ptr(), out.data_ptr(), _ptr(lse), groups, seq, heads, head_dim,
-                                     float(dropout_p), int(seed), _stream()), "attention_fwd")
+                                     float(dropout_p), int(seed), _ptr(seed_dev), _stream()), "attention_fwd")
     return out, lse
 
 
-def attention_bwd(qkv, out, lse, dout, groups, seq, heads, head_dim, dropout_p=0.0, seed=0):
+def attention_bwd(qkv, out, lse, dout, groups, seq, heads, head_dim, dropout_p=0.0, seed=0, seed_dev=None):
     dqkv = torch.empty_like(qkv)
     check(lib.bbbp_attention_bwd_f32(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
-                                     groups, seq, heads, head_dim, float(dropout_p), int(seed), _stream()),
-          "attention_bwd")
+                                     groups, seq, heads, head_dim, float(dropout_p), int(seed), _ptr(seed_dev),
+                                     _stream()), "attention_bwd")
     return dqkv
 
 
@@ -478,10 +482,11 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def dropout(x, p, seed, offset=0):
+def dropout(x, p, seed, offset=0, seed_dev=None):
+    """``seed_dev``: optional device uint64 (int64 tensor) added to ``seed`` when the kernel runs (CUDA-graph replay)."""
     y = torch.empty_like(x)
-    check(lib.bbbp_dropout_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset), _stream()),
-          "dropout")
+    check(lib.bbbp_dropout_f32(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), int(offset), _ptr(seed_dev),
+                               _stream()), "dropout")
     return y
 
 
@@ -509,6 +514,26 @@ def adamw(ptr_table, sizes, chunk_tensor, chunk_offset, ntensors, nchunks, lr, b
     check(lib.bbbp_adamw_f32(ptr_table.data_ptr(), sizes.data_ptr(), chunk_tensor.data_ptr(), chunk_offset.data_ptr(),
                              ntensors, nchunks, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
                              int(step), float(grad_scale), _stream()), "adamw")
+
+
+def adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> list[float]:
+    """The eight per-step float scalars of the update, formed by the library exactly as bbbp_adamw_f32 forms them."""
+    buf = (ctypes.c_float * 8)()
+    check(lib.bbbp_adamw_hyper(float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                               float(grad_scale), ctypes.cast(buf, ctypes.c_void_p)), "adamw_hyper")
+    return list(buf)
+
+
+def store_small(payload: bytes, dst: torch.Tensor) -> None:
+    """dst's first len(payload) <= 64 bytes = payload, sent as kernel parameters (asynchronous, stream-ordered)."""
+    assert len(payload) <= 64 and dst.numel() * dst.element_size() >= len(payload)
+    check(lib.bbbp_store_small(payload, len(payload), dst.data_ptr(), _stream()), "store_small")
+
+
+def adamw_dev(ptr_table, sizes, chunk_tensor, chunk_offset, ntensors, nchunks, hyper_dev):
+    """AdamW with the per-step scalars read from device memory at run time (graph-replayable)."""
+    check(lib.bbbp_adamw_dev_f32(ptr_table.data_ptr(), sizes.data_ptr(), chunk_tensor.data_ptr(), chunk_offset.data_ptr(),
+                                 ntensors, nchunks, hyper_dev.data_ptr(), _stream()), "adamw_dev")
 
 
 # ---- input contracts ------------------------------------------------------------------------------------------------------

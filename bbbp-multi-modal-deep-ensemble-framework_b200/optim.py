@@ -8,6 +8,8 @@ _transformer_cnn.py:161, ``ReduceLROnPlateau`` in _opt_more.py:162) keep working
 """
 from __future__ import annotations
 
+import struct
+
 import torch
 
 from . import ops
@@ -48,6 +50,71 @@ class AdamW(torch.optim.Optimizer):
                len(params), len(chunk_t))
         self._tables[gi] = (key, tab)
         return tab
+
+    # -- CUDA-graph form (train.GraphedTrainStep) ---------------------------------------------------------------------
+    def graph_prepare(self):
+        """Before capture: moment buffers and EMPTY device tables for every group (their contents are only read when
+        the captured kernel runs, so they are filled by graph_bind() once the capture has fixed the gradient
+        addresses).  Returns one (8-float hyper tensor) per group."""
+        plan = []
+        for group in self.param_groups:
+            params = [p for p in group["params"] if p.requires_grad]
+            if not params:
+                plan.append(None)
+                continue
+            dev = params[0].device
+            for p in params:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("bbbp_b200.AdamW needs contiguous float32 CUDA parameters")
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            sizes, chunk_t, chunk_o = [], [], []
+            for t, p in enumerate(params):
+                sizes.append(p.numel())
+                for off in range(0, p.numel(), _CHUNK):
+                    chunk_t.append(t)
+                    chunk_o.append(off)
+            plan.append(dict(params=params, ptrs=torch.zeros(4 * len(params), dtype=torch.int64, device=dev),
+                             sizes=torch.tensor(sizes, dtype=torch.int64).to(dev),
+                             chunk_t=torch.tensor(chunk_t, dtype=torch.int32).to(dev),
+                             chunk_o=torch.tensor(chunk_o, dtype=torch.int64).to(dev), nchunks=len(chunk_t),
+                             hyper=torch.zeros(8, dtype=torch.float32, device=dev)))
+        return plan
+
+    def graph_step(self, plan):
+        """Inside capture: one adamw_dev launch per group reading tables + hyper-parameters from device memory."""
+        for entry in plan:
+            if entry is not None:
+                ops.adamw_dev(entry["ptrs"], entry["sizes"], entry["chunk_t"], entry["chunk_o"], len(entry["params"]),
+                              entry["nchunks"], entry["hyper"])
+
+    def graph_bind(self, plan):
+        """After capture: the gradients now have their (static) graph-pool addresses."""
+        for entry in plan:
+            if entry is None:
+                continue
+            params = entry["params"]
+            missing = [i for i, p in enumerate(params) if p.grad is None]
+            if missing:
+                raise RuntimeError(f"{len(missing)} parameters received no gradient in the captured step")
+            ptrs = []
+            for sel in (lambda p: p, lambda p: p.grad, lambda p: self.state[p]["exp_avg"],
+                        lambda p: self.state[p]["exp_avg_sq"]):
+                ptrs += [sel(p).data_ptr() for p in params]
+            entry["ptrs"].copy_(torch.tensor(ptrs, dtype=torch.int64))
+
+    def graph_advance(self, plan, grad_scale: float = 1.0):
+        """Before each replay: bump the step counts and send this step's scalars (lr may have been changed by a torch
+        LR scheduler) to the device as kernel parameters (bbbp_store_small)."""
+        for group, entry in zip(self.param_groups, plan):
+            if entry is None:
+                continue
+            group["step"] = group.get("step", 0) + 1
+            b1, b2 = group["betas"]
+            h = ops.adamw_hyper(group["lr"], b1, b2, group["eps"], group["weight_decay"], group["step"], grad_scale)
+            ops.store_small(struct.pack("8f", *h), entry["hyper"])
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):

@@ -57,7 +57,12 @@ uint64_t bbbp_launch_count(void);
 /* C[M,N] = act( opA(A)[M,K] * opB(B)[K,N] + bias[N] ) (+ C_in when accumulate != 0), fp32 CUDA cores.
  * transA == 0: A stored [M,K] (lda >= K); != 0: A stored [K,M] (lda >= M).  Same for B with [K,N]/[N,K].
  * nn.Linear forward is transA=0, transB=1 with B = weight[N,K].  bias may be NULL.
- * split_k > 1 needs workspace of split_k*M*N floats (deterministic two-pass reduction). */
+ * split_k > 1 needs workspace of split_k*M*N floats (deterministic two-pass reduction).
+ * split_k == 0 is the latency mode of the training path: the library picks the kernel (a one-shot shared-memory kernel
+ * when M <= 32, i.e. one reference training batch) and the K partition from (M, N, K); results are deterministic for a
+ * given shape but the reduction order depends on M, so the inference path (bit-identical scores however batches are
+ * grouped) passes an explicit split_k instead.  Workspace for split_k == 0: bbbp_gemm_f32_auto_workspace() bytes. */
+size_t bbbp_gemm_f32_auto_workspace(int M, int N, int K);
 int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                   float* C, int ldc, const float* bias, int act, int accumulate, int split_k, float* workspace,
                   size_t workspace_bytes, bbbp_stream_t stream);
@@ -109,8 +114,9 @@ int bbbp_conv3x3_f32(const float* x, const float* w, const float* b, float* y, u
 /* dpre[N,C,H,W] = scatter of dy[N,C,H/2,W/2] to the arg-max position, zero where y <= 0 (ReLU) */
 int bbbp_relu_pool_bwd_f32(const float* dy, const float* y, const uint8_t* argmax, float* dpre, int N, int C, int H,
                            int W, bbbp_stream_t stream);
-/* dw[Cout,Cin,3,3] and db[Cout] from dpre[N,Cout,H,W] and x[N,Cin,H,W]; deterministic two-pass.
- * workspace: N * (8*Cout*Cin*9 + Cout) floats (partials per image and per band of image rows). */
+/* dw[Cout,Cin,3,3] and db[Cout] from dpre[N,Cout,H,W] and x[N,Cin,H,W]; deterministic two-pass (partials per image
+ * group, 8-row strip and row slice, summed in a fixed order).  workspace: bbbp_conv3x3_wgrad_workspace() bytes. */
+size_t bbbp_conv3x3_wgrad_workspace(int N, int Cin, int Cout, int H, int W);
 int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* dw, float* db, int N, int Cin, int Cout, int H,
                            int W, float* workspace, size_t workspace_bytes, bbbp_stream_t stream);
 /* w_t[Cin,Cout,3,3] = spatially flipped, channel-transposed w[Cout,Cin,3,3] (weights of the data-gradient conv) */
@@ -151,11 +157,13 @@ int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, 
  * out[groups*seq, E]; lse[groups*seq, heads] (log-sum-exp of the scaled scores, may be NULL). */
 /* dropout_p > 0 drops attention probabilities after the softmax (nn.MultiheadAttention dropout, train mode);
  * the keep mask is Philox(seed; group, head, query, key), so backward regenerates it from the same seed. */
+/* seed_dev (may be NULL): DEVICE uint64 added to ``seed`` when the kernel RUNS, so a training step captured in a CUDA
+ * graph draws a fresh mask at every replay (the host refreshes *seed_dev before replaying; see bbbp_adamw_dev_f32). */
 int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, int groups, int seq, int heads, int head_dim,
-                           float dropout_p, uint64_t seed, bbbp_stream_t stream);
+                           float dropout_p, uint64_t seed, const uint64_t* seed_dev, bbbp_stream_t stream);
 int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
                            int groups, int seq, int heads, int head_dim, float dropout_p, uint64_t seed,
-                           bbbp_stream_t stream);
+                           const uint64_t* seed_dev, bbbp_stream_t stream);
 
 /* ---- normalisation: nn.LayerNorm (post-norm residual, eps 1e-5) and nn.BatchNorm1d C:101 ------- */
 
@@ -223,7 +231,8 @@ int bbbp_copy2d_f32(const float* src, int ld_src, float* dst, int ld_dst, int ro
 int bbbp_gather_rows_f32(const float* src, const int64_t* idx, float* dst, int rows, long long cols, bbbp_stream_t stream);
 /* Philox-4x32-10 dropout: y = x * keep / (1-p); the mask is a function of (seed, element index).  Not
  * stream-compatible with torch's generator (SURVEY hard part f). */
-int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset, bbbp_stream_t stream);
+int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,
+                     bbbp_stream_t stream);
 
 /* ---- loss C:143,189 and optimiser C:172,191 ----------------------------------------------------- */
 /* loss[0] = mean((pred - target)^2); dpred = 2 (pred - target) / n * grad_scale (dpred may be NULL) */
@@ -239,6 +248,20 @@ int bbbp_bce_logits_loss_f32(const float* logit, const float* target, float* los
 int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor, const int64_t* chunk_offset,
                    int ntensors, int nchunks, double lr, double beta1, double beta2, double eps, double weight_decay,
                    int step, float grad_scale, bbbp_stream_t stream);
+/* The same update with the per-step scalars read from DEVICE memory when the kernel runs, so that a whole training step
+ * (forward + backward + this launch) can be captured once in a CUDA graph and replayed while the step count, the
+ * learning rate (torch LR schedulers) and the dropout seed keep changing.  hyper_dev = 8 floats produced by
+ * bbbp_adamw_hyper(); the host copies them to the device before each replay. */
+int bbbp_adamw_dev_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor, const int64_t* chunk_offset,
+                       int ntensors, int nchunks, const float* hyper_dev, bbbp_stream_t stream);
+/* dst_dev[0:n_bytes) = host_src[0:n_bytes), n_bytes <= 64, travelling as KERNEL PARAMETERS: host_src is read before the
+ * call returns, so no pinned staging buffer has to outlive the call and the store is ordered on the stream like any
+ * launch.  This is how the per-step scalars (hyper_dev, seed_dev) are refreshed between CUDA-graph replays. */
+int bbbp_store_small(const void* host_src, int n_bytes, void* dst_dev, bbbp_stream_t stream);
+/* HOST helper (no device work): hyper_out[8] (host) = {1-beta1, beta2, 1-beta2, eps, 1-lr*wd, lr/(1-beta1^step),
+ * sqrt(1-beta2^step), grad_scale}, each formed in double exactly as bbbp_adamw_f32 forms it. */
+int bbbp_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int step, float grad_scale,
+                     float* hyper_out);
 
 /* ---- input contracts P1/P2 (extensions; oracle = oracle/preprocess.py) --------------------------- */
 /* packed little-endian bit rows (bytes_per_row = ceil(n_bits/8)) -> per-molecule z-scored fp32 rows */

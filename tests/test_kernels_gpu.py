@@ -48,6 +48,24 @@ def test_gemm_f32_linear(ops, M, N, K, split, act):
     close(y, ref, atol=2e-5 * max(1.0, math.sqrt(K) / 16), what=f"gemm_f32 {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K", [(32, 167, 167), (32, 2048, 167), (32, 167, 2048), (10, 128, 65536), (2, 3, 64),
+                                   (2, 501, 300), (32, 4096, 128), (33, 167, 2048), (256, 167, 2048)])
+def test_gemm_f32_latency_mode_all_layouts(ops, M, N, K):
+    """split_k = 0 (training path): the one-shot kernel for M <= 32 and the tiled kernel with a library-chosen split
+    above, for the three operand layouts the autograd functions use (forward NT, dX NN, dW TN)."""
+    x, w, b = rnd(M, K, seed=15), rnd(N, K, seed=16, scale=K ** -0.5), rnd(N, seed=17)
+    tol = 2e-5 * max(1.0, math.sqrt(K) / 16)
+    close(ops.gemm_f32(x.cuda(), w.cuda(), trans_b=True, bias=b.cuda(), act="relu", split_k=0),
+          torch.relu(x.double() @ w.double().t() + b.double()).float(), tol, what="NT")
+    close(ops.gemm_f32(x.cuda(), w.t().contiguous().cuda(), split_k=0), (x.double() @ w.double().t()).float(), tol, what="NN")
+    close(ops.gemm_f32(x.t().contiguous().cuda(), w.t().contiguous().cuda(), trans_a=True, split_k=0),
+          (x.double() @ w.double().t()).float(), tol, what="TN")
+    c = rnd(M, N, seed=18)
+    out = c.clone().cuda()
+    ops.gemm_f32(x.cuda(), w.cuda(), trans_b=True, out=out, accumulate=True, split_k=0)
+    close(out, (c.double() + x.double() @ w.double().t()).float(), tol, what="accumulate")
+
+
 def test_gemm_f32_transposes_and_accumulate(ops):
     a, b = rnd(40, 23, seed=4), rnd(23, 31, seed=5)
     close(ops.gemm_f32(a.cuda(), b.cuda()), a @ b, 1e-5, what="NN")
@@ -89,7 +107,8 @@ def test_gemm_bf16_epilogues(ops, act):
 
 
 # ---- convolution block -----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 3, 32, 128), (3, 32, 64, 64), (1, 64, 128, 32), (1, 128, 256, 16), (2, 3, 64, 32)])
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 3, 32, 128), (3, 32, 64, 64), (1, 64, 128, 32), (1, 128, 256, 16), (2, 3, 64, 32),
+                                           (35, 3, 32, 32), (34, 8, 32, 16), (33, 20, 64, 16)])
 def test_conv_relu_pool_forward_backward(ops, N, Cin, Cout, H):
     x = rnd(N, Cin, H, H, seed=20).requires_grad_()
     w = rnd(Cout, Cin, 3, 3, seed=21, scale=1 / math.sqrt(9 * Cin)).requires_grad_()
@@ -132,23 +151,29 @@ def test_attention_forward_backward(ops, groups, seq, heads, d):
     close(dqkv, qkv.grad, 5e-5, what="attention bwd")
 
 
-def test_attention_dropout_is_consistent_between_forward_and_backward(ops):
-    groups, seq, heads, d, p = 1, 64, 2, 32, 0.25
+@pytest.mark.parametrize("groups,seq,heads,d", [(1, 64, 2, 32), (2, 32, 1, 167), (1, 10, 3, 8)])
+def test_attention_dropout_is_consistent_between_forward_and_backward(ops, groups, seq, heads, d):
+    p = 0.25
     E = heads * d
-    qkv = rnd(seq, 3 * E, seed=32).cuda()
+    qkv = rnd(groups * seq, 3 * E, seed=32).cuda()
     o1, lse = ops.attention_fwd(qkv, groups, seq, heads, d, p, 1234)
     o2, _ = ops.attention_fwd(qkv, groups, seq, heads, d, p, 1234)
     o3, _ = ops.attention_fwd(qkv, groups, seq, heads, d, p, 99)
     assert torch.equal(o1, o2) and not torch.equal(o1, o3)
     # directional derivative check of the dropped attention against a finite difference in float64 is
     # not available on device; instead check linearity in dout and agreement with p=0 in expectation
-    dout = rnd(seq, E, seed=33).cuda()
+    dout = rnd(groups * seq, E, seed=33).cuda()
     g1 = ops.attention_bwd(qkv, o1, lse, dout, groups, seq, heads, d, p, 1234)
     g2 = ops.attention_bwd(qkv, o1, lse, 2 * dout, groups, seq, heads, d, p, 1234)
     close(g2, 2 * g1, 1e-5, what="linearity")
     o0, _ = ops.attention_fwd(qkv, groups, seq, heads, d)
     outs = torch.stack([ops.attention_fwd(qkv, groups, seq, heads, d, p, s)[0] for s in range(200)]).mean(0)
     assert float((outs - o0).abs().mean()) < 0.05
+    # the per-step part of the seed may live in device memory (CUDA-graph replay): seed + *seed_dev is the seed
+    sd = torch.tensor([234], dtype=torch.int64, device="cuda")
+    o4, lse4 = ops.attention_fwd(qkv, groups, seq, heads, d, p, 1000, seed_dev=sd)
+    assert torch.equal(o4, o1)
+    assert torch.equal(ops.attention_bwd(qkv, o4, lse4, dout, groups, seq, heads, d, p, 1000, seed_dev=sd), g1)
 
 
 # ---- normalisation ----------------------------------------------------------------------------------------------------------

@@ -417,3 +417,63 @@ def test_mixed_precision_training_tracks_fp32(cuda_device):
     np.testing.assert_allclose(losses["bf16"][0], losses["fp32"][0], rtol=1e-3)
     np.testing.assert_allclose(losses["bf16"], losses["fp32"], rtol=5e-2)
     assert losses["fp32"][-1] < losses["fp32"][0] * 1.5      # sanity: finite, not diverging
+
+
+@pytest.mark.parametrize("variant,fp_dim,precision", [("tcnn", 167, "fp32"), ("tcnn", 167, "bf16"), ("mlp_more", 64, "fp32")])
+def test_graphed_train_step_is_bit_identical_to_eager_steps(cuda_device, variant, fp_dim, precision):
+    """GraphedTrainStep replays the SAME kernels in the same order as the reference loop body run eagerly
+    (zero_grad / forward / loss / backward / AdamW, 20250113.py:186-191), so with dropout off the loss of every step, the
+    gradients of the last one and every parameter / BatchNorm buffer afterwards must be bit-identical -- including a
+    learning-rate change between steps (torch LR schedulers) and a second input shape (the ragged last batch)."""
+    import bbbp_b200
+    img_dim = IMG if variant == "tcnn" else 128
+    runs = {}
+    for mode in ("eager", "graph"):
+        _, model = make_pair(variant, fp_dim, 128, 4, cuda_device)
+        nets.zero_dropout(model)
+        model.train().set_precision(precision)
+        opt = bbbp_b200.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+        crit = bbbp_b200.MSELoss()
+        step = bbbp_b200.GraphedTrainStep(model, opt, crit)
+        losses = []
+        for i, batch in enumerate((32, 32, 32, 10, 32)):
+            if i == 2:
+                opt.param_groups[0]["lr"] = 3e-5
+            fp, img, y = (t.cuda() for t in seeded_inputs(900 + i, batch, fp_dim, img_dim))
+            if mode == "graph":
+                loss = step(fp, img, y)
+            else:
+                opt.zero_grad()
+                loss = crit(model(fp, img).squeeze(), y)
+                loss.backward()
+                opt.step()
+            losses.append(float(loss))
+        runs[mode] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()},
+                      {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    assert runs["graph"][0] == runs["eager"][0]
+    for k, v in runs["eager"][1].items():
+        assert torch.equal(runs["graph"][1][k], v), k
+    for k, v in runs["eager"][2].items():
+        assert torch.equal(runs["graph"][2][k], v), k
+
+
+def test_graphed_train_step_draws_fresh_dropout_masks_and_leaves_no_warmup_trace(cuda_device):
+    import bbbp_b200
+    _, model = make_pair("tcnn", 167, 128, 5, cuda_device)
+    model.train()
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    opt = bbbp_b200.AdamW(model.parameters(), lr=0.0, weight_decay=0.0)      # lr 0: replays must not move the weights
+    step = bbbp_b200.GraphedTrainStep(model, opt, bbbp_b200.MSELoss())
+    fp, img, y = (t.cuda() for t in seeded_inputs(950, 32, 167, IMG))
+    losses = [float(step(fp, img, y)) for _ in range(4)]
+    assert len(set(losses)) == 4, losses             # same weights, same inputs: only the dropout masks differ
+    after = model.state_dict()
+    for k, v in before.items():
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert torch.equal(after[k], v), k
+    assert int(after["fc.2.num_batches_tracked"]) == 4    # the two warm-up steps before capture were rolled back
+    # and inference after graph training sees the current weights (derived-weight caches invalidated per replay)
+    model.eval()
+    with torch.no_grad():
+        assert torch.isfinite(model(fp, img)).all()

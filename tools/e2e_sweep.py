@@ -1,0 +1,28 @@
+"""predict_from_host on the compact formats: chunk-size sweep (pipeline fill/drain vs per-chunk kernel efficiency)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, bbbp_b200
+dev = torch.device("cuda:0"); torch.manual_seed(0)
+m = bbbp_b200.MixedInputModel(167, 128).to(dev).eval().set_precision("bf16")
+n = int(os.environ.get("N", 8192))
+packed = torch.randint(0, 256, (n, 21), dtype=torch.uint8).pin_memory()
+img8 = torch.randint(0, 256, (n, 3, 128, 128), dtype=torch.uint8).pin_memory()
+out_host = torch.empty(n, dtype=torch.float32).pin_memory()
+res = {}
+for chunk in (256, 512, 1024, 2048, 4096):
+    fn = lambda: m.predict_from_host(packed, img8, 256, chunk_molecules=chunk, packed=True, out_host=out_host)
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(8): fn()
+    e1.record(); torch.cuda.synchronize()
+    res[chunk] = e0.elapsed_time(e1) / 8
+    print(chunk, res[chunk], n / res[chunk] * 1e3, flush=True)
+# H2D alone
+d = torch.empty_like(img8, device=dev)
+torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(8): d.copy_(img8, non_blocking=True)
+e1.record(); torch.cuda.synchronize()
+res["h2d_only_ms"] = e0.elapsed_time(e1) / 8
+print(json.dumps(res))
