@@ -35,11 +35,17 @@ def set_seed_tensor(t):
 # backward dependency chain -- nothing but the optimizer consumes them -- so forking them keeps only the dX chain on the
 # captured graph's critical path.  GraphedTrainStep joins the stream before the optimizer node.
 _wgrad_stream = None
+# Tensors the forked products still read.  Holding a reference matters for CORRECTNESS, not only for memory: when a
+# gradient has two consumers (the post-norm residual), autograd's input buffer accumulates IN PLACE into the first
+# arrival once it is the sole owner -- which would overwrite a dy that the side stream is still reading.  A live
+# reference makes the engine add out of place instead.  Cleared when the capture ends.
+_wgrad_keepalive: list = []
 
 
 def set_wgrad_stream(s):
     global _wgrad_stream
     prev, _wgrad_stream = _wgrad_stream, s
+    _wgrad_keepalive.clear()
     return prev
 
 
@@ -119,6 +125,7 @@ class Linear(Function):
             side.wait_stream(torch.cuda.current_stream())
             dpre.record_stream(side)
             x.record_stream(side)
+            _wgrad_keepalive.append((dpre, x))
         with torch.cuda.stream(side):       # stream(None) is a no-op
             if ctx.needs_input_grad[1]:
                 dw = ops.gemm_f32(dpre, x, trans_a=True, split_k=0)

@@ -339,59 +339,98 @@ __global__ void __launch_bounds__(256) attention_small_head_fwd_kernel(const flo
 
 
 // ---- short attention scopes (seq <= 32: one reference training batch) ---------------------------------------------
-// One CTA per (group, head) holds Q, K, V (and dO) of the whole scope in shared memory, one WARP per row: forward is
-// scores -> softmax -> PV in one launch, backward produces dQ, dK and dV in one launch.  The streaming kernels above
-// need 2 + 8 + 8 CTAs of 4 warps for this shape and re-stage K/V per query block; here every product is a 32 x 32 x d
-// block and the whole scope is fetched with one round of cp.async.
+// One CTA (32 warps) per (group, head) holds Q, K, V (and dO) of the whole scope in shared memory: forward is scores ->
+// softmax -> PV in one launch, backward produces dQ, dK and dV in one launch.  The streaming kernels above need 2 + 8 +
+// 8 CTAs of 4 warps for this shape and re-stage K/V per query block.  A single SM is instruction-issue bound on this
+// much work, so every product runs on 128-bit shared-memory accesses:
+//   scores   warp = query, lane = key:        Q row broadcast, K rows at a pitch of ld = 4*odd floats (conflict free)
+//   outputs  warp = 4-column block, lane = row: the V / K / Q / dO operand is one broadcast float4 per j, the P / dS
+//            operand a contiguous row of the (transposed where needed) 32 x 32 matrix
 constexpr int SS = 32;          // maximum scope = warps per CTA
+constexpr int SP = 33;          // pitch of the 32 x 32 matrices
+__host__ __device__ inline int short_ld(int d) { return 4 * (((d + 3) / 4) | 1); }
 
-// smem: Q[SS][ld] | K[SS][ld] | V[SS][ld] | P[SS][SS+1]
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ void axpy4(float a, float4 x, float4& y) {
+  y.x = fmaf(a, x.x, y.x);
+  y.y = fmaf(a, x.y, y.y);
+  y.z = fmaf(a, x.z, y.z);
+  y.w = fmaf(a, x.w, y.w);
+}
+// rows [0, SS) x columns [0, 4*ceil(d/4)) of a (seq, d) block with row pitch ld_src -> smem rows of pitch ld, zero outside
+__device__ __forceinline__ void short_stage(float* dst, int ld, const float* src, size_t ld_src, int seq, int d) {
+  const int row = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int d4 = (d + 3) / 4 * 4;
+  for (int dd = lane; dd < d4; dd += 32) {
+    const bool ok = row < seq && dd < d;
+    cp_async_f32(dst + row * ld + dd, ok ? src + row * ld_src + dd : src, ok);
+  }
+}
+
+// smem: Q[SS][ld] | K[SS][ld] | V[SS][ld] | PT[SS][SP] (PT[key][query])
 __global__ void __launch_bounds__(SS * 32) attention_short_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                                       float* __restrict__ lse, int seq, int heads, int d,
                                                                       float drop_p, uint64_t seed,
                                                                       const uint64_t* __restrict__ seed_dev) {
   if (seed_dev) seed += *seed_dev;
-  extern __shared__ float smem[];
-  const int ld = d | 1;
+  extern __shared__ __align__(16) float smem[];
+  const int ld = short_ld(d), n4 = (d + 3) / 4;
   float* Qs = smem;
   float* Ks = Qs + SS * ld;
   float* Vs = Ks + SS * ld;
-  float* Ps = Vs + SS * ld;
-  const int qi = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float* PT = Vs + SS * ld;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int h = blockIdx.x, g = blockIdx.y;
   const int E = heads * d, ldq = 3 * E;
   const size_t row0 = (size_t)g * seq;
   const float scale = rsqrtf((float)d);
   const float inv_keep = 1.0f / (1.0f - drop_p);
-  for (int i = threadIdx.x; i < SS * d; i += SS * 32) {
-    const int j = i / d, dd = i - j * d;
-    const bool ok = j < seq;
-    const float* src = ok ? qkv + (row0 + j) * ldq + h * d + dd : qkv;
-    cp_async_f32(Qs + j * ld + dd, src, ok);
-    cp_async_f32(Ks + j * ld + dd, src + (ok ? E : 0), ok);
-    cp_async_f32(Vs + j * ld + dd, src + (ok ? 2 * E : 0), ok);
-  }
+  const float* base = qkv + row0 * ldq + h * d;
+  short_stage(Qs, ld, base, ldq, seq, d);
+  short_stage(Ks, ld, base + E, ldq, seq, d);
+  short_stage(Vs, ld, base + 2 * E, ldq, seq, d);
   cp_async_wait_all();
   __syncthreads();
-  if (qi >= seq) return;                       // warp-uniform; no block barrier below
-  float s = 0.0f;
-  for (int dd = 0; dd < d; ++dd) s = fmaf(Qs[qi * ld + dd], Ks[lane * ld + dd], s);
-  s = lane < seq ? s * scale : -INFINITY;
-  const float m = warp_max(s);
-  const float p = __expf(s - m);
-  const float l = warp_sum(p);
-  // dropout acts on the normalised probabilities: the normaliser l keeps every key
-  Ps[qi * (SS + 1) + lane] = p * keep_scale(drop_p, inv_keep, seed, row0 + qi, row0 + lane, h) / l;
-  if (lse && lane == 0) lse[(row0 + qi) * heads + h] = m + __logf(l);
-  __syncwarp();
-  for (int dd = lane; dd < d; dd += 32) {
-    float o = 0.0f;
-    for (int j = 0; j < seq; ++j) o = fmaf(Ps[qi * (SS + 1) + j], Vs[j * ld + dd], o);
-    out[(row0 + qi) * E + h * d + dd] = o;
+  {  // scores and softmax of query `warp`
+    const int qi = warp;
+    float s = 0.0f;
+    const float4* q4 = reinterpret_cast<const float4*>(Qs + qi * ld);
+    const float4* k4 = reinterpret_cast<const float4*>(Ks + lane * ld);
+    for (int c = 0; c < n4; ++c) s = dot4(q4[c], k4[c], s);
+    s = (qi < seq && lane < seq) ? s * scale : -INFINITY;
+    float p = 0.0f;
+    if (qi < seq) {                                 // warp-uniform
+      const float m = warp_max(s);
+      p = __expf(s - m);
+      const float l = warp_sum(p);
+      // dropout acts on the normalised probabilities: the normaliser l keeps every key
+      p = p * keep_scale(drop_p, inv_keep, seed, row0 + qi, row0 + lane, h) / l;
+      if (lse && lane == 0) lse[(row0 + qi) * heads + h] = m + __logf(l);
+    }
+    PT[lane * SP + qi] = p;
+  }
+  __syncthreads();
+  // O = P V: warp = 4-column block c, lane = query
+  for (int c = warp; c < n4; c += SS) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < seq; ++j) axpy4(PT[j * SP + lane], *reinterpret_cast<const float4*>(Vs + j * ld + 4 * c), o);
+    if (lane < seq) {
+      float* dst = out + (row0 + lane) * E + h * d + 4 * c;
+      const int left = d - 4 * c;
+      dst[0] = o.x;
+      if (left > 1) dst[1] = o.y;
+      if (left > 2) dst[2] = o.z;
+      if (left > 3) dst[3] = o.w;
+    }
   }
 }
 
-// smem: Q[SS][ld] | K | V | dO | P[SS][SS+1] (kept probabilities) | dS[SS][SS+1]
+// smem: Q | K | V | dO (each [SS][ld]) | P[SS][SP] (kept probabilities, [query][key]) | dS[SS][SP] | dST[SS][SP]
 __global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const float* __restrict__ qkv,
                                                                       const float* __restrict__ out,
                                                                       const float* __restrict__ lse,
@@ -399,69 +438,77 @@ __global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const floa
                                                                       int seq, int heads, int d, float drop_p, uint64_t seed,
                                                                       const uint64_t* __restrict__ seed_dev) {
   if (seed_dev) seed += *seed_dev;
-  extern __shared__ float smem[];
-  const int ld = d | 1;
+  extern __shared__ __align__(16) float smem[];
+  const int ld = short_ld(d), n4 = (d + 3) / 4;
   float* Qs = smem;
   float* Ks = Qs + SS * ld;
   float* Vs = Ks + SS * ld;
   float* dOs = Vs + SS * ld;
   float* Ps = dOs + SS * ld;
-  float* dSs = Ps + SS * (SS + 1);
-  const int row = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float* dSs = Ps + SS * SP;
+  float* dST = dSs + SS * SP;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int h = blockIdx.x, g = blockIdx.y;
   const int E = heads * d, ldq = 3 * E;
   const size_t row0 = (size_t)g * seq;
   const float scale = rsqrtf((float)d);
   const float inv_keep = 1.0f / (1.0f - drop_p);
-  for (int i = threadIdx.x; i < SS * d; i += SS * 32) {
-    const int j = i / d, dd = i - j * d;
-    const bool ok = j < seq;
-    const float* src = ok ? qkv + (row0 + j) * ldq + h * d + dd : qkv;
-    cp_async_f32(Qs + j * ld + dd, src, ok);
-    cp_async_f32(Ks + j * ld + dd, src + (ok ? E : 0), ok);
-    cp_async_f32(Vs + j * ld + dd, src + (ok ? 2 * E : 0), ok);
-    cp_async_f32(dOs + j * ld + dd, ok ? dout + (row0 + j) * E + h * d + dd : dout, ok);
-  }
+  const float* base = qkv + row0 * ldq + h * d;
+  short_stage(Qs, ld, base, ldq, seq, d);
+  short_stage(Ks, ld, base + E, ldq, seq, d);
+  short_stage(Vs, ld, base + 2 * E, ldq, seq, d);
+  short_stage(dOs, ld, dout + row0 * E + h * d, E, seq, d);
   // D_i = <dO_i, O_i> straight from global memory while the copies fly
   float D = 0.0f, L = 0.0f;
-  if (row < seq) {
+  if (warp < seq) {
     for (int dd = lane; dd < d; dd += 32)
-      D = fmaf(dout[(row0 + row) * E + h * d + dd], out[(row0 + row) * E + h * d + dd], D);
+      D = fmaf(dout[(row0 + warp) * E + h * d + dd], out[(row0 + warp) * E + h * d + dd], D);
     D = warp_sum(D);
-    L = lse[(row0 + row) * heads + h];
+    L = lse[(row0 + warp) * heads + h];
   }
   cp_async_wait_all();
   __syncthreads();
-  {  // P and dS of query `row` (lane = key)
+  {  // P and dS of query `warp` (lane = key)
+    const int qi = warp;
     float s = 0.0f, dp = 0.0f;
-    for (int dd = 0; dd < d; ++dd) {
-      s = fmaf(Qs[row * ld + dd], Ks[lane * ld + dd], s);
-      dp = fmaf(dOs[row * ld + dd], Vs[lane * ld + dd], dp);
+    const float4* q4 = reinterpret_cast<const float4*>(Qs + qi * ld);
+    const float4* g4 = reinterpret_cast<const float4*>(dOs + qi * ld);
+    const float4* k4 = reinterpret_cast<const float4*>(Ks + lane * ld);
+    const float4* v4 = reinterpret_cast<const float4*>(Vs + lane * ld);
+    for (int c = 0; c < n4; ++c) {
+      s = dot4(q4[c], k4[c], s);
+      dp = dot4(g4[c], v4[c], dp);
     }
-    const float p = (row < seq && lane < seq) ? __expf(s * scale - L) : 0.0f;
-    const float keep = keep_scale(drop_p, inv_keep, seed, row0 + row, row0 + lane, h);
-    Ps[row * (SS + 1) + lane] = p * keep;
-    dSs[row * (SS + 1) + lane] = p * (dp * keep - D);
+    const float p = (qi < seq && lane < seq) ? __expf(s * scale - L) : 0.0f;
+    const float keep = keep_scale(drop_p, inv_keep, seed, row0 + qi, row0 + lane, h);
+    const float ds = p * (dp * keep - D);
+    Ps[qi * SP + lane] = p * keep;
+    dSs[qi * SP + lane] = ds;
+    dST[lane * SP + qi] = ds;
   }
   __syncthreads();
-  if (row >= seq) return;
-  // dQ_i = scale * sum_j dS_ij K_j ; dK_j = scale * sum_i dS_ij Q_i ; dV_j = sum_i P_ij dO_i
-  for (int dd = lane; dd < d; dd += 32) {
-    float dq = 0.0f, dk = 0.0f, dv = 0.0f;
+  // warp = 4-column block c, lane = row r:
+  //   dQ_r = scale * sum_j dS[r][j] K_j ; dK_r = scale * sum_j dS[j][r] Q_j ; dV_r = sum_j P[j][r] dO_j
+  for (int c = warp; c < n4; c += SS) {
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dk = dq, dv = dq;
     for (int j = 0; j < seq; ++j) {
-      dq = fmaf(dSs[row * (SS + 1) + j], Ks[j * ld + dd], dq);
-      dk = fmaf(dSs[j * (SS + 1) + row], Qs[j * ld + dd], dk);
-      dv = fmaf(Ps[j * (SS + 1) + row], dOs[j * ld + dd], dv);
+      axpy4(dST[j * SP + lane], *reinterpret_cast<const float4*>(Ks + j * ld + 4 * c), dq);
+      axpy4(dSs[j * SP + lane], *reinterpret_cast<const float4*>(Qs + j * ld + 4 * c), dk);
+      axpy4(Ps[j * SP + lane], *reinterpret_cast<const float4*>(dOs + j * ld + 4 * c), dv);
     }
-    float* dst = dqkv + (row0 + row) * ldq + h * d + dd;
-    dst[0] = dq * scale;
-    dst[E] = dk * scale;
-    dst[2 * E] = dv;
+    if (lane < seq) {
+      float* dst = dqkv + (row0 + lane) * ldq + h * d + 4 * c;
+      const int left = d - 4 * c;
+      dst[0] = dq.x * scale, dst[E] = dk.x * scale, dst[2 * E] = dv.x;
+      if (left > 1) dst[1] = dq.y * scale, dst[E + 1] = dk.y * scale, dst[2 * E + 1] = dv.y;
+      if (left > 2) dst[2] = dq.z * scale, dst[E + 2] = dk.z * scale, dst[2 * E + 2] = dv.z;
+      if (left > 3) dst[3] = dq.w * scale, dst[E + 3] = dk.w * scale, dst[2 * E + 3] = dv.w;
+    }
   }
 }
 
-static size_t short_fwd_smem(int d) { return ((size_t)3 * SS * (d | 1) + SS * (SS + 1)) * sizeof(float); }
-static size_t short_bwd_smem(int d) { return ((size_t)4 * SS * (d | 1) + 2 * SS * (SS + 1)) * sizeof(float); }
+static size_t short_fwd_smem(int d) { return ((size_t)3 * SS * short_ld(d) + SS * SP) * sizeof(float); }
+static size_t short_bwd_smem(int d) { return ((size_t)4 * SS * short_ld(d) + 3 * SS * SP) * sizeof(float); }
 
 // Query (or key) rows per CTA: 16 (four passes of the CTA's four warps over one staged K/V tile stream) when that
 // already fills the GPU, otherwise 4 (one pass) -- a reference training batch (seq 32, one head) is 2 CTAs at 16 rows

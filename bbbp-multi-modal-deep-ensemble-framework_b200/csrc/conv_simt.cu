@@ -223,12 +223,23 @@ __global__ void __launch_bounds__(256) conv_bgrad_partial_kernel(const float* __
   }
 }
 
-__global__ void sum_over_images_kernel(const float* __restrict__ part, float* __restrict__ out, int N, size_t per_image) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= per_image) return;
+// out[i] = sum_n part[n][i]: block = 32 outputs x 8 partial lanes (lane l sums n = l, l+8, ...), then a fixed-order
+// combine of the 8 lanes -- deterministic, coalesced, and 8x the parallelism of one thread per output
+__global__ void __launch_bounds__(256) sum_over_images_kernel(const float* __restrict__ part, float* __restrict__ out, int N,
+                                                              size_t per_image) {
+  __shared__ float red[8][33];
+  const size_t i = blockIdx.x * (size_t)32 + threadIdx.x;
   float s = 0.0f;
-  for (int n = 0; n < N; ++n) s += part[(size_t)n * per_image + i];
-  out[i] = s;
+  if (i < per_image)
+    for (int n = threadIdx.y; n < N; n += 8) s += part[(size_t)n * per_image + i];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < per_image) {
+    float t = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][threadIdx.x];
+    out[i] = t;
+  }
 }
 
 __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout) {
@@ -309,11 +320,11 @@ extern "C" int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* 
 #undef BBBP_WGRAD
   int st = launch_status("conv3x3_wgrad partial");
   if (st != BBBP_OK) return st;
-  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)256), 256, 0, s>>>(part_w, dw, (int)n_part, per_w);
+  sum_over_images_kernel<<<(unsigned)ceil_div(per_w, (size_t)32), dim3(32, 8), 0, s>>>(part_w, dw, (int)n_part, per_w);
   st = launch_status("conv3x3_wgrad reduce");
   if (st != BBBP_OK || !db) return st;
   conv_bgrad_partial_kernel<<<dim3(Cout, N), 256, 0, s>>>(dpre, part_b, Cout, H * W);
-  sum_over_images_kernel<<<(unsigned)ceil_div(per_b, (size_t)256), 256, 0, s>>>(part_b, db, N, per_b);
+  sum_over_images_kernel<<<(unsigned)ceil_div(per_b, (size_t)32), dim3(32, 8), 0, s>>>(part_b, db, N, per_b);
   note_launches(1);
   return launch_status("conv3x3 bias grad");
 }

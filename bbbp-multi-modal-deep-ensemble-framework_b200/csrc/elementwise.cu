@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ pr
 }
 
 // ---- fused multi-tensor AdamW (torch.optim.AdamW single-tensor semantics, 20250113.py:172,191) -------------------
-constexpr int ADAMW_CHUNK = 65536;
+constexpr int ADAMW_CHUNK = 16384;   // bbbp_adamw_chunk(): ~820 CTAs for the 13.5 M-parameter net (5.5 per SM)
 struct AdamwHyper { float v[8]; };  // bbbp_adamw_hyper() layout
 
 // ONE kernel behind both entry points, so an eager step and a graph replay round identically: the eight per-step
@@ -468,6 +468,8 @@ extern "C" int bbbp_store_small(const void* host_src, int n_bytes, void* dst_dev
   store_small_kernel<<<1, 64, 0, as_stream(stream)>>>(blob, static_cast<uint8_t*>(dst_dev), n_bytes);
   return launch_status("store_small");
 }
+
+extern "C" int bbbp_adamw_chunk(void) { return bbbp::ADAMW_CHUNK; }
 
 extern "C" int bbbp_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                                 float grad_scale, float* h) {

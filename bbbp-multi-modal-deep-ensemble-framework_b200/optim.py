@@ -14,7 +14,9 @@ import torch
 
 from . import ops
 
-_CHUNK = 65536
+from ._lib import lib as _lib
+
+_CHUNK = _lib.bbbp_adamw_chunk()      # elements per CTA of the fused update
 
 
 class AdamW(torch.optim.Optimizer):

@@ -19,6 +19,7 @@ forked onto a second stream so the graph keeps them as parallel branches (forwar
 """
 from __future__ import annotations
 
+import os
 import struct
 
 import torch
@@ -45,6 +46,8 @@ class GraphedTrainStep:
         self._graphs: dict = {}
         self._seed_step = 0
         self._last = None
+        self.high_priority_chain = os.environ.get("BBBP_GRAPH_PRIORITY", "1") == "1"
+        self.fork_weight_grads = os.environ.get("BBBP_GRAPH_WGRAD_FORK", "1") == "1"
 
     # -- the step body, shared by warm-up, capture and the eager fallback -------------------------------------------------
     def _body(self, fp, img, y):
@@ -124,11 +127,15 @@ class GraphedTrainStep:
     def _capture_once(self, s_fp, s_img, s_y, plan, forked):
         graph = torch.cuda.CUDAGraph()
         if hasattr(self.model, "fork_image_branch"):
-            self.model.fork_image_branch = forked
-        wgrad = torch.cuda.Stream(s_fp.device) if forked else None
+            self.model.fork_image_branch = forked and getattr(self, "fork_image", True)
+        wgrad = torch.cuda.Stream(s_fp.device) if (forked and self.fork_weight_grads) else None
         prev = ag.set_wgrad_stream(wgrad)
         try:
-            with torch.cuda.graph(graph):
+            # The encoder chain is ~200 microsecond-scale dependent kernels, the forked conv branch a few SM-filling ones:
+            # capture the chain on a HIGH-priority stream so its CTAs are dispatched ahead of the conv kernels' pending
+            # waves instead of queueing behind them (the branch streams keep the default priority).
+            main = torch.cuda.Stream(s_fp.device, priority=-1) if (forked and self.high_priority_chain) else None
+            with torch.cuda.graph(graph, stream=main):
                 s_loss = self._body(s_fp, s_img, s_y)
                 if wgrad is not None:
                     torch.cuda.current_stream().wait_stream(wgrad)     # join the dW / db branch before the update

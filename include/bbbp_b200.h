@@ -243,8 +243,10 @@ int bbbp_bce_logits_loss_f32(const float* logit, const float* target, float* los
                              float grad_scale, bbbp_stream_t stream);
 /* torch.optim.AdamW semantics, one launch for all tensors.  ptrs is a DEVICE array of 4*ntensors pointers
  * laid out [param | grad | exp_avg | exp_avg_sq] and sizes a DEVICE array of ntensors element counts;
- * chunk_tensor / chunk_offset (DEVICE, nchunks entries) enumerate 64Ki-element chunks. step is 1-based.
+ * chunk_tensor / chunk_offset (DEVICE, nchunks entries) enumerate chunks of bbbp_adamw_chunk() elements (one CTA each).
+ * step is 1-based.
  * Hyper-parameters are doubles so that 1-beta, lr/bias_correction etc. round exactly as torch's do. */
+int bbbp_adamw_chunk(void);
 int bbbp_adamw_f32(void* const* ptrs, const int64_t* sizes, const int32_t* chunk_tensor, const int64_t* chunk_offset,
                    int ntensors, int nchunks, double lr, double beta1, double beta2, double eps, double weight_decay,
                    int step, float grad_scale, bbbp_stream_t stream);
