@@ -13,6 +13,7 @@ from .model import (  # noqa: F401
 from .optim import AdamW  # noqa: F401
 from .train import GraphedTrainStep  # noqa: F401
 from .feeder import DeviceBatchFeeder  # noqa: F401
+from .ensemble import OutOfFoldScores, stack_columns  # noqa: F401
 from .screening import average_gradients, gather_scores, partition_batches, screen  # noqa: F401
 from .preprocess import pca_transform, unpack_zscore, u8_image_zscore  # noqa: F401
 
@@ -20,5 +21,5 @@ __all__ = [
     "MixedInputModel", "MixedInputModelBig", "MixedInputModelNoFusion", "MixedInputModelMLP", "MixedInputModelMLPMore",
     "MixedInputModelMLPRdkit", "MultiHeadAttentionFusion", "AttentionFusion", "MultiModalAttentionFusion", "MSELoss",
     "BCEWithLogitsLoss", "AdamW", "build", "VARIANTS", "ops", "partition_batches", "gather_scores", "screen",
-    "average_gradients", "DeviceBatchFeeder", "GraphedTrainStep", "pca_transform", "unpack_zscore", "u8_image_zscore",
+    "average_gradients", "DeviceBatchFeeder", "GraphedTrainStep", "OutOfFoldScores", "stack_columns", "pca_transform", "unpack_zscore", "u8_image_zscore",
 ]

@@ -92,7 +92,7 @@ class Linear(Function):
     """y = act(x W^T + b); precision "fp32" (CUDA-core FMA) or "bf16" (tcgen05, fp32 accumulate)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, precision):
+    def forward(ctx, x, weight, bias, act, precision, training=False):
         x = contig(x)
         M, K = x.shape
         N = weight.shape[0]
@@ -102,7 +102,8 @@ class Linear(Function):
         else:
             # inference keeps a K-only split (bit-identical scores however batches are grouped); a training forward
             # has no such contract and takes the latency mode (one-shot kernel at M <= 32)
-            training = any(ctx.needs_input_grad[:3])       # all False under torch.no_grad()
+            # (``training`` is sampled by linear() OUTSIDE this function: inside Function.forward grad mode is always
+            # off and needs_input_grad ignores torch.no_grad())
             y = ops.gemm_f32(x, weight, trans_b=True, bias=bias, act=act,
                              split_k=0 if training else ops.fixed_split_k_f32(K))
         ctx.act = act
@@ -131,7 +132,7 @@ class Linear(Function):
                 dw = ops.gemm_f32(dpre, x, trans_a=True, split_k=0)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = ops.colsum(dpre)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class ConvReluPool(Function):
@@ -346,7 +347,8 @@ class BCEWithLogitsLoss(Function):
 
 
 def linear(x, weight, bias=None, act=None, precision="fp32"):
-    return Linear.apply(x, weight, bias, act, precision)
+    training = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad))
+    return Linear.apply(x, weight, bias, act, precision, training)
 
 
 def dropout(x, p, training):

@@ -553,7 +553,7 @@ extern "C" int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, 
     }
     return launch_status("attention_fwd (small heads)");
   }
-  if (seq <= SS && (long long)groups * heads <= 4096 && short_fwd_smem(head_dim) <= 200 * 1024) {
+  if (seq <= SS && short_fwd_smem(head_dim) <= 200 * 1024) {   // a function of the scope only: bit-identical for any grouping
     const size_t sm = short_fwd_smem(head_dim);
     cudaFuncSetAttribute(attention_short_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attention_short_fwd_kernel<<<dim3(heads, groups), SS * 32, sm, as_stream(stream)>>>(qkv, out, lse, seq, heads, head_dim,
@@ -577,7 +577,7 @@ extern "C" int bbbp_attention_bwd_f32(const float* qkv, const float* out, const 
   BBBP_CHECK_ARG(qkv && out && lse && dout && dqkv, "attention_bwd: null operand");
   if (!attention_args_ok("attention_bwd", groups, seq, heads, head_dim)) return BBBP_EINVAL;
   if (groups == 0) return BBBP_OK;
-  if (seq <= SS && (long long)groups * heads <= 4096 && short_bwd_smem(head_dim) <= 200 * 1024) {
+  if (seq <= SS && short_bwd_smem(head_dim) <= 200 * 1024) {
     const size_t sm = short_bwd_smem(head_dim);
     cudaFuncSetAttribute(attention_short_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attention_short_bwd_kernel<<<dim3(heads, groups), SS * 32, sm, as_stream(stream)>>>(

@@ -541,6 +541,21 @@ extern "C" int bbbp_softmax_rows_bwd_f32(const float* w, const float* dw, float*
   return launch_status("softmax_rows_bwd");
 }
 
+namespace bbbp {
+__global__ void scatter_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* __restrict__ dst,
+                               size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[i];
+}
+}  // namespace bbbp
+
+extern "C" int bbbp_scatter_f32(const float* src, const int64_t* idx, float* dst, size_t n, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(src && idx && dst, "scatter: null operand");
+  if (n == 0) return BBBP_OK;
+  bbbp::scatter_kernel<<<(unsigned)ceil_div(n, (size_t)256), 256, 0, as_stream(stream)>>>(src, idx, dst, n);
+  return launch_status("scatter");
+}
+
 extern "C" int bbbp_gather_rows_f32(const float* src, const int64_t* idx, float* dst, int rows, long long cols,
                                     bbbp_stream_t stream) {
   BBBP_CHECK_ARG(src && idx && dst && rows >= 0 && cols > 0, "gather_rows: bad argument");

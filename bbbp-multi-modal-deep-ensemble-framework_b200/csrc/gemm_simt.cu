@@ -106,34 +106,32 @@ __global__ void __launch_bounds__(256) gemm_f32_skinny_kernel(int M, int N, int 
   const int n0 = blockIdx.x * SK_TN;
   const int kbeg = blockIdx.y * SK_KC;
   const int kc = min(SK_KC, K - kbeg);
-  const int total = SK_M * kc;
-  // every load of the slab is issued before anything waits (cp.async, zero fill outside the matrix); src pointers of
-  // masked elements are clamped to the matrix base so no out-of-range address is ever formed
-  if (sAk == 1) {
-    for (int i = tid; i < total; i += 256) {
-      const int m = i / kc, k = i - m * kc;
+  // every load of the slab is issued before anything waits (cp.async, zero fill outside the matrix).  The fast global
+  // axis runs along the lanes and the slow one along the warps, so the index arithmetic is additions only (the first
+  // version divided by the runtime slab width per element and spent more issue slots on addresses than on FMAs);
+  // src pointers of masked elements are clamped to the matrix base so no out-of-range address is ever formed
+  const int lane = tid % 32, warp = tid / 32;
+  if (sAk == 1) {          // k along lanes, rows along warps
+    for (int m = warp; m < SK_M; m += 8) {
       const bool ok = m < M;
-      cp_async_f32(As + k * SK_PITCH + m, ok ? A + m * sAm + kbeg + k : A, ok);
+      const float* src = ok ? A + m * sAm + kbeg : A;
+      for (int k = lane; k < kc; k += 32) cp_async_f32(As + k * SK_PITCH + m, ok ? src + k : src, ok);
     }
-  } else {
-    for (int i = tid; i < total; i += 256) {
-      const int k = i / SK_M, m = i % SK_M;
-      const bool ok = m < M;
-      cp_async_f32(As + k * SK_PITCH + m, ok ? A + m * sAm + (kbeg + k) * sAk : A, ok);
-    }
+  } else {                 // rows along lanes (SK_M == 32), k along warps
+    const bool ok = lane < M;
+    const float* src = ok ? A + lane * sAm + kbeg * sAk : A;
+    for (int k = warp; k < kc; k += 8) cp_async_f32(As + k * SK_PITCH + lane, ok ? src + k * sAk : src, ok);
   }
   if (sBk == 1) {
-    for (int i = tid; i < total; i += 256) {
-      const int n = i / kc, k = i - n * kc;
+    for (int n = warp; n < SK_TN; n += 8) {
       const bool ok = n0 + n < N;
-      cp_async_f32(Bs + k * SK_PITCH + n, ok ? B + (n0 + n) * sBn + kbeg + k : B, ok);
+      const float* src = ok ? B + (n0 + n) * sBn + kbeg : B;
+      for (int k = lane; k < kc; k += 32) cp_async_f32(Bs + k * SK_PITCH + n, ok ? src + k : src, ok);
     }
   } else {
-    for (int i = tid; i < total; i += 256) {
-      const int k = i / SK_TN, n = i % SK_TN;
-      const bool ok = n0 + n < N;
-      cp_async_f32(Bs + k * SK_PITCH + n, ok ? B + (kbeg + k) * sBk + (n0 + n) * sBn : B, ok);
-    }
+    const bool ok = n0 + lane < N;
+    const float* src = ok ? B + kbeg * sBk + (n0 + lane) * sBn : B;
+    for (int k = warp; k < kc; k += 8) cp_async_f32(Bs + k * SK_PITCH + lane, ok ? src + k * sBk : src, ok);
   }
   cp_async_wait_all();
   __syncthreads();

@@ -482,6 +482,14 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def scatter(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[idx[i]] = src[i] (float32 vectors, device int64 unique indices)."""
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32 and idx.dtype == torch.int64
+    assert src.is_contiguous() and dst.is_contiguous() and idx.is_contiguous() and idx.numel() == src.numel()
+    check(lib.bbbp_scatter_f32(src.data_ptr(), idx.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "scatter")
+    return dst
+
+
 def dropout(x, p, seed, offset=0, seed_dev=None):
     """``seed_dev``: optional device uint64 (int64 tensor) added to ``seed`` when the kernel runs (CUDA-graph replay)."""
     y = torch.empty_like(x)

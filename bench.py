@@ -30,6 +30,10 @@ BATCH = 256
 METRIC, UNIT = "molecules/sec multi-input NN inference", "molecules/s"
 # algorithmic work (SURVEY 8d / DESIGN.md): conv2 = 75.50 MMAC per molecule
 CONV2_FLOP_PER_MOL = 2 * 64 * 64 * 64 * 288
+# DRAM bytes of the conv2 kernel per molecule from the committed `ncu --set full` capture
+# (profiles/r01_ncu_conv_umma_full.txt: dram__bytes_read 2.150264 GB + dram__bytes_write 1.043248 GB per 8192-molecule
+# launch); the algorithmic figure is 256 KiB in + 128 KiB out = 393 216 B, i.e. no re-reads
+CONV2_DRAM_BYTES_PER_MOL = (2.150264e9 + 1.043248e9) / 8192
 FWD_FLOP_PER_MOL = 207.2e6
 IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
 
@@ -141,33 +145,42 @@ def cpu_reference_rate(n_batches, threads, warm=1):
 def train_step_ms(torch, bbbp_b200, nets, dev, with_cpu=True):
     """Secondary figure of BASELINE.json's metric ("train step ms"): fwd + bwd + AdamW of the same network with the
     reference's settings (20250113.py:172,187-191: batch 32, AdamW lr 1e-4 wd 1e-5, MSE), fp32 kernels, dropout off
-    (the reference's dominant regime).  CUDA events, 3 warm-ups, inputs resident."""
-    out = {"precision": "fp32", "optimizer": "bbbp_b200.AdamW (one fused launch)", "loss": "bbbp_b200.MSELoss"}
+    (the reference's dominant regime).  CUDA events, 3 warm-ups, inputs resident.  ``ms_batch*`` is the
+    public training API (bbbp_b200.GraphedTrainStep: the whole step as one CUDA-graph replay, bit-identical to the
+    eager loop body); ``eager_ms_batch*`` is the reference's loop body issued launch by launch from Python."""
+    out = {"precision": "fp32", "optimizer": "bbbp_b200.AdamW (one fused launch)", "loss": "bbbp_b200.MSELoss",
+           "api": "bbbp_b200.GraphedTrainStep(model, optimizer, criterion)(fingerprint, image, target)"}
     torch.manual_seed(0)
     model = bbbp_b200.MixedInputModel(F_BITS, 128).to(dev)
     nets.zero_dropout(model)
     model.train()
     opt = bbbp_b200.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
     crit = bbbp_b200.MSELoss()
+    graphed = bbbp_b200.GraphedTrainStep(model, opt, crit)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     for batch in (32, 256):
         fp, img = synthetic_inputs(batch, 3, dev)
         y = torch.randn(batch, device=dev) * 0.75 - 0.1
 
-        def step():
+        def eager():
             opt.zero_grad()
             loss = crit(model(fp, img).squeeze(), y)
             loss.backward()
             opt.step()
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        out[f"ms_batch{batch}"] = e0.elapsed_time(e1) / 10
+        out[f"eager_ms_batch{batch}"] = timed(eager, 10)
+        out[f"ms_batch{batch}"] = timed(lambda: graphed(fp, img, y), 20)
     if with_cpu:
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
@@ -336,7 +349,9 @@ def main():
         flop = CONV2_FLOP_PER_MOL * statistics.mean(conv2_mols)
         ach = flop / (per_launch_ms * 1e-3) / 1e12
         roof = {"kernel": "conv2 (3x3, 32->64, +bias+ReLU+maxpool) implicit GEMM", "bound": "tensor", "achieved": ach,
-                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+                "traffic": CONV2_DRAM_BYTES_PER_MOL * statistics.mean(conv2_mols), "traffic_unit": "bytes/launch",
+                "traffic_source": "ncu --set full (profiles/r01_ncu_conv_umma_full.txt), scaled to this launch's molecules",
                 "peak_source": pk["src"] + " bf16_tflops_sustained", "launch_ms": per_launch_ms,
                 "share_of_step": sum(conv2_ms) / ms, "whole_model_tflops": FWD_FLOP_PER_MOL * value / 1e12,
                 "conv1_launch_ms": statistics.mean(conv1_ms) if conv1_ms else None}

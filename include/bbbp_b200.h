@@ -229,6 +229,9 @@ int bbbp_copy2d_f32(const float* src, int ld_src, float* dst, int ld_dst, int ro
 /* dst[r, 0:cols) = src[idx[r], 0:cols): the device-resident batch feeder that replaces MixedDataset.__getitem__ + the
  * DataLoader collate (C:31-45, 165-168); idx is a DEVICE int64 array of `rows` dataset indices. */
 int bbbp_gather_rows_f32(const float* src, const int64_t* idx, float* dst, int rows, long long cols, bbbp_stream_t stream);
+/* dst[idx[i]] = src[i], i < n (idx: DEVICE int64, unique): a cross-validation fold's scores written to their dataset
+ * positions, the device form of ``nn_predictions[test_idx] = nn_fold_predictions`` (C:237). */
+int bbbp_scatter_f32(const float* src, const int64_t* idx, float* dst, size_t n, bbbp_stream_t stream);
 /* Philox-4x32-10 dropout: y = x * keep / (1-p); the mask is a function of (seed, element index).  Not
  * stream-compatible with torch's generator (SURVEY hard part f). */
 int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev,

@@ -190,3 +190,18 @@ def test_device_batch_feeder_reproduces_dataloader_order():
             assert torch.equal(a, x) and torch.equal(b, y) and torch.equal(c, z)
     plain = list(bbbp_b200.DeviceBatchFeeder(fps, imgs, ys, batch_size=bs, shuffle=False, device="cpu"))
     assert torch.equal(plain[-1][2], torch.tensor(ys[64:], dtype=torch.float32))
+
+
+def test_stack_columns_matches_reference_vstack_transpose():
+    """20250113.py:403: ``np.vstack([nn, rf, xgb, cat]).T``."""
+    import numpy as np
+    import torch
+    import bbbp_b200
+    rng = np.random.default_rng(1)
+    nn_col, rf, xgb = rng.normal(size=7).astype(np.float32), rng.normal(size=7), rng.normal(size=7)
+    want = np.vstack([nn_col, rf, xgb]).T
+    np.testing.assert_array_equal(bbbp_b200.stack_columns(nn_col, rf, xgb), want)
+    np.testing.assert_array_equal(bbbp_b200.stack_columns(torch.from_numpy(nn_col), rf, xgb), want)
+    import pytest
+    with pytest.raises(ValueError):
+        bbbp_b200.stack_columns(nn_col, rf[:5])

@@ -477,3 +477,34 @@ def test_graphed_train_step_draws_fresh_dropout_masks_and_leaves_no_warmup_trace
     model.eval()
     with torch.no_grad():
         assert torch.isfinite(model(fp, img)).all()
+
+
+def test_out_of_fold_column_equals_the_reference_loop_and_feeds_the_meta_learner(cuda_device):
+    """K-fold out-of-fold NN column assembled on the device (one scatter per fold, one D2H in total) versus
+    the reference's per-batch ``.cpu()`` + ``extend`` + ``nn_predictions[test_idx] = ...`` (20250113.py:227-238), then
+    the stacked design matrix fed to the reference's meta-learner (Ridge, _opt_more.py:201-203)."""
+    import bbbp_b200
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import KFold
+    n, bs = 150, 32
+    ref, ours = make_pair("tcnn", 167, 128, 6, cuda_device)
+    ref.eval(), ours.eval()
+    fp, img, y = seeded_inputs(77, n, 167, IMG)
+    oof = bbbp_b200.OutOfFoldScores(n, cuda_device)
+    want = np.zeros(n)
+    for _, test_idx in KFold(n_splits=3, shuffle=True, random_state=42).split(np.arange(n)):
+        fold_ref = []
+        with torch.no_grad():
+            for a in range(0, len(test_idx), bs):           # DataLoader(test_dataset, batch_size=bs, shuffle=False)
+                rows = test_idx[a:a + bs]
+                fold_ref.extend(ref(fp[rows], img[rows]).squeeze(1).numpy())
+        want[test_idx] = fold_ref
+        oof.add_fold(ours, fp[test_idx].cuda(), img[test_idx].cuda(), test_idx, batch_size=bs)
+    assert oof.complete()
+    got = oof.to_numpy()
+    assert float(np.abs(got - want).max()) <= FP32_TOL
+    other = np.random.default_rng(0).normal(size=n)           # a CPU member's column (RF / XGB / CatBoost stay on CPU)
+    X_ours, X_ref = bbbp_b200.stack_columns(oof, other), np.vstack([want, other]).T
+    assert X_ours.shape == (n, 2)
+    m_ours, m_ref = Ridge(alpha=1.0).fit(X_ours, y.numpy()), Ridge(alpha=1.0).fit(X_ref, y.numpy())
+    np.testing.assert_allclose(m_ours.predict(X_ours), m_ref.predict(X_ref), atol=1e-3)
