@@ -366,10 +366,24 @@ class TransformerCnnModel(_KernelModule):
     graph_max_rows = 1024
     _graphs = None
 
+    _sig_tensors = None
+
+    def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .float() replace parameter storage
+        self._sig_tensors = None
+        self._graphs = None
+        self._chunk_graphs = None if self._chunk_graphs is not False else False
+        return super()._apply(fn, *args, **kwargs)
+
+    def _weight_signature(self):
+        """Changes whenever any parameter or buffer may have changed: torch's per-tensor version counters (in-place
+        updates by load_state_dict / stock optimizers) plus the epoch the fused bbbp AdamW bumps.  The tensor list is
+        cached (walking the module tree costs ~0.7 ms per call, more than a reference-sized forward)."""
+        if self._sig_tensors is None:
+            self._sig_tensors = list(self.parameters()) + list(self.buffers())
+        return (ag._weight_epoch, self._sig_tensors[0].data_ptr()) + tuple(t._version for t in self._sig_tensors)
+
     def _graph_signature(self, fingerprint, image, groups):
-        wsig = hash(tuple((p.data_ptr(), p._version) for p in self.parameters()) +
-                    tuple((b.data_ptr(), b._version) for b in self.buffers()))
-        return (fingerprint.shape[0], groups, image.dtype, tuple(image.shape), self.precision, ag._weight_epoch, wsig,
+        return (fingerprint.shape[0], groups, image.dtype, tuple(image.shape), self.precision, self._weight_signature(),
                 fingerprint.device.index)
 
     def _forward_graphed(self, fingerprint, image, groups):
@@ -391,8 +405,12 @@ class TransformerCnnModel(_KernelModule):
                     self._forward_groups_eager(s_fp, s_img, groups)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                s_out = self._forward_groups_eager(s_fp, s_img, groups)
+            prev_fork, self.fork_image_branch = self.fork_image_branch, True    # conv branch || encoder inside the graph
+            try:
+                with torch.cuda.graph(graph):
+                    s_out = self._forward_groups_eager(s_fp, s_img, groups)
+            finally:
+                self.fork_image_branch = prev_fork
             entry = (graph, s_fp, s_img, s_out)
             self._graphs[key] = entry
         graph, s_fp, s_img, s_out = entry
@@ -481,8 +499,24 @@ class TransformerCnnModel(_KernelModule):
         fp = ops.unpack_zscore(packed_bits.contiguous(), n_bits)
         return self.predict_batches(fp, image_u8, batch_size, max_rows_per_pass)
 
+    @staticmethod
+    def _pipeline_spans(n: int, chunk: int, batch_size: int):
+        """Chunk schedule of the copy/compute pipeline: equal chunks of whole reference batches; the ragged tail batch
+        (n mod batch_size molecules) rides on the last span.  Measured on B200 (tools/e2e_sched.py, 8 192 molecules, H2D
+        alone 7.25 ms): equal 1 024-molecule chunks 8.33 ms, 2 048 -> 8.55 ms, ramped schedules (short first / last
+        chunks) 8.6-8.9 ms -- a chunk's graph replay costs ~0.55 ms + 0.34 ms per 1 024 molecules (the encoder is a chain
+        of ~85 dependent kernels), so chunks much shorter than 1 024 no longer hide behind their own copy."""
+        full = n // batch_size * batch_size
+        spans = [(a, min(full, a + chunk)) for a in range(0, full, chunk)]
+        if n > full:
+            if spans and spans[-1][1] - spans[-1][0] + (n - full) <= chunk:
+                spans[-1] = (spans[-1][0], n)
+            else:
+                spans.append((full, n))
+        return spans
+
     @torch.no_grad()
-    def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int = 2048,
+    def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int = 1024,
                           packed: bool = False, out_host: torch.Tensor | None = None, return_device: bool = False):
         """End-to-end scoring of HOST-resident molecules (pinned tensors recommended): the host->device copy of chunk
         c+1 runs on a second stream while chunk c is being scored, so a pass costs max(copy, compute) instead of their
@@ -508,7 +542,7 @@ class TransformerCnnModel(_KernelModule):
         _, copier, slots = pipe
         copier.wait_stream(compute)                  # earlier work on the slots (previous call) is ordered before us
         ready, freed = [None, None], [None, None]
-        spans = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+        spans = self._pipeline_spans(n, chunk, batch_size)
 
         def stage(i):
             a, b = spans[i]
@@ -529,7 +563,7 @@ class TransformerCnnModel(_KernelModule):
             slot = i % 2
             compute.wait_event(ready[slot])
             fp, img = slots[slot][0][: b - a], slots[slot][1][: b - a]
-            part = (self.predict_batches_packed if packed else self.predict_batches)(fp, img, batch_size, max_rows_per_pass=chunk)
+            part = self._score_staged_chunk(slot, fp, img, batch_size, chunk, packed)
             scores[a:b].copy_(part)
             freed[slot] = torch.cuda.Event()
             freed[slot].record(compute)
@@ -537,6 +571,51 @@ class TransformerCnnModel(_KernelModule):
             out_host = torch.empty((n,), dtype=torch.float32, pin_memory=True)
         out_host.copy_(scores, non_blocking=True)
         return (out_host, scores) if return_device else out_host
+
+    _chunk_graphs = None
+
+    def _score_staged_chunk(self, slot, fp, img, batch_size, chunk, packed):
+        """Scores of one staged chunk.  The staging slots are persistent buffers, so the whole chunk computation (unpack +
+        z-score + forward of every reference batch, conv branch forked beside the encoder) is captured ONCE per (slot,
+        chunk length) into a CUDA graph that reads the slot in place -- no copy into graph-private inputs, one launch per
+        chunk instead of ~90, which is what lets the short first / last chunks of the ramped schedule cost less than
+        their own H2D copy."""
+        fn = self.predict_batches_packed if packed else self.predict_batches
+        if not self.use_cuda_graphs or self._chunk_graphs is False or torch.cuda.is_current_stream_capturing():
+            return fn(fp, img, batch_size, max_rows_per_pass=chunk)
+        if self._chunk_graphs is None:
+            self._chunk_graphs = {}
+        key = (fp.data_ptr(), img.data_ptr(), fp.shape[0], fp.dtype, img.dtype, batch_size, chunk, packed, self.precision,
+               self._weight_signature())
+        entry = self._chunk_graphs.get(key)
+        if entry is None:
+            if len(self._chunk_graphs) >= 24:
+                self._chunk_graphs.pop(next(iter(self._chunk_graphs)))
+            prev_graphs, prev_fork = self.use_cuda_graphs, self.fork_image_branch
+            self.use_cuda_graphs = False                 # warm-up must run the plain launches, not per-call graphs
+            try:
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream(fp.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        fn(fp, img, batch_size, max_rows_per_pass=chunk)
+                cur.wait_stream(side)
+                self.fork_image_branch = True
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = fn(fp, img, batch_size, max_rows_per_pass=chunk)
+                entry = (graph, out, fp, img)            # fp / img keep the slot views alive
+                self._chunk_graphs[key] = entry
+            except Exception as e:      # capture is an optimisation: fall back to plain launches of the same kernels
+                warnings.warn(f"bbbp_b200: chunk-graph capture disabled for this model ({e})")
+                self._chunk_graphs = False
+            finally:
+                self.use_cuda_graphs, self.fork_image_branch = prev_graphs, prev_fork
+            if entry is None:
+                return fn(fp, img, batch_size, max_rows_per_pass=chunk)
+        entry[0].replay()
+        return entry[1]
 
     @torch.no_grad()
     def predict_batches(self, fingerprint, image, batch_size: int, max_rows_per_pass: int = 16384):

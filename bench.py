@@ -297,7 +297,7 @@ def main():
 
     def step_e2e_compact():
         # the user-facing host API: chunked H2D on a copy stream overlapped with scoring, D2H of the scores
-        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=2048, packed=True, out_host=scores_host,
+        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=1024, packed=True, out_host=scores_host,
                                        return_device=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
