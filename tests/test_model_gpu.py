@@ -508,3 +508,41 @@ def test_out_of_fold_column_equals_the_reference_loop_and_feeds_the_meta_learner
     assert X_ours.shape == (n, 2)
     m_ours, m_ref = Ridge(alpha=1.0).fit(X_ours, y.numpy()), Ridge(alpha=1.0).fit(X_ref, y.numpy())
     np.testing.assert_allclose(m_ours.predict(X_ours), m_ref.predict(X_ref), atol=1e-3)
+
+
+def test_graphed_train_step_morgan_variant_with_bce(cuda_device):
+    """BASELINE configs[2]: the 2048-bit fingerprint variant (256 heads x 8, 160 M parameters) trained with the
+    BCE-with-logits extension.  The graphed step must equal the eager loop body bit for bit, and the very first loss
+    must equal the oracle's (torch CPU, same weights) to 1e-4."""
+    import bbbp_b200
+    runs = {}
+    fp, img, _ = seeded_inputs(960, 32, 2048, IMG)
+    g = torch.Generator().manual_seed(961)
+    y = (torch.rand(32, generator=g) < 0.64).float()
+    for mode in ("eager", "graph"):
+        ref, model = make_pair("tcnn", 2048, 128, 7, cuda_device)
+        nets.zero_dropout(model)
+        model.train()
+        opt = bbbp_b200.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+        crit = bbbp_b200.BCEWithLogitsLoss()
+        step = bbbp_b200.GraphedTrainStep(model, opt, crit)
+        losses = []
+        for _ in range(2):
+            if mode == "graph":
+                loss = step(fp.cuda(), img.cuda(), y.cuda())
+            else:
+                opt.zero_grad()
+                loss = crit(model(fp.cuda(), img.cuda()).squeeze(), y.cuda())
+                loss.backward()
+                opt.step()
+            losses.append(float(loss.detach()))
+        runs[mode] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()})
+        del model, opt, step
+        torch.cuda.empty_cache()
+    assert runs["graph"][0] == runs["eager"][0]
+    for k, v in runs["eager"][1].items():
+        assert torch.equal(runs["graph"][1][k], v), k
+    nets.zero_dropout(ref)
+    ref.train()
+    want = torch.nn.functional.binary_cross_entropy_with_logits(ref(fp, img).squeeze(), y)
+    assert abs(runs["eager"][0][0] - float(want)) <= 1e-4

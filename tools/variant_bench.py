@@ -24,3 +24,13 @@ for name, variant, F, img_dim, groups in [("Morgan-2048 canonical", "tcnn", 2048
                 ms = t(lambda: m(fp, img))
         print(f"{name:24s} {prec}: {n} molecules in {ms:8.2f} ms = {n / ms * 1e3:10.0f} mol/s", flush=True)
     del m, fp, img
+# training step of the Morgan-2048 variant (BASELINE configs[2]: BCE loss, batch 32): eager loop body vs graph replay
+from oracle import nets
+torch.manual_seed(0)
+m = bbbp_b200.build("tcnn", 2048, 128).to(dev); nets.zero_dropout(m); m.train()
+opt = bbbp_b200.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5); crit = bbbp_b200.BCEWithLogitsLoss()
+fp, img, y = torch.randn(32, 2048, device=dev), torch.randn(32, 49152, device=dev), (torch.rand(32, device=dev) < 0.64).float()
+def eager():
+    opt.zero_grad(); loss = crit(m(fp, img).squeeze(), y); loss.backward(); opt.step()
+step = bbbp_b200.GraphedTrainStep(m, opt, crit)
+print(f"Morgan-2048 train step batch 32 (fp32, BCE): eager {t(eager):.2f} ms, graph {t(lambda: step(fp, img, y)):.2f} ms", flush=True)
