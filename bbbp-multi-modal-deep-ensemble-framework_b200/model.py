@@ -313,8 +313,11 @@ class TransformerCnnModel(_KernelModule):
     def _image_branch(self, image):
         side = self.IMAGE_SIDE
         mods = list(self.image_cnn)
-        if (self.precision == "bf16" and self.kind != "big" and side == 128
+        if (self.precision == "bf16" and side == 128
                 and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.image_cnn.parameters()))):
+            if self.kind == "big":
+                x = self._image_branch_im2col(image, mods)
+                return self._drop(x, mods[-1]) if isinstance(mods[-1], nn.Dropout) else x
             return self._image_branch_tensor_core(image, mods)
         x = image.reshape(-1, 3, side, side)
         i = 0
@@ -328,6 +331,41 @@ class TransformerCnnModel(_KernelModule):
         return x
 
     tensor_core_chunk = 0   # images per pass of the tcgen05 image branch (0 = all at once)
+    im2col_chunk = 256      # images per pass of the im2col route (bounds the im2col buffer: 4.7 MB per image at 64 -> 128)
+
+    def _image_branch_im2col(self, image, mods):
+        """Inference path of conv stacks the implicit-GEMM kernel is not instantiated for (the big variant's 3 -> 64 ->
+        128 -> 256, 20250107_network.py:133-141): per layer bf16 im2col -> tcgen05 GEMM with bias + ReLU in the epilogue
+        (NHWC bf16 out) -> 2x2 max-pool; the last activation IS the fc's K-major A operand (weight re-laid to (H,W,C))."""
+        from . import ops
+        convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+        fc = next(m for m in mods if isinstance(m, nn.Linear))
+        side = self.IMAGE_SIDE
+        if image.dtype == torch.uint8:
+            image = ops.u8_zscore(image.reshape(-1, 3 * side * side).contiguous())
+        img = image if image.is_contiguous() else image.contiguous()
+        n = img.numel() // (3 * side * side)
+        img = img.reshape(n, 3 * side * side)
+        final_side = side >> len(convs)
+        wfc = ag.derived_weight(fc.weight, "hwc_bf16",
+                                lambda w: ops.fc_weight_to_hwc_bf16(w, convs[-1].out_channels, final_side * final_side))
+        outs = []
+        for a in range(0, n, self.im2col_chunk):
+            part = img[a:a + self.im2col_chunk]
+            x = ops.image_to_nhwc8_bf16(part, 3, side, side)              # (n, H, W, 8): channels 3..7 zero
+            for conv in convs:
+                nb, H, W, C = x.shape
+                w16 = ag.derived_weight(conv.weight, f"im2col_{C}", lambda w, C=C: ops.conv3x3_weight_im2col_bf16(w, C))
+                cols = ops.im2col3x3_bf16(x)
+                _, y = ops.gemm_bf16(cols, 9 * C, w16, conv.out_channels, bias=conv.bias, act="relu", out_f32=False,
+                                     out_bf16=True)
+                del cols
+                x = ops.maxpool2x2_nhwc_bf16(y.view(nb, H, W, conv.out_channels))
+            flat = x.view(x.shape[0], -1)
+            K = flat.shape[1]
+            o, _ = ops.gemm_bf16(flat, K, wfc, fc.out_features, bias=fc.bias, act="relu", split_k=ops.fixed_split_k(K))
+            outs.append(o)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def _image_branch_tensor_core(self, image, mods):
         """Inference path: planar CHW image (fp32 standardised, or raw uint8 normalised in the producer) -> tcgen05

@@ -302,6 +302,29 @@ def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int) -> torch.Tensor:
     return out
 
 
+def im2col3x3_bf16(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """(N, H, W, C) bf16 -> (N*H*W, 9*C) bf16 rows in (tap, channel) order, zero padding at the image border."""
+    N, H, W, C = x_nhwc.shape
+    out = torch.empty((N * H * W, 9 * C), device=x_nhwc.device, dtype=torch.bfloat16)
+    check(lib.bbbp_im2col3x3_bf16(x_nhwc.data_ptr(), out.data_ptr(), N, H, W, C, _stream()), "im2col3x3_bf16")
+    return out
+
+
+def maxpool2x2_nhwc_bf16(x_nhwc: torch.Tensor) -> torch.Tensor:
+    N, H, W, C = x_nhwc.shape
+    y = torch.empty((N, H // 2, W // 2, C), device=x_nhwc.device, dtype=torch.bfloat16)
+    check(lib.bbbp_maxpool2x2_nhwc_bf16(x_nhwc.data_ptr(), y.data_ptr(), N, H, W, C, _stream()), "maxpool2x2_nhwc_bf16")
+    return y
+
+
+def conv3x3_weight_im2col_bf16(w: torch.Tensor, c_pad: int | None = None) -> torch.Tensor:
+    Cout, Cin = w.shape[:2]
+    c_pad = -(-Cin // 8) * 8 if c_pad is None else c_pad
+    out = torch.empty((Cout, 9 * c_pad), device=w.device, dtype=torch.bfloat16)
+    check(lib.bbbp_conv3x3_weight_im2col_bf16(w.data_ptr(), out.data_ptr(), Cin, c_pad, Cout, _stream()), "conv3x3_weight_im2col")
+    return out
+
+
 # ---- attention --------------------------------------------------------------------------------------------------------
 def attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p=0.0, seed=0, want_lse=True, seed_dev=None):
     E = heads * head_dim

@@ -149,6 +149,16 @@ int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int 
  * activation (20250113.py:91-92) */
 int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, int HW, bbbp_stream_t stream);
 
+/* Generic tensor-core route for channel counts the implicit-GEMM kernel is not instantiated for (the 64/128/256-channel
+ * stack of 20250107_network.py:133-141): explicit bf16 im2col -> bbbp_gemm_bf16 (bias + ReLU epilogue) -> 2x2 max-pool.
+ * out[(n*H + y)*W + x][tap*C + c] = x[n][y+dy][x+dx][c], zero outside the image, tap = 3*(dy+1) + (dx+1); C % 8 == 0. */
+int bbbp_im2col3x3_bf16(const void* x_nhwc, void* out, int N, int H, int W, int C, bbbp_stream_t stream);
+/* y[N,H/2,W/2,C] = 2x2 max-pool of x[N,H,W,C], bf16 NHWC, C % 8 == 0 */
+int bbbp_maxpool2x2_nhwc_bf16(const void* x_nhwc, void* y_nhwc, int N, int H, int W, int C, bbbp_stream_t stream);
+/* out[Cout][9*Cpad] bf16 with out[co][tap*Cpad + c] = w[co][c][tap] (zero for c >= Cin): the W operand matching the
+ * im2col row order */
+int bbbp_conv3x3_weight_im2col_bf16(const float* w, void* out_bf16, int Cin, int Cpad, int Cout, bbbp_stream_t stream);
+
 /* ---- encoder self-attention across the molecules of a reference batch: the (B,1,F)
  *      input of C:110-111 is read by nn.TransformerEncoder as seq_len = B, batch = 1.  ``groups``
  *      independent reference batches of ``seq`` molecules each are processed in one launch. ------ */

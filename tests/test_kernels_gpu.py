@@ -396,6 +396,24 @@ def test_conv2_tcgen05(ops, N):
     close(y, ref, atol=3e-3, rtol=1e-2, what="conv2 tcgen05")
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H", [(2, 8, 64, 32), (3, 64, 128, 16), (1, 128, 256, 16), (5, 8, 64, 128)])
+def test_conv_im2col_gemm_pool_route(ops, N, Cin, Cout, H):
+    """The generic tensor-core route of the big variant's conv stack: bf16 im2col (exact data movement) -> tcgen05 GEMM with
+    bias + ReLU -> 2x2 max-pool, against F.conv2d on the bf16-rounded operands."""
+    x = rnd(N, Cin, H, H, seed=130)
+    w, b = rnd(Cout, Cin, 3, 3, seed=131, scale=1 / math.sqrt(9 * Cin)), rnd(Cout, seed=132, scale=0.1)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    cols = ops.im2col3x3_bf16(x_nhwc)
+    want_cols = F.unfold(x.bfloat16().float(), 3, padding=1).view(N, Cin, 9, H * H).permute(0, 3, 2, 1).reshape(N * H * H, 9 * Cin)
+    assert torch.equal(cols.float().cpu(), want_cols)                              # (tap, channel) order, zero border: exact
+    w16 = ops.conv3x3_weight_im2col_bf16(w.cuda(), Cin)
+    assert torch.equal(w16.float().cpu(), w.bfloat16().float().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin))
+    _, y = ops.gemm_bf16(cols, 9 * Cin, w16, Cout, bias=b.cuda(), act="relu", out_f32=False, out_bf16=True)
+    pooled = ops.maxpool2x2_nhwc_bf16(y.view(N, H, H, Cout))
+    assert torch.equal(pooled.float().cpu(), F.max_pool2d(y.view(N, H, H, Cout).float().cpu().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+    close(pooled, _conv_ref_bf16(x, w, b).permute(0, 2, 3, 1), atol=3e-3, rtol=1e-2, what="im2col route")
+
+
 def test_conv_tcgen05_localises_each_tap(ops):
     """Delta images: one hot pixel / channel at a time must land on exactly the taps the reference conv gives it
     (catches any tap / window-member / parity mix-up that random data could average away)."""

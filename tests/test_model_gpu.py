@@ -225,7 +225,8 @@ def test_cross_molecule_attention_semantics(cuda_device):
     assert float((whole[0] - moved[0]).abs()) > 1e-7
 
 
-@pytest.mark.parametrize("variant,fp_dim,b", [("tcnn", 167, 32), ("tcnn", 2048, 16), ("mlp", 64, 256)])
+@pytest.mark.parametrize("variant,fp_dim,b", [("tcnn", 167, 32), ("tcnn", 2048, 16), ("mlp", 64, 256), ("tcnn_big", 167, 12),
+                                              ("tcnn_nofusion", 167, 9)])
 def test_bf16_tensor_core_mode_tolerance(cuda_device, variant, fp_dim, b):
     ref, ours = make_pair(variant, fp_dim, 128, 2, cuda_device)
     ref.eval(), ours.eval()
