@@ -237,12 +237,14 @@ class TransformerCnnModel(_KernelModule):
     # -- encoder, inference fast path: every contraction on tcgen05, activations stay bf16 between GEMMs -----------------
     def _encoder_tensor_core_ok(self, seq: int) -> bool:
         attn = self.fingerprint_transformer.layers[0].self_attn
-        return (self.precision == "bf16" and not self.training and attn.num_heads == 1
+        head_dim = attn.embed_dim // attn.num_heads
+        return (self.precision == "bf16" and not self.training and (attn.num_heads == 1 or head_dim in (8, 16))
                 and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.fingerprint_transformer.parameters())))
 
     def _encoder_tensor_core(self, x, groups: int, seq: int):
         """6 x [in_proj GEMM -> (QK^T + row softmax) GEMM -> V transpose -> PV GEMM -> out_proj GEMM (+residual) -> LN
-        -> FFN1 GEMM (+ReLU, bf16 out) -> FFN2 GEMM (+residual) -> LN], then fingerprint_fc.  9 launches per layer."""
+        -> FFN1 GEMM (+ReLU, bf16 out) -> FFN2 GEMM (+residual) -> LN], then fingerprint_fc.  9 launches per layer (7 for
+        the many-small-heads variants, whose attention is one mma.sync flash kernel)."""
         from . import ops
         F_ = x.shape[1]
         Fq = -(-F_ // 8) * 8                          # q | k | v each start on a 16-byte boundary
@@ -273,10 +275,13 @@ class TransformerCnnModel(_KernelModule):
             w_in = ag.derived_weight(attn.in_proj_weight, "qkv_pad16", padded_in_proj)
             b_in = ag.derived_weight(attn.in_proj_bias, "qkv_pad", padded_in_bias)
             _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True)
-            p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5)
-            ldp = p16.shape[1]
-            vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
-            _, a16 = ops.gemm_bf16_batched(groups, seq, F_, seq, p16, ldp, seq * ldp, vt, ldp, F_ * ldp, ld_out16=Fq)
+            if attn.num_heads == 1:
+                p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5)
+                ldp = p16.shape[1]
+                vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
+                _, a16 = ops.gemm_bf16_batched(groups, seq, F_, seq, p16, ldp, seq * ldp, vt, ldp, F_ * ldp, ld_out16=Fq)
+            else:       # 256 heads x 8 (2048-bit fingerprints): warp-level MMA flash kernel on the packed qkv, bf16 out
+                a16 = ops.attention_heads_bf16(qkv16, Fq, 2 * Fq, groups, seq, attn.num_heads, F_ // attn.num_heads, ld_out=Fq)
             s32, _ = ops.gemm_bf16(a16, F_, ag.weight_bf16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32,
                                    ld_out=Fq)
             x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,

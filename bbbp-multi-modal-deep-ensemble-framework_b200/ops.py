@@ -343,6 +343,17 @@ def attention_bwd(qkv, out, lse, dout, groups, seq, heads, head_dim, dropout_p=0
     return dqkv
 
 
+def attention_heads_bf16(qkv16: torch.Tensor, k_offset: int, v_offset: int, groups: int, seq: int, heads: int, head_dim: int,
+                         ld_out: int | None = None) -> torch.Tensor:
+    """Multi-head attention (head_dim 8 or 16) on the packed bf16 in_proj output; returns (groups*seq, ld_out) bf16."""
+    E = heads * head_dim
+    ld_out = -(-E // 8) * 8 if ld_out is None else ld_out
+    out = (torch.empty if ld_out == E else torch.zeros)((groups * seq, ld_out), device=qkv16.device, dtype=torch.bfloat16)
+    check(lib.bbbp_attention_heads_bf16(qkv16.data_ptr(), qkv16.stride(0), k_offset, v_offset, out.data_ptr(), ld_out, groups, seq,
+                                        heads, head_dim, _stream()), "attention_heads_bf16")
+    return out
+
+
 # ---- norms ------------------------------------------------------------------------------------------------------------
 def add_layernorm_fwd(x, res, gamma, beta, eps=1e-5, save=False, bf16_ld=0):
     rows, dim = x.shape

@@ -175,6 +175,13 @@ int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse,
                            int groups, int seq, int heads, int head_dim, float dropout_p, uint64_t seed,
                            const uint64_t* seed_dev, bbbp_stream_t stream);
 
+/* Many small heads on the bf16 inference path (the 2048-bit fingerprint variants: 256 heads of dimension 8, C:71-73):
+ * out[r, h*D + c] = softmax(q_h k_h^T / sqrt(D)) v_h per group, warp-level mma.sync m16n8k16 with an online softmax.
+ * qkv rows (bf16, pitch ld) hold q at column 0, k at column k_offset, v at column v_offset (all multiples of 8);
+ * head_dim 8 or 16; any seq. */
+int bbbp_attention_heads_bf16(const void* qkv_bf16, int ld, int k_offset, int v_offset, void* out_bf16, int ld_out, int groups,
+                              int seq, int heads, int head_dim, bbbp_stream_t stream);
+
 /* ---- normalisation: nn.LayerNorm (post-norm residual, eps 1e-5) and nn.BatchNorm1d C:101 ------- */
 
 /* s = x + res (res may be NULL); y = LN(s)*gamma + beta.  Optional outputs: sum_out (= s), mean[rows],

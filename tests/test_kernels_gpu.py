@@ -176,6 +176,23 @@ def test_attention_dropout_is_consistent_between_forward_and_backward(ops, group
     assert torch.equal(ops.attention_bwd(qkv, o4, lse4, dout, groups, seq, heads, d, p, 1000, seed_dev=sd), g1)
 
 
+@pytest.mark.parametrize("groups,seq,heads,d", [(2, 256, 256, 8), (1, 33, 5, 8), (3, 64, 4, 16), (1, 1, 2, 8), (1, 300, 3, 16),
+                                                (1, 1000, 2, 8)])
+def test_attention_many_small_heads_bf16(ops, groups, seq, heads, d):
+    """mma.sync flash kernel of the 2048-bit variants (256 heads x 8) against SDPA in fp64 on the bf16-rounded q, k, v;
+    the error budget is the bf16 rounding of the probabilities and of the output."""
+    E = heads * d
+    ld = 3 * E + 8                                       # a padded pitch: q | k | v at multiples of 8
+    qkv = torch.zeros(groups * seq, ld)
+    qkv[:, :3 * E] = rnd(groups * seq, 3 * E, seed=34, scale=1.5)
+    q16 = qkv.bfloat16()
+    out = ops.attention_heads_bf16(q16.cuda(), E, 2 * E, groups, seq, heads, d)
+    assert out.shape == (groups * seq, E) and out.dtype == torch.bfloat16
+    q, k, v = q16[:, :3 * E].double().view(groups, seq, 3, heads, d).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(groups * seq, E).float()
+    close(out, ref, atol=1.5e-2, rtol=2e-2, what="many-small-heads attention")
+
+
 # ---- normalisation ----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("rows,dim", [(1, 167), (33, 167), (256, 2048), (7, 8)])
 @pytest.mark.parametrize("with_res", [False, True])
