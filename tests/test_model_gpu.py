@@ -547,3 +547,41 @@ def test_graphed_train_step_morgan_variant_with_bce(cuda_device):
     ref.train()
     want = torch.nn.functional.binary_cross_entropy_with_logits(ref(fp, img).squeeze(), y)
     assert abs(runs["eager"][0][0] - float(want)) <= 1e-4
+
+
+def test_screen_library_files_to_results_table(cuda_device, tmp_path):
+    """``morgan_fingerprints.npy``-style bit rows + uint8 depictions on disk -> the reference's results
+    table (virtualscreening.py:13-19 columns).  Scores must equal predict_batches on the exactly preprocessed inputs
+    (bit-exact unpack, oracle z-scores), whatever the staging / chunking, and survive a weight update between calls."""
+    import pandas as pd
+    import bbbp_b200
+    from oracle import preprocess
+    n, bs = 300, 32
+    _, ours = make_pair("tcnn", 167, 128, 11, cuda_device)
+    ours.eval()
+    rng = np.random.default_rng(5)
+    bits = (rng.random((n, 167)) < 0.25).astype(np.int64)
+    bits[:, 0] = 0
+    img = rng.integers(0, 256, size=(n, 3, 128, 128), dtype=np.uint8)
+    np.save(tmp_path / "maccs_fingerprints.npy", bits)
+    np.save(tmp_path / "depictions.npy", img)
+    ids = [f"ZINC{i:08d}" for i in range(n)]
+    table = bbbp_b200.screen_library(ours, str(tmp_path / "maccs_fingerprints.npy"), str(tmp_path / "depictions.npy"),
+                                     out_csv=str(tmp_path / "virtual_screening_results.csv"), ids=ids, batch_size=bs,
+                                     chunk_molecules=96)
+    fp_ref = torch.from_numpy(preprocess.zscore_rows(bits)).cuda()
+    img_ref = torch.from_numpy(preprocess.u8_image_zscore(img)).cuda()
+    want = ours.predict_batches(fp_ref, img_ref, bs).cpu().numpy()
+    assert float(np.abs(table["Prediction"] - want).max()) <= FP32_TOL
+    csv = pd.read_csv(tmp_path / "virtual_screening_results.csv")
+    assert list(csv.columns) == ["ZINC_ID", "Prediction"] and len(csv) == n and csv["ZINC_ID"][7] == ids[7]
+    np.testing.assert_allclose(csv["Prediction"].to_numpy(), table["Prediction"], rtol=1e-6)
+    packed = bbbp_b200.pack_fingerprint_bits(bits)
+    assert torch.equal(packed, torch.from_numpy(preprocess.pack_bits(bits)))
+    cls = bbbp_b200.screen_library(ours, packed.numpy(), img, batch_size=bs, classification=True)
+    np.testing.assert_allclose(cls["Probability"], 1 / (1 + np.exp(-table["Prediction"].astype(np.float64))), atol=1e-6)
+    assert set(np.unique(cls["Prediction"])) <= {0, 1}
+    with torch.no_grad():                                  # a weight update between calls must invalidate the chunk graphs
+        ours.fc[7].bias.add_(1.0)
+    again = bbbp_b200.screen_library(ours, packed.numpy(), img, batch_size=bs)
+    np.testing.assert_allclose(again["Prediction"], table["Prediction"] + 1.0, atol=1e-5)
