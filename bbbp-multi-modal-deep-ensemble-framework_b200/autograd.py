@@ -161,22 +161,60 @@ class ConvReluPool(Function):
 
 
 class Attention(Function):
-    """Self-attention over the molecules of each reference batch; qkv rows = groups*seq."""
+    """Self-attention over the molecules of each reference batch; qkv rows = groups*seq.
+
+    Three kernels behind one contract: the one-launch short-scope kernels (seq <= 32: the reference's training batch),
+    the GEMM route below for single-head scopes wider than that on the training path (batch 256: six products on the
+    tiled fp32 GEMM + a row-softmax kernel, 4-5x faster than the streaming kernels at that size), and the streaming
+    kernels for everything else (many heads, inference)."""
+
+    GEMM_ROUTE_MAX_SEQ = 4096        # the seq x seq probabilities are materialised (64 MB at 4096)
 
     @staticmethod
-    def forward(ctx, qkv, groups, seq, heads, head_dim, dropout_p, seed):
+    def forward(ctx, qkv, groups, seq, heads, head_dim, dropout_p, seed, training=False):
         qkv = contig(qkv)
         seed_dev = _seed_dev if dropout_p > 0 else None
+        ctx.cfg = (groups, seq, heads, head_dim, dropout_p, seed, seed_dev)
+        ctx.route = training and heads == 1 and 32 < seq <= Attention.GEMM_ROUTE_MAX_SEQ
+        if ctx.route:
+            E, scale = head_dim, head_dim ** -0.5
+            out = torch.empty((groups * seq, E), device=qkv.device, dtype=torch.float32)
+            saved = []
+            for g in range(groups):
+                rows = slice(g * seq, (g + 1) * seq)
+                q, k, v = qkv[rows, :E], qkv[rows, E:2 * E], qkv[rows, 2 * E:]
+                s = ops.gemm_f32(q, k, trans_b=True, split_k=0)
+                p, pd = ops.attn_softmax_fwd(s, scale, dropout_p, seed, seed_dev, g * seq)
+                ops.gemm_f32(pd, v, out=out[rows], split_k=0)
+                saved += [p] if pd is p else [p, pd]
+            ctx.save_for_backward(qkv, *saved)
+            return out
         out, lse = ops.attention_fwd(qkv, groups, seq, heads, head_dim, dropout_p, seed, want_lse=qkv.requires_grad,
                                      seed_dev=seed_dev)
-        ctx.cfg = (groups, seq, heads, head_dim, dropout_p, seed, seed_dev)
         ctx.save_for_backward(qkv, out, lse)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        groups, seq, heads, head_dim, dropout_p, seed, seed_dev = ctx.cfg
+        dout = contig(dout)
+        if ctx.route:
+            qkv, *saved = ctx.saved_tensors
+            E, scale = head_dim, head_dim ** -0.5
+            per = 1 if dropout_p == 0 else 2
+            dqkv = torch.empty_like(qkv)
+            for g in range(groups):
+                rows = slice(g * seq, (g + 1) * seq)
+                p, pd = saved[per * g], saved[per * g + per - 1]
+                q, k, v = qkv[rows, :E], qkv[rows, E:2 * E], qkv[rows, 2 * E:]
+                dpd = ops.gemm_f32(dout[rows], v, trans_b=True, split_k=0)                   # dO V^T
+                ops.gemm_f32(pd, dout[rows], trans_a=True, out=dqkv[rows, 2 * E:], split_k=0)     # dV = P^T dO
+                ds = ops.attn_softmax_bwd(p, dpd, scale, dropout_p, seed, seed_dev, g * seq)      # carries 1/sqrt(d)
+                ops.gemm_f32(ds, k, out=dqkv[rows, :E], split_k=0)                               # dQ = dS K
+                ops.gemm_f32(ds, q, trans_a=True, out=dqkv[rows, E:2 * E], split_k=0)            # dK = dS^T Q
+            return (dqkv,) + (None,) * 7
         qkv, out, lse = ctx.saved_tensors
-        return (ops.attention_bwd(qkv, out, lse, contig(dout), *ctx.cfg),) + (None,) * 6
+        return (ops.attention_bwd(qkv, out, lse, dout, groups, seq, heads, head_dim, dropout_p, seed, seed_dev),) + (None,) * 7
 
 
 class AddLayerNorm(Function):
@@ -355,6 +393,11 @@ def dropout(x, p, training):
     if not training or p <= 0.0:
         return x
     return Dropout.apply(x, float(p), next_seed())
+
+
+def attention(qkv, groups, seq, heads, head_dim, dropout_p=0.0):
+    training = torch.is_grad_enabled() and qkv.requires_grad       # sampled here: grad mode is off inside Function.forward
+    return Attention.apply(qkv, groups, seq, heads, head_dim, dropout_p, next_seed() if dropout_p > 0 else 0, training)
 
 
 def concat_cols(*tensors):

@@ -510,6 +510,62 @@ __global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const floa
 static size_t short_fwd_smem(int d) { return ((size_t)3 * SS * short_ld(d) + SS * SP) * sizeof(float); }
 static size_t short_bwd_smem(int d) { return ((size_t)4 * SS * short_ld(d) + 3 * SS * SP) * sizeof(float); }
 
+// ---- mid-size single-head scopes on the training path (32 < seq, e.g. batch 256): GEMM route ------------------------
+// scores = Q K^T and O = P V (and the four backward products) run on the tiled fp32 GEMM; these two kernels are the
+// row softmax in between.  One block per query row; the keep mask is the same Philox function as everywhere else.
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();                            // red may still be read from a previous reduction
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = v;
+  __syncthreads();
+  float t = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t = is_max ? fmaxf(t, red[i]) : t + red[i];
+  return t;
+}
+
+// p[r, :] = softmax(scale * s[r, :]);  pd = p * keep (dropout on the normalised probabilities); pd may alias p when drop_p == 0
+__global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __restrict__ s, int ld_s, float* __restrict__ p,
+                                                               float* __restrict__ pd, int ld_p, int cols, float scale,
+                                                               float drop_p, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                                               size_t row_base) {
+  if (seed_dev) seed += *seed_dev;
+  __shared__ float red[8];
+  const size_t r = blockIdx.x;
+  const float* sr = s + r * ld_s;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, sr[c] * scale);
+  mx = block_reduce(mx, red, true);
+  float sum = 0.0f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += __expf(sr[c] * scale - mx);
+  sum = block_reduce(sum, red, false);
+  const float inv = 1.0f / sum, inv_keep = 1.0f / (1.0f - drop_p);
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float v = __expf(sr[c] * scale - mx) * inv;
+    p[r * ld_p + c] = v;
+    if (drop_p > 0.0f) pd[r * ld_p + c] = v * keep_scale(drop_p, inv_keep, seed, row_base + r, row_base + c, 0);
+  }
+}
+
+// ds[r, :] = scale * p * (dpd * keep - D_r),  D_r = sum_c dpd * keep * p
+__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dpd,
+                                                               float* __restrict__ ds, int ld, int cols, float scale,
+                                                               float drop_p, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                                               size_t row_base) {
+  if (seed_dev) seed += *seed_dev;
+  __shared__ float red[8];
+  const size_t r = blockIdx.x;
+  const float inv_keep = 1.0f / (1.0f - drop_p);
+  float D = 0.0f;
+  for (int c = threadIdx.x; c < cols; c += 256)
+    D = fmaf(dpd[r * ld + c] * keep_scale(drop_p, inv_keep, seed, row_base + r, row_base + c, 0), p[r * ld + c], D);
+  D = block_reduce(D, red, false);
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float dp = dpd[r * ld + c] * keep_scale(drop_p, inv_keep, seed, row_base + r, row_base + c, 0);
+    ds[r * ld + c] = scale * p[r * ld + c] * (dp - D);
+  }
+}
+
 // Query (or key) rows per CTA: 16 (four passes of the CTA's four warps over one staged K/V tile stream) when that
 // already fills the GPU, otherwise 4 (one pass) -- a reference training batch (seq 32, one head) is 2 CTAs at 16 rows
 // per CTA and the kernel is pure latency.
@@ -568,6 +624,30 @@ extern "C" int bbbp_attention_fwd_f32(const float* qkv, float* out, float* lse, 
   attention_fwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(qkv, out, lse, seq, heads, head_dim, qpb,
                                                                           dropout_p, seed, seed_dev);
   return launch_status("attention_fwd");
+}
+
+extern "C" int bbbp_attn_softmax_fwd_f32(const float* scores, int ld_scores, float* p, float* p_dropped, int ld_p, int rows,
+                                         int cols, float scale, float dropout_p, uint64_t seed, const uint64_t* seed_dev,
+                                         long long row_base, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(scores && p && rows >= 0 && cols > 0 && dropout_p >= 0.0f && dropout_p < 1.0f, "attn_softmax_fwd: bad argument");
+  BBBP_CHECK_ARG(dropout_p == 0.0f || p_dropped, "attn_softmax_fwd: dropout needs the p_dropped output");
+  if (rows == 0) return BBBP_OK;
+  attn_softmax_fwd_kernel<<<rows, 256, 0, as_stream(stream)>>>(scores, ld_scores, p, p_dropped, ld_p, cols, scale, dropout_p, seed,
+                                                               seed_dev, (size_t)row_base);
+  return launch_status("attn_softmax_fwd");
+}
+
+extern "C" int bbbp_attn_softmax_bwd_f32(const float* p, const float* dp_dropped, float* dscores, int ld, int rows, int cols,
+                                         float scale, float dropout_p, uint64_t seed, const uint64_t* seed_dev, long long row_base,
+                                         bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(p && dp_dropped && dscores && rows >= 0 && cols > 0 && dropout_p >= 0.0f && dropout_p < 1.0f,
+                 "attn_softmax_bwd: bad argument");
+  if (rows == 0) return BBBP_OK;
+  attn_softmax_bwd_kernel<<<rows, 256, 0, as_stream(stream)>>>(p, dp_dropped, dscores, ld, cols, scale, dropout_p, seed, seed_dev,
+                                                               (size_t)row_base);
+  return launch_status("attn_softmax_bwd");
 }
 
 extern "C" int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse, const float* dout,

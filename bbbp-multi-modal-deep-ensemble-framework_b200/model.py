@@ -227,7 +227,7 @@ class TransformerCnnModel(_KernelModule):
         head_dim = x.shape[1] // heads
         p_attn = float(attn.dropout) if self.training else 0.0
         qkv = ag.linear(x, attn.in_proj_weight, attn.in_proj_bias, None, self.precision)
-        a = ag.Attention.apply(qkv, groups, seq, heads, head_dim, p_attn, ag.next_seed() if p_attn > 0 else 0)
+        a = ag.attention(qkv, groups, seq, heads, head_dim, p_attn)
         sa = self._drop(self._lin(a, attn.out_proj), layer.dropout1)
         x = ag.AddLayerNorm.apply(sa, x, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
         h = self._drop(self._lin(x, layer.linear1, "relu"), layer.dropout)

@@ -343,6 +343,24 @@ def attention_bwd(qkv, out, lse, dout, groups, seq, heads, head_dim, dropout_p=0
     return dqkv
 
 
+def attn_softmax_fwd(scores, scale, dropout_p=0.0, seed=0, seed_dev=None, row_base=0):
+    """(rows, cols) fp32 logits -> (p, p_dropped): row softmax of scale * logits and its dropped copy (p itself at p = 0)."""
+    rows, cols = scores.shape
+    p = torch.empty((rows, cols), device=scores.device, dtype=torch.float32)
+    pd = torch.empty_like(p) if dropout_p > 0 else None
+    check(lib.bbbp_attn_softmax_fwd_f32(scores.data_ptr(), scores.stride(0), p.data_ptr(), _ptr(pd), cols, rows, cols, float(scale),
+                                        float(dropout_p), int(seed), _ptr(seed_dev), int(row_base), _stream()), "attn_softmax_fwd")
+    return p, (pd if pd is not None else p)
+
+
+def attn_softmax_bwd(p, dpd, scale, dropout_p=0.0, seed=0, seed_dev=None, row_base=0):
+    rows, cols = p.shape
+    ds = torch.empty_like(p)
+    check(lib.bbbp_attn_softmax_bwd_f32(p.data_ptr(), dpd.data_ptr(), ds.data_ptr(), cols, rows, cols, float(scale), float(dropout_p),
+                                        int(seed), _ptr(seed_dev), int(row_base), _stream()), "attn_softmax_bwd")
+    return ds
+
+
 def attention_heads_bf16(qkv16: torch.Tensor, k_offset: int, v_offset: int, groups: int, seq: int, heads: int, head_dim: int,
                          ld_out: int | None = None) -> torch.Tensor:
     """Multi-head attention (head_dim 8 or 16) on the packed bf16 in_proj output; returns (groups*seq, ld_out) bf16."""

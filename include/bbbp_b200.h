@@ -175,6 +175,16 @@ int bbbp_attention_bwd_f32(const float* qkv, const float* out, const float* lse,
                            int groups, int seq, int heads, int head_dim, float dropout_p, uint64_t seed,
                            const uint64_t* seed_dev, bbbp_stream_t stream);
 
+/* Row softmax of the GEMM route the training path takes for mid-size single-head scopes (seq > 32, e.g. batch 256: the six
+ * products Q K^T, P V, dO V^T, P^T dO, dS K, dS^T Q run on bbbp_gemm_f32).  p = softmax(scale * scores) row-wise;
+ * p_dropped = p * keep with the Philox keep mask of (seed (+ *seed_dev); row_base + r, row_base + c) -- only written
+ * when dropout_p > 0.  Backward: dscores = scale * p * (dp_dropped * keep - sum_c dp_dropped * keep * p). */
+int bbbp_attn_softmax_fwd_f32(const float* scores, int ld_scores, float* p, float* p_dropped, int ld_p, int rows, int cols,
+                              float scale, float dropout_p, uint64_t seed, const uint64_t* seed_dev, long long row_base,
+                              bbbp_stream_t stream);
+int bbbp_attn_softmax_bwd_f32(const float* p, const float* dp_dropped, float* dscores, int ld, int rows, int cols, float scale,
+                              float dropout_p, uint64_t seed, const uint64_t* seed_dev, long long row_base, bbbp_stream_t stream);
+
 /* Many small heads on the bf16 inference path (the 2048-bit fingerprint variants: 256 heads of dimension 8, C:71-73):
  * out[r, h*D + c] = softmax(q_h k_h^T / sqrt(D)) v_h per group, warp-level mma.sync m16n8k16 with an online softmax.
  * qkv rows (bf16, pitch ld) hold q at column 0, k at column k_offset, v at column v_offset (all multiples of 8);

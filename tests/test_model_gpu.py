@@ -585,3 +585,37 @@ def test_screen_library_files_to_results_table(cuda_device, tmp_path):
         ours.fc[7].bias.add_(1.0)
     again = bbbp_b200.screen_library(ours, packed.numpy(), img, batch_size=bs)
     np.testing.assert_allclose(again["Prediction"], table["Prediction"] + 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("groups,seq,d", [(1, 256, 167), (2, 33, 167), (1, 300, 64)])
+def test_training_attention_gemm_route_matches_sdpa(cuda_device, groups, seq, d):
+    """Single-head scopes wider than 32 on the TRAINING path (batch 256) run as six tiled-GEMM products + a row-softmax
+    kernel; forward and the q/k/v gradients against torch SDPA autograd in fp64."""
+    from bbbp_b200 import autograd as ag
+    g = torch.Generator().manual_seed(3)
+    qkv = (torch.randn(groups * seq, 3 * d, generator=g) * 0.7).requires_grad_()
+    dout = torch.randn(groups * seq, d, generator=g)
+    q, k, v = qkv.double().view(groups, seq, 3, 1, d).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(groups * seq, d)
+    ref.backward(dout.double())
+    x = qkv.detach().cuda().requires_grad_()
+    out = ag.attention(x, groups, seq, 1, d)
+    assert out.grad_fn is not None and out.grad_fn.route if hasattr(out.grad_fn, "route") else True
+    out.backward(dout.cuda())
+    assert float((out.detach().cpu() - ref.float()).abs().max()) <= 2e-5
+    assert float((x.grad.cpu() - qkv.grad).abs().max()) <= 5e-5
+    # inference (no grad) keeps the streaming kernels, so scores stay bit-identical under any grouping
+    with torch.no_grad():
+        a = ag.attention(x.detach(), groups, seq, 1, d)
+    assert float((a - out.detach()).abs().max()) <= 2e-5
+    # dropout: same seed -> same mask in forward and backward (gradient linear in dout), different seeds differ
+    torch.manual_seed(0)
+    x2 = qkv.detach().cuda().requires_grad_()
+    o1 = ag.Attention.apply(x2, groups, seq, 1, d, 0.25, 1234, True)
+    (g1,) = torch.autograd.grad(o1, x2, dout.cuda(), retain_graph=True)
+    (g2,) = torch.autograd.grad(o1, x2, 2 * dout.cuda())
+    assert float((g2 - 2 * g1).abs().max()) <= 1e-4
+    o2 = ag.Attention.apply(x2, groups, seq, 1, d, 0.25, 99, True)
+    assert not torch.equal(o1, o2)
+    frac = float((ag.Attention.apply(x2, groups, seq, 1, d, 0.25, 7, True) == 0).float().mean())
+    assert frac < 0.01        # outputs mix many keys: zeros would mean a broken mask
