@@ -9,7 +9,7 @@ from . import ops  # noqa: F401
 from .model import (  # noqa: F401
     AttentionFusion, BCEWithLogitsLoss, MixedInputModel, MixedInputModelBig, MixedInputModelMLP, MixedInputModelMLPMore,
     MixedInputModelMLPRdkit, MixedInputModelNoFusion, MlpModel, MSELoss, MultiHeadAttentionFusion,
-    MultiModalAttentionFusion, TransformerCnnModel, VARIANTS, build, encoder_heads)
+    MultiModalAttentionFusion, TransformerCnnModel, VARIANTS, build, encoder_heads, zero_dropout)
 from .optim import AdamW  # noqa: F401
 from .train import GraphedTrainStep  # noqa: F401
 from .feeder import DeviceBatchFeeder  # noqa: F401

@@ -567,12 +567,19 @@ class TransformerCnnModel(_KernelModule):
 
     @torch.no_grad()
     def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int = 1024,
-                          packed: bool = False, out_host: torch.Tensor | None = None, return_device: bool = False):
+                          packed: bool = False, out_host: torch.Tensor | None = None, return_device: bool = False,
+                          synchronize: bool = True):
         """End-to-end scoring of HOST-resident molecules (pinned tensors recommended): the host->device copy of chunk
         c+1 runs on a second stream while chunk c is being scored, so a pass costs max(copy, compute) instead of their
         sum.  ``packed`` selects the compact formats of predict_batches_packed.  Chunks are whole reference batches, so
         scores are identical to predict_batches on the same data.  Returns the (N,) scores on the host (and, with
-        ``return_device``, also the device copy, e.g. for a cross-rank gather)."""
+        ``return_device``, also the device copy, e.g. for a cross-rank gather).
+
+        ``synchronize=True`` (default) waits for the device->host copy, so the returned host tensor is ready to read.
+        ``synchronize=False`` is the streaming mode for back-to-back shards: the call only enqueues work (the staging
+        slots are guarded by per-slot events that persist across calls, so the first copies of the next call overlap the
+        last chunk of this one); the caller synchronises the stream before reading ``out_host`` and must not reuse one
+        ``out_host`` buffer for two calls in flight."""
         assert not self.training, "call model.eval() first"
         dev = next(self.parameters()).device
         n = fingerprint_host.shape[0]
@@ -587,11 +594,11 @@ class TransformerCnnModel(_KernelModule):
         if pipe is None or pipe[0] != key:
             slots = [(torch.empty((chunk,) + tuple(fingerprint_host.shape[1:]), device=dev, dtype=fingerprint_host.dtype),
                       torch.empty((chunk,) + tuple(image_host.shape[1:]), device=dev, dtype=image_host.dtype)) for _ in range(2)]
-            pipe = (key, torch.cuda.Stream(dev), slots)
+            pipe = (key, torch.cuda.Stream(dev), slots, [None, None])
             self._host_pipe = pipe
-        _, copier, slots = pipe
-        copier.wait_stream(compute)                  # earlier work on the slots (previous call) is ordered before us
-        ready, freed = [None, None], [None, None]
+            pipe[1].wait_stream(compute)
+        _, copier, slots, freed = pipe               # freed[s]: last compute that read slot s (this call or a previous one)
+        ready = [None, None]
         spans = self._pipeline_spans(n, chunk, batch_size)
 
         def stage(i):
@@ -620,6 +627,10 @@ class TransformerCnnModel(_KernelModule):
         if out_host is None:
             out_host = torch.empty((n,), dtype=torch.float32, pin_memory=True)
         out_host.copy_(scores, non_blocking=True)
+        if synchronize:
+            done = torch.cuda.Event()
+            done.record(compute)
+            done.synchronize()
         return (out_host, scores) if return_device else out_host
 
     _chunk_graphs = None
@@ -775,6 +786,17 @@ VARIANTS = {
 def build(variant: str, fingerprint_size: int, image_feature_size: int) -> nn.Module:
     """Variant names follow the reference script each class comes from (see VARIANTS)."""
     return VARIANTS[variant](fingerprint_size, image_feature_size)
+
+
+def zero_dropout(model: nn.Module) -> nn.Module:
+    """Set every dropout probability of ``model`` to 0 (nn.Dropout modules and nn.MultiheadAttention's own): the
+    deterministic regime the parity tests and the train-step measurements run in."""
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, nn.MultiheadAttention):
+            m.dropout = 0.0
+    return model
 
 
 class MSELoss(nn.Module):

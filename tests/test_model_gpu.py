@@ -357,8 +357,16 @@ def test_predict_from_host_overlapped_pipeline(cuda_device):
     img8 = torch.from_numpy(rng.integers(0, 256, size=(n, 3, 128, 128), dtype=np.uint8)).pin_memory()
     want = ours.predict_batches_packed(packed.cuda(), img8.cuda(), bs).cpu()
     got = ours.predict_from_host(packed, img8, bs, chunk_molecules=96, packed=True)
+    assert torch.equal(got, want)                       # synchronize=True (default): readable on return
+    # streaming mode: consecutive shards in flight at once (per-slot events carry across calls), distinct result buffers
+    packed2 = torch.from_numpy(rng.integers(0, 256, size=(n, 21), dtype=np.uint8)).pin_memory()
+    want2 = ours.predict_batches_packed(packed2.cuda(), img8.cuda(), bs).cpu()
+    out_a, out_b = torch.empty(n).pin_memory(), torch.empty(n).pin_memory()
+    for _ in range(3):
+        ours.predict_from_host(packed, img8, bs, chunk_molecules=96, packed=True, out_host=out_a, synchronize=False)
+        ours.predict_from_host(packed2, img8, bs, chunk_molecules=96, packed=True, out_host=out_b, synchronize=False)
     torch.cuda.synchronize()
-    assert torch.equal(got, want)
+    assert torch.equal(out_a, want) and torch.equal(out_b, want2)
 
 
 def test_bf16_mode_with_attention_scope_wider_than_one_tile(cuda_device):
