@@ -7,15 +7,26 @@ namespace bbbp {
 
 constexpr int CI_CHUNK = 8;
 
-// block: 256 threads = 64 pooling windows (16x16 pre-pool tile) x 4 channel groups of CPT channels
+// block: 256 threads = 64 pooling windows (16x16 pre-pool tile) x 4 channel groups of CPT channels.
+// The input-channel chunks are double buffered: chunk c+1 (halo tile + weight slice) is fetched with cp.async while
+// chunk c is multiplied, so the FMA pipe no longer idles through a global-load round trip per chunk (ncu before:
+// FMA pipe 48 % active, top stall long_scoreboard at 16 resident warps).
+template <int CPT>
+struct ConvF32Smem {
+  static constexpr int CB = 4 * CPT;
+  static constexpr int XS = CI_CHUNK * 18 * 18, WS = CI_CHUNK * 9 * CB;
+  static constexpr int STAGE = XS + WS;                     // floats per buffer
+  static constexpr size_t BYTES = 2 * (size_t)STAGE * sizeof(float);
+};
+
 template <int CPT>
 __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ y,
                                                           uint8_t* __restrict__ argmax, int Cin, int Cout, int H, int W,
                                                           int pool) {
-  constexpr int CB = 4 * CPT;  // channels per block
-  __shared__ float xs[CI_CHUNK][18][18];
-  __shared__ float ws[CI_CHUNK][9][CB];
+  using S = ConvF32Smem<CPT>;
+  constexpr int CB = S::CB;  // channels per block
+  extern __shared__ __align__(16) float conv_smem[];
   const int tid = threadIdx.x;
   const int tiles_x = W / 16;
   const int tx0 = (blockIdx.x % tiles_x) * 16, ty0 = (blockIdx.x / tiles_x) * 16;
@@ -30,38 +41,56 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
     for (int p = 0; p < 4; ++p) acc[c][p] = 0.0f;
 
   const float* xn = x + (size_t)n * Cin * H * W;
-  for (int ci0 = 0; ci0 < Cin; ci0 += CI_CHUNK) {
+  auto fetch = [&](int ci0, float* buf) {
+    float* xs = buf;
+    float* ws = buf + S::XS;
     const int nci = min(CI_CHUNK, Cin - ci0);
     for (int i = tid; i < nci * 324; i += 256) {
-      int ci = i / 324, r = (i % 324) / 18, c = i % 18;
-      int gy = ty0 + r - 1, gx = tx0 + c - 1;
-      xs[ci][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? xn[((size_t)(ci0 + ci) * H + gy) * W + gx] : 0.0f;
+      const int ci = i / 324, rc = i % 324, r = rc / 18, c = rc % 18;
+      const int gy = ty0 + r - 1, gx = tx0 + c - 1;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      cp_async_f32(xs + i, ok ? xn + ((size_t)(ci0 + ci) * H + gy) * W + gx : xn, ok);
     }
     for (int i = tid; i < nci * 9 * CB; i += 256) {
-      int co = i % CB, tap = (i / CB) % 9, ci = i / (CB * 9);
-      ws[ci][tap][co] = w[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + tap];
+      const int co = i % CB, tap = (i / CB) % 9, ci = i / (CB * 9);
+      cp_async_f32(ws + i, w + ((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + tap, true);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  const int chunks = ceil_div(Cin, CI_CHUNK);
+  fetch(0, conv_smem);
+  for (int ch = 0; ch < chunks; ++ch) {
+    float* buf = conv_smem + (ch & 1) * S::STAGE;
+    if (ch + 1 < chunks) {
+      fetch((ch + 1) * CI_CHUNK, conv_smem + ((ch + 1) & 1) * S::STAGE);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // chunk ch has landed, chunk ch+1 may still fly
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
+    const float* xs = buf;
+    const float* ws = buf + S::XS;
+    const int nci = min(CI_CHUNK, Cin - ch * CI_CHUNK);
     for (int ci = 0; ci < nci; ++ci) {
       float p[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) p[i][j] = xs[ci][2 * wy + i][2 * wx + j];
+        for (int j = 0; j < 4; ++j) p[i][j] = xs[ci * 324 + (2 * wy + i) * 18 + 2 * wx + j];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            float wv = ws[ci][kh * 3 + kw][cg * CPT + c];
+            float wv = ws[(ci * 9 + kh * 3 + kw) * CB + cg * CPT + c];
             acc[c][0] = fmaf(p[kh][kw], wv, acc[c][0]);
             acc[c][1] = fmaf(p[kh][kw + 1], wv, acc[c][1]);
             acc[c][2] = fmaf(p[kh + 1][kw], wv, acc[c][2]);
             acc[c][3] = fmaf(p[kh + 1][kw + 1], wv, acc[c][3]);
           }
     }
-    __syncthreads();
+    __syncthreads();        // everyone is done with buf before the fetch of chunk ch+2 overwrites it
   }
 
   const int gy = ty0 + 2 * wy, gx = tx0 + 2 * wx;
@@ -115,15 +144,24 @@ __global__ void relu_pool_bwd_kernel(const float* __restrict__ dy, const float* 
 // 13 of its 16 ci lanes idle on the 3-channel first layer, which the SLICES split over rows now fills).
 // Partials [z][band][slice][Cout][Cin][9] are summed by sum_over_images_kernel in a fixed order (deterministic).
 constexpr int WG_ROWS = 8, WG_COLS = 16;
+template <int CI_T, int COT>
+struct WgradSmem {
+  static constexpr int CO_TILE = 16 * COT, XS_PITCH = (WG_ROWS + 2) * (WG_COLS + 2) + 1;   // odd: conflict-free across ci
+  static constexpr int DS = CO_TILE * WG_ROWS * WG_COLS, XS = CI_T * XS_PITCH;
+  static constexpr int STAGE = DS + XS;                                                     // floats per buffer
+  static constexpr size_t BYTES = 2 * (size_t)STAGE * sizeof(float);
+};
+
+// (image, x tile) pairs are double buffered: tile t+1 is fetched with cp.async while tile t is accumulated.
 template <int CI_T, int SLICES, int COT>
 __global__ void __launch_bounds__(256) conv3x3_wgrad_tiled_kernel(const float* __restrict__ dpre, const float* __restrict__ x,
                                                                   float* __restrict__ part, int N, int Cin, int Cout, int H,
                                                                   int W) {
   static_assert(CI_T * SLICES == 16 && WG_ROWS % SLICES == 0, "lane split");
-  constexpr int CO_TILE = 16 * COT, XS_PITCH = (WG_ROWS + 2) * (WG_COLS + 2) + 1;   // odd: conflict-free across ci
+  using S = WgradSmem<CI_T, COT>;
+  constexpr int CO_TILE = S::CO_TILE, XS_PITCH = S::XS_PITCH;
   constexpr int ROWS_PER_SLICE = WG_ROWS / SLICES;
-  __shared__ float ds[CO_TILE][WG_ROWS * WG_COLS];
-  __shared__ float xs[CI_T * XS_PITCH];
+  extern __shared__ __align__(16) float wg_smem[];
   const int tid = threadIdx.x;
   const int bands = H / WG_ROWS;
   const int band = blockIdx.x % bands, ci0 = (blockIdx.x / bands) * CI_T, co0 = blockIdx.y * CO_TILE;
@@ -137,50 +175,66 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_tiled_kernel(const float* _
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[j][t] = 0.0f;
 
-  for (int n = blockIdx.z; n < N; n += gridDim.z) {
+  const int tiles_x = W / WG_COLS;
+  const int my_images = (N - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int total = my_images * tiles_x;
+  auto fetch = [&](int t, float* buf) {
+    const int n = blockIdx.z + (t / tiles_x) * gridDim.z, tx0 = (t % tiles_x) * WG_COLS;
     const float* xn = x + (size_t)n * Cin * H * W;
     const float* dn = dpre + (size_t)n * Cout * H * W;
-    for (int tx0 = 0; tx0 < W; tx0 += WG_COLS) {
-      for (int i = tid; i < CO_TILE * WG_ROWS * WG_COLS; i += 256) {
-        const int co = i / (WG_ROWS * WG_COLS), p = i % (WG_ROWS * WG_COLS);
-        ds[co][p] = dn[((size_t)(co0 + co) * H + ty0 + p / WG_COLS) * W + tx0 + p % WG_COLS];
-      }
-      for (int i = tid; i < CI_T * (WG_ROWS + 2) * (WG_COLS + 2); i += 256) {
-        const int ci = i / ((WG_ROWS + 2) * (WG_COLS + 2)), rc = i % ((WG_ROWS + 2) * (WG_COLS + 2));
-        const int gy = ty0 + rc / (WG_COLS + 2) - 1, gx = tx0 + rc % (WG_COLS + 2) - 1;
-        xs[ci * XS_PITCH + rc] =
-            (ci < nci && gy >= 0 && gy < H && gx >= 0 && gx < W) ? xn[((size_t)(ci0 + ci) * H + gy) * W + gx] : 0.0f;
-      }
-      __syncthreads();
-      const float* xc = xs + ci_l * XS_PITCH;
-#pragma unroll
-      for (int rr = 0; rr < ROWS_PER_SLICE; ++rr) {
-        const int py = slice * ROWS_PER_SLICE + rr;
-        const float* r0 = xc + py * (WG_COLS + 2);           // input rows py-1, py, py+1 in tile coordinates (+1 halo)
-        const float* r1 = r0 + (WG_COLS + 2);
-        const float* r2 = r1 + (WG_COLS + 2);
-        float w00 = r0[0], w01 = r0[1], w10 = r1[0], w11 = r1[1], w20 = r2[0], w21 = r2[1];
-#pragma unroll
-        for (int px = 0; px < WG_COLS; ++px) {
-          const float w02 = r0[px + 2], w12 = r1[px + 2], w22 = r2[px + 2];
-#pragma unroll
-          for (int j = 0; j < COT; ++j) {
-            const float d = ds[cog * COT + j][py * WG_COLS + px];
-            acc[j][0] = fmaf(d, w00, acc[j][0]);
-            acc[j][1] = fmaf(d, w01, acc[j][1]);
-            acc[j][2] = fmaf(d, w02, acc[j][2]);
-            acc[j][3] = fmaf(d, w10, acc[j][3]);
-            acc[j][4] = fmaf(d, w11, acc[j][4]);
-            acc[j][5] = fmaf(d, w12, acc[j][5]);
-            acc[j][6] = fmaf(d, w20, acc[j][6]);
-            acc[j][7] = fmaf(d, w21, acc[j][7]);
-            acc[j][8] = fmaf(d, w22, acc[j][8]);
-          }
-          w00 = w01; w01 = w02; w10 = w11; w11 = w12; w20 = w21; w21 = w22;
-        }
-      }
-      __syncthreads();
+    float* ds = buf;
+    float* xs = buf + S::DS;
+    for (int i = tid; i < CO_TILE * WG_ROWS * WG_COLS; i += 256) {
+      const int co = i / (WG_ROWS * WG_COLS), p = i % (WG_ROWS * WG_COLS);
+      cp_async_f32(ds + i, dn + ((size_t)(co0 + co) * H + ty0 + p / WG_COLS) * W + tx0 + p % WG_COLS, true);
     }
+    for (int i = tid; i < CI_T * (WG_ROWS + 2) * (WG_COLS + 2); i += 256) {
+      const int ci = i / ((WG_ROWS + 2) * (WG_COLS + 2)), rc = i % ((WG_ROWS + 2) * (WG_COLS + 2));
+      const int gy = ty0 + rc / (WG_COLS + 2) - 1, gx = tx0 + rc % (WG_COLS + 2) - 1;
+      const bool ok = ci < nci && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      cp_async_f32(xs + ci * XS_PITCH + rc, ok ? xn + ((size_t)(ci0 + ci) * H + gy) * W + gx : xn, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  if (total > 0) fetch(0, wg_smem);
+  for (int t = 0; t < total; ++t) {
+    const float* buf = wg_smem + (t & 1) * S::STAGE;
+    if (t + 1 < total) {
+      fetch(t + 1, wg_smem + ((t + 1) & 1) * S::STAGE);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    const float* ds = buf;
+    const float* xc = buf + S::DS + ci_l * XS_PITCH;
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_SLICE; ++rr) {
+      const int py = slice * ROWS_PER_SLICE + rr;
+      const float* r0 = xc + py * (WG_COLS + 2);           // input rows py-1, py, py+1 in tile coordinates (+1 halo)
+      const float* r1 = r0 + (WG_COLS + 2);
+      const float* r2 = r1 + (WG_COLS + 2);
+      float w00 = r0[0], w01 = r0[1], w10 = r1[0], w11 = r1[1], w20 = r2[0], w21 = r2[1];
+#pragma unroll
+      for (int px = 0; px < WG_COLS; ++px) {
+        const float w02 = r0[px + 2], w12 = r1[px + 2], w22 = r2[px + 2];
+#pragma unroll
+        for (int j = 0; j < COT; ++j) {
+          const float d = ds[(cog * COT + j) * (WG_ROWS * WG_COLS) + py * WG_COLS + px];
+          acc[j][0] = fmaf(d, w00, acc[j][0]);
+          acc[j][1] = fmaf(d, w01, acc[j][1]);
+          acc[j][2] = fmaf(d, w02, acc[j][2]);
+          acc[j][3] = fmaf(d, w10, acc[j][3]);
+          acc[j][4] = fmaf(d, w11, acc[j][4]);
+          acc[j][5] = fmaf(d, w12, acc[j][5]);
+          acc[j][6] = fmaf(d, w20, acc[j][6]);
+          acc[j][7] = fmaf(d, w21, acc[j][7]);
+          acc[j][8] = fmaf(d, w22, acc[j][8]);
+        }
+        w00 = w01; w01 = w02; w10 = w11; w11 = w12; w20 = w21; w21 = w22;
+      }
+    }
+    __syncthreads();        // done with buf before the fetch of tile t+2 overwrites it
   }
   if (ci_l < nci) {
     const size_t per_w = (size_t)Cout * Cin * 9;
@@ -260,12 +314,18 @@ extern "C" int bbbp_conv3x3_f32(const float* x, const float* w, const float* b, 
   if (N == 0) return BBBP_OK;
   BBBP_CHECK_ARG(N <= 65535, "conv3x3_f32: N=%d exceeds 65535 images per launch", N);
   cudaStream_t s = as_stream(stream);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv3x3_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvF32Smem<16>::BYTES);
+    cudaFuncSetAttribute(conv3x3_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvF32Smem<8>::BYTES);
+    attr_done = true;
+  }
   if (Cout % 64 == 0) {
     dim3 grid((H / 16) * (W / 16), Cout / 64, N);
-    conv3x3_f32_kernel<16><<<grid, 256, 0, s>>>(x, w, b, y, argmax, Cin, Cout, H, W, pool);
+    conv3x3_f32_kernel<16><<<grid, 256, ConvF32Smem<16>::BYTES, s>>>(x, w, b, y, argmax, Cin, Cout, H, W, pool);
   } else {
     dim3 grid((H / 16) * (W / 16), Cout / 32, N);
-    conv3x3_f32_kernel<8><<<grid, 256, 0, s>>>(x, w, b, y, argmax, Cin, Cout, H, W, pool);
+    conv3x3_f32_kernel<8><<<grid, 256, ConvF32Smem<8>::BYTES, s>>>(x, w, b, y, argmax, Cin, Cout, H, W, pool);
   }
   return launch_status("conv3x3_f32");
 }
@@ -308,8 +368,12 @@ extern "C" int bbbp_conv3x3_wgrad_f32(const float* dpre, const float* x, float* 
   float* part_w = workspace;
   float* part_b = workspace + n_part * per_w;
   const dim3 grid(ceil_div(Cin, p.ci_t) * p.bands, Cout / (16 * p.cot), p.zn);
-#define BBBP_WGRAD(CI, SL, CT) \
-  conv3x3_wgrad_tiled_kernel<CI, SL, CT><<<grid, 256, 0, s>>>(dpre, x, part_w, N, Cin, Cout, H, W)
+#define BBBP_WGRAD(CI, SL, CT)                                                                                              \
+  do {                                                                                                                     \
+    cudaFuncSetAttribute(conv3x3_wgrad_tiled_kernel<CI, SL, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                         (int)WgradSmem<CI, CT>::BYTES);                                                                   \
+    conv3x3_wgrad_tiled_kernel<CI, SL, CT><<<grid, 256, WgradSmem<CI, CT>::BYTES, s>>>(dpre, x, part_w, N, Cin, Cout, H, W); \
+  } while (0)
   if (p.cot == 4) {
     if (p.ci_t == 4) BBBP_WGRAD(4, 4, 4); else if (p.ci_t == 8) BBBP_WGRAD(8, 2, 4); else BBBP_WGRAD(16, 1, 4);
   } else if (p.cot == 2) {
