@@ -398,10 +398,10 @@ class TransformerCnnModel(_KernelModule):
             outs.append(o)
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
-    fork_image_branch = False   # set by train.GraphedTrainStep while it captures
-    # large eager inference passes: run the conv branch on a second stream beside the encoder's ~55 small GEMM / norm
-    # kernels (0 disables)
-    fork_eager_rows = int(os.environ.get("BBBP_FORK_EAGER_ROWS", "0"))
+    # Set while a CUDA graph is being captured (train.GraphedTrainStep, the inference graphs below): the conv branch is
+    # forked onto a second stream so the graph keeps it parallel to the encoder chain.  Forking EAGER launches of a large
+    # pass was measured and dropped (8 192 molecules: 4.03 vs 3.77 ms -- the persistent conv kernels own every SM).
+    fork_image_branch = False
     _side_stream = None
 
     # -- CUDA-graph replay for small inference calls -------------------------------------------------------------------
@@ -500,13 +500,9 @@ class TransformerCnnModel(_KernelModule):
         rows = fingerprint.shape[0]
         if rows % groups:
             raise ValueError(f"{rows} molecules do not split into {groups} equal reference batches")
-        from . import ops
         x = fingerprint if fingerprint.is_contiguous() else fingerprint.contiguous()
         side = None
-        capturing = torch.cuda.is_current_stream_capturing()
-        eager_fork = (not capturing and self.fork_eager_rows and rows >= self.fork_eager_rows and not self.training
-                      and not torch.is_grad_enabled() and not ops.KERNEL_TIMER.names)
-        if (self.fork_image_branch and capturing) or eager_fork:
+        if self.fork_image_branch and torch.cuda.is_current_stream_capturing():
             # the conv branch does not depend on the encoder: fork it so the captured graph has two parallel branches
             cur = torch.cuda.current_stream()
             if self._side_stream is None:

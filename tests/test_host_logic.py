@@ -205,3 +205,41 @@ def test_stack_columns_matches_reference_vstack_transpose():
     import pytest
     with pytest.raises(ValueError):
         bbbp_b200.stack_columns(nn_col, rf[:5])
+
+
+def test_host_pipeline_chunk_spans_cover_whole_batches():
+    """predict_from_host's chunk schedule: contiguous, whole reference batches per chunk, the ragged tail on the last span."""
+    import bbbp_b200
+    spans = bbbp_b200.TransformerCnnModel._pipeline_spans
+    for n, chunk, bs in [(8192, 1024, 256), (1058, 64, 32), (1058, 96, 32), (300, 2048, 256), (31, 64, 32), (0, 64, 32), (32, 64, 32),
+                         (10_000, 1024, 256)]:
+        sp = spans(n, chunk, bs)
+        if n == 0:
+            assert sp == []
+            continue
+        assert sp[0][0] == 0 and sp[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(sp, sp[1:]))
+        assert all(a % bs == 0 for a, _ in sp)                      # every chunk starts on a reference-batch boundary
+        assert all(b - a <= max(chunk, bs) for a, b in sp)          # and fits its staging slot
+        assert all((b - a) % bs == 0 for a, b in sp[:-1])           # only the last span may carry the ragged tail batch
+
+
+def test_graphed_train_step_rejects_foreign_optimizers():
+    """The captured update reads its scalars from device memory: only bbbp_b200.AdamW provides that entry point."""
+    import pytest
+    import torch
+    import bbbp_b200
+    model = bbbp_b200.MixedInputModelMLP(64, 128)
+    with pytest.raises(TypeError, match="bbbp_b200.AdamW"):
+        bbbp_b200.GraphedTrainStep(model, torch.optim.AdamW(model.parameters()), bbbp_b200.MSELoss())
+
+
+def test_pack_fingerprint_bits_is_little_endian_packbits():
+    import numpy as np
+    import bbbp_b200
+    from oracle import preprocess
+    rng = np.random.default_rng(3)
+    bits = (rng.random((5, 167)) < 0.3).astype(np.int64)
+    packed = bbbp_b200.pack_fingerprint_bits(bits).numpy()
+    np.testing.assert_array_equal(packed, preprocess.pack_bits(bits))
+    np.testing.assert_array_equal(preprocess.unpack_bits(packed, 167), bits)
