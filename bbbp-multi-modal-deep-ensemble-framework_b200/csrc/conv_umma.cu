@@ -51,8 +51,12 @@ struct Cfg {
   // (measured: conv2 1.21 -> 1.14 ms).  conv1 keeps four: with eight, two CTAs per SM need a 72-register cap that spills
   // in the epilogue and costs more than the producers gain.
   static constexpr int PROD_WARPS = (KC == 1 && !PACK4) ? 4 : 8, PROD_THREADS = PROD_WARPS * 32;
-  static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 32;
-  static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS;
+  // + one MMA warp + one STORE warp.  The store warp exists because ISSUING the tile's bulk tensor store costs its thread
+  // ~1 200 cycles (cycle probe: 1 205 on conv1, 1 362 on conv2 -- the 128 swizzled rows of the box are walked at issue),
+  // and when epilogue thread 0 paid that, every epilogue warp paid it too at the next per-tile barrier: a third of
+  // conv1's tile time.  Now the epilogue warps only ARRIVE on the "tile written" barrier and go on to the next tile.
+  static constexpr int EPI_THREADS = EPI_WARPS * 32, THREADS = EPI_THREADS + PROD_THREADS + 64;
+  static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS, STORE_WARP = MMA_WARP + 1;
   // the first layer runs two small CTAs per SM (measured: one CTA with 8 + 8 + 1 warps and a 6-deep ring is slower,
   // 1.65 ms vs 1.42 ms per 8 192 images)
   static constexpr int MIN_CTAS = KC == 1 ? 2 : 1;
@@ -154,6 +158,9 @@ __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_
 }
 
 enum { SRC_NHWC_BF16 = 0, SRC_CHW_F32 = 1, SRC_CHW_U8 = 2 };
+#ifndef BBBP_CONV1_PF
+#define BBBP_CONV1_PF 3
+#endif
 
 // Optional cycle probe (bbbp_debug_conv_probe): when set, CTA 0 accumulates clock64() deltas of its role loops into
 // probe[0..15]: MMA thread {wait acc_empty, wait full, issue}, epilogue thread 0 {wait acc_full, tmem+math+sts, barriers+
@@ -358,18 +365,43 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
         mbar_arrive(&full[s]);
         PROBE_ADD(10, tp);
       };
-      Vec bufA[TPT][CH], bufB[TPT][CH];
-      uint32_t okA = 0, okB = 0;
-      if (my_tiles > 0) load_tile(0, bufA, okA);
-      for (int i = 0; i < my_tiles; i += 2) {
-        if (i + 1 < my_tiles) load_tile(i + 1, bufB, okB);
-        store_tile(i, bufA, okA);
-        if (i + 1 < my_tiles) {
-          if (i + 2 < my_tiles) load_tile(i + 2, bufA, okA);
-          store_tile(i + 1, bufB, okB);
+      // Register prefetch ring, PF tiles deep (loop unrolled by PF, no register copies): PF - 1 tile loads stay in flight
+      // per CTA while tile i is converted and stored.  With the store warp in place the producers' global-load latency
+      // is what the first layer waits for (cycle probe: producers 1 766 cycles per tile in "wait data").
+      constexpr int PF = BBBP_CONV1_PF;
+      Vec buf[PF][TPT][CH];
+      uint32_t okm[PF];
+#pragma unroll
+      for (int q = 0; q < PF - 1; ++q)
+        if (q < my_tiles) load_tile(q, buf[q], okm[q]);
+      for (int i = 0; i < my_tiles; i += PF) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          if (i + q < my_tiles) {
+            if (i + q + PF - 1 < my_tiles) load_tile(i + q + PF - 1, buf[(q + PF - 1) % PF], okm[(q + PF - 1) % PF]);
+            store_tile(i + q, buf[q], okm[q]);
+          }
         }
       }
     }
+  } else if (warp == C::STORE_WARP) {
+    // ===== store warp: one bulk tensor store per tile, off the epilogue warps' critical path ============================
+    // bar 1 ("output buffer b is free"): this warp arrives, the epilogue threads wait.  bar 2 ("tile written and fenced"):
+    // the epilogue threads arrive, this warp waits.  Both count EPI_THREADS + 32.
+    const int PH = H / 2;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = blockIdx.x + i * gridDim.x;
+      const int n = t / tiles_per_img, r = t % tiles_per_img;
+      if (lane == 0 && i >= 2) bulk_store_wait_read<1>();   // the store of tile i-2 has finished reading buffer i & 1
+      __syncwarp();
+      named_bar_arrive(1, EPI_THREADS + 32);
+      named_bar_sync(2, EPI_THREADS + 32);
+      if (lane == 0) {
+        tma_store_3d(&tmOut, sOut + (i & 1) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
+        bulk_store_commit();
+      }
+    }
+    if (lane == 0) bulk_store_wait_all();   // shared memory must outlive the last store's reads
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer ==================================================================================================
     // The whole warp runs this loop (warp-uniform control flow, descriptor arithmetic on the uniform datapath); one
@@ -408,15 +440,11 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
     // pipe this kernel is bound by).
     constexpr int SWZ_SHIFT = C::OUT_ROW_B == 128 ? 0 : 1, SWZ_MASK = C::OUT_ROW_B / 16 - 1;
     const int swz = (m >> SWZ_SHIFT) & SWZ_MASK;
-    const bool issuer = warp == 0 && lane == 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int t = blockIdx.x + i * gridDim.x;
-      const int n = t / tiles_per_img, r = t % tiles_per_img;
       const int b = i & 1;
       uint8_t* otile = sOut + b * C::OUT_BYTES;
       long long tp = probe ? clock64() : 0;
-      if (issuer) bulk_store_wait_read<1>();   // the store of tile i-2 has finished reading this buffer
-      named_bar_sync(1, EPI_THREADS);
+      named_bar_sync(1, EPI_THREADS + 32);     // the store warp: tile i-2 has been read out of this buffer
       PROBE_ADD(6, tp);
       mbar_wait(&acc_full[b], (i >> 1) & 1);
       PROBE_ADD(4, tp);
@@ -468,14 +496,9 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
       mbar_arrive(&acc_empty[b]);   // TMEM reads done: the MMA warp may start the tile after next
       PROBE_ADD(5, tp);
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA (async proxy)
-      named_bar_sync(2, EPI_THREADS);
-      if (issuer) {
-        tma_store_3d(&tmOut, otile, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
-        bulk_store_commit();
-      }
+      named_bar_arrive(2, EPI_THREADS + 32);   // tile written: the store warp takes it from here
       PROBE_ADD(7, tp);
     }
-    if (issuer) bulk_store_wait_all();   // shared memory must outlive the last store's reads
   }
   tc_fence_before_sync();
   __syncthreads();

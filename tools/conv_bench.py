@@ -28,7 +28,7 @@ print(f"conv2                  : {ms:.3f} ms  {N * 2 * 64 * 64 * 64 * 288 / ms /
 # ---- cycle probe of CTA 0's pipeline roles -------------------------------------------------------------------------
 from bbbp_b200._lib import lib, check
 names = ["mma: wait acc_empty", "mma: wait full", "mma: issue+commit", "mma: tiles", "epi: wait acc_full", "epi: tmem+math+sts",
-         "epi: wait store/bar1", "epi: fence+bar2+tma", "prod: wait empty", "prod: issue loads", "prod: wait data+arrive"]
+         "epi: wait buffer free (bar1)", "epi: fence + arrive", "prod: wait empty", "prod: issue loads", "prod: wait data+arrive"]
 for label, fn in [("conv2", lambda: ops.conv3x3_relu_pool_bf16(y1, w2, b2, 64)),
                   ("conv1 NHWC8", lambda: ops.conv3x3_relu_pool_bf16(x8, w1, b1, 32)),
                   ("conv1 fp32 planes", lambda: ops.conv1_from_image_bf16(img, w1, b1)),
