@@ -65,11 +65,13 @@ struct Cfg {
   // instructions per tile: conv1 issues one N=COUT MMA per (member, step); conv2 pairs the two members of a pooling
   // row that read the SAME halo view (dx=0 with tap kw+1, dx=1 with tap kw) into one N=2*COUT MMA: 24 per K-chunk pair
   // PACK4 (planar first-layer sources): 4 channels (8 bytes) per pixel, two pixels per 16-byte chunk, so one K=16 MMA
-  // covers a whole kernel ROW (kw = 0..2 and a zero-weight dummy): 3 MMAs per window member instead of 5, i.e. 40 %
-  // fewer shared-memory operand wavefronts on the first layer, which is bound by exactly those.
-  static constexpr int NISSUE = PACK4 ? 12 : KC == 1 ? 4 * NMMA : 24 * (KC / 2);
+  // covers the four pixels X .. X+3 of a halo row with X = 2*pw.  Both window members of a pooling row need three of
+  // them (dx = 0: X..X+2, dx = 1: X+1..X+3), so ONE N = 2*COUT MMA per (dy, kernel row) computes both -- their weights
+  // sit side by side in the B image with a zero tap at the unused pixel: 6 MMAs per tile instead of 12 (an M = 128 MMA
+  // costs the tensor pipe ~90 cycles whatever its N, and that issue cost is what bounded the first layer).
+  static constexpr int NISSUE = PACK4 ? 6 : KC == 1 ? 4 * NMMA : 24 * (KC / 2);
   static constexpr int W8_BYTES = 2 * 5 * 2 * COUT * 16;                  // conv1 weight image for the NHWC8 source
-  static constexpr int W_BYTES = PACK4 ? 3 * 2 * COUT * 16 : KC == 1 ? W8_BYTES : 9 * KC * COUT * 16;
+  static constexpr int W_BYTES = PACK4 ? 3 * 2 * (2 * COUT) * 16 : KC == 1 ? W8_BYTES : 9 * KC * COUT * 16;
   static constexpr int W_OFFSET = PACK4 ? W8_BYTES : 0;                   // the prepared blob holds both conv1 images
   static constexpr int ACC_COLS = 4 * COUT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -105,13 +107,12 @@ struct MmaOp {
 template <int KC, int COUT, bool PACK4>
 __host__ __device__ constexpr MmaOp mma_op(int I) {
   if (PACK4) {
-    // member q = 2*dy + dx reads copy dx of the halo (chunk j = pixels 2j+dx, 2j+dx+1); kernel row kh is one MMA:
-    // K chunk 0 = pixels (X, X+1), chunk 1 = (X+2, X+3) with X = 2*pw + dx, i.e. kw = 0..3 (kw = 3 has zero weights)
-    // issue order: kernel row outermost, the four members innermost -- consecutive MMAs then accumulate into DIFFERENT
-    // TMEM accumulators and pipeline in the tensor core instead of serialising on the accumulator dependency
-    const int q = I % 4, kh = I / 4, dy = q >> 1, dx = q & 1;
-    return MmaOp{(uint32_t)(dx * PAR_B + (dy + kh) * ROW_B), 16u, (uint32_t)(kh * (2 * COUT * 16)), (uint32_t)(COUT * 16),
-                 (uint32_t)(q * COUT), (uint32_t)COUT, (uint32_t)(kh != 0)};
+    // I = 2*kh + dy: kernel row outermost, the pooling row innermost -- consecutive MMAs accumulate into DIFFERENT TMEM
+    // accumulators (columns [2*dy*COUT, +2*COUT) = members (dy, 0) | (dy, 1)) and pipeline in the tensor core.
+    // A: halo row dy + kh, K chunk 0 = pixels (X, X+1), chunk 1 = (X+2, X+3) through the leading byte offset.
+    const int dy = I % 2, kh = I / 2;
+    return MmaOp{(uint32_t)((dy + kh) * ROW_B), 16u, (uint32_t)(kh * (2 * (2 * COUT) * 16)), (uint32_t)((2 * COUT) * 16),
+                 (uint32_t)(dy * 2 * COUT), (uint32_t)(2 * COUT), (uint32_t)(kh != 0)};
   }
   if (KC == 1) {
     // conv1: member q = 2*dy + dx, step m covers the tap pair (2m, 2m+1) through the leading byte offset
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
 
   // ---- one-time setup: weights + bias to smem, barriers, TMEM -----------------------------------------------------
   for (int i = threadIdx.x; i < C::W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wprep[C::W_OFFSET / 16 + i];
-  if constexpr (C::PACK4)   // pixel 18 of copy 1 is read under zero weights and never written: keep it finite
+  if constexpr (C::PACK4)   // pad bytes of the stage are never written by the producers: keep them finite
     for (int i = threadIdx.x; i < STAGES * C::A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < COUT; i += THREADS) sBias[i] = bias[i];
   if (threadIdx.x == 0) {
@@ -354,9 +355,8 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(px[e][0], px[e][1]), h1 = __floats2bfloat162_rn(px[e][2], 0.0f);
                 const uint2 pix = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
                 uint8_t* row = stage + tY[k] * ROW_B;
-                // copy 0: chunk j = pixels (2j, 2j+1); copy 1: chunk j = pixels (2j+1, 2j+2)
+                // chunk j = pixels (2j, 2j+1): one copy serves both window members of a pooling row (see mma_op)
                 *reinterpret_cast<uint2*>(row + X * 8) = pix;
-                if (X >= 1) *reinterpret_cast<uint2*>(row + PAR_B + (X - 1) * 8) = pix;
               }
             }
           }
@@ -528,13 +528,14 @@ __global__ void prep_weights_c8_kernel(const float* __restrict__ w, __nv_bfloat1
   const bool zero = chunk == tp.zero_slot || c >= Cin;
   wp[i] = __float2bfloat16(zero ? 0.0f : w[((size_t)n * Cin + c) * 9 + tap]);
 }
-// PACK4 image (planar sources): wp[kh][chunk][n][8], K index k = chunk*8 + e = kw*4 + c, zero for kw = 3 or c >= Cin
+// PACK4 image (planar sources): wp[kh][chunk][n2][8], n2 = dx*Cout + n.  K index k = chunk*8 + e = j*4 + c addresses pixel
+// X + j of the halo row (X = 2*pw) and channel c; member dx uses tap kw = j - dx: zero where that is not in 0..2 or c >= Cin
 __global__ void prep_weights_pack4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 3 * 2 * Cout * 8) return;
-  const int e = i % 8, n = (i / 8) % Cout, chunk = (i / (8 * Cout)) % 2, kh = i / (16 * Cout);
-  const int k = chunk * 8 + e, kw = k / 4, c = k % 4;
-  wp[i] = __float2bfloat16((kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f);
+  if (i >= 3 * 2 * (2 * Cout) * 8) return;
+  const int e = i % 8, n2 = (i / 8) % (2 * Cout), chunk = (i / (16 * Cout)) % 2, kh = i / (32 * Cout);
+  const int k = chunk * 8 + e, j = k / 4, c = k % 4, dx = n2 / Cout, n = n2 % Cout, kw = j - dx;
+  wp[i] = __float2bfloat16((kw >= 0 && kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f);
 }
 // fp32 NCHW image (C <= 8 planes) -> bf16 NHWC with 8 channels per pixel (zero padded): one 16-byte store per pixel
 __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ img, uint4* __restrict__ out,
@@ -656,7 +657,7 @@ int launch(const void* x, const float* stats, const void* wprep, const float* bi
 using namespace bbbp;
 
 extern "C" size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout) {
-  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)3 * 2 * Cout * 16;   // NHWC8 image | PACK4 image
+  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)3 * 2 * (2 * Cout) * 16;   // NHWC8 image | PACK4 image
   return (size_t)9 * (Cin / 8) * Cout * 16;
 }
 
@@ -666,7 +667,7 @@ extern "C" int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, i
                  "conv3x3_prepare: only (3->32) and (32->64) are built for the tcgen05 path, got %d->%d", Cin, Cout);
   const int total = (int)(bbbp_conv3x3_prepared_bytes(Cin, Cout) / 2);
   if (Cin <= 8) {
-    const int n8 = 2 * 5 * 2 * Cout * 8, n4 = 3 * 2 * Cout * 8;
+    const int n8 = 2 * 5 * 2 * Cout * 8, n4 = 3 * 2 * (2 * Cout) * 8;
     conv::prep_weights_c8_kernel<<<ceil_div(n8, 256), 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wprep),
                                                                                  Cin, Cout);
     conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(
