@@ -31,9 +31,9 @@ METRIC, UNIT = "molecules/sec multi-input NN inference", "molecules/s"
 # algorithmic work (SURVEY 8d / DESIGN.md): conv2 = 75.50 MMAC per molecule
 CONV2_FLOP_PER_MOL = 2 * 64 * 64 * 64 * 288
 # DRAM bytes of the conv2 kernel per molecule from the committed `ncu --set full` capture
-# (profiles/r01_ncu_conv_umma_full.txt: dram__bytes_read 2.150264 GB + dram__bytes_write 1.043248 GB per 8192-molecule
+# (profiles/r01_ncu_conv_umma_full.txt: dram__bytes_read 2.186054 GB + dram__bytes_write 1.046418 GB per 8192-molecule
 # launch); the algorithmic figure is 256 KiB in + 128 KiB out = 393 216 B, i.e. no re-reads
-CONV2_DRAM_BYTES_PER_MOL = (2.150264e9 + 1.043248e9) / 8192
+CONV2_DRAM_BYTES_PER_MOL = (2.186054e9 + 1.046418e9) / 8192
 FWD_FLOP_PER_MOL = 207.2e6
 IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
 
