@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BBBP_ABI_VERSION 1
+#define BBBP_ABI_VERSION 2
 
 enum { BBBP_OK = 0, BBBP_EINVAL = -1, BBBP_ECUDA = -2, BBBP_EWORKSPACE = -3, BBBP_EUNSUPPORTED = -4 };
 
