@@ -29,6 +29,15 @@ namespace bbbp {
 namespace conv {
 using namespace sm100;
 
+#ifndef BBBP_CONV1_PF
+#define BBBP_CONV1_PF 3
+#endif
+#ifndef BBBP_CONV1_PROD_WARPS
+#define BBBP_CONV1_PROD_WARPS 8
+#endif
+#ifndef BBBP_CONV1_CS
+#define BBBP_CONV1_CS 8
+#endif
 constexpr int TILE_PW = 8, TILE_PH = 16;       // pooled tile
 constexpr int HALO_W = 2 * TILE_PW + 2;        // 18
 constexpr int HALO_H = 2 * TILE_PH + 2;        // 34
@@ -50,7 +59,7 @@ struct Cfg {
   // eight warps halve the per-thread chunk count
   // (measured: conv2 1.21 -> 1.14 ms).  conv1 keeps four: with eight, two CTAs per SM need a 72-register cap that spills
   // in the epilogue and costs more than the producers gain.
-  static constexpr int PROD_WARPS = (KC == 1 && !PACK4) ? 4 : 8, PROD_THREADS = PROD_WARPS * 32;
+  static constexpr int PROD_WARPS = (KC == 1 && !PACK4) ? 4 : (PACK4 ? BBBP_CONV1_PROD_WARPS : 8), PROD_THREADS = PROD_WARPS * 32;
   // + one MMA warp + one STORE warp.  The store warp exists because ISSUING the tile's bulk tensor store costs its thread
   // ~1 200 cycles (cycle probe: 1 205 on conv1, 1 362 on conv2 -- the 128 swizzled rows of the box are walked at issue),
   // and when epilogue thread 0 paid that, every epilogue warp paid it too at the next per-tile barrier: a third of
@@ -159,9 +168,7 @@ __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_
 }
 
 enum { SRC_NHWC_BF16 = 0, SRC_CHW_F32 = 1, SRC_CHW_U8 = 2 };
-#ifndef BBBP_CONV1_PF
-#define BBBP_CONV1_PF 3
-#endif
+
 
 // Optional cycle probe (bbbp_debug_conv_probe): when set, CTA 0 accumulates clock64() deltas of its role loops into
 // probe[0..15]: MMA thread {wait acc_empty, wait full, issue}, epilogue thread 0 {wait acc_full, tmem+math+sts, barriers+
@@ -453,7 +460,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
       uint8_t* orow = otile + m * C::OUT_ROW_B;
       // CS channels per step (CS/8 output chunks): 4*CS live accumulator registers.  The first layer uses 8 so that its
       // variants fit the register cap of two CTAs per SM with eight producer warps; conv2 (no cap) uses 16.
-      constexpr int CS = COUT >= 64 ? 16 : 8;
+      constexpr int CS = COUT >= 64 ? 16 : (C::PACK4 ? BBBP_CONV1_CS : 8);
 #pragma unroll
       for (int c0 = 0; c0 < CH; c0 += CS) {
         uint32_t r0[CS], r1[CS], r2[CS], r3[CS];
