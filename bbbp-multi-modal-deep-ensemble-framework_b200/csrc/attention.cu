@@ -415,18 +415,18 @@ __global__ void __launch_bounds__(SS * 32) attention_short_fwd_kernel(const floa
     PT[lane * SP + qi] = p;
   }
   __syncthreads();
-  // O = P V: warp = 4-column block c, lane = query
+  // O = P V: warp = 4-column block c, lane = query.  The result is staged in Qs (no longer read: every warp passed the
+  // barrier above after its last use) so that the global store below is one contiguous row per warp -- storing straight
+  // from this (lane = row) mapping would touch 32 different rows per instruction.
   for (int c = warp; c < n4; c += SS) {
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < seq; ++j) axpy4(PT[j * SP + lane], *reinterpret_cast<const float4*>(Vs + j * ld + 4 * c), o);
-    if (lane < seq) {
-      float* dst = out + (row0 + lane) * E + h * d + 4 * c;
-      const int left = d - 4 * c;
-      dst[0] = o.x;
-      if (left > 1) dst[1] = o.y;
-      if (left > 2) dst[2] = o.z;
-      if (left > 3) dst[3] = o.w;
-    }
+    *reinterpret_cast<float4*>(Qs + lane * ld + 4 * c) = o;
+  }
+  __syncthreads();
+  if (warp < seq) {
+    float* dst = out + (row0 + warp) * E + h * d;
+    for (int dd = lane; dd < d; dd += 32) dst[dd] = Qs[warp * ld + dd];
   }
 }
 
@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const floa
   float* Ps = dOs + SS * ld;
   float* dSs = Ps + SS * SP;
   float* dST = dSs + SS * SP;
+  float* Gs = dST + SS * SP;        // dQ | dK | dV staging, [3][SS][ld]: coalesced row stores at the end
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int h = blockIdx.x, g = blockIdx.y;
   const int E = heads * d, ldq = 3 * E;
@@ -496,19 +497,25 @@ __global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const floa
       axpy4(dSs[j * SP + lane], *reinterpret_cast<const float4*>(Qs + j * ld + 4 * c), dk);
       axpy4(Ps[j * SP + lane], *reinterpret_cast<const float4*>(dOs + j * ld + 4 * c), dv);
     }
-    if (lane < seq) {
-      float* dst = dqkv + (row0 + lane) * ldq + h * d + 4 * c;
-      const int left = d - 4 * c;
-      dst[0] = dq.x * scale, dst[E] = dk.x * scale, dst[2 * E] = dv.x;
-      if (left > 1) dst[1] = dq.y * scale, dst[E + 1] = dk.y * scale, dst[2 * E + 1] = dv.y;
-      if (left > 2) dst[2] = dq.z * scale, dst[E + 2] = dk.z * scale, dst[2 * E + 2] = dv.z;
-      if (left > 3) dst[3] = dq.w * scale, dst[E + 3] = dk.w * scale, dst[2 * E + 3] = dv.w;
+    dq.x *= scale, dq.y *= scale, dq.z *= scale, dq.w *= scale;
+    dk.x *= scale, dk.y *= scale, dk.z *= scale, dk.w *= scale;
+    *reinterpret_cast<float4*>(Gs + lane * ld + 4 * c) = dq;
+    *reinterpret_cast<float4*>(Gs + (SS + lane) * ld + 4 * c) = dk;
+    *reinterpret_cast<float4*>(Gs + (2 * SS + lane) * ld + 4 * c) = dv;
+  }
+  __syncthreads();
+  if (warp < seq) {           // one contiguous row of dq, dk and dv per warp
+    float* dst = dqkv + (row0 + warp) * ldq + h * d;
+    for (int dd = lane; dd < d; dd += 32) {
+      dst[dd] = Gs[warp * ld + dd];
+      dst[E + dd] = Gs[(SS + warp) * ld + dd];
+      dst[2 * E + dd] = Gs[(2 * SS + warp) * ld + dd];
     }
   }
 }
 
 static size_t short_fwd_smem(int d) { return ((size_t)3 * SS * short_ld(d) + SS * SP) * sizeof(float); }
-static size_t short_bwd_smem(int d) { return ((size_t)4 * SS * short_ld(d) + 3 * SS * SP) * sizeof(float); }
+static size_t short_bwd_smem(int d) { return ((size_t)7 * SS * short_ld(d) + 3 * SS * SP) * sizeof(float); }
 
 // ---- mid-size single-head scopes on the training path (32 < seq, e.g. batch 256): GEMM route ------------------------
 // scores = Q K^T and O = P V (and the four backward products) run on the tiled fp32 GEMM; these two kernels are the
