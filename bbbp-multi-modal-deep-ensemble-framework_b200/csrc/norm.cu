@@ -96,7 +96,7 @@ __global__ void layernorm_bwd_param_final_kernel(const float* __restrict__ part,
 }
 
 // Few rows (a reference training batch is 32 molecules): ONE launch.  Blocks [0, row_blocks) compute dx exactly as
-// layernorm_bwd_dx_kernel does; the remaining blocks own 128 columns each and walk all rows for dgamma / dbeta.
+// layernorm_bwd_dx_kernel does; the remaining blocks own 32 columns each and reduce over the rows for dgamma / dbeta.
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_small_kernel(const float* __restrict__ dy,
                                                                             const float* __restrict__ s,
                                                                             const float* __restrict__ mean,
@@ -126,16 +126,34 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_small_kernel(cons
     }
     return;
   }
-  const int col = (blockIdx.x - row_blocks) * (LN_WARPS * 32) + threadIdx.x;
-  if (col >= dim) return;
+  // parameter gradients: 32 columns x 4 row lanes per block (lane l walks rows l, l+4, ...; eight independent loads in
+  // flight per thread), then a fixed-order combine of the four lanes -- deterministic, and a quarter of the dependent
+  // load round trips of one thread per column
+  __shared__ float red[2][LN_WARPS][33];
+  const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+  const int col = (blockIdx.x - row_blocks) * 32 + cx;
   float dg = 0.0f, db = 0.0f;
-  for (int r = 0; r < rows; ++r) {
-    float d = dy[(size_t)r * dim + col];
-    dg = fmaf(d, (s[(size_t)r * dim + col] - mean[r]) * rstd[r], dg);
-    db += d;
+  if (col < dim) {
+#pragma unroll 4
+    for (int r = ry; r < rows; r += LN_WARPS) {
+      const float d = dy[(size_t)r * dim + col];
+      dg = fmaf(d, (s[(size_t)r * dim + col] - mean[r]) * rstd[r], dg);
+      db += d;
+    }
   }
-  dgamma[col] = dg;
-  dbeta[col] = db;
+  red[0][ry][cx] = dg;
+  red[1][ry][cx] = db;
+  __syncthreads();
+  if (ry == 0 && col < dim) {
+    float tg = 0.0f, tb = 0.0f;
+#pragma unroll
+    for (int l = 0; l < LN_WARPS; ++l) {
+      tg += red[0][l][cx];
+      tb += red[1][l][cx];
+    }
+    dgamma[col] = tg;
+    dbeta[col] = tb;
+  }
 }
 
 // ---- BatchNorm1d: block = 32 channels x 8 row lanes -------------------------------------------------------------
@@ -281,7 +299,7 @@ extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const flo
   cudaStream_t st = as_stream(stream);
   if (rows <= 256) {
     const int row_blocks = ceil_div(rows, LN_WARPS);
-    layernorm_bwd_small_kernel<<<row_blocks + ceil_div(dim, LN_WARPS * 32), LN_WARPS * 32, 0, st>>>(
+    layernorm_bwd_small_kernel<<<row_blocks + ceil_div(dim, 32), LN_WARPS * 32, 0, st>>>(
         dy, s, mean, rstd, gamma, dx, dgamma, dbeta, rows, dim, row_blocks);
     return launch_status("layernorm_bwd (small)");
   }
