@@ -46,8 +46,11 @@ class GraphedTrainStep:
         self._graphs: dict = {}
         self._seed_step = 0
         self._last = None
-        self.high_priority_chain = os.environ.get("BBBP_GRAPH_PRIORITY", "1") == "1"
+        # diagnostic switches for the three graph-level optimisations (all on by default; the bit-identity test holds for
+        # every combination): conv branch on its own stream, dW / db products on their own stream, chain at high priority
+        self.fork_image = True
         self.fork_weight_grads = os.environ.get("BBBP_GRAPH_WGRAD_FORK", "1") == "1"
+        self.high_priority_chain = os.environ.get("BBBP_GRAPH_PRIORITY", "1") == "1"
 
     # -- the step body, shared by warm-up, capture and the eager fallback -------------------------------------------------
     def _body(self, fp, img, y):
@@ -127,7 +130,7 @@ class GraphedTrainStep:
     def _capture_once(self, s_fp, s_img, s_y, plan, forked):
         graph = torch.cuda.CUDAGraph()
         if hasattr(self.model, "fork_image_branch"):
-            self.model.fork_image_branch = forked and getattr(self, "fork_image", True)
+            self.model.fork_image_branch = forked and self.fork_image
         wgrad = torch.cuda.Stream(s_fp.device) if (forked and self.fork_weight_grads) else None
         prev = ag.set_wgrad_stream(wgrad)
         try:
