@@ -4,13 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bbbp_b200
 dev = torch.device("cuda:0"); torch.manual_seed(0)
 m = bbbp_b200.MixedInputModel(167, 128).to(dev).eval().set_precision("bf16")
-n = 8192
+n = int(os.environ.get('N', 16384))
 packed = torch.randint(0, 256, (n, 21), dtype=torch.uint8).pin_memory()
 img8 = torch.randint(0, 256, (n, 3, 128, 128), dtype=torch.uint8).pin_memory()
 out_host = torch.empty(n, dtype=torch.float32).pin_memory()
-scheds = [[2048] * 4, [4096, 4096], [1024] * 8, [1024, 2048, 2048, 2048, 1024], [2048, 4096, 2048], [3072, 3072, 2048], [4096, 3072, 1024],
-          [4096, 2048, 1024, 1024], [1024, 3072, 3072, 1024], [512, 1536, 2048, 2048, 1536, 512], [2048, 2048, 2048, 1024, 1024], [3072, 3072, 1024, 1024],
-          [1024, 3072, 2048, 1024, 1024], [4096, 2048, 2048]]
+scheds = [[1024] * (n // 1024), [2048] * (n // 2048), [1536] * (n // 1536) + ([n % 1536] if n % 1536 else []), [768] * (n // 768) + ([n % 768] if n % 768 else []),
+          [4096] * (n // 4096)]
 for sizes in scheds:
     spans, a = [], 0
     for s in sizes: spans.append((a, a + s)); a += s
