@@ -67,29 +67,31 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_dx_kernel(const f
   }
 }
 
-constexpr int LN_PARTS = 64;
+// parts = gridDim.x row classes (rows r = part, part + parts, ...): enough of them to fill the GPU at any row count
+__host__ __device__ inline int ln_parts(int rows) { return rows <= 8192 ? 64 : (rows / 128 < 2048 ? rows / 128 : 2048); }
 __global__ void layernorm_bwd_param_partial_kernel(const float* __restrict__ dy, const float* __restrict__ s,
                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                    float* __restrict__ part, int rows, int dim) {
   const int col = blockIdx.y * blockDim.x + threadIdx.x;
   if (col >= dim) return;
+  const int parts = gridDim.x;
   float dg = 0.0f, db = 0.0f;
-  for (int r = blockIdx.x; r < rows; r += LN_PARTS) {
+  for (int r = blockIdx.x; r < rows; r += parts) {
     float d = dy[(size_t)r * dim + col];
     dg = fmaf(d, (s[(size_t)r * dim + col] - mean[r]) * rstd[r], dg);
     db += d;
   }
   part[(size_t)blockIdx.x * dim + col] = dg;
-  part[(size_t)(LN_PARTS + blockIdx.x) * dim + col] = db;
+  part[(size_t)(parts + blockIdx.x) * dim + col] = db;
 }
 __global__ void layernorm_bwd_param_final_kernel(const float* __restrict__ part, float* __restrict__ dgamma,
-                                                 float* __restrict__ dbeta, int dim) {
+                                                 float* __restrict__ dbeta, int dim, int parts) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= dim) return;
   float dg = 0.0f, db = 0.0f;
-  for (int p = 0; p < LN_PARTS; ++p) {
+  for (int p = 0; p < parts; ++p) {
     dg += part[(size_t)p * dim + col];
-    db += part[(size_t)(LN_PARTS + p) * dim + col];
+    db += part[(size_t)(parts + p) * dim + col];
   }
   dgamma[col] = dg;
   dbeta[col] = db;
@@ -285,13 +287,18 @@ extern "C" int bbbp_add_layernorm_fwd_pitched_f32(const float* x, int ld_x, cons
   return launch_status("add_layernorm_fwd_pitched");
 }
 
+extern "C" size_t bbbp_layernorm_bwd_workspace(int rows, int dim) {
+  return rows > 0 && dim > 0 ? (size_t)2 * bbbp::ln_parts(rows) * dim * sizeof(float) : 0;
+}
+
 extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const float* mean, const float* rstd,
                                       const float* gamma, float* dx, float* dgamma, float* dbeta, int rows, int dim,
                                       float* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
   using namespace bbbp;
   BBBP_CHECK_ARG(dy && s && mean && rstd && gamma && dx && dgamma && dbeta && rows > 0 && dim > 0,
                  "layernorm_bwd: bad argument");
-  size_t need = (size_t)2 * LN_PARTS * dim * sizeof(float);
+  const int parts = ln_parts(rows);
+  size_t need = bbbp_layernorm_bwd_workspace(rows, dim);
   if (!workspace || workspace_bytes < need) {
     set_error("layernorm_bwd: needs %zu workspace bytes, got %zu", need, workspace_bytes);
     return BBBP_EWORKSPACE;
@@ -304,9 +311,8 @@ extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const flo
     return launch_status("layernorm_bwd (small)");
   }
   layernorm_bwd_dx_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, st>>>(dy, s, mean, rstd, gamma, dx, rows, dim);
-  layernorm_bwd_param_partial_kernel<<<dim3(LN_PARTS, ceil_div(dim, 128)), 128, 0, st>>>(dy, s, mean, rstd, workspace,
-                                                                                         rows, dim);
-  layernorm_bwd_param_final_kernel<<<ceil_div(dim, 128), 128, 0, st>>>(workspace, dgamma, dbeta, dim);
+  layernorm_bwd_param_partial_kernel<<<dim3(parts, ceil_div(dim, 128)), 128, 0, st>>>(dy, s, mean, rstd, workspace, rows, dim);
+  layernorm_bwd_param_final_kernel<<<ceil_div(dim, 128), 128, 0, st>>>(workspace, dgamma, dbeta, dim, parts);
   note_launches(2);
   return launch_status("layernorm_bwd");
 }

@@ -403,7 +403,7 @@ def layernorm_bwd(dy, s, mean, rstd, gamma):
     dx = torch.empty_like(s)
     dg = torch.empty_like(gamma)
     db = torch.empty_like(gamma)
-    ws = torch.empty((2 * 64 * dim,), device=s.device, dtype=torch.float32)
+    ws = torch.empty((lib.bbbp_layernorm_bwd_workspace(rows, dim) // 4,), device=s.device, dtype=torch.float32)
     check(lib.bbbp_layernorm_bwd_f32(dy.data_ptr(), s.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                      dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, dim, ws.data_ptr(),
                                      ws.numel() * 4, _stream()), "layernorm_bwd")
@@ -513,7 +513,9 @@ def scale_by_device_scalar(x, scalar):
 def colsum(x):
     rows, cols = x.shape
     out = torch.empty((cols,), device=x.device, dtype=torch.float32)
-    check(lib.bbbp_colsum_f32(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, _stream()), "colsum")
+    need = lib.bbbp_colsum_workspace(rows, cols)
+    ws = torch.empty((need // 4,), device=x.device, dtype=torch.float32) if need else None
+    check(lib.bbbp_colsum_f32(x.data_ptr(), x.stride(0), out.data_ptr(), rows, cols, _ptr(ws), need, _stream()), "colsum")
     return out
 
 

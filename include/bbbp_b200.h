@@ -205,7 +205,8 @@ int bbbp_add_layernorm_fwd_pitched_f32(const float* x, int ld_x, const float* re
                                        const float* beta, float* y, int ld_y, void* y_bf16, int ld_bf16, int rows, int dim,
                                        float eps, bbbp_stream_t stream);
 /* dx (= gradient wrt s, which is also the gradient of both x and res), dgamma[dim], dbeta[dim].
- * workspace: 2 * 64 * dim floats. */
+ * workspace: bbbp_layernorm_bwd_workspace() bytes (partials of dgamma / dbeta per row chunk, summed in a fixed order). */
+size_t bbbp_layernorm_bwd_workspace(int rows, int dim);
 int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
                            float* dx, float* dgamma, float* dbeta, int rows, int dim, float* workspace,
                            size_t workspace_bytes, bbbp_stream_t stream);
@@ -249,8 +250,11 @@ int bbbp_act_bwd_f32(const float* dy, int ld_dy, const float* y, int ld_y, float
                      int act, bbbp_stream_t stream);
 /* y[i] = x[i] * scalar[0] with the scalar read from DEVICE memory (chain-rule factor of a loss, no host sync) */
 int bbbp_scale_by_device_scalar_f32(const float* x, const float* scalar, float* y, size_t n, bbbp_stream_t stream);
-/* out[c] = sum_r x[r, c] (bias gradients), deterministic */
-int bbbp_colsum_f32(const float* x, int ldx, float* out, int rows, int cols, bbbp_stream_t stream);
+/* out[c] = sum_r x[r, c] (bias gradients), deterministic.  More than 2048 rows are reduced in two passes over row chunks and
+ * need bbbp_colsum_workspace() bytes of workspace (0 below that; workspace may then be NULL). */
+size_t bbbp_colsum_workspace(int rows, int cols);
+int bbbp_colsum_f32(const float* x, int ldx, float* out, int rows, int cols, float* workspace, size_t workspace_bytes,
+                    bbbp_stream_t stream);
 /* dst[r, 0:cols) = src[r, 0:cols) with independent pitches (concatenation / slicing) */
 int bbbp_copy2d_f32(const float* src, int ld_src, float* dst, int ld_dst, int rows, int cols, bbbp_stream_t stream);
 /* dst[r, 0:cols) = src[idx[r], 0:cols): the device-resident batch feeder that replaces MixedDataset.__getitem__ + the

@@ -194,7 +194,7 @@ def test_attention_many_small_heads_bf16(ops, groups, seq, heads, d):
 
 
 # ---- normalisation ----------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,dim", [(1, 167), (33, 167), (256, 2048), (7, 8)])
+@pytest.mark.parametrize("rows,dim", [(1, 167), (33, 167), (256, 2048), (7, 8), (300, 167), (20011, 167)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_add_layernorm_forward_backward(ops, rows, dim, with_res):
     x = rnd(rows, dim, seed=40).requires_grad_()
@@ -295,6 +295,9 @@ def test_act_bwd_colsum_copy2d_scale(ops):
     t = torch.tanh(rnd(33, 167, seed=72))
     close(ops.act_bwd(dy.cuda(), t.cuda(), "tanh"), dy * (1 - t * t), 1e-6, what="tanh bwd")
     close(ops.colsum(dy.cuda()), dy.sum(0), 2e-5, what="colsum")
+    big = rnd(20011, 167, seed=77)                        # > 2048 rows: two-pass reduction over row chunks
+    close(ops.colsum(big.cuda()), big.double().sum(0).float(), 2e-3, what="colsum (row chunks)")
+    assert torch.equal(ops.colsum(big.cuda()), ops.colsum(big.cuda()))
     big = torch.zeros(33, 400).cuda()
     ops.copy2d(dy.cuda(), big[:, 100:267])
     assert torch.equal(big[:, 100:267].cpu(), dy) and float(big[:, :100].abs().sum()) == 0
