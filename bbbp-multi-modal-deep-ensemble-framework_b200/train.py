@@ -150,8 +150,9 @@ class GraphedTrainStep:
     def __call__(self, fingerprint, image, target):
         if not self.model.training:
             raise RuntimeError("GraphedTrainStep: call model.train() first")
+        # a capture is tied to the parameter storage it updates in place: .to() / .cuda() after a capture re-captures
         key = (tuple(fingerprint.shape), tuple(image.shape), image.dtype, tuple(target.shape),
-               getattr(self.model, "precision", None), fingerprint.device.index)
+               getattr(self.model, "precision", None), fingerprint.device.index, next(self.model.parameters()).data_ptr())
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) >= self.max_graphs:
