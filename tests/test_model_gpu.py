@@ -627,3 +627,26 @@ def test_training_attention_gemm_route_matches_sdpa(cuda_device, groups, seq, d)
     assert not torch.equal(o1, o2)
     frac = float((ag.Attention.apply(x2, groups, seq, 1, d, 0.25, 7, True) == 0).float().mean())
     assert frac < 0.01        # outputs mix many keys: zeros would mean a broken mask
+
+
+def test_morgan_classification_auc_matches_to_three_decimals(cuda_device):
+    """BASELINE configs[2] / north_star "identical R2 / MSE / AUC to three decimals": the 2048-bit variant as a classifier
+    (logit -> BCE), 512 molecules at the reference batch 256, synthetic B3DB-like labels (64 % positives): per-molecule
+    |d logit| <= 1e-3 and the ROC AUC equal to the oracle's to three decimals (fp32 mode)."""
+    from sklearn.metrics import roc_auc_score
+    ref, ours = make_pair("tcnn", 2048, 128, 13, cuda_device)
+    ref.eval(), ours.eval()
+    n, bs = 512, 256
+    g = torch.Generator().manual_seed(20250115)
+    bits = (torch.rand(n, 2048, generator=g) < 0.022).float()                 # ~45 on-bits per Morgan fingerprint
+    fp = (bits - bits.mean(1, keepdim=True)) / bits.std(1, unbiased=False, keepdim=True)
+    img = torch.randn(n, IMG, generator=g)
+    with torch.no_grad():
+        want = torch.cat([ref(fp[i:i + bs], img[i:i + bs]).reshape(-1) for i in range(0, n, bs)])
+        got = ours.predict_batches(fp.cuda(), img.cuda(), bs).cpu()
+    assert float((got - want).abs().max()) <= 1e-3
+    # labels correlated with the oracle's score so that the AUC is informative (not 0.5 +- noise)
+    y = ((want - want.median()) * 200 + torch.randn(n, generator=g) > 0).numpy().astype(int)
+    assert 0.2 < y.mean() < 0.8
+    auc_want, auc_got = roc_auc_score(y, want.numpy()), roc_auc_score(y, got.numpy())
+    assert round(auc_got, 3) == round(auc_want, 3), (auc_got, auc_want)
