@@ -79,8 +79,18 @@ def derived_weight(w: torch.Tensor, tag: str, make):
     return val
 
 
+# Tensor-core precision modes -> (16-bit operand format, split passes).  "strict" carries structured activations as
+# hi + lo fp16 pairs (and splits both operands of the small GEMMs): |d logBB| <= 1e-3 at trained scale.
+TENSOR_CORE = {"bf16": (ops.FMT_BF16, False), "fp16": (ops.FMT_F16, False), "strict": (ops.FMT_F16, True)}
+
+
+def weight16(w: torch.Tensor, fmt: int, want_lo: bool = False):
+    """Cached 16-bit copy of a weight as (hi, lo | None); lo = rn(w - hi) for the split GEMMs of the strict mode."""
+    return derived_weight(w, f"w16_{fmt}_{int(want_lo)}", lambda d: ops.cast16(d.reshape(d.shape[0], -1), fmt, want_lo=want_lo))
+
+
 def weight_bf16(w: torch.Tensor) -> torch.Tensor:
-    return derived_weight(w, "bf16", lambda d: ops.cast_bf16(d.reshape(d.shape[0], -1)))
+    return weight16(w, ops.FMT_BF16)[0]
 
 
 def clear_weight_cache() -> None:
@@ -96,9 +106,14 @@ class Linear(Function):
         x = contig(x)
         M, K = x.shape
         N = weight.shape[0]
-        if precision == "bf16":
-            a16 = ops.cast_bf16(x)
-            y, _ = ops.gemm_bf16(a16, K, weight_bf16(weight), N, bias=bias, act=act, split_k=ops.fixed_split_k(K))
+        if precision in TENSOR_CORE:
+            # generic nn.Linear call sites (head, fusion heads, fingerprint_fc, MLP family): tiny GEMMs, so the strict mode
+            # splits BOTH operands here (hi*hi + lo*hi + hi*lo: three MMAs per K step, fp32-class products)
+            fmt, split = TENSOR_CORE[precision]
+            a_hi, a_lo = ops.cast16(x, fmt, want_lo=split)
+            w_hi, w_lo = weight16(weight, fmt, split)
+            y, _ = ops.gemm_bf16(a_hi, K, w_hi, N, bias=bias, act=act, split_k=ops.fixed_split_k(K), fmt=fmt, a_lo=a_lo,
+                                 w_lo=w_lo)
         else:
             # inference keeps a K-only split (bit-identical scores however batches are grouped); a training forward
             # has no such contract and takes the latency mode (one-shot kernel at M <= 32)

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const flo
                                                                        int seq, int heads, int d, int q_per_block,
                                                                        float drop_p, uint64_t seed,
                                                                        const uint64_t* __restrict__ seed_dev) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   extern __shared__ float smem[];
   const int ld = d | 1;  // odd pitch: conflict-free row-per-lane reads
   float* Ks = smem;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dq_kernel(const 
                                                                           int d, int q_per_block, float drop_p,
                                                                           uint64_t seed,
                                                                           const uint64_t* __restrict__ seed_dev) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   const float inv_keep = 1.0f / (1.0f - drop_p);
   extern __shared__ float smem[];
   const int ld = d | 1;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_dkv_kernel(const
                                                                            int d, int k_per_block, float drop_p,
                                                                            uint64_t seed,
                                                                            const uint64_t* __restrict__ seed_dev) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   const float inv_keep = 1.0f / (1.0f - drop_p);
   extern __shared__ float smem[];
   const int ld = d | 1;
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(SS * 32) attention_short_fwd_kernel(const floa
                                                                       float* __restrict__ lse, int seq, int heads, int d,
                                                                       float drop_p, uint64_t seed,
                                                                       const uint64_t* __restrict__ seed_dev) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   extern __shared__ __align__(16) float smem[];
   const int ld = short_ld(d), n4 = (d + 3) / 4;
   float* Qs = smem;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(SS * 32) attention_short_bwd_kernel(const floa
                                                                       const float* __restrict__ dout, float* __restrict__ dqkv,
                                                                       int seq, int heads, int d, float drop_p, uint64_t seed,
                                                                       const uint64_t* __restrict__ seed_dev) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   extern __shared__ __align__(16) float smem[];
   const int ld = short_ld(d), n4 = (d + 3) / 4;
   float* Qs = smem;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const float* __re
                                                                float* __restrict__ pd, int ld_p, int cols, float scale,
                                                                float drop_p, uint64_t seed, const uint64_t* __restrict__ seed_dev,
                                                                size_t row_base) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   __shared__ float red[8];
   const size_t r = blockIdx.x;
   const float* sr = s + r * ld_s;
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
                                                                float* __restrict__ ds, int ld, int cols, float scale,
                                                                float drop_p, uint64_t seed, const uint64_t* __restrict__ seed_dev,
                                                                size_t row_base) {
-  if (seed_dev) seed += *seed_dev;
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   __shared__ float red[8];
   const size_t r = blockIdx.x;
   const float inv_keep = 1.0f / (1.0f - drop_p);

@@ -17,6 +17,21 @@ void note_launches(int n);
 
 inline cudaStream_t as_stream(bbbp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property: a process driving several GPUs must set it
+// once on each of them.  `static PerDeviceOnce once; if (once.first()) { ... }` at the launch site.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+// SM count of the CURRENT device (cached per device ordinal)
+int current_sm_count();
+
 constexpr int kWarp = 32;
 
 template <typename T>
@@ -42,6 +57,20 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Per-site dropout seed (host, baked into a CUDA graph) combined with the per-step seed that lives in device memory.
+// NOT additive: with seed_site = a + i*C and seed_step = a + s*C a plain sum makes (site i, step s) and
+// (site i+1, step s-1) share one Philox key, i.e. the same mask travels down the layer stack on successive steps.
+// splitmix64 of the step value, xor-ed into the site seed and mixed again, keys every (site, step) pair differently.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t mix_seed(uint64_t seed, const uint64_t* __restrict__ seed_dev) {
+  return seed_dev ? splitmix64(seed ^ splitmix64(*seed_dev)) : seed;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

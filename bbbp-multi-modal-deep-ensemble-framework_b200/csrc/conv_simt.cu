@@ -314,11 +314,10 @@ extern "C" int bbbp_conv3x3_f32(const float* x, const float* w, const float* b, 
   if (N == 0) return BBBP_OK;
   BBBP_CHECK_ARG(N <= 65535, "conv3x3_f32: N=%d exceeds 65535 images per launch", N);
   cudaStream_t s = as_stream(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(conv3x3_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvF32Smem<16>::BYTES);
     cudaFuncSetAttribute(conv3x3_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvF32Smem<8>::BYTES);
-    attr_done = true;
   }
   if (Cout % 64 == 0) {
     dim3 grid((H / 16) * (W / 16), Cout / 64, N);

@@ -20,8 +20,15 @@
 // single-thread MMA issue.  Persistent
 // over tiles: 3-stage halo ring (full/empty mbarriers) and a double-buffered accumulator (acc_full/acc_empty), so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand format and split passes (half16.cuh): FMT selects bf16 or fp16 operands (weights, staged halo, output).  SPLIT = 2
+// is the strict mode: the input activation arrives as a hi + lo pair (two NHWC tensors, or both parts formed by the planar
+// producers from the fp32 / uint8 image), each part is staged as its own ring slot and multiplied against the same
+// once-rounded weights into the same TMEM accumulators (2x the MMAs), and the epilogue emits its output as a hi + lo pair
+// for the next layer.
 #include "common.cuh"
 #include "umma.cuh"
+#include "half16.cuh"
 #include <utility>
 #include <type_traits>
 
@@ -48,7 +55,7 @@ constexpr int ROW_B = XH * 16;                 // 144 bytes per (parity, y) row
 constexpr int PAR_B = HALO_H * ROW_B + 32;     // 4928 = 64 (mod 128)
 constexpr int KC_B = 2 * PAR_B + 16;           // 9872 = 16 (mod 128) bytes per 8-channel chunk plane
 
-template <int KC, int COUT, int SRC = 0>
+template <int KC, int COUT, int SRC = 0, int FMT = BBBP_FMT_BF16, int SPLIT = 1>
 struct Cfg {
   // conv2's epilogue (64 channels) gets two warps per TMEM lane quadrant; conv1's (32 channels) one, which also keeps
   // its CTA small enough for two CTAs per SM
@@ -87,7 +94,12 @@ struct Cfg {
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int OUT_ROW_B = COUT * 2;            // bytes of one pooled pixel (= the TMA store's swizzle span)
   static constexpr int OUT_BYTES = 128 * OUT_ROW_B;     // one output tile: 128 pooled pixels x COUT bf16
-  static constexpr int SMEM_BYTES = 1024 + 2 * OUT_BYTES + STAGES * A_BYTES + W_BYTES + COUT * 4 + BAR_BYTES;
+  static constexpr int OUT_BUFS = 2 * SPLIT;            // double-buffered hi (and lo) output tiles
+  // strict mode, first layer: the WEIGHTS are split as well (w = hi + lo, the lo image follows the hi image in the prepared
+  // blob and in shared memory) -- K is tiny there, so the third pass costs little, and the first layer's weight rounding
+  // is the largest remaining term of the strict mode's error budget (tests/precision_study.py: 6e-4 of 8e-4)
+  static constexpr int W_PARTS = (SPLIT == 2 && PACK4) ? 2 : 1;
+  static constexpr int SMEM_BYTES = 1024 + OUT_BUFS * OUT_BYTES + STAGES * A_BYTES + W_PARTS * W_BYTES + COUT * 4 + BAR_BYTES;
 };
 
 __host__ __device__ constexpr int halo_offset(int dy, int dx, int tap) {
@@ -151,20 +163,21 @@ __host__ __device__ constexpr MmaOp mma_op(int I) {
 }
 
 // descriptor words: lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 (bit 46) | no swizzle
-template <int KC, int COUT, bool PACK4, int I>
+template <int KC, int COUT, bool PACK4, int FMT, bool FORCE_ACC, int I>
 __device__ __forceinline__ void issue_one(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc) {
   constexpr MmaOp op = mma_op<KC, COUT, PACK4>(I);
   constexpr uint32_t a_lo_c = (op.a_off >> 4) | ((op.a_lbo >> 4) << 16);
   constexpr uint32_t b_lo_c = (op.b_off >> 4) | ((op.b_lbo >> 4) << 16);
   constexpr uint64_t a_hi = (uint64_t)(((2 * ROW_B) >> 4) | (1u << 14)) << 32;
   constexpr uint64_t b_hi = (uint64_t)((128 >> 4) | (1u << 14)) << 32;
-  constexpr uint32_t idesc = make_idesc_bf16(128, op.n);
-  umma_bf16(tmem_acc + op.d_col, a_hi | (a_lo + a_lo_c), b_hi | (w_lo + b_lo_c), idesc, op.accumulate != 0);
+  constexpr uint32_t idesc = make_idesc_16(128, op.n, FMT);
+  umma_bf16(tmem_acc + op.d_col, a_hi | (a_lo + a_lo_c), b_hi | (w_lo + b_lo_c), idesc, FORCE_ACC || op.accumulate != 0);
 }
-template <int KC, int COUT, bool PACK4, int... I>
+// FORCE_ACC: the lo part of a split tile adds into the accumulators the hi part has just initialised
+template <int KC, int COUT, bool PACK4, int FMT, bool FORCE_ACC, int... I>
 __device__ __forceinline__ void issue_tile(uint32_t a_lo, uint32_t w_lo, uint32_t tmem_acc,
                                            std::integer_sequence<int, I...>) {
-  (issue_one<KC, COUT, PACK4, I>(a_lo, w_lo, tmem_acc), ...);
+  (issue_one<KC, COUT, PACK4, FMT, FORCE_ACC, I>(a_lo, w_lo, tmem_acc), ...);
 }
 
 enum { SRC_NHWC_BF16 = 0, SRC_CHW_F32 = 1, SRC_CHW_U8 = 2 };
@@ -182,24 +195,21 @@ __device__ unsigned long long* g_conv_probe = nullptr;
 // per-image (mean, 1/std) pair (ToTensor + per-molecule StandardScaler, Descriptors/..._preprocess_maccs_opt.py:52-67,
 // 121-124).  In both planar cases the 3 channels are packed to one 16-byte bf16 chunk per pixel in registers, so the
 // NHWC8 image never exists in HBM.
-template <int KC, int COUT, int SRC>
-__global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC>::MIN_CTAS) conv3x3_umma_kernel(const void* __restrict__ src_any,
-                                                               const float2* __restrict__ stats,
-                                                               const uint4* __restrict__ wprep,
-                                                               const float* __restrict__ bias,
-                                                               const __grid_constant__ CUtensorMap tmOut, int n_img,
-                                                               int H, int W) {
-  using C = Cfg<KC, COUT, SRC>;
+template <int KC, int COUT, int SRC, int FMT, int SPLIT>
+__global__ void __launch_bounds__(Cfg<KC, COUT, SRC, FMT, SPLIT>::THREADS, Cfg<KC, COUT, SRC, FMT, SPLIT>::MIN_CTAS)
+conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ src_lo_any, const float2* __restrict__ stats,
+                    const uint4* __restrict__ wprep, const float* __restrict__ bias, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmOutLo, int n_img, int H, int W) {
+  using C = Cfg<KC, COUT, SRC, FMT, SPLIT>;
   static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
-  const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(src_any);
-  constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
+    constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
   constexpr int PROD_THREADS = C::PROD_THREADS, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sOut = base;                     // 2 swizzled output tiles (1024-byte aligned) for the TMA stores
-  uint8_t* sA = sOut + 2 * C::OUT_BYTES;
+  uint8_t* sOut = base;                     // 2 (x2 with a lo part) swizzled output tiles (1024-byte aligned) for the TMA stores
+  uint8_t* sA = sOut + C::OUT_BUFS * C::OUT_BYTES;
   uint8_t* sW = sA + STAGES * C::A_BYTES;
-  float* sBias = reinterpret_cast<float*>(sW + C::W_BYTES);
+  float* sBias = reinterpret_cast<float*>(sW + C::W_PARTS * C::W_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sBias + COUT);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
@@ -213,7 +223,8 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // ---- one-time setup: weights + bias to smem, barriers, TMEM -----------------------------------------------------
-  for (int i = threadIdx.x; i < C::W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sW)[i] = wprep[C::W_OFFSET / 16 + i];
+  for (int i = threadIdx.x; i < C::W_PARTS * C::W_BYTES / 16; i += THREADS)
+    reinterpret_cast<uint4*>(sW)[i] = wprep[C::W_OFFSET / 16 + i];
   if constexpr (C::PACK4)   // pad bytes of the stage are never written by the producers: keep them finite
     for (int i = threadIdx.x; i < STAGES * C::A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < COUT; i += THREADS) sBias[i] = bias[i];
@@ -245,8 +256,10 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
     constexpr int PIX_B = KC * 16;
     const int Yi = ptid / ROWC, ji = ptid % ROWC;      // first chunk of this thread: the same for every tile
     if constexpr (SRC == SRC_NHWC_BF16) {
-      for (int i = 0; i < my_tiles; ++i) {
-        const int t = blockIdx.x + i * gridDim.x;
+      // a ring slot holds one PART of one tile: unit u = tile * SPLIT + part (part 1 = the lo tensor of a split input)
+      const int my_units = my_tiles * SPLIT;
+      for (int i = 0; i < my_units; ++i) {
+        const int t = blockIdx.x + (i / SPLIT) * gridDim.x;
         const int n = t / tiles_per_img, r = t % tiles_per_img;
         const int y0 = 2 * (r / tiles_x) * TILE_PH - 1, x0 = 2 * (r % tiles_x) * TILE_PW - 1;
         const int s = i % STAGES;
@@ -254,7 +267,8 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
         mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
         PROBE_ADD(8, tp);
         const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
-        const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * H * W * PIX_B;
+        const uint8_t* img = reinterpret_cast<const uint8_t*>((SPLIT == 2 && (i & 1)) ? src_lo_any : src_any) +
+                             (size_t)n * H * W * PIX_B;
         int Y = Yi, j = ji;
   #pragma unroll 4
         for (int c = ptid; c < CHUNKS; c += PROD_THREADS) {
@@ -279,10 +293,10 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
         }
         PROBE_ADD(10, tp);
       }
-      if (my_tiles > 0) {
+      if (my_units > 0) {
         cp_async_wait<0>();
         fence_proxy_async_smem();
-        mbar_arrive(&full[(my_tiles - 1) % STAGES]);
+        mbar_arrive(&full[(my_units - 1) % STAGES]);
       }
     } else {
       // planar source.  The halo row [x0, x0+18) with x0 = 16*tx - 1 is covered by six ALIGNED groups of four pixels
@@ -335,9 +349,12 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
           const float2 st = __ldg(stats + (blockIdx.x + i * gridDim.x) / tiles_per_img);
           scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
         }
-        const int s = i % STAGES;
+#pragma unroll
+        for (int part = 0; part < SPLIT; ++part) {
+        const int u = i * SPLIT + part;       // ring unit: part 1 stages the lo halves (x - rn16(x)) of the same pixels
+        const int s = u % STAGES;
         long long tp = probe ? clock64() : 0;
-        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        mbar_wait(&empty[s], ((u / STAGES) & 1) ^ 1);
         PROBE_ADD(8, tp);
         uint8_t* stage = sA + s * C::A_BYTES;
 #pragma unroll
@@ -359,8 +376,13 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
             for (int e = 0; e < 4; ++e) {
               const int X = 4 * tG[k] + e - 3;   // halo column of this pixel; groups 0 and 5 keep one pixel each
               if (X >= 0 && X < HALO_W) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(px[e][0], px[e][1]), h1 = __floats2bfloat162_rn(px[e][2], 0.0f);
-                const uint2 pix = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                uint2 pix;
+                if (part == 0) {
+                  pix = make_uint2(pack16<FMT>(px[e][0], px[e][1]), pack16<FMT>(px[e][2], 0.0f));
+                } else {
+                  pix = make_uint2(pack16<FMT>(px[e][0] - round16<FMT>(px[e][0]), px[e][1] - round16<FMT>(px[e][1])),
+                                   pack16<FMT>(px[e][2] - round16<FMT>(px[e][2]), 0.0f));
+                }
                 uint8_t* row = stage + tY[k] * ROW_B;
                 // chunk j = pixels (2j, 2j+1): one copy serves both window members of a pooling row (see mma_op)
                 *reinterpret_cast<uint2*>(row + X * 8) = pix;
@@ -371,6 +393,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
         fence_proxy_async_smem();
         mbar_arrive(&full[s]);
         PROBE_ADD(10, tp);
+        }
       };
       // Register prefetch ring, PF tiles deep (loop unrolled by PF, no register copies): PF - 1 tile loads stay in flight
       // per CTA while tile i is converted and stored.  With the store warp in place the producers' global-load latency
@@ -405,6 +428,8 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
       named_bar_sync(2, EPI_THREADS + 32);
       if (lane == 0) {
         tma_store_3d(&tmOut, sOut + (i & 1) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
+        if constexpr (SPLIT == 2)   // the lo tile travels in the same bulk group
+          tma_store_3d(&tmOutLo, sOut + (2 + (i & 1)) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
         bulk_store_commit();
       }
     }
@@ -415,18 +440,44 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
     // elected lane issues the MMAs and the commits.
     const uint32_t w_lo = smem_u32(sW) >> 4;
     for (int i = 0; i < my_tiles; ++i) {
-      const int s = i % STAGES, b = i & 1;
+      [[maybe_unused]] const int s = i % STAGES;
+      const int b = i & 1;
       long long tp = probe ? clock64() : 0;
       mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
       PROBE_ADD(0, tp);
-      mbar_wait(&full[s], (i / STAGES) & 1);
-      PROBE_ADD(1, tp);
-      tc_fence_after_sync();
-      if (elect_one_sync()) {
-        issue_tile<KC, COUT, C::PACK4>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
-                                       std::make_integer_sequence<int, C::NISSUE>{});
-        umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
-        umma_commit(&acc_full[b]);   // accumulators of this tile complete
+      if constexpr (SPLIT == 1) {
+        mbar_wait(&full[s], (i / STAGES) & 1);
+        PROBE_ADD(1, tp);
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          issue_tile<KC, COUT, C::PACK4, FMT, false>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+                                                     std::make_integer_sequence<int, C::NISSUE>{});
+          umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
+          umma_commit(&acc_full[b]);   // accumulators of this tile complete
+        }
+      } else {
+        // split input: ring units 2i (hi) and 2i + 1 (lo) feed the same accumulators
+        const int u0 = 2 * i, s0 = u0 % STAGES, s1 = (u0 + 1) % STAGES;
+        mbar_wait(&full[s0], (u0 / STAGES) & 1);
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          issue_tile<KC, COUT, C::PACK4, FMT, false>(smem_u32(sA + s0 * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+                                                     std::make_integer_sequence<int, C::NISSUE>{});
+          if constexpr (C::W_PARTS == 2)      // + x_hi * w_lo
+            issue_tile<KC, COUT, C::PACK4, FMT, true>(smem_u32(sA + s0 * C::A_BYTES) >> 4, w_lo + (C::W_BYTES >> 4),
+                                                      tmem_base + b * C::ACC_COLS, std::make_integer_sequence<int, C::NISSUE>{});
+          umma_commit(&empty[s0]);
+        }
+        __syncwarp();
+        mbar_wait(&full[s1], ((u0 + 1) / STAGES) & 1);
+        PROBE_ADD(1, tp);
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          issue_tile<KC, COUT, C::PACK4, FMT, true>(smem_u32(sA + s1 * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+                                                    std::make_integer_sequence<int, C::NISSUE>{});
+          umma_commit(&empty[s1]);
+          umma_commit(&acc_full[b]);
+        }
       }
       __syncwarp();
       PROBE_ADD(2, tp);
@@ -458,6 +509,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
       uint8_t* orow = otile + m * C::OUT_ROW_B;
+      [[maybe_unused]] uint8_t* orow_lo = sOut + (2 + b) * C::OUT_BYTES + m * C::OUT_ROW_B;
       // CS channels per step (CS/8 output chunks): 4*CS live accumulator registers.  The first layer uses 8 so that its
       // variants fit the register cap of two CTAs per SM with eight producer warps; conv2 (no cap) uses 16.
       constexpr int CS = COUT >= 64 ? 16 : (C::PACK4 ? BBBP_CONV1_CS : 8);
@@ -477,6 +529,7 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
         }
         tmem_ld_wait();
         uint32_t packed[CS / 2];
+        [[maybe_unused]] uint32_t packed_lo[CS / 2];
 #pragma unroll
         for (int j = 0; j < CS; j += 4) {
           const float4 bv = *reinterpret_cast<const float4*>(sBias + half * CH + c0 + j);
@@ -489,15 +542,19 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
                              fmaxf(__uint_as_float(r2[j + k + 1]), __uint_as_float(r3[j + k + 1])));
             v0 = fmaxf(v0 + bb[k], 0.0f);
             v1 = fmaxf(v1 + bb[k + 1], 0.0f);
-            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-            packed[(j + k) / 2] = *reinterpret_cast<uint32_t*>(&h);
+            if constexpr (SPLIT == 2) split16<FMT>(v0, v1, packed[(j + k) / 2], packed_lo[(j + k) / 2]);
+            else packed[(j + k) / 2] = pack16<FMT>(v0, v1);
           }
         }
         const int chunk = (half * CH + c0) / 8;
 #pragma unroll
-        for (int g = 0; g < CS / 8; ++g)
+        for (int g = 0; g < CS / 8; ++g) {
           *reinterpret_cast<uint4*>(orow + (((chunk + g) ^ swz) << 4)) =
               make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          if constexpr (SPLIT == 2)
+            *reinterpret_cast<uint4*>(orow_lo + (((chunk + g) ^ swz) << 4)) =
+                make_uint4(packed_lo[4 * g], packed_lo[4 * g + 1], packed_lo[4 * g + 2], packed_lo[4 * g + 3]);
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[b]);   // TMEM reads done: the MMA warp may start the tile after next
@@ -518,31 +575,34 @@ __global__ void __launch_bounds__(Cfg<KC, COUT, SRC>::THREADS, Cfg<KC, COUT, SRC
 // ---- weight / input re-layout (prepare-time and per-call helpers) --------------------------------------------------
 // conv2-style (KC >= 2): wp[kc][8 - tap][n][8] = w[n][kc*8 + c][kh][kw]; taps are stored in REVERSE order so that the
 // weights of taps (kh, kw) and (kh, kw-1) -- the two B halves of a paired MMA -- are adjacent 64-row blocks
-__global__ void prep_weights_kc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
+__global__ void prep_weights_kc_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Cin, int Cout, int fmt) {
   const int KC = Cin / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * KC * Cout * 8) return;
   const int c = i % 8, n = (i / 8) % Cout, u = (i / (8 * Cout)) % 9, kc = i / (8 * Cout * 9);
-  wp[i] = __float2bfloat16(w[((size_t)n * Cin + kc * 8 + c) * 9 + (8 - u)]);
+  wp[i] = cvt16_rt(w[((size_t)n * Cin + kc * 8 + c) * 9 + (8 - u)], fmt);
 }
 // conv1-style (Cin <= 8, one chunk): wp[dx][pair][chunk][n][8]
-__global__ void prep_weights_c8_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
+__global__ void prep_weights_c8_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Cin, int Cout, int fmt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * 5 * 2 * Cout * 8) return;
   const int c = i % 8, n = (i / 8) % Cout, chunk = (i / (8 * Cout)) % 2, pair = (i / (16 * Cout)) % 5, dx = i / (80 * Cout);
   const TapPair tp = conv1_pair(dx, pair);
   const int tap = chunk == 0 ? tp.first : tp.second;
   const bool zero = chunk == tp.zero_slot || c >= Cin;
-  wp[i] = __float2bfloat16(zero ? 0.0f : w[((size_t)n * Cin + c) * 9 + tap]);
+  wp[i] = cvt16_rt(zero ? 0.0f : w[((size_t)n * Cin + c) * 9 + tap], fmt);
 }
 // PACK4 image (planar sources): wp[kh][chunk][n2][8], n2 = dx*Cout + n.  K index k = chunk*8 + e = j*4 + c addresses pixel
 // X + j of the halo row (X = 2*pw) and channel c; member dx uses tap kw = j - dx: zero where that is not in 0..2 or c >= Cin
-__global__ void prep_weights_pack4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cin, int Cout) {
+// lo != 0: the low part rn(w - rn(w)) of the same image (strict mode)
+__global__ void prep_weights_pack4_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Cin, int Cout, int fmt,
+                                          int lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * 2 * (2 * Cout) * 8) return;
   const int e = i % 8, n2 = (i / 8) % (2 * Cout), chunk = (i / (16 * Cout)) % 2, kh = i / (32 * Cout);
   const int k = chunk * 8 + e, j = k / 4, c = k % 4, dx = n2 / Cout, n = n2 % Cout, kw = j - dx;
-  wp[i] = __float2bfloat16((kw >= 0 && kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f);
+  const float v = (kw >= 0 && kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f;
+  wp[i] = cvt16_rt(lo ? v - round16_rt(v, fmt) : v, fmt);
 }
 // fp32 NCHW image (C <= 8 planes) -> bf16 NHWC with 8 channels per pixel (zero padded): one 16-byte store per pixel
 __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ img, uint4* __restrict__ out,
@@ -561,14 +621,14 @@ __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __rest
                       *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
 }
 // Linear weight over a flattened (C,H,W) activation -> the same weight over the (H,W,C) flattening, bf16
-__global__ void fc_weight_to_hwc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int HW,
-                                        size_t total) {
+__global__ void fc_weight_to_hwc_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int C, int HW,
+                                        size_t total, int fmt) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t K = (size_t)C * HW;
   const size_t o = i / K, k = i % K;
   const size_t hw = k / C, c = k % C;
-  out[i] = __float2bfloat16(w[o * K + c * HW + hw]);
+  out[i] = cvt16_rt(w[o * K + c * HW + hw], fmt);
 }
 
 // per-image mean and 1/std of x/255 over all C*H*W values, fp64 accumulation (sklearn StandardScaler on one molecule's
@@ -619,21 +679,16 @@ __global__ void __launch_bounds__(256) u8_image_stats_kernel(const uint8_t* __re
   }
 }
 
-template <int KC, int COUT, int SRC>
-int launch(const void* x, const float* stats, const void* wprep, const float* bias, void* y, int N, int H, int W,
-           cudaStream_t stream) {
-  using C = Cfg<KC, COUT, SRC>;
-  static int sms = 0;
-  static bool attr = false;
-  if (!attr) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    attr = true;
-  }
+template <int KC, int COUT, int SRC, int FMT, int SPLIT>
+int launch(const void* x, const void* x_lo, const float* stats, const void* wprep, const float* bias, void* y, void* y_lo, int N,
+           int H, int W, cudaStream_t stream) {
+  using C = Cfg<KC, COUT, SRC, FMT, SPLIT>;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
+    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  const int sms = current_sm_count();
   // NHWC output as a 3-D tensor {COUT, PW, N*PH}; one box = one tile (COUT x 8 x 16), swizzle span = one pixel row
-  CUtensorMap tmOut;
+  CUtensorMap tmOut, tmOutLo;
   {
     tensormap_encode_fn enc = get_tensormap_encoder();
     if (!enc) return BBBP_ECUDA;
@@ -642,20 +697,37 @@ int launch(const void* x, const float* stats, const void* wprep, const float* bi
     cuuint64_t strides[2] = {(cuuint64_t)COUT * 2, (cuuint64_t)PW * COUT * 2};
     cuuint32_t box[3] = {(cuuint32_t)COUT, TILE_PW, TILE_PH};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     COUT * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("conv3x3_relu_pool_bf16: cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
-      return BBBP_ECUDA;
+    for (int part = 0; part < SPLIT; ++part) {
+      CUresult r = enc(part ? &tmOutLo : &tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, part ? y_lo : y, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, COUT * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("conv3x3_relu_pool16: cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
+        return BBBP_ECUDA;
+      }
     }
+    if (SPLIT == 1) tmOutLo = tmOut;
   }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
   const int per_sm = C::MIN_CTAS;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
-  conv3x3_umma_kernel<KC, COUT, SRC><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
-      x, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, tmOut, N, H, W);
-  return launch_status("conv3x3_relu_pool_bf16");
+  conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
+      x, x_lo, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, tmOut, tmOutLo, N, H, W);
+  return launch_status("conv3x3_relu_pool16");
+}
+
+// (fmt, split) -> instantiation.  Built: bf16 one pass (fast mode), fp16 one pass, fp16 split (strict mode).
+template <int KC, int COUT, int SRC>
+int dispatch(int fmt, int split, const void* x, const void* x_lo, const float* stats, const void* wprep, const float* bias,
+             void* y, void* y_lo, int N, int H, int W, cudaStream_t stream) {
+  if (fmt == BBBP_FMT_BF16 && split == 1)
+    return launch<KC, COUT, SRC, BBBP_FMT_BF16, 1>(x, nullptr, stats, wprep, bias, y, nullptr, N, H, W, stream);
+  if (fmt == BBBP_FMT_F16 && split == 1)
+    return launch<KC, COUT, SRC, BBBP_FMT_F16, 1>(x, nullptr, stats, wprep, bias, y, nullptr, N, H, W, stream);
+  if (fmt == BBBP_FMT_F16 && split == 2)
+    return launch<KC, COUT, SRC, BBBP_FMT_F16, 2>(x, x_lo, stats, wprep, bias, y, y_lo, N, H, W, stream);
+  set_error("tcgen05 conv: (fmt %d, split %d) is not built (bf16 x1, fp16 x1, fp16 x2)", fmt, split);
+  return BBBP_EUNSUPPORTED;
 }
 
 }  // namespace conv
@@ -664,41 +736,53 @@ int launch(const void* x, const float* stats, const void* wprep, const float* bi
 using namespace bbbp;
 
 extern "C" size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout) {
-  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)3 * 2 * (2 * Cout) * 16;   // NHWC8 image | PACK4 image
+  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)2 * 3 * 2 * (2 * Cout) * 16;   // NHWC8 image | PACK4 hi | PACK4 lo
   return (size_t)9 * (Cin / 8) * Cout * 16;
 }
 
-extern "C" int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream) {
+extern "C" int bbbp_conv3x3_prepare16(int fmt, const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "conv3x3_prepare: bad fmt %d", fmt);
   BBBP_CHECK_ARG(w && wprep, "conv3x3_prepare: null operand");
   BBBP_CHECK_ARG((Cin == 3 && Cout == 32) || (Cin == 32 && Cout == 64),
                  "conv3x3_prepare: only (3->32) and (32->64) are built for the tcgen05 path, got %d->%d", Cin, Cout);
   const int total = (int)(bbbp_conv3x3_prepared_bytes(Cin, Cout) / 2);
+  uint16_t* wp = static_cast<uint16_t*>(wprep);
   if (Cin <= 8) {
     const int n8 = 2 * 5 * 2 * Cout * 8, n4 = 3 * 2 * (2 * Cout) * 8;
-    conv::prep_weights_c8_kernel<<<ceil_div(n8, 256), 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wprep),
-                                                                                 Cin, Cout);
-    conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(
-        w, static_cast<__nv_bfloat16*>(wprep) + n8, Cin, Cout);
-    note_launches(1);
+    conv::prep_weights_c8_kernel<<<ceil_div(n8, 256), 256, 0, as_stream(stream)>>>(w, wp, Cin, Cout, fmt);
+    conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(w, wp + n8, Cin, Cout, fmt, 0);
+    conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(w, wp + n8 + n4, Cin, Cout, fmt, 1);
+    note_launches(2);
   } else
-    conv::prep_weights_kc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
-        w, static_cast<__nv_bfloat16*>(wprep), Cin, Cout);
+    conv::prep_weights_kc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, wp, Cin, Cout, fmt);
   return launch_status("conv3x3_prepare");
 }
+extern "C" int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream) {
+  return bbbp_conv3x3_prepare16(BBBP_FMT_BF16, w, wprep, Cin, Cout, stream);
+}
 
-extern "C" int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep, const float* bias, void* y_nhwc, int N,
-                                           int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream) {
-  BBBP_CHECK_ARG(x_nhwc && wprep && bias && y_nhwc, "conv3x3_relu_pool_bf16: null operand");
+extern "C" int bbbp_conv3x3_relu_pool16(int fmt, int split, const void* x_nhwc, const void* x_lo, const void* wprep,
+                                        const float* bias, void* y_nhwc, void* y_lo, int N, int Cin_pad, int Cout, int H, int W,
+                                        bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x_nhwc && wprep && bias && y_nhwc, "conv3x3_relu_pool16: null operand");
+  BBBP_CHECK_ARG(split == 1 || (split == 2 && x_lo && y_lo), "conv3x3_relu_pool16: split must be 1, or 2 with both lo tensors");
   BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
-                 "conv3x3_relu_pool_bf16: H=%d must be a multiple of 32 and W=%d of 16", H, W);
-  BBBP_CHECK_ARG(((uintptr_t)x_nhwc % 16) == 0 && ((uintptr_t)y_nhwc % 16) == 0 && ((uintptr_t)wprep % 16) == 0,
-                 "conv3x3_relu_pool_bf16: operands must be 16-byte aligned");
+                 "conv3x3_relu_pool16: H=%d must be a multiple of 32 and W=%d of 16", H, W);
+  BBBP_CHECK_ARG(((uintptr_t)x_nhwc % 16) == 0 && ((uintptr_t)y_nhwc % 16) == 0 && ((uintptr_t)wprep % 16) == 0 &&
+                     ((uintptr_t)x_lo % 16) == 0 && ((uintptr_t)y_lo % 16) == 0,
+                 "conv3x3_relu_pool16: operands must be 16-byte aligned");
   if (N == 0) return BBBP_OK;
   cudaStream_t s = as_stream(stream);
-  if (Cin_pad == 8 && Cout == 32) return conv::launch<1, 32, conv::SRC_NHWC_BF16>(x_nhwc, nullptr, wprep, bias, y_nhwc, N, H, W, s);
-  if (Cin_pad == 32 && Cout == 64) return conv::launch<4, 64, conv::SRC_NHWC_BF16>(x_nhwc, nullptr, wprep, bias, y_nhwc, N, H, W, s);
-  set_error("conv3x3_relu_pool_bf16: unsupported channels %d->%d (built: 8->32, 32->64)", Cin_pad, Cout);
+  if (Cin_pad == 8 && Cout == 32 && fmt == BBBP_FMT_BF16 && split == 1)
+    return conv::launch<1, 32, conv::SRC_NHWC_BF16, BBBP_FMT_BF16, 1>(x_nhwc, nullptr, nullptr, wprep, bias, y_nhwc, nullptr, N, H, W, s);
+  if (Cin_pad == 32 && Cout == 64)
+    return conv::dispatch<4, 64, conv::SRC_NHWC_BF16>(fmt, split, x_nhwc, x_lo, nullptr, wprep, bias, y_nhwc, y_lo, N, H, W, s);
+  set_error("conv3x3_relu_pool16: unsupported channels %d->%d (built: 8->32 [bf16], 32->64)", Cin_pad, Cout);
   return BBBP_EUNSUPPORTED;
+}
+extern "C" int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep, const float* bias, void* y_nhwc, int N,
+                                           int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream) {
+  return bbbp_conv3x3_relu_pool16(BBBP_FMT_BF16, 1, x_nhwc, nullptr, wprep, bias, y_nhwc, nullptr, N, Cin_pad, Cout, H, W, stream);
 }
 
 extern "C" int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W,
@@ -711,12 +795,16 @@ extern "C" int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, 
   return launch_status("image_to_nhwc8");
 }
 
-extern "C" int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, int HW, bbbp_stream_t stream) {
-  BBBP_CHECK_ARG(w && out_bf16 && rows > 0 && C > 0 && HW > 0, "fc_weight_to_hwc: bad argument");
+extern "C" int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int C, int HW, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "fc_weight_to_hwc: bad fmt %d", fmt);
+  BBBP_CHECK_ARG(w && out16 && rows > 0 && C > 0 && HW > 0, "fc_weight_to_hwc: bad argument");
   const size_t total = (size_t)rows * C * HW;
   conv::fc_weight_to_hwc_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
-      w, static_cast<__nv_bfloat16*>(out_bf16), C, HW, total);
+      w, static_cast<uint16_t*>(out16), C, HW, total, fmt);
   return launch_status("fc_weight_to_hwc");
+}
+extern "C" int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, int HW, bbbp_stream_t stream) {
+  return bbbp_fc_weight_to_hwc16(BBBP_FMT_BF16, w, out_bf16, rows, C, HW, stream);
 }
 
 extern "C" int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, bbbp_stream_t stream) {
@@ -726,16 +814,23 @@ extern "C" int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int row
   return launch_status("u8_image_stats");
 }
 
-extern "C" int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
-                                          const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream) {
+extern "C" int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats,
+                                       const void* wprep, const float* bias, void* y_nhwc, void* y_lo, int N, int H, int W,
+                                       bbbp_stream_t stream) {
   BBBP_CHECK_ARG(img_chw && wprep && bias && y_nhwc, "conv1_from_image: null operand");
+  BBBP_CHECK_ARG(split == 1 || (split == 2 && y_lo), "conv1_from_image: split must be 1, or 2 with y_lo");
   BBBP_CHECK_ARG(!img_is_u8 || stats, "conv1_from_image: uint8 input needs the per-image (mean, 1/std) table");
   BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
                  "conv1_from_image: H=%d must be a multiple of 32 and W=%d of 16", H, W);
   if (N == 0) return BBBP_OK;
   cudaStream_t s = as_stream(stream);
-  if (img_is_u8) return conv::launch<1, 32, conv::SRC_CHW_U8>(img_chw, stats, wprep, bias, y_nhwc, N, H, W, s);
-  return conv::launch<1, 32, conv::SRC_CHW_F32>(img_chw, nullptr, wprep, bias, y_nhwc, N, H, W, s);
+  if (img_is_u8)
+    return conv::dispatch<1, 32, conv::SRC_CHW_U8>(fmt, split, img_chw, nullptr, stats, wprep, bias, y_nhwc, y_lo, N, H, W, s);
+  return conv::dispatch<1, 32, conv::SRC_CHW_F32>(fmt, split, img_chw, nullptr, nullptr, wprep, bias, y_nhwc, y_lo, N, H, W, s);
+}
+extern "C" int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
+                                          const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream) {
+  return bbbp_conv1_from_image16(BBBP_FMT_BF16, 1, img_chw, img_is_u8, stats, wprep, bias, y_nhwc, nullptr, N, H, W, stream);
 }
 
 // debug: probe = device array of 16 uint64 counters (zero it first), or NULL to switch the probe off

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <string.h>
 #include "common.cuh"
+#include "half16.cuh"
 
 namespace bbbp {
 
@@ -169,6 +170,35 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int ld_src, float* 
   dst[(size_t)r * ld_dst + c] = src[(size_t)r * ld_src + c];
 }
 
+// fp32 rows -> 16-bit rows (bf16 or fp16), optional lo part (hi + lo carries ~2x the mantissa), zero fill of the pad columns.
+// One thread = 8 output columns = one 16-byte store per output (the scalar version sat at 0.28 of the HBM roofline).
+template <int FMT>
+__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ src, int ld_src, uint16_t* __restrict__ hi,
+                                                     uint16_t* __restrict__ lo, int ld_dst, int rows, int cols, int cols_pad) {
+  const int groups = cols_pad / 8;            // cols_pad is a multiple of 8 on this path
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * groups) return;
+  const int r = (int)(i / groups), c0 = (int)(i % groups) * 8;
+  const float* s = src + (size_t)r * ld_src + c0;
+  float v[8];
+  if (c0 + 8 <= cols && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+    const float4 a = reinterpret_cast<const float4*>(s)[0], b = reinterpret_cast<const float4*>(s)[1];
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = c0 + k < cols ? s[k] : 0.0f;
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (lo) split16<FMT>(v[2 * k], v[2 * k + 1], h[k], l[k]);
+    else h[k] = pack16<FMT>(v[2 * k], v[2 * k + 1]);
+  }
+  const size_t at = (size_t)r * ld_dst + c0;
+  *reinterpret_cast<uint4*>(hi + at) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + at) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
                                  int rows, int cols, int cols_pad) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -212,7 +242,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
                                uint64_t seed, uint64_t offset, const uint64_t* __restrict__ seed_dev) {
   size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // one Philox block = 4 elements
   if (q * 4 >= n) return;
-  if (seed_dev) seed += *seed_dev;  // graph replay: the per-step part of the seed lives in device memory
+  seed = mix_seed(seed, seed_dev);  // per-site seed x per-step device seed (common.cuh)
   uint64_t ctr = q + offset;
   uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -504,6 +534,53 @@ extern "C" int bbbp_cast_bf16(const float* src, int ld_src, void* dst_bf16, int 
   cast_bf16_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, as_stream(stream)>>>(
       src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst, rows, cols, cols_pad);
   return launch_status("cast_bf16");
+}
+
+namespace bbbp {
+template <typename T>
+__global__ void __launch_bounds__(256) fill_zero_kernel(T* __restrict__ dst, size_t rows, size_t row_elems, size_t pitch_elems) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= rows * row_elems) return;
+  dst[(i / row_elems) * pitch_elems + i % row_elems] = T{};
+}
+}  // namespace bbbp
+
+extern "C" int bbbp_fill_zero(void* dst, long long rows, long long row_bytes, long long pitch_bytes, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(dst && rows >= 0 && row_bytes >= 0 && pitch_bytes >= row_bytes, "fill_zero: bad argument");
+  if (rows == 0 || row_bytes == 0) return BBBP_OK;
+  const uintptr_t mix = (uintptr_t)dst | (uintptr_t)row_bytes | (uintptr_t)pitch_bytes;
+  cudaStream_t s = as_stream(stream);
+#define BBBP_FILL(T)                                                                                                \
+  do {                                                                                                              \
+    const size_t re = (size_t)row_bytes / sizeof(T), total = (size_t)rows * re;                                     \
+    fill_zero_kernel<T><<<(unsigned)ceil_div(total, (size_t)256), 256, 0, s>>>(static_cast<T*>(dst), (size_t)rows, re, \
+                                                                               (size_t)pitch_bytes / sizeof(T));    \
+  } while (0)
+  if (mix % 16 == 0) BBBP_FILL(uint4);
+  else if (mix % 4 == 0) BBBP_FILL(uint32_t);
+  else if (mix % 2 == 0) BBBP_FILL(uint16_t);
+  else BBBP_FILL(uint8_t);
+#undef BBBP_FILL
+  return launch_status("fill_zero");
+}
+
+extern "C" int bbbp_cast16(int fmt, const float* src, int ld_src, void* dst_hi, void* dst_lo, int ld_dst, int rows, int cols,
+                           int cols_pad, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "cast16: bad fmt %d", fmt);
+  BBBP_CHECK_ARG(src && dst_hi && rows >= 0 && cols >= 0 && cols_pad >= cols && ld_dst >= cols_pad, "cast16: bad argument");
+  BBBP_CHECK_ARG(cols_pad % 8 == 0 && ld_dst % 8 == 0 && ((uintptr_t)dst_hi % 16) == 0 && ((uintptr_t)dst_lo % 16) == 0,
+                 "cast16: cols_pad and ld_dst must be multiples of 8, destinations 16-byte aligned");
+  const size_t total = (size_t)rows * (cols_pad / 8);
+  if (total == 0) return BBBP_OK;
+  const unsigned blocks = (unsigned)ceil_div(total, (size_t)256);
+  if (fmt == BBBP_FMT_F16)
+    cast16_kernel<BBBP_FMT_F16><<<blocks, 256, 0, as_stream(stream)>>>(src, ld_src, static_cast<uint16_t*>(dst_hi),
+                                                                       static_cast<uint16_t*>(dst_lo), ld_dst, rows, cols, cols_pad);
+  else
+    cast16_kernel<BBBP_FMT_BF16><<<blocks, 256, 0, as_stream(stream)>>>(src, ld_src, static_cast<uint16_t*>(dst_hi),
+                                                                        static_cast<uint16_t*>(dst_lo), ld_dst, rows, cols, cols_pad);
+  return launch_status("cast16");
 }
 
 extern "C" int bbbp_dropout_f32(const float* x, float* y, size_t n, float p, uint64_t seed, uint64_t offset,

@@ -203,11 +203,9 @@ extern "C" int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const 
       const int slabs = ceil_div(K, SK_KC);
       float* partial = slabs > 1 ? workspace : nullptr;
       const size_t smem = (size_t)2 * SK_KC * SK_PITCH * sizeof(float);
-      static bool attr_done = false;
-      if (!attr_done) {
+      static PerDeviceOnce attr_once;
+      if (attr_once.first())
         cudaFuncSetAttribute(gemm_f32_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-      }
       gemm_f32_skinny_kernel<<<dim3(ceil_div(N, SK_TN), slabs), 256, smem, as_stream(stream)>>>(
           M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, bias, act, accumulate, partial);
       int st = launch_status("gemm_f32 (skinny)");

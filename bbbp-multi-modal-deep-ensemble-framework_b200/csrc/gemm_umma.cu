@@ -13,8 +13,14 @@
 //   warps 4-7 epilogue      tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual (or row softmax) -> global
 // K tails and M/N tails are covered by TMA out-of-bounds zero fill; nothing has to be padded in HBM except the row
 // pitch (multiple of 8 elements).
+//
+// Operand formats and split passes (half16.cuh): the 16-bit operands are bf16 or fp16 (Params::fmt); an optional second A
+// tile ("lo" part of hi + lo activations) and an optional second W tile add one MMA each per K step into the SAME
+// accumulator:  D += A_hi W_hi^T (+ A_lo W_hi^T) (+ A_hi W_lo^T).  The epilogue can emit its 16-bit output as a hi + lo
+// pair for the next split GEMM.
 #include "common.cuh"
 #include "umma.cuh"
+#include "half16.cuh"
 
 namespace bbbp {
 
@@ -64,13 +70,21 @@ constexpr int BM = 128, BK = 64;
 constexpr int THREADS = 256;
 enum { EPI_LINEAR = 0, EPI_SOFTMAX = 1 };
 
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_BUDGET = 220 * 1024;   // tile ring budget (227 KB per CTA minus barriers / bias / alignment slack)
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = BN == 64 ? 4 : 3;
+  static constexpr int STAGES = BN == 64 ? 4 : 3;          // ring depth of the plain (one A tile, one W tile) product
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // tiles | full[STAGES] empty[STAGES] accum | tmem slot ; +1024 for manual alignment of the tile area
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 16 + BN * 4;
+  static constexpr int stage_bytes(int n_a, int n_w) { return n_a * A_BYTES + n_w * B_BYTES; }
+  static constexpr int stages(int n_a, int n_w) {
+    const int fit = SMEM_BUDGET / stage_bytes(n_a, n_w);
+    return fit < STAGES ? (fit < 2 ? 2 : fit) : STAGES;
+  }
+  // tiles | full[MAX_STAGES] empty[MAX_STAGES] accum | tmem slot | bias ; +1024 for manual alignment of the tile area
+  static constexpr int smem_bytes(int n_a, int n_w) {
+    return 1024 + stages(n_a, n_w) * stage_bytes(n_a, n_w) + (2 * MAX_STAGES + 1) * 8 + 16 + 16 + BN * 4;
+  }
 };
 
 struct Params {
@@ -82,14 +96,34 @@ struct Params {
   float* out;
   int ld_out;
   long long out_bs;
-  __nv_bfloat16* out16;
+  uint16_t* out16;
   int ld_out16;
   long long out16_bs;
   int act;
   float* partial;
   int M_pad, N_pad;
   float scale;  // EPI_SOFTMAX: logits are scale * (A W^T)
+  int fmt;      // BBBP_FMT_BF16 | BBBP_FMT_F16: format of A, W and of the 16-bit outputs
+  int n_a, n_w; // 1, or 2 when a "lo" tile of A / W rides along (split passes)
+  int stages;   // ring depth chosen by the host for this (n_a, n_w)
+  uint16_t* out16_lo;   // optional lo part of the 16-bit output (same pitch / batch stride as out16)
 };
+
+// 32 fp32 values -> 32 16-bit values as four 16-byte stores (and the matching lo parts when lo != nullptr)
+template <int FMT>
+__device__ __forceinline__ void store16_chunk(const float (&v)[32], uint16_t* o, uint16_t* lo) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t hi4[4], lo4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (lo) split16<FMT>(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi4[j], lo4[j]);
+      else hi4[j] = pack16<FMT>(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
+    }
+    reinterpret_cast<uint4*>(o)[g] = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+    if (lo) reinterpret_cast<uint4*>(lo)[g] = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+  }
+}
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1, int c2) {
   asm volatile(
@@ -102,15 +136,19 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
+                                                            const __grid_constant__ CUtensorMap tmA2,
+                                                            const __grid_constant__ CUtensorMap tmB2,
                                                             const __grid_constant__ Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = tiles;
-  uint8_t* sB = tiles + C::STAGES * C::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE_BYTES);
-  uint64_t* empty = full + C::STAGES;
-  uint64_t* accum = empty + C::STAGES;
+  // one ring slot = [A hi][A lo?][W hi][W lo?], every tile 1024-byte aligned (128B-swizzle atoms)
+  const int STAGES = p.stages;
+  const int stage_bytes = p.n_a * C::A_BYTES + p.n_w * C::B_BYTES;
+  const int b_off = p.n_a * C::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * stage_bytes);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* accum = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
   float* sBias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // bias of this CTA's columns
 
@@ -126,7 +164,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -142,30 +180,38 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (i / C::STAGES) & 1;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
-        tma_load_3d(&tmA, &full[s], sA + s * C::A_BYTES, (kb_begin + i) * BK, m0, batch);
-        tma_load_3d(&tmB, &full[s], sB + s * C::B_BYTES, (kb_begin + i) * BK, n0, batch);
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        uint8_t* st = tiles + s * stage_bytes;
+        const int kc = (kb_begin + i) * BK;
+        tma_load_3d(&tmA, &full[s], st, kc, m0, batch);
+        if (p.n_a == 2) tma_load_3d(&tmA2, &full[s], st + C::A_BYTES, kc, m0, batch);
+        tma_load_3d(&tmB, &full[s], st + b_off, kc, n0, batch);
+        if (p.n_w == 2) tma_load_3d(&tmB2, &full[s], st + b_off + C::B_BYTES, kc, n0, batch);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t idesc = make_idesc_16(BM, BN, p.fmt);
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (i / C::STAGES) & 1;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(sA + s * C::A_BYTES), b_addr = smem_u32(sB + s * C::B_BYTES);
+        const uint32_t a_addr = smem_u32(tiles + s * stage_bytes), b_addr = a_addr + b_off;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // K-major, 128B swizzle: 8-row atoms 1024 B apart (SBO); one atom along K, advance 32 B per UMMA_K
           const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSw128);
           const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSw128);
           umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0);
+          if (p.n_a == 2)      // + A_lo W_hi^T
+            umma_bf16(tmem_base, make_smem_desc(a_addr + C::A_BYTES + k * 32, 0, 1024, kLayoutSw128), bd, idesc, true);
+          if (p.n_w == 2)      // + A_hi W_lo^T
+            umma_bf16(tmem_base, ad, make_smem_desc(b_addr + C::B_BYTES + k * 32, 0, 1024, kLayoutSw128), idesc, true);
         }
         umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       }
@@ -206,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
           if (c * 32 + j < N) sum += exp2f(fmaf(__uint_as_float(r[j]), sl2, -off));
       }
       const float inv = 1.0f / sum;
-      __nv_bfloat16* dst = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16;
+      uint16_t* dst = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         if (c * 32 >= p.ld_out16) break;
@@ -219,8 +265,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
           for (int j = 0; j < 32; j += 2) {
             const float v0 = c * 32 + j < N ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -off)) * inv : 0.0f;
             const float v1 = c * 32 + j + 1 < N ? exp2f(fmaf(__uint_as_float(r[j + 1]), sl2, -off)) * inv : 0.0f;
-            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-            pk[j / 2] = *reinterpret_cast<uint32_t*>(&h);
+            pk[j / 2] = pack16_rt(v0, v1, p.fmt);
           }
           // ld_out16 is a multiple of 8: write whole 16-byte groups, zero in the pad columns
 #pragma unroll
@@ -234,7 +279,8 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
       // chunk, never per element: with one epilogue warp per scheduler the per-element instruction count is what the
       // epilogue costs.  Thread = output row; it owns 32 consecutive columns per chunk (128 B fp32 / 64 B bf16).
       const bool al32 = p.out && p.ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_bs % 4 == 0;
-      const bool al16 = p.out16 && p.ld_out16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0 && p.out16_bs % 8 == 0;
+      const bool al16 = p.out16 && p.ld_out16 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0 && p.out16_bs % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.out16_lo) & 15) == 0;
       const bool alres = p.residual && p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && p.res_bs % 4 == 0;
       const float4* bias4 = reinterpret_cast<const float4*>(sBias);
 #pragma unroll 1
@@ -301,22 +347,19 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
           }
         }
         if (p.out16) {
-          __nv_bfloat16* o = p.out16 + (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16 + col0;
+          const size_t at = (size_t)batch * p.out16_bs + (size_t)row * p.ld_out16 + col0;
+          uint16_t* o = p.out16 + at;
+          uint16_t* olo = p.out16_lo ? p.out16_lo + at : nullptr;
           if (al16 && col0 + 32 <= p.ld_out16) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              reinterpret_cast<uint4*>(o)[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
+            if (p.fmt == BBBP_FMT_F16) store16_chunk<BBBP_FMT_F16>(v, o, olo);
+            else store16_chunk<BBBP_FMT_BF16>(v, o, olo);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.ld_out16) o[j] = __float2bfloat16(v[j]);
+              if (col0 + j < p.ld_out16) {
+                o[j] = cvt16_rt(v[j], p.fmt);
+                if (olo) olo[j] = cvt16_rt(v[j] - round16_rt(v[j], p.fmt), p.fmt);
+              }
           }
         }
       }
@@ -335,8 +378,9 @@ __global__ void __launch_bounds__(256) splitk_finish_bf16_kernel(const float* __
                                                                  const float* __restrict__ bias,
                                                                  const float* __restrict__ residual, int ld_res,
                                                                  float* __restrict__ out, int ld_out,
-                                                                 __nv_bfloat16* __restrict__ out16, int ld_out16,
-                                                                 int act) {
+                                                                 uint16_t* __restrict__ out16,
+                                                                 uint16_t* __restrict__ out16_lo, int ld_out16,
+                                                                 int act, int fmt) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= (size_t)M * N) return;
   const int m = i / N, n = i % N;
@@ -346,7 +390,8 @@ __global__ void __launch_bounds__(256) splitk_finish_bf16_kernel(const float* __
   v = apply_act(v, act);
   if (residual) v += residual[(size_t)m * ld_res + n];
   if (out) out[(size_t)m * ld_out + n] = v;
-  if (out16) out16[(size_t)m * ld_out16 + n] = __float2bfloat16(v);
+  if (out16) out16[(size_t)m * ld_out16 + n] = cvt16_rt(v, fmt);
+  if (out16_lo) out16_lo[(size_t)m * ld_out16 + n] = cvt16_rt(v - round16_rt(v, fmt), fmt);
 }
 
 struct Problem {
@@ -358,19 +403,37 @@ struct Problem {
   int ldw;
   long long w_bs;
   Params p;
+  const void* A_lo = nullptr;   // optional lo parts (same pitch / batch stride as the hi parts)
+  const void* W_lo = nullptr;
 };
 
 template <int BN, int EPI>
 int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   using C = Cfg<BN>;
-  CUtensorMap tmA, tmB;
+  // (fp16 tiles go through the same 2-byte tensor maps: the element type only selects the out-of-bounds fill, zero in both)
+  CUtensorMap tmA, tmB, tmA2, tmB2;
   int st = make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
                              (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != BBBP_OK) return st;
   st = make_tmap_bf16_3d(&tmB, pr.W, (uint64_t)pr.N, (uint64_t)pr.K, (uint64_t)pr.ldw, (uint64_t)pr.batches,
                          (uint64_t)pr.w_bs, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != BBBP_OK) return st;
+  tmA2 = tmA, tmB2 = tmB;
+  if (pr.A_lo) {
+    st = make_tmap_bf16_3d(&tmA2, pr.A_lo, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
+                           (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st != BBBP_OK) return st;
+  }
+  if (pr.W_lo) {
+    st = make_tmap_bf16_3d(&tmB2, pr.W_lo, (uint64_t)pr.N, (uint64_t)pr.K, (uint64_t)pr.ldw, (uint64_t)pr.batches,
+                           (uint64_t)pr.w_bs, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st != BBBP_OK) return st;
+  }
   Params p = pr.p;
+  p.n_a = pr.A_lo ? 2 : 1;
+  p.n_w = pr.W_lo ? 2 : 1;
+  p.stages = C::stages(p.n_a, p.n_w);
+  const int smem_bytes = C::smem_bytes(p.n_a, p.n_w);
   p.M = pr.M;
   p.N = pr.N;
   p.total_kb = ceil_div(pr.K, BK);
@@ -379,19 +442,18 @@ int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   p.M_pad = ceil_div(pr.M, 128) * 128;
   p.N_pad = ceil_div(pr.N, 128) * 128;
   if (p.splits <= 1) p.partial = nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())    // the largest configuration this instantiation can be asked for
+    cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         max(max(C::smem_bytes(1, 1), C::smem_bytes(2, 1)), max(C::smem_bytes(1, 2), C::smem_bytes(2, 2))));
   dim3 grid(ceil_div(pr.N, BN), ceil_div(pr.M, BM), pr.batches * p.splits);
-  gemm_bf16_kernel<BN, EPI><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN, EPI><<<grid, THREADS, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
   st = launch_status("gemm_bf16");
   if (st != BBBP_OK || p.splits <= 1) return st;
   const size_t total = (size_t)pr.M * pr.N;
   splitk_finish_bf16_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, stream>>>(
-      p.partial, p.splits, pr.M, pr.N, p.M_pad, p.N_pad, p.bias, p.residual, p.ld_res, p.out, p.ld_out, p.out16, p.ld_out16,
-      p.act);
+      p.partial, p.splits, pr.M, pr.N, p.M_pad, p.N_pad, p.bias, p.residual, p.ld_res, p.out, p.ld_out, p.out16, p.out16_lo,
+      p.ld_out16, p.act, p.fmt);
   return launch_status("gemm_bf16 split-k finish");
 }
 
@@ -418,11 +480,11 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
 // Row softmax of fp32 logits -> bf16 probabilities for attention scopes wider than one CTA tile (S > 256):
 // p[r, c] = softmax_c(scale * s[r, c]); one block per row, three passes (max, sum, write) of 128-bit loads.
 __global__ void __launch_bounds__(256) softmax_rows_scaled_bf16_kernel(const float* __restrict__ s, size_t ld_s,
-                                                                       __nv_bfloat16* __restrict__ p, size_t ld_p, int cols,
-                                                                       float scale) {
+                                                                       uint16_t* __restrict__ p, size_t ld_p, int cols,
+                                                                       float scale, int fmt) {
   __shared__ float red[8];
   const float* row = s + (size_t)blockIdx.x * ld_s;
-  __nv_bfloat16* out = p + (size_t)blockIdx.x * ld_p;
+  uint16_t* out = p + (size_t)blockIdx.x * ld_p;
   const int n4 = cols / 4;
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < n4; i += 256) {
@@ -455,7 +517,7 @@ __global__ void __launch_bounds__(256) softmax_rows_scaled_bf16_kernel(const flo
     const int c = 2 * i;
     const float a = c < cols ? exp2f(fmaf(row[c], sl2, -off)) * inv : 0.0f;
     const float b = c + 1 < cols ? exp2f(fmaf(row[c + 1], sl2, -off)) * inv : 0.0f;
-    reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
+    reinterpret_cast<uint32_t*>(out)[i] = pack16_rt(a, b, fmt);
   }
 }
 
@@ -489,16 +551,28 @@ static int check_operands(const char* who, int M, int N, int K, const void* A, i
   return BBBP_OK;
 }
 
-extern "C" int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, const void* W_bf16, int ldw,
-                              const float* bias, const float* residual, int ld_res, float* out_f32, int ld_out,
-                              void* out_bf16, int ld_out16, int act, int split_k, void* workspace,
-                              size_t workspace_bytes, bbbp_stream_t stream) {
+static int check_fmt(const char* who, int fmt) {
+  if (fmt != BBBP_FMT_BF16 && fmt != BBBP_FMT_F16) {
+    bbbp::set_error("%s: fmt=%d (BBBP_FMT_BF16 or BBBP_FMT_F16)", who, fmt);
+    return BBBP_EINVAL;
+  }
+  return BBBP_OK;
+}
+
+extern "C" int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
+                           const void* W_lo, int ldw, const float* bias, const float* residual, int ld_res, float* out_f32,
+                           int ld_out, void* out16_hi, void* out16_lo, int ld_out16, int act, int split_k, void* workspace,
+                           size_t workspace_bytes, bbbp_stream_t stream) {
   using namespace bbbp;
-  int st = check_operands("gemm_bf16", M, N, K, A_bf16, lda, W_bf16, ldw);
+  int st = check_fmt("gemm16", fmt);
   if (st != BBBP_OK) return st;
-  BBBP_CHECK_ARG(out_f32 || out_bf16, "gemm_bf16: no output given");
-  BBBP_CHECK_ARG(!residual || ld_res >= N, "gemm_bf16: ld_res < N");
-  BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out_bf16 || ld_out16 >= N), "gemm_bf16: output pitch < N");
+  st = check_operands("gemm16", M, N, K, A_hi, lda, W_hi, ldw);
+  if (st != BBBP_OK) return st;
+  BBBP_CHECK_ARG(((uintptr_t)A_lo % 16) == 0 && ((uintptr_t)W_lo % 16) == 0, "gemm16: lo operands must be 16-byte aligned");
+  BBBP_CHECK_ARG(out_f32 || out16_hi, "gemm16: no output given");
+  BBBP_CHECK_ARG(!out16_lo || out16_hi, "gemm16: out16_lo without out16_hi");
+  BBBP_CHECK_ARG(!residual || ld_res >= N, "gemm16: ld_res < N");
+  BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out16_hi || ld_out16 >= N), "gemm16: output pitch < N");
   if (M == 0 || N == 0) return BBBP_OK;
   if (split_k < 1) split_k = 1;
   const int total_kb = ceil_div(K, gemm::BK);
@@ -507,61 +581,89 @@ extern "C" int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, 
     // the effective split count may shrink inside launch(); size for the requested one
     const size_t need = bbbp_gemm_bf16_workspace(M, N, split_k);
     if (!workspace || workspace_bytes < need) {
-      set_error("gemm_bf16: split_k=%d needs %zu workspace bytes, got %zu", split_k, need, workspace_bytes);
+      set_error("gemm16: split_k=%d needs %zu workspace bytes, got %zu", split_k, need, workspace_bytes);
       return BBBP_EWORKSPACE;
     }
   }
   gemm::Problem pr{};
   pr.M = M, pr.N = N, pr.K = K, pr.batches = 1;
-  pr.A = A_bf16, pr.lda = lda, pr.W = W_bf16, pr.ldw = ldw;
+  pr.A = A_hi, pr.A_lo = A_lo, pr.lda = lda, pr.W = W_hi, pr.W_lo = W_lo, pr.ldw = ldw;
   pr.p.bias = bias, pr.p.residual = residual, pr.p.ld_res = ld_res;
   pr.p.out = out_f32, pr.p.ld_out = ld_out;
-  pr.p.out16 = static_cast<__nv_bfloat16*>(out_bf16), pr.p.ld_out16 = ld_out16;
-  pr.p.act = act, pr.p.partial = static_cast<float*>(workspace);
+  pr.p.out16 = static_cast<uint16_t*>(out16_hi), pr.p.out16_lo = static_cast<uint16_t*>(out16_lo), pr.p.ld_out16 = ld_out16;
+  pr.p.act = act, pr.p.partial = static_cast<float*>(workspace), pr.p.fmt = fmt;
   cudaStream_t s = as_stream(stream);
   if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, split_k, s);
   if (N >= 512 && split_k == 1) return gemm::launch<256, gemm::EPI_LINEAR>(pr, split_k, s);
   return gemm::launch<128, gemm::EPI_LINEAR>(pr, split_k, s);
 }
 
-extern "C" int bbbp_gemm_bf16_batched(int batches, int M, int N, int K, const void* A_bf16, int lda, long long a_batch_stride,
-                                      const void* W_bf16, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
-                                      long long out_batch_stride, void* out_bf16, int ld_out16,
-                                      long long out16_batch_stride, bbbp_stream_t stream) {
+extern "C" int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, const void* W_bf16, int ldw,
+                              const float* bias, const float* residual, int ld_res, float* out_f32, int ld_out,
+                              void* out_bf16, int ld_out16, int act, int split_k, void* workspace,
+                              size_t workspace_bytes, bbbp_stream_t stream) {
+  return bbbp_gemm16(BBBP_FMT_BF16, M, N, K, A_bf16, nullptr, lda, W_bf16, nullptr, ldw, bias, residual, ld_res, out_f32,
+                     ld_out, out_bf16, nullptr, ld_out16, act, split_k, workspace, workspace_bytes, stream);
+}
+
+extern "C" int bbbp_gemm16_batched(int fmt, int batches, int M, int N, int K, const void* A, int lda, long long a_batch_stride,
+                                   const void* W, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
+                                   long long out_batch_stride, void* out16, int ld_out16, long long out16_batch_stride,
+                                   bbbp_stream_t stream) {
   using namespace bbbp;
-  int st = check_operands("gemm_bf16_batched", M, N, K, A_bf16, lda, W_bf16, ldw);
+  int st = check_fmt("gemm16_batched", fmt);
   if (st != BBBP_OK) return st;
-  BBBP_CHECK_ARG(batches >= 0 && batches <= 65535, "gemm_bf16_batched: batches=%d out of range", batches);
-  BBBP_CHECK_ARG(a_batch_stride % 8 == 0 && w_batch_stride % 8 == 0, "gemm_bf16_batched: batch strides must be multiples of 8");
-  BBBP_CHECK_ARG(out_f32 || out_bf16, "gemm_bf16_batched: no output given");
-  BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out_bf16 || ld_out16 >= N), "gemm_bf16_batched: output pitch < N");
+  st = check_operands("gemm16_batched", M, N, K, A, lda, W, ldw);
+  if (st != BBBP_OK) return st;
+  BBBP_CHECK_ARG(batches >= 0 && batches <= 65535, "gemm16_batched: batches=%d out of range", batches);
+  BBBP_CHECK_ARG(a_batch_stride % 8 == 0 && w_batch_stride % 8 == 0, "gemm16_batched: batch strides must be multiples of 8");
+  BBBP_CHECK_ARG(out_f32 || out16, "gemm16_batched: no output given");
+  BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out16 || ld_out16 >= N), "gemm16_batched: output pitch < N");
   if (M == 0 || N == 0 || batches == 0) return BBBP_OK;
   gemm::Problem pr{};
   pr.M = M, pr.N = N, pr.K = K, pr.batches = batches;
-  pr.A = A_bf16, pr.lda = lda, pr.a_bs = a_batch_stride, pr.W = W_bf16, pr.ldw = ldw, pr.w_bs = w_batch_stride;
+  pr.A = A, pr.lda = lda, pr.a_bs = a_batch_stride, pr.W = W, pr.ldw = ldw, pr.w_bs = w_batch_stride;
   pr.p.out = out_f32, pr.p.ld_out = ld_out, pr.p.out_bs = out_batch_stride;
-  pr.p.out16 = static_cast<__nv_bfloat16*>(out_bf16), pr.p.ld_out16 = ld_out16, pr.p.out16_bs = out16_batch_stride;
+  pr.p.out16 = static_cast<uint16_t*>(out16), pr.p.ld_out16 = ld_out16, pr.p.out16_bs = out16_batch_stride;
+  pr.p.fmt = fmt;
   cudaStream_t s = as_stream(stream);
   if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, 1, s);
   return gemm::launch<128, gemm::EPI_LINEAR>(pr, 1, s);
 }
 
-extern "C" int bbbp_attention_scores_softmax_bf16(int groups, int seq, int head_dim, const void* q_bf16, int ldq,
-                                                  const void* k_bf16, int ldk, long long group_stride, float scale,
-                                                  void* p_bf16, int ldp, bbbp_stream_t stream) {
+extern "C" int bbbp_gemm_bf16_batched(int batches, int M, int N, int K, const void* A_bf16, int lda, long long a_batch_stride,
+                                      const void* W_bf16, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
+                                      long long out_batch_stride, void* out_bf16, int ld_out16,
+                                      long long out16_batch_stride, bbbp_stream_t stream) {
+  return bbbp_gemm16_batched(BBBP_FMT_BF16, batches, M, N, K, A_bf16, lda, a_batch_stride, W_bf16, ldw, w_batch_stride, out_f32,
+                             ld_out, out_batch_stride, out_bf16, ld_out16, out16_batch_stride, stream);
+}
+
+extern "C" int bbbp_attention_scores_softmax16(int fmt, int groups, int seq, int head_dim, const void* q, int ldq,
+                                               const void* k, int ldk, long long group_stride, float scale, void* p_out,
+                                               int ldp, bbbp_stream_t stream) {
   using namespace bbbp;
-  int st = check_operands("attention_scores_softmax", seq, seq, head_dim, q_bf16, ldq, k_bf16, ldk);
+  int st = check_fmt("attention_scores_softmax", fmt);
+  if (st != BBBP_OK) return st;
+  st = check_operands("attention_scores_softmax", seq, seq, head_dim, q, ldq, k, ldk);
   if (st != BBBP_OK) return st;
   BBBP_CHECK_ARG(seq <= 256, "attention_scores_softmax: seq=%d > 256 (one CTA must own a full row of scores)", seq);
   BBBP_CHECK_ARG(groups >= 0 && groups <= 65535 && group_stride % 8 == 0, "attention_scores_softmax: bad groups/stride");
-  BBBP_CHECK_ARG(p_bf16 && ldp >= seq && ldp % 8 == 0 && ldp <= 256, "attention_scores_softmax: ldp=%d must be a multiple of 8 in [seq, 256]", ldp);
+  BBBP_CHECK_ARG(p_out && ldp >= seq && ldp % 8 == 0 && ldp <= 256, "attention_scores_softmax: ldp=%d must be a multiple of 8 in [seq, 256]", ldp);
   if (groups == 0 || seq == 0) return BBBP_OK;
   gemm::Problem pr{};
   pr.M = seq, pr.N = seq, pr.K = head_dim, pr.batches = groups;
-  pr.A = q_bf16, pr.lda = ldq, pr.a_bs = group_stride, pr.W = k_bf16, pr.ldw = ldk, pr.w_bs = group_stride;
-  pr.p.out16 = static_cast<__nv_bfloat16*>(p_bf16), pr.p.ld_out16 = ldp, pr.p.out16_bs = (long long)seq * ldp;
-  pr.p.scale = scale;
+  pr.A = q, pr.lda = ldq, pr.a_bs = group_stride, pr.W = k, pr.ldw = ldk, pr.w_bs = group_stride;
+  pr.p.out16 = static_cast<uint16_t*>(p_out), pr.p.ld_out16 = ldp, pr.p.out16_bs = (long long)seq * ldp;
+  pr.p.scale = scale, pr.p.fmt = fmt;
   return gemm::launch<256, gemm::EPI_SOFTMAX>(pr, 1, as_stream(stream));
+}
+
+extern "C" int bbbp_attention_scores_softmax_bf16(int groups, int seq, int head_dim, const void* q_bf16, int ldq,
+                                                  const void* k_bf16, int ldk, long long group_stride, float scale,
+                                                  void* p_bf16, int ldp, bbbp_stream_t stream) {
+  return bbbp_attention_scores_softmax16(BBBP_FMT_BF16, groups, seq, head_dim, q_bf16, ldq, k_bf16, ldk, group_stride, scale,
+                                         p_bf16, ldp, stream);
 }
 
 extern "C" int bbbp_transpose_bf16(int batches, int rows, int cols, const void* src, int ld_src, long long src_batch_stride,
@@ -579,7 +681,13 @@ extern "C" int bbbp_transpose_bf16(int batches, int rows, int cols, const void* 
 
 extern "C" int bbbp_softmax_rows_scaled_bf16(const float* scores, long long ld_scores, void* p_bf16, long long ld_p,
                                              long long rows, int cols, float scale, bbbp_stream_t stream) {
+  return bbbp_softmax_rows_scaled16(BBBP_FMT_BF16, scores, ld_scores, p_bf16, ld_p, rows, cols, scale, stream);
+}
+
+extern "C" int bbbp_softmax_rows_scaled16(int fmt, const float* scores, long long ld_scores, void* p_bf16, long long ld_p,
+                                          long long rows, int cols, float scale, bbbp_stream_t stream) {
   using namespace bbbp;
+  if (check_fmt("softmax_rows_scaled", fmt) != BBBP_OK) return BBBP_EINVAL;
   BBBP_CHECK_ARG(scores && p_bf16 && rows >= 0 && cols > 0, "softmax_rows_scaled: bad argument");
   BBBP_CHECK_ARG(ld_scores >= cols && ld_scores % 4 == 0 && ((uintptr_t)scores % 16) == 0,
                  "softmax_rows_scaled: ld_scores must be >= cols and a multiple of 4, base 16-byte aligned");
@@ -587,6 +695,6 @@ extern "C" int bbbp_softmax_rows_scaled_bf16(const float* scores, long long ld_s
   BBBP_CHECK_ARG(rows <= 0x7fffffffLL, "softmax_rows_scaled: too many rows");
   if (rows == 0) return BBBP_OK;
   gemm::softmax_rows_scaled_bf16_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
-      scores, (size_t)ld_scores, static_cast<__nv_bfloat16*>(p_bf16), (size_t)ld_p, cols, scale);
+      scores, (size_t)ld_scores, static_cast<uint16_t*>(p_bf16), (size_t)ld_p, cols, scale, fmt);
   return launch_status("softmax_rows_scaled_bf16");
 }

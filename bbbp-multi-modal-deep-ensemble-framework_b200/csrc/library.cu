@@ -26,6 +26,18 @@ int launch_status(const char* what) {
   }
   return BBBP_OK;
 }
+
+int current_sm_count() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
+}
 }  // namespace bbbp
 
 extern "C" int bbbp_abi_version(void) { return BBBP_ABI_VERSION; }

@@ -2,6 +2,7 @@
 // and BatchNorm1d (20250113.py:101).  Memory-bound single-purpose kernels: one warp per row for LN
 // (warp-shuffle statistics over the TRUE width, never a padded one), column-strip blocks for BN.
 #include "common.cuh"
+#include "half16.cuh"
 
 namespace bbbp {
 
@@ -10,8 +11,8 @@ constexpr int LN_WARPS = 4;
 __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ sum_out, float* __restrict__ mean_out,
-    float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y16, int ld16, int rows, int dim, float eps, int ld_x,
-    int ld_res, int ld_y) {
+    float* __restrict__ rstd_out, uint16_t* __restrict__ y16, int ld16, int rows, int dim, float eps, int ld_x,
+    int ld_res, int ld_y, int fmt) {
   const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -31,10 +32,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(
     float o = (t - mean) * rstd * gamma[i] + beta[i];
     y[(size_t)row * ld_y + i] = o;
     if (sum_out) sum_out[(size_t)row * dim + i] = t;
-    if (y16) y16[(size_t)row * ld16 + i] = __float2bfloat16(o);
+    if (y16) y16[(size_t)row * ld16 + i] = cvt16_rt(o, fmt);
   }
   if (y16)
-    for (int i = dim + lane; i < ld16; i += 32) y16[(size_t)row * ld16 + i] = __float2bfloat16(0.0f);
+    for (int i = dim + lane; i < ld16; i += 32) y16[(size_t)row * ld16 + i] = 0;
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
     if (rstd_out) rstd_out[row] = rstd;
@@ -268,22 +269,30 @@ extern "C" int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, cons
   BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd: ld_bf16 < dim");
   if (rows == 0) return BBBP_OK;
   add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
-      x, res, gamma, beta, y, sum_out, mean, rstd, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf16, rows, dim, eps, dim, dim,
-      dim);
+      x, res, gamma, beta, y, sum_out, mean, rstd, reinterpret_cast<uint16_t*>(y_bf16), ld_bf16, rows, dim, eps, dim, dim,
+      dim, BBBP_FMT_BF16);
   return launch_status("add_layernorm_fwd");
 }
 
 extern "C" int bbbp_add_layernorm_fwd_pitched_f32(const float* x, int ld_x, const float* res, int ld_res, const float* gamma,
                                                   const float* beta, float* y, int ld_y, void* y_bf16, int ld_bf16, int rows,
                                                   int dim, float eps, bbbp_stream_t stream) {
+  return bbbp_add_layernorm_fwd_pitched16(BBBP_FMT_BF16, x, ld_x, res, ld_res, gamma, beta, y, ld_y, y_bf16, ld_bf16, rows, dim,
+                                          eps, stream);
+}
+
+extern "C" int bbbp_add_layernorm_fwd_pitched16(int fmt, const float* x, int ld_x, const float* res, int ld_res,
+                                                const float* gamma, const float* beta, float* y, int ld_y, void* y_bf16,
+                                                int ld_bf16, int rows, int dim, float eps, bbbp_stream_t stream) {
   using namespace bbbp;
+  BBBP_CHECK_ARG(fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "add_layernorm_fwd_pitched: bad fmt %d", fmt);
   BBBP_CHECK_ARG(x && gamma && beta && y && rows >= 0 && dim > 0 && ld_x >= dim && ld_y >= dim && (!res || ld_res >= dim),
                  "add_layernorm_fwd_pitched: bad argument");
   BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd_pitched: ld_bf16 < dim");
   if (rows == 0) return BBBP_OK;
   add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
-      x, res, gamma, beta, y, nullptr, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(y_bf16), ld_bf16, rows, dim, eps, ld_x,
-      ld_res, ld_y);
+      x, res, gamma, beta, y, nullptr, nullptr, nullptr, reinterpret_cast<uint16_t*>(y_bf16), ld_bf16, rows, dim, eps, ld_x,
+      ld_res, ld_y, fmt);
   return launch_status("add_layernorm_fwd_pitched");
 }
 

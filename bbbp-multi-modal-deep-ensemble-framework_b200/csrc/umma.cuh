@@ -90,6 +90,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// the same with the 16-bit operand format chosen at run time: fmt 0 = bf16 (A/B format code 1), 1 = fp16 (code 0)
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t m, uint32_t n, int fmt) {
+  return (1u << 4) | (fmt == 0 ? ((1u << 7) | (1u << 10)) : 0u) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(

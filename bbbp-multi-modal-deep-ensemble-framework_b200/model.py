@@ -29,6 +29,9 @@ from . import autograd as ag
 _DEFAULT_PRECISION = os.environ.get("BBBP_PRECISION", "fp32")
 
 
+PRECISIONS = ("fp32", "bf16", "fp16", "strict")
+
+
 def encoder_heads(fingerprint_size: int, start: int | None = None) -> int:
     """20250113.py:71-73 (start = max(1, F // 8)); 20250107_network.py:112-117 (start = 8)."""
     nhead = max(1, fingerprint_size // 8) if start is None else start
@@ -50,10 +53,30 @@ def _score_mlp(in_dim: int, hidden: int, out_dim: int) -> nn.Sequential:
 class _KernelModule(nn.Module):
     """Shared helpers: every op dispatches to the CUDA library."""
 
-    precision = _DEFAULT_PRECISION  # "fp32" (CUDA-core FMA) | "bf16" (tcgen05 GEMMs, fp32 accumulation)
+    # "fp32"   CUDA-core FMA kernels (training / validation path)
+    # "bf16"   tcgen05, bf16 operands, one pass (fastest; 8-bit operand mantissa)
+    # "fp16"   tcgen05, fp16 operands, one pass (same speed; 11-bit mantissa = TF32-class operands)
+    # "strict" tcgen05, fp16 operands with hi + lo activation pairs through the image branch and fully split small GEMMs:
+    #          |d logBB| <= 1e-3 against the fp32 reference at trained output scale (DESIGN section 2)
+    precision = _DEFAULT_PRECISION
+
+    # Run-time caches that must not travel with the module: CUDA graphs, streams and events cannot be pickled, and a
+    # copy must not share another instance's captured buffers.  The reference pickles the whole model right after its
+    # eval loop (20250113.py:229-244), i.e. AFTER graphs have been captured, and deep-copies work the same way
+    # (copy.deepcopy goes through __reduce_ex__ -> __getstate__).
+    _RUNTIME_STATE = ("_graphs", "_chunk_graphs", "_host_pipe", "_side_stream", "_sig_tensors", "_stack_cache")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._RUNTIME_STATE:
+            state.pop(k, None)
+        return state
 
     def set_precision(self, precision: str):
-        assert precision in ("fp32", "bf16")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision {precision!r}: one of {PRECISIONS}")
+        if getattr(self, "kind", None) == "big" and precision in ("fp16", "strict"):
+            raise ValueError("the big variant (20250107) is built for the fp32 and bf16 modes")
         for m in self.modules():
             if isinstance(m, _KernelModule):
                 m.precision = precision
@@ -100,8 +123,9 @@ class MultiHeadAttentionFusion(_KernelModule):
         block-diagonal (heads, heads*hidden) operand (exact: the off-diagonal zeros contribute nothing), both bf16,
         cached until any of the 4*heads tensors changes."""
         from . import ops
+        fmt, split = ag.TENSOR_CORE[self.precision]
         tensors = [t for head in self.attention_heads for t in (head[0].weight, head[0].bias, head[2].weight, head[2].bias)]
-        key = tuple((t.data_ptr(), t._version) for t in tensors) + (ag._weight_epoch,)
+        key = tuple((t.data_ptr(), t._version) for t in tensors) + (ag._weight_epoch, fmt, split)
         hit = getattr(self, "_stack_cache", None)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -109,23 +133,25 @@ class MultiHeadAttentionFusion(_KernelModule):
             nh, hid = len(self.attention_heads), self.attention_heads[0][0].out_features
             w1 = torch.cat([h[0].weight for h in self.attention_heads], dim=0)          # (nh*hid, in)   (layout only)
             b1 = torch.cat([h[0].bias for h in self.attention_heads], dim=0).contiguous()
-            w2 = torch.zeros((nh, nh * hid), device=w1.device, dtype=torch.float32)
+            w2 = ops.fill_zero(torch.empty((nh, nh * hid), device=w1.device, dtype=torch.float32))
             for i, h in enumerate(self.attention_heads):
                 ops.copy2d(h[2].weight.reshape(1, hid), w2[i:i + 1, i * hid:(i + 1) * hid])
             b2 = torch.cat([h[2].bias for h in self.attention_heads], dim=0).contiguous()
-            val = (ops.cast_bf16(w1.contiguous()), b1, ops.cast_bf16(w2), b2, nh, hid)
+            val = (ops.cast16(w1.contiguous(), fmt, want_lo=split), b1, ops.cast16(w2, fmt, want_lo=split), b2, nh, hid)
         self._stack_cache = (key, val)
         return val
 
     def forward(self, x1, x2):
         both = ag.concat_cols(x1, x2)
-        if self.precision == "bf16" and not torch.is_grad_enabled():
-            # inference: 2 tensor-core GEMMs for all heads instead of 2 per head
+        if self.precision in ag.TENSOR_CORE and not torch.is_grad_enabled():
+            # inference: 2 tensor-core GEMMs for all heads instead of 2 per head (both operands split in the strict mode)
             from . import ops
-            w1, b1, w2, b2, nh, hid = self._stacked_heads()
-            _, h16 = ops.gemm_bf16(ops.cast_bf16(both), both.shape[1], w1, nh * hid, bias=b1, act="tanh", out_f32=False,
-                                   out_bf16=True)
-            scores, _ = ops.gemm_bf16(h16, nh * hid, w2, nh, bias=b2)
+            fmt, split = ag.TENSOR_CORE[self.precision]
+            (w1, w1_lo), b1, (w2, w2_lo), b2, nh, hid = self._stacked_heads()
+            a_hi, a_lo = ops.cast16(both, fmt, want_lo=split)
+            _, h16, h16_lo = ops.gemm_bf16(a_hi, both.shape[1], w1, nh * hid, bias=b1, act="tanh", out_f32=False, out_bf16=True,
+                                           fmt=fmt, a_lo=a_lo, w_lo=w1_lo, out16_lo=split)    # h16_lo is None unless split
+            scores, _ = ops.gemm_bf16(h16, nh * hid, w2, nh, bias=b2, fmt=fmt, a_lo=h16_lo, w_lo=w2_lo)
             out, _ = ops.fusion_softmax_mix_fwd(scores, both)
             return out
         scores = [self._lin(self._lin(both, head[0], "tanh"), head[2]) for head in self.attention_heads]
@@ -238,7 +264,7 @@ class TransformerCnnModel(_KernelModule):
     def _encoder_tensor_core_ok(self, seq: int) -> bool:
         attn = self.fingerprint_transformer.layers[0].self_attn
         head_dim = attn.embed_dim // attn.num_heads
-        return (self.precision == "bf16" and not self.training and (attn.num_heads == 1 or head_dim in (8, 16))
+        return (self.precision in ag.TENSOR_CORE and not self.training and (attn.num_heads == 1 or head_dim in (8, 16))
                 and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.fingerprint_transformer.parameters())))
 
     def _encoder_tensor_core(self, x, groups: int, seq: int):
@@ -246,6 +272,8 @@ class TransformerCnnModel(_KernelModule):
         -> FFN1 GEMM (+ReLU, bf16 out) -> FFN2 GEMM (+residual) -> LN], then fingerprint_fc.  9 launches per layer (7 for
         the many-small-heads variants, whose attention is one mma.sync flash kernel)."""
         from . import ops
+        fmt, split = ag.TENSOR_CORE[self.precision]
+        w16 = lambda w: ag.weight16(w, fmt)[0]
         F_ = x.shape[1]
         Fq = -(-F_ // 8) * 8                          # q | k | v each start on a 16-byte boundary
         rows = x.shape[0]
@@ -256,44 +284,51 @@ class TransformerCnnModel(_KernelModule):
             ops.copy2d(x, x32[:, :F_])
         else:
             x32 = x
-        x16 = ops.cast_bf16(x, ld=Fq)
+        x16, _ = ops.cast16(x, fmt, ld=Fq)
 
-        def padded_in_proj(w):                       # (3F, F) -> bf16 (3*Fq, Fq), zero rows/cols in the pads
-            out = torch.zeros((3 * Fq, Fq), device=w.device, dtype=torch.bfloat16)
+        def padded_in_proj(w):                       # (3F, F) -> 16-bit (3*Fq, Fq), zero rows/cols in the pads
+            out = ops.fill_zero(torch.empty((3 * Fq, Fq), device=w.device, dtype=ops._DT16[fmt]))
             for part in range(3):
-                ops.cast_bf16(w[part * F_:(part + 1) * F_], out=out[part * Fq: part * Fq + F_])
+                ops.cast16(w[part * F_:(part + 1) * F_], fmt, out=out[part * Fq: part * Fq + F_])
             return out
 
         def padded_in_bias(b):
-            out = torch.zeros((1, 3 * Fq), device=b.device, dtype=torch.float32)
+            out = ops.fill_zero(torch.empty((1, 3 * Fq), device=b.device, dtype=torch.float32))
             for part in range(3):
                 ops.copy2d(b[part * F_:(part + 1) * F_].reshape(1, F_), out[:, part * Fq: part * Fq + F_])
             return out.reshape(-1)
 
         for layer in self.fingerprint_transformer.layers:
             attn = layer.self_attn
-            w_in = ag.derived_weight(attn.in_proj_weight, "qkv_pad16", padded_in_proj)
+            w_in = ag.derived_weight(attn.in_proj_weight, f"qkv_pad16_{fmt}", padded_in_proj)
             b_in = ag.derived_weight(attn.in_proj_bias, "qkv_pad", padded_in_bias)
-            _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True)
+            _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True, fmt=fmt)
             if attn.num_heads == 1:
-                p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5)
+                p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, fmt=fmt)
                 ldp = p16.shape[1]
                 vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
-                _, a16 = ops.gemm_bf16_batched(groups, seq, F_, seq, p16, ldp, seq * ldp, vt, ldp, F_ * ldp, ld_out16=Fq)
-            else:       # 256 heads x 8 (2048-bit fingerprints): warp-level MMA flash kernel on the packed qkv, bf16 out
-                a16 = ops.attention_heads_bf16(qkv16, Fq, 2 * Fq, groups, seq, attn.num_heads, F_ // attn.num_heads, ld_out=Fq)
-            s32, _ = ops.gemm_bf16(a16, F_, ag.weight_bf16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32,
-                                   ld_out=Fq)
+                _, a16 = ops.gemm_bf16_batched(groups, seq, F_, seq, p16, ldp, seq * ldp, vt, ldp, F_ * ldp, ld_out16=Fq,
+                                               fmt=fmt)
+            else:       # 256 heads x 8 (2048-bit fingerprints): warp-level MMA flash kernel on the packed qkv, 16-bit out
+                a16 = ops.attention_heads_bf16(qkv16, Fq, 2 * Fq, groups, seq, attn.num_heads, F_ // attn.num_heads, ld_out=Fq,
+                                               fmt=fmt)
+            s32, _ = ops.gemm_bf16(a16, F_, w16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32,
+                                   ld_out=Fq, fmt=fmt)
             x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,
-                                                 bf16_ld=Fq)
-            _, h16 = ops.gemm_bf16(x16, F_, ag.weight_bf16(layer.linear1.weight), layer.linear1.out_features,
-                                   bias=layer.linear1.bias, act="relu", out_f32=False, out_bf16=True)
-            f32, _ = ops.gemm_bf16(h16, layer.linear1.out_features, ag.weight_bf16(layer.linear2.weight), F_,
-                                   bias=layer.linear2.bias, residual=x32, ld_out=Fq)
+                                                 bf16_ld=Fq, fmt=fmt)
+            _, h16 = ops.gemm_bf16(x16, F_, w16(layer.linear1.weight), layer.linear1.out_features,
+                                   bias=layer.linear1.bias, act="relu", out_f32=False, out_bf16=True, fmt=fmt)
+            f32, _ = ops.gemm_bf16(h16, layer.linear1.out_features, w16(layer.linear2.weight), F_,
+                                   bias=layer.linear2.bias, residual=x32, ld_out=Fq, fmt=fmt)
             x32, x16 = ops.layernorm_fwd_pitched(f32, F_, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, ld_y=Fq,
-                                                 bf16_ld=Fq)
+                                                 bf16_ld=Fq, fmt=fmt)
         fc = self.fingerprint_fc[0]
-        out, _ = ops.gemm_bf16(x16, F_, ag.weight_bf16(fc.weight), fc.out_features, bias=fc.bias, act="relu")
+        if split:       # strict mode: fingerprint_fc with both operands split (the encoder itself is insensitive: 3e-5)
+            x_hi, x_lo = ops.cast16(x32[:, :F_], fmt, ld=Fq, want_lo=True)
+            w_hi, w_lo = ag.weight16(fc.weight, fmt, True)
+            out, _ = ops.gemm_bf16(x_hi, F_, w_hi, fc.out_features, bias=fc.bias, act="relu", fmt=fmt, a_lo=x_lo, w_lo=w_lo)
+        else:
+            out, _ = ops.gemm_bf16(x16, F_, w16(fc.weight), fc.out_features, bias=fc.bias, act="relu", fmt=fmt)
         return out
 
     def _head(self, x):
@@ -318,7 +353,7 @@ class TransformerCnnModel(_KernelModule):
     def _image_branch(self, image):
         side = self.IMAGE_SIDE
         mods = list(self.image_cnn)
-        if (self.precision == "bf16" and side == 128
+        if (self.precision in ag.TENSOR_CORE and side == 128
                 and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.image_cnn.parameters()))):
             if self.kind == "big":
                 x = self._image_branch_im2col(image, mods)
@@ -378,10 +413,11 @@ class TransformerCnnModel(_KernelModule):
         the (H,W,C)-re-laid fc weight.  No activation leaves the chip in fp32 and the flatten is free (NHWC rows ARE
         the fc's K-major A operand)."""
         from . import ops
+        fmt, split = ag.TENSOR_CORE[self.precision]
         conv1, conv2, fc = mods[0], mods[3], mods[7]
-        w1 = ag.derived_weight(conv1.weight, "conv_umma", ops.conv3x3_prepare_bf16)
-        w2 = ag.derived_weight(conv2.weight, "conv_umma", ops.conv3x3_prepare_bf16)
-        wfc = ag.derived_weight(fc.weight, "hwc_bf16", lambda w: ops.fc_weight_to_hwc_bf16(w, 64, 32 * 32))
+        w1 = ag.derived_weight(conv1.weight, f"conv_umma_{fmt}", lambda w: ops.conv3x3_prepare_bf16(w, fmt))
+        w2 = ag.derived_weight(conv2.weight, f"conv_umma_{fmt}", lambda w: ops.conv3x3_prepare_bf16(w, fmt))
+        wfc = ag.derived_weight(fc.weight, f"hwc_{fmt}", lambda w: ops.fc_weight_to_hwc_bf16(w, 64, 32 * 32, fmt))
         img = image if image.is_contiguous() else image.contiguous()
         n = img.numel() // (3 * 128 * 128)
         img = img.reshape(n, 3 * 128 * 128)
@@ -390,11 +426,19 @@ class TransformerCnnModel(_KernelModule):
         for a in range(0, n, chunk):
             part = img[a:a + chunk]
             stats = ops.u8_image_stats(part) if part.dtype == torch.uint8 else None
-            y1 = ops.conv1_from_image_bf16(part, w1, conv1.bias, stats)
-            y2 = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64)
-            flat = y2.view(y2.shape[0], 65536)
-            o, _ = ops.gemm_bf16(flat, 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
-                                 split_k=ops.fixed_split_k(65536))
+            if split:
+                # strict mode: every activation of the branch is a (hi, lo) fp16 pair -- a depiction is mostly one
+                # background value, so the rounding of a single 16-bit activation is the SAME at every background pixel
+                # and adds up coherently through conv1 -> conv2 -> Linear(65536, 128); the lo parts remove it
+                y1, y1_lo = ops.conv1_from_image_bf16(part, w1, conv1.bias, stats, fmt=fmt, split=True)
+                y2, y2_lo = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64, fmt=fmt, x_lo=y1_lo)
+                o, _ = ops.gemm_bf16(y2.view(y2.shape[0], 65536), 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
+                                     split_k=ops.fixed_split_k(65536), fmt=fmt, a_lo=y2_lo.view(y2.shape[0], 65536))
+            else:
+                y1 = ops.conv1_from_image_bf16(part, w1, conv1.bias, stats, fmt=fmt)
+                y2 = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64, fmt=fmt)
+                o, _ = ops.gemm_bf16(y2.view(y2.shape[0], 65536), 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
+                                     split_k=ops.fixed_split_k(65536), fmt=fmt)
             outs.append(o)
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
@@ -429,7 +473,16 @@ class TransformerCnnModel(_KernelModule):
         return (ag._weight_epoch, self._sig_tensors[0].data_ptr()) + tuple(t._version for t in self._sig_tensors)
 
     def _graph_signature(self, fingerprint, image, groups):
-        return (fingerprint.shape[0], groups, image.dtype, tuple(image.shape), self.precision, self._weight_signature(),
+        if self.precision == "fp32":
+            # the fp32 kernels read the parameters and BatchNorm buffers in place (no derived copies), so a captured graph
+            # stays valid across in-place weight updates: key it on storage identity only.  A per-epoch validation loop
+            # (20250113.py:195-203) then replays one graph instead of re-capturing after every optimizer step.
+            if self._sig_tensors is None:
+                self._sig_tensors = list(self.parameters()) + list(self.buffers())
+            weights = tuple(t.data_ptr() for t in self._sig_tensors)
+        else:
+            weights = self._weight_signature()
+        return (fingerprint.shape[0], groups, image.dtype, tuple(image.shape), self.precision, weights,
                 fingerprint.device.index)
 
     def _forward_graphed(self, fingerprint, image, groups):
@@ -467,6 +520,10 @@ class TransformerCnnModel(_KernelModule):
 
     def forward_groups(self, fingerprint, image, groups: int = 1):
         """``groups`` independent reference batches of equal size stacked along dim 0 (see _forward_groups_eager)."""
+        if fingerprint.is_cuda and fingerprint.device.index != torch.cuda.current_device():
+            # kernels are enqueued on the CURRENT device's stream: make the tensors' device current for the call
+            with torch.cuda.device(fingerprint.device):
+                return self.forward_groups(fingerprint, image, groups)
         from . import ops
         if (self.use_cuda_graphs and not self.training and not torch.is_grad_enabled() and fingerprint.is_cuda
                 and fingerprint.shape[0] <= self.graph_max_rows and not ops.KERNEL_TIMER.names
@@ -490,7 +547,7 @@ class TransformerCnnModel(_KernelModule):
             # every other path gets the exact ToTensor + per-molecule z-score first
             if not image.is_cuda:
                 raise RuntimeError("bbbp_b200 models run on CUDA (sm_100a) tensors only: there is no CPU fallback")
-            if not (self.precision == "bf16" and self.kind != "big" and not torch.is_grad_enabled()):
+            if not (self.precision in ag.TENSOR_CORE and self.kind != "big" and not torch.is_grad_enabled()):
                 from . import ops
                 image = ops.u8_zscore(image.reshape(fingerprint.shape[0], -1).contiguous())
         else:
@@ -578,6 +635,10 @@ class TransformerCnnModel(_KernelModule):
         ``out_host`` buffer for two calls in flight."""
         assert not self.training, "call model.eval() first"
         dev = next(self.parameters()).device
+        if dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return self.predict_from_host(fingerprint_host, image_host, batch_size, chunk_molecules, packed, out_host,
+                                              return_device, synchronize)
         n = fingerprint_host.shape[0]
         chunk = max(1, chunk_molecules // batch_size) * batch_size
         scores = torch.empty((n,), device=dev, dtype=torch.float32)
@@ -746,6 +807,9 @@ class MlpModel(_KernelModule):
 
     def forward(self, fingerprint, image):
         self._check_inputs(fingerprint, image)
+        if fingerprint.device.index != torch.cuda.current_device():
+            with torch.cuda.device(fingerprint.device):
+                return self.forward(fingerprint, image)
         fused = self.attention_fusion(self._branch(fingerprint, self.fingerprint_fc), self._branch(image, self.image_fc))
         return TransformerCnnModel._head(self, fused)
 

@@ -15,6 +15,10 @@ from ._lib import lib, check
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 _ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2, 0: 0, 1: 1, 2: 2}
 
+# 16-bit operand formats of the tensor-core entry points (include/bbbp_b200.h: BBBP_FMT_*)
+FMT_BF16, FMT_F16 = 0, 1
+_DT16 = {FMT_BF16: torch.bfloat16, FMT_F16: torch.float16}
+
 _SM_COUNT = {}
 
 
@@ -136,68 +140,104 @@ def cast_bf16(x: torch.Tensor, ld: int | None = None, out: torch.Tensor | None =
     return out
 
 
+def cast16(x: torch.Tensor, fmt: int = FMT_BF16, ld: int | None = None, want_lo: bool = False, out: torch.Tensor | None = None):
+    """(rows, cols) float32 -> (rows, ld) 16-bit rows in format ``fmt`` (pad columns zero, ld a multiple of 8).  With
+    ``want_lo`` also the low part ``rn(x - hi)``: returns (hi, lo | None).  128-bit stores (one thread = 8 columns).
+    ``out``: a pitched 2-D destination view for hi (row stride = pitch, width = pad-to, both multiples of 8)."""
+    rows, cols = x.shape
+    if out is not None:
+        assert not want_lo and out.shape[0] == rows
+        check(lib.bbbp_cast16(fmt, x.data_ptr(), x.stride(0), out.data_ptr(), None, out.stride(0), rows, cols, out.shape[1],
+                              _stream()), "cast16")
+        return out, None
+    ld = -(-cols // 8) * 8 if ld is None else ld
+    hi = torch.empty((rows, ld), device=x.device, dtype=_DT16[fmt])
+    lo = torch.empty((rows, ld), device=x.device, dtype=_DT16[fmt]) if want_lo else None
+    check(lib.bbbp_cast16(fmt, x.data_ptr(), x.stride(0), hi.data_ptr(), _ptr(lo), ld, rows, cols, ld, _stream()), "cast16")
+    return hi, lo
+
+
 def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, out_bf16=False, split_k=1,
-              ld_out=None, ld_out16=None):
-    """act(a16[:, :K] @ w16[:N, :K]^T + bias) (+ residual) on the tcgen05 path.  Returns (f32 | None, bf16 | None);
-    outputs are (M, ld) buffers whose first N columns are the result (bf16 pad columns are zero)."""
+              ld_out=None, ld_out16=None, fmt=FMT_BF16, a_lo=None, w_lo=None, out16_lo=None):
+    """act(a16[:, :K] @ w16[:N, :K]^T + bias) (+ residual) on the tcgen05 path.  Returns (f32 | None, 16-bit | None);
+    outputs are (M, ld) buffers whose first N columns are the result (16-bit pad columns are zero).  ``fmt``: operand
+    format; ``a_lo`` / ``w_lo``: optional low parts (one more MMA each per K step); ``out16_lo`` (True / False, default
+    None): return a 3-tuple (f32, hi, lo) whose lo is the low part of the 16-bit output when True, None when False."""
     M = a16.shape[0]
     ld_out = N if ld_out is None else ld_out
     ld16 = -(-N // 8) * 8 if ld_out16 is None else ld_out16
     o32 = torch.empty((M, ld_out), device=a16.device, dtype=torch.float32) if out_f32 else None
-    o16 = torch.empty((M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
+    o16 = torch.empty((M, ld16), device=a16.device, dtype=_DT16[fmt]) if out_bf16 else None
+    o16lo = torch.empty((M, ld16), device=a16.device, dtype=_DT16[fmt]) if (out_bf16 and out16_lo) else None
     ws_bytes = lib.bbbp_gemm_bf16_workspace(M, N, split_k)
     ws = torch.empty((ws_bytes,), device=a16.device, dtype=torch.uint8) if ws_bytes else None
     if o16 is not None and ws_bytes and ld16 > N:
-        o16[:, N:].zero_()          # the split-K finish kernel writes only the N result columns
-    check(lib.bbbp_gemm_bf16(M, N, K, a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), _ptr(bias),
-                             _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(o32), ld_out, _ptr(o16),
-                             ld16, _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
-    return o32, o16
+        fill_zero(o16[:, N:])          # the split-K finish kernel writes only the N result columns
+        if o16lo is not None:
+            fill_zero(o16lo[:, N:])
+    check(lib.bbbp_gemm16(fmt, M, N, K, a16.data_ptr(), _ptr(a_lo), a16.stride(0), w16.data_ptr(), _ptr(w_lo), w16.stride(0),
+                          _ptr(bias), _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(o32), ld_out,
+                          _ptr(o16), _ptr(o16lo), ld16, _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm16")
+    return (o32, o16, o16lo) if out16_lo is not None else (o32, o16)
+
+
+def fill_zero(t: torch.Tensor) -> torch.Tensor:
+    """Zero a (possibly pitched) 2-D view or a contiguous tensor with the library's fill kernel."""
+    if t.numel() == 0:
+        return t
+    if t.dim() == 2 and not t.is_contiguous():
+        rows, cols, pitch = t.shape[0], t.shape[1], t.stride(0)
+    else:
+        assert t.is_contiguous()
+        rows, cols, pitch = 1, t.numel(), t.numel()
+    esz = t.element_size()
+    check(lib.bbbp_fill_zero(t.data_ptr(), rows, cols * esz, pitch * esz, _stream()), "fill_zero")
+    return t
 
 
 def gemm_bf16_batched(batches, M, N, K, a16, lda, a_bs, w16, ldw, w_bs, out_bf16=True, out_f32=False, ld_out16=None,
-                      ld_out=None):
+                      ld_out=None, fmt=FMT_BF16):
     """out[b] = A[b] @ W[b]^T for b < batches; outputs are (batches*M, ld) with batch b at rows [b*M, (b+1)*M)."""
     ld16 = -(-N // 8) * 8 if ld_out16 is None else ld_out16
     ld32 = N if ld_out is None else ld_out
     o32 = torch.empty((batches * M, ld32), device=a16.device, dtype=torch.float32) if out_f32 else None
-    o16 = torch.empty((batches * M, ld16), device=a16.device, dtype=torch.bfloat16) if out_bf16 else None
-    check(lib.bbbp_gemm_bf16_batched(batches, M, N, K, a16.data_ptr(), lda, a_bs, w16.data_ptr(), ldw, w_bs, _ptr(o32), ld32,
-                                     M * ld32, _ptr(o16), ld16, M * ld16, _stream()), "gemm_bf16_batched")
+    o16 = torch.empty((batches * M, ld16), device=a16.device, dtype=_DT16[fmt]) if out_bf16 else None
+    check(lib.bbbp_gemm16_batched(fmt, batches, M, N, K, a16.data_ptr(), lda, a_bs, w16.data_ptr(), ldw, w_bs, _ptr(o32), ld32,
+                                  M * ld32, _ptr(o16), ld16, M * ld16, _stream()), "gemm16_batched")
     return o32, o16
 
 
-def softmax_rows_scaled_bf16(scores: torch.Tensor, cols: int, scale: float) -> torch.Tensor:
-    """(rows, ld) fp32 logits -> (rows, ceil8(cols)) bf16 softmax(scale * logits) with zero pad columns."""
+def softmax_rows_scaled_bf16(scores: torch.Tensor, cols: int, scale: float, fmt=FMT_BF16) -> torch.Tensor:
+    """(rows, ld) fp32 logits -> (rows, ceil8(cols)) 16-bit softmax(scale * logits) with zero pad columns."""
     rows = scores.shape[0]
     ldp = -(-cols // 8) * 8
-    p = torch.empty((rows, ldp), device=scores.device, dtype=torch.bfloat16)
-    check(lib.bbbp_softmax_rows_scaled_bf16(scores.data_ptr(), scores.stride(0), p.data_ptr(), ldp, rows, cols, float(scale),
-                                            _stream()), "softmax_rows_scaled_bf16")
+    p = torch.empty((rows, ldp), device=scores.device, dtype=_DT16[fmt])
+    check(lib.bbbp_softmax_rows_scaled16(fmt, scores.data_ptr(), scores.stride(0), p.data_ptr(), ldp, rows, cols, float(scale),
+                                         _stream()), "softmax_rows_scaled16")
     return p
 
 
-def attention_scores_softmax_bf16(q16, k16, ld, groups, seq, head_dim, scale):
+def attention_scores_softmax_bf16(q16, k16, ld, groups, seq, head_dim, scale, fmt=FMT_BF16):
     """softmax(scale * Q K^T) per group as bf16 (groups*seq, ldp); q16 / k16 are views into the packed qkv buffer.
     seq <= 256: one GEMM with the softmax in its TMEM epilogue.  Wider scopes: batched GEMM to fp32 logits, then a
     row-softmax kernel (the S x S logits are materialised: 4*S*S bytes per group)."""
     if seq > 256:
         ld_s = -(-seq // 4) * 4
         s32, _ = gemm_bf16_batched(groups, seq, seq, head_dim, q16, ld, seq * ld, k16, ld, seq * ld, out_bf16=False,
-                                   out_f32=True, ld_out=ld_s)
-        return softmax_rows_scaled_bf16(s32, seq, scale)
+                                   out_f32=True, ld_out=ld_s, fmt=fmt)
+        return softmax_rows_scaled_bf16(s32, seq, scale, fmt)
     ldp = -(-seq // 8) * 8
-    p = torch.empty((groups * seq, ldp), device=q16.device, dtype=torch.bfloat16)
+    p = torch.empty((groups * seq, ldp), device=q16.device, dtype=_DT16[fmt])
     t0 = KERNEL_TIMER.start("attn_scores")
-    check(lib.bbbp_attention_scores_softmax_bf16(groups, seq, head_dim, q16.data_ptr(), ld, k16.data_ptr(), ld, seq * ld,
-                                                 float(scale), p.data_ptr(), ldp, _stream()), "attention_scores_softmax")
+    check(lib.bbbp_attention_scores_softmax16(fmt, groups, seq, head_dim, q16.data_ptr(), ld, k16.data_ptr(), ld, seq * ld,
+                                              float(scale), p.data_ptr(), ldp, _stream()), "attention_scores_softmax")
     KERNEL_TIMER.stop("attn_scores", t0, groups * seq)
     return p
 
 
 def transpose_bf16(src, batches, rows, cols, ld_src, src_bs, ld_dst):
     """(batches, rows, cols) pitched bf16 -> (batches, cols, ld_dst) with zero fill of columns >= rows."""
-    dst = torch.empty((batches, cols, ld_dst), device=src.device, dtype=torch.bfloat16)
+    dst = torch.empty((batches, cols, ld_dst), device=src.device, dtype=src.dtype)
     check(lib.bbbp_transpose_bf16(batches, rows, cols, src.data_ptr(), ld_src, src_bs, dst.data_ptr(), ld_dst, cols * ld_dst,
                                   _stream()), "transpose_bf16")
     return dst
@@ -247,11 +287,11 @@ def conv3x3_flip_weights(w):
 
 
 # ---- tcgen05 image branch (inference) ---------------------------------------------------------------------------------
-def conv3x3_prepare_bf16(w: torch.Tensor) -> torch.Tensor:
+def conv3x3_prepare_bf16(w: torch.Tensor, fmt=FMT_BF16) -> torch.Tensor:
     Cout, Cin = w.shape[:2]
     n = lib.bbbp_conv3x3_prepared_bytes(Cin, Cout)
     wp = torch.empty((n,), device=w.device, dtype=torch.uint8)
-    check(lib.bbbp_conv3x3_prepare_bf16(w.data_ptr(), wp.data_ptr(), Cin, Cout, _stream()), "conv3x3_prepare_bf16")
+    check(lib.bbbp_conv3x3_prepare16(fmt, w.data_ptr(), wp.data_ptr(), Cin, Cout, _stream()), "conv3x3_prepare16")
     return wp
 
 
@@ -262,15 +302,20 @@ def image_to_nhwc8_bf16(img: torch.Tensor, C=3, H=128, W=128) -> torch.Tensor:
     return out
 
 
-def conv3x3_relu_pool_bf16(x_nhwc: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, Cout: int) -> torch.Tensor:
+def conv3x3_relu_pool_bf16(x_nhwc: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, Cout: int, fmt=FMT_BF16,
+                           x_lo: torch.Tensor | None = None):
+    """tcgen05 conv3x3 + bias + ReLU + 2x2 max-pool on NHWC 16-bit activations.  ``x_lo`` (strict mode): the low part of a
+    (hi, lo) input pair; the output is then a (hi, lo) pair as well -> returns (y, y_lo)."""
     N, H, W, Cin_pad = x_nhwc.shape
-    y = torch.empty((N, H // 2, W // 2, Cout), device=x_nhwc.device, dtype=torch.bfloat16)
+    y = torch.empty((N, H // 2, W // 2, Cout), device=x_nhwc.device, dtype=_DT16[fmt])
+    y_lo = torch.empty_like(y) if x_lo is not None else None
     name = "conv1" if Cin_pad == 8 else "conv2"
     t0 = KERNEL_TIMER.start(name)
-    check(lib.bbbp_conv3x3_relu_pool_bf16(x_nhwc.data_ptr(), wprep.data_ptr(), bias.data_ptr(), y.data_ptr(), N, Cin_pad,
-                                          Cout, H, W, _stream()), "conv3x3_relu_pool_bf16")
+    check(lib.bbbp_conv3x3_relu_pool16(fmt, 2 if x_lo is not None else 1, x_nhwc.data_ptr(), _ptr(x_lo), wprep.data_ptr(),
+                                       bias.data_ptr(), y.data_ptr(), _ptr(y_lo), N, Cin_pad, Cout, H, W, _stream()),
+          "conv3x3_relu_pool16")
     KERNEL_TIMER.stop(name, t0, N)
-    return y
+    return y if x_lo is None else (y, y_lo)
 
 
 def u8_image_stats(img_u8: torch.Tensor) -> torch.Tensor:
@@ -282,23 +327,26 @@ def u8_image_stats(img_u8: torch.Tensor) -> torch.Tensor:
     return stats
 
 
-def conv1_from_image_bf16(img: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, stats=None, H=128, W=128):
-    """conv1 + ReLU + pool straight from the planar (N, 3, H, W) input: fp32 (standardised) or uint8 (+ stats)."""
+def conv1_from_image_bf16(img: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, stats=None, H=128, W=128,
+                          fmt=FMT_BF16, split=False):
+    """conv1 + ReLU + pool straight from the planar (N, 3, H, W) input: fp32 (standardised) or uint8 (+ stats).
+    ``split`` (strict mode): the producers stage the image as a (hi, lo) pair and the output is a (hi, lo) pair."""
     N = img.numel() // (3 * H * W)
-    y = torch.empty((N, H // 2, W // 2, 32), device=img.device, dtype=torch.bfloat16)
+    y = torch.empty((N, H // 2, W // 2, 32), device=img.device, dtype=_DT16[fmt])
+    y_lo = torch.empty_like(y) if split else None
     is_u8 = img.dtype == torch.uint8
     assert is_u8 or img.dtype == torch.float32
     t0 = KERNEL_TIMER.start("conv1")
-    check(lib.bbbp_conv1_from_image_bf16(img.data_ptr(), int(is_u8), _ptr(stats), wprep.data_ptr(), bias.data_ptr(),
-                                         y.data_ptr(), N, H, W, _stream()), "conv1_from_image_bf16")
+    check(lib.bbbp_conv1_from_image16(fmt, 2 if split else 1, img.data_ptr(), int(is_u8), _ptr(stats), wprep.data_ptr(),
+                                      bias.data_ptr(), y.data_ptr(), _ptr(y_lo), N, H, W, _stream()), "conv1_from_image16")
     KERNEL_TIMER.stop("conv1", t0, N)
-    return y
+    return (y, y_lo) if split else y
 
 
-def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int) -> torch.Tensor:
+def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int, fmt=FMT_BF16) -> torch.Tensor:
     rows = w.shape[0]
-    out = torch.empty((rows, C * HW), device=w.device, dtype=torch.bfloat16)
-    check(lib.bbbp_fc_weight_to_hwc_bf16(w.data_ptr(), out.data_ptr(), rows, C, HW, _stream()), "fc_weight_to_hwc")
+    out = torch.empty((rows, C * HW), device=w.device, dtype=_DT16[fmt])
+    check(lib.bbbp_fc_weight_to_hwc16(fmt, w.data_ptr(), out.data_ptr(), rows, C, HW, _stream()), "fc_weight_to_hwc")
     return out
 
 
@@ -362,13 +410,15 @@ def attn_softmax_bwd(p, dpd, scale, dropout_p=0.0, seed=0, seed_dev=None, row_ba
 
 
 def attention_heads_bf16(qkv16: torch.Tensor, k_offset: int, v_offset: int, groups: int, seq: int, heads: int, head_dim: int,
-                         ld_out: int | None = None) -> torch.Tensor:
+                         ld_out: int | None = None, fmt=FMT_BF16) -> torch.Tensor:
     """Multi-head attention (head_dim 8 or 16) on the packed bf16 in_proj output; returns (groups*seq, ld_out) bf16."""
     E = heads * head_dim
     ld_out = -(-E // 8) * 8 if ld_out is None else ld_out
-    out = (torch.empty if ld_out == E else torch.zeros)((groups * seq, ld_out), device=qkv16.device, dtype=torch.bfloat16)
-    check(lib.bbbp_attention_heads_bf16(qkv16.data_ptr(), qkv16.stride(0), k_offset, v_offset, out.data_ptr(), ld_out, groups, seq,
-                                        heads, head_dim, _stream()), "attention_heads_bf16")
+    out = torch.empty((groups * seq, ld_out), device=qkv16.device, dtype=_DT16[fmt])
+    if ld_out != E:
+        fill_zero(out[:, E:])
+    check(lib.bbbp_attention_heads16(fmt, qkv16.data_ptr(), qkv16.stride(0), k_offset, v_offset, out.data_ptr(), ld_out, groups,
+                                     seq, heads, head_dim, _stream()), "attention_heads16")
     return out
 
 
@@ -386,14 +436,14 @@ def add_layernorm_fwd(x, res, gamma, beta, eps=1e-5, save=False, bf16_ld=0):
     return y, s, mean, rstd, y16
 
 
-def layernorm_fwd_pitched(x, dim, gamma, beta, eps=1e-5, ld_y=None, bf16_ld=0):
-    """LN over the first ``dim`` columns of a pitched (rows, ld) buffer -> (rows, ld_y) fp32 [+ (rows, bf16_ld) bf16]."""
+def layernorm_fwd_pitched(x, dim, gamma, beta, eps=1e-5, ld_y=None, bf16_ld=0, fmt=FMT_BF16):
+    """LN over the first ``dim`` columns of a pitched (rows, ld) buffer -> (rows, ld_y) fp32 [+ (rows, bf16_ld) 16-bit]."""
     rows = x.shape[0]
     ld_y = dim if ld_y is None else ld_y
     y = torch.empty((rows, ld_y), device=x.device, dtype=torch.float32)
-    y16 = torch.empty((rows, bf16_ld), device=x.device, dtype=torch.bfloat16) if bf16_ld else None
-    check(lib.bbbp_add_layernorm_fwd_pitched_f32(x.data_ptr(), x.stride(0), None, 0, gamma.data_ptr(), beta.data_ptr(),
-                                                 y.data_ptr(), ld_y, _ptr(y16), bf16_ld, rows, dim, float(eps), _stream()),
+    y16 = torch.empty((rows, bf16_ld), device=x.device, dtype=_DT16[fmt]) if bf16_ld else None
+    check(lib.bbbp_add_layernorm_fwd_pitched16(fmt, x.data_ptr(), x.stride(0), None, 0, gamma.data_ptr(), beta.data_ptr(),
+                                               y.data_ptr(), ld_y, _ptr(y16), bf16_ld, rows, dim, float(eps), _stream()),
           "add_layernorm_fwd_pitched")
     return y, y16
 

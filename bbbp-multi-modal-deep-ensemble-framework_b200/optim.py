@@ -24,6 +24,32 @@ class AdamW(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self._tables = {}
+        self._step_mirror = {}
+
+    # -- state layout shared with torch.optim.AdamW ------------------------------------------------------------------------
+    # torch keeps the step count per parameter (state[p]["step"], a CPU float32 scalar); this optimizer counts per group
+    # (one launch updates the whole group).  Both are maintained so checkpoints interchange in either direction: a stock
+    # AdamW state_dict loaded here resumes bias correction at its step, and ours loads into stock AdamW.
+    def _group_step(self, gi, group, params) -> int:
+        if "step" not in group:
+            prior = [float(self.state[p]["step"]) for p in params if "step" in self.state.get(p, {})]
+            group["step"] = int(max(prior)) if prior else 0
+        return group["step"]
+
+    def _mirror_step(self, gi, group, params) -> None:
+        shared = self._step_mirror.get(gi)
+        if shared is None:
+            shared = self._step_mirror[gi] = torch.zeros((), dtype=torch.float32)
+        shared.fill_(float(group["step"]))
+        for p in params:
+            st = self.state[p]
+            if st.get("step") is not shared:
+                st["step"] = shared
+
+    @staticmethod
+    def _to_device(values, dtype, dev):
+        """Small host table -> device through pinned memory (no synchronous pageable copy in the middle of training)."""
+        return torch.tensor(values, dtype=dtype, pin_memory=True).to(dev, non_blocking=True)
 
     def _table(self, gi, params):
         """Device tables for one param group: [param | grad | exp_avg | exp_avg_sq] pointers, sizes, chunks."""
@@ -47,8 +73,8 @@ class AdamW(torch.optim.Optimizer):
             for off in range(0, n, _CHUNK):
                 chunk_t.append(t)
                 chunk_o.append(off)
-        tab = (torch.tensor(ptrs, dtype=torch.int64).to(dev), torch.tensor(sizes, dtype=torch.int64).to(dev),
-               torch.tensor(chunk_t, dtype=torch.int32).to(dev), torch.tensor(chunk_o, dtype=torch.int64).to(dev),
+        tab = (self._to_device(ptrs, torch.int64, dev), self._to_device(sizes, torch.int64, dev),
+               self._to_device(chunk_t, torch.int32, dev), self._to_device(chunk_o, torch.int64, dev),
                len(params), len(chunk_t))
         self._tables[gi] = (key, tab)
         return tab
@@ -110,10 +136,11 @@ class AdamW(torch.optim.Optimizer):
     def graph_advance(self, plan, grad_scale: float = 1.0):
         """Before each replay: bump the step counts and send this step's scalars (lr may have been changed by a torch
         LR scheduler) to the device as kernel parameters (bbbp_store_small)."""
-        for group, entry in zip(self.param_groups, plan):
+        for gi, (group, entry) in enumerate(zip(self.param_groups, plan)):
             if entry is None:
                 continue
-            group["step"] = group.get("step", 0) + 1
+            group["step"] = self._group_step(gi, group, entry["params"]) + 1
+            self._mirror_step(gi, group, entry["params"])
             b1, b2 = group["betas"]
             h = ops.adamw_hyper(group["lr"], b1, b2, group["eps"], group["weight_decay"], group["step"], grad_scale)
             ops.store_small(struct.pack("8f", *h), entry["hyper"])
@@ -131,8 +158,9 @@ class AdamW(torch.optim.Optimizer):
             for p in params:
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
                     raise RuntimeError("bbbp_b200.AdamW needs contiguous float32 CUDA parameters and gradients")
-            group["step"] = group.get("step", 0) + 1
+            group["step"] = self._group_step(gi, group, params) + 1
             ptrs, sizes, chunk_t, chunk_o, nt, nc = self._table(gi, params)
+            self._mirror_step(gi, group, params)
             b1, b2 = group["betas"]
             ops.adamw(ptrs, sizes, chunk_t, chunk_o, nt, nc, group["lr"], b1, b2, group["eps"], group["weight_decay"],
                       group["step"], grad_scale)

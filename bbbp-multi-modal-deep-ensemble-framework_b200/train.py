@@ -150,6 +150,9 @@ class GraphedTrainStep:
     def __call__(self, fingerprint, image, target):
         if not self.model.training:
             raise RuntimeError("GraphedTrainStep: call model.train() first")
+        if fingerprint.is_cuda and fingerprint.device.index != torch.cuda.current_device():
+            with torch.cuda.device(fingerprint.device):
+                return self(fingerprint, image, target)
         # a capture is tied to the parameter storage it updates in place: .to() / .cuda() after a capture re-captures
         key = (tuple(fingerprint.shape), tuple(image.shape), image.dtype, tuple(target.shape),
                getattr(self.model, "precision", None), fingerprint.device.index, next(self.model.parameters()).data_ptr())

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BBBP_ABI_VERSION 2
+#define BBBP_ABI_VERSION 3
 
 enum { BBBP_OK = 0, BBBP_EINVAL = -1, BBBP_ECUDA = -2, BBBP_EWORKSPACE = -3, BBBP_EUNSUPPORTED = -4 };
 
@@ -38,6 +38,10 @@ enum {
   BBBP_PREC_FP32 = 0, /* CUDA-core fp32 FMA everywhere (validation mode, 1e-4 class parity)       */
   BBBP_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 TMEM accumulation, fp32 statistics (default)  */
 };
+
+/* 16-bit operand format of the tensor-core entry points (the *16 functions; the *_bf16 names are the fmt = BF16 forms) */
+#define BBBP_FMT_BF16 0 /* 8-bit mantissa, fp32 range                                                              */
+#define BBBP_FMT_F16 1  /* 11-bit mantissa = the precision of a TF32 operand; conversions saturate at +-65504       */
 
 typedef void* bbbp_stream_t; /* cudaStream_t */
 
@@ -71,6 +75,15 @@ int bbbp_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, i
 int bbbp_cast_bf16(const float* src, int ld_src, void* dst_bf16, int ld_dst, int rows, int cols, int cols_pad,
                    bbbp_stream_t stream);
 
+/* dst[r][0:row_bytes) = 0 for r < rows, rows pitch_bytes apart (any alignment; 128-bit stores when everything is 16-byte
+ * aligned).  Pad columns of pitched operands, accumulators. */
+int bbbp_fill_zero(void* dst, long long rows, long long row_bytes, long long pitch_bytes, bbbp_stream_t stream);
+/* fp32 rows -> 16-bit rows in format fmt: dst_hi = rn(src), optional dst_lo = rn(src - dst_hi) (NULL to skip), zero fill of
+ * [cols, cols_pad).  cols_pad and ld_dst multiples of 8, destinations 16-byte aligned.  A (hi, lo) pair carries ~2x the
+ * mantissa of one 16-bit operand; the strict inference mode feeds both through the same weights. */
+int bbbp_cast16(int fmt, const float* src, int ld_src, void* dst_hi, void* dst_lo, int ld_dst, int rows, int cols, int cols_pad,
+                bbbp_stream_t stream);
+
 /* tcgen05 / TMEM / TMA GEMM: out = act( A[M,K] * W[N,K]^T + bias ) (+ residual), bf16 operands, fp32
  * accumulate.  A and W are bf16 row-major with K contiguous; lda/ldw in elements, multiples of 8, 16-byte
  * aligned bases.  Columns >= K are never read (TMA zero fill), so K need not be padded.
@@ -81,6 +94,22 @@ size_t bbbp_gemm_bf16_workspace(int M, int N, int split_k);
 int bbbp_gemm_bf16(int M, int N, int K, const void* A_bf16, int lda, const void* W_bf16, int ldw, const float* bias,
                    const float* residual, int ld_res, float* out_f32, int ld_out, void* out_bf16, int ld_out16,
                    int act, int split_k, void* workspace, size_t workspace_bytes, bbbp_stream_t stream);
+
+/* General form: operands in format fmt; optional lo parts A_lo / W_lo (same pitch as the hi parts, NULL to skip) add one
+ * MMA each per K step into the same TMEM accumulator: out = act((A_hi + A_lo) W_hi^T + A_hi W_lo^T + bias) (+ residual).
+ * The 16-bit output can be emitted as a (hi, lo) pair for the next split GEMM (out16_lo may be NULL). */
+int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi, const void* W_lo,
+                int ldw, const float* bias, const float* residual, int ld_res, float* out_f32, int ld_out, void* out16_hi,
+                void* out16_lo, int ld_out16, int act, int split_k, void* workspace, size_t workspace_bytes,
+                bbbp_stream_t stream);
+int bbbp_gemm16_batched(int fmt, int batches, int M, int N, int K, const void* A, int lda, long long a_batch_stride,
+                        const void* W, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
+                        long long out_batch_stride, void* out16, int ld_out16, long long out16_batch_stride,
+                        bbbp_stream_t stream);
+int bbbp_attention_scores_softmax16(int fmt, int groups, int seq, int head_dim, const void* q, int ldq, const void* k, int ldk,
+                                    long long group_stride, float scale, void* p_out, int ldp, bbbp_stream_t stream);
+int bbbp_softmax_rows_scaled16(int fmt, const float* scores, long long ld_scores, void* p_out, long long ld_p, long long rows,
+                               int cols, float scale, bbbp_stream_t stream);
 
 /* Batched form (blockIdx.z = batch): out[b] = A[b][M,K] * W[b][N,K]^T, no bias/activation; batch strides in elements
  * (multiples of 8 for the operands).  Used for the attention P V product with W = V^T. */
@@ -137,6 +166,16 @@ int bbbp_conv3x3_relu_pool_bf16(const void* x_nhwc, const void* wprep, const flo
  * The producers pack 3 channels to one bf16 chunk per pixel in registers; output as bbbp_conv3x3_relu_pool_bf16. */
 int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
                                const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream);
+/* General forms.  fmt: operand / output format.  split = 2 is the strict mode: the input is a (hi, lo) pair -- x_lo, or
+ * both parts formed by the first layer's producers from the fp32 / uint8 image -- each part staged as its own ring slot and
+ * multiplied against the same once-rounded weights into the same accumulators, and the output is emitted as a (hi, lo)
+ * pair (y_lo).  Built: (BF16, 1), (F16, 1), (F16, 2). */
+int bbbp_conv3x3_prepare16(int fmt, const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream);
+int bbbp_conv3x3_relu_pool16(int fmt, int split, const void* x_nhwc, const void* x_lo, const void* wprep, const float* bias,
+                             void* y_nhwc, void* y_lo, int N, int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream);
+int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
+                            const float* bias, void* y_nhwc, void* y_lo, int N, int H, int W, bbbp_stream_t stream);
+int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int C, int HW, bbbp_stream_t stream);
 /* stats[r] = {mean, 1/std} of img[r, 0:n] / 255 (population std, 0 -> 1), exact integer sums, fp64 finish */
 int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, bbbp_stream_t stream);
 /* Diagnostics: probe = DEVICE array of 16 uint64 cycle counters that CTA 0 of the tcgen05 conv kernels accumulates
@@ -192,6 +231,9 @@ int bbbp_attn_softmax_bwd_f32(const float* p, const float* dp_dropped, float* ds
 int bbbp_attention_heads_bf16(const void* qkv_bf16, int ld, int k_offset, int v_offset, void* out_bf16, int ld_out, int groups,
                               int seq, int heads, int head_dim, bbbp_stream_t stream);
 
+int bbbp_attention_heads16(int fmt, const void* qkv, int ld, int k_offset, int v_offset, void* out, int ld_out, int groups,
+                           int seq, int heads, int head_dim, bbbp_stream_t stream);
+
 /* ---- normalisation: nn.LayerNorm (post-norm residual, eps 1e-5) and nn.BatchNorm1d C:101 ------- */
 
 /* s = x + res (res may be NULL); y = LN(s)*gamma + beta.  Optional outputs: sum_out (= s), mean[rows],
@@ -204,6 +246,9 @@ int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, const float* ga
 int bbbp_add_layernorm_fwd_pitched_f32(const float* x, int ld_x, const float* res, int ld_res, const float* gamma,
                                        const float* beta, float* y, int ld_y, void* y_bf16, int ld_bf16, int rows, int dim,
                                        float eps, bbbp_stream_t stream);
+int bbbp_add_layernorm_fwd_pitched16(int fmt, const float* x, int ld_x, const float* res, int ld_res, const float* gamma,
+                                     const float* beta, float* y, int ld_y, void* y16, int ld16, int rows, int dim, float eps,
+                                     bbbp_stream_t stream);
 /* dx (= gradient wrt s, which is also the gradient of both x and res), dgamma[dim], dbeta[dim].
  * workspace: bbbp_layernorm_bwd_workspace() bytes (partials of dgamma / dbeta per row chunk, summed in a fixed order). */
 size_t bbbp_layernorm_bwd_workspace(int rows, int dim);

@@ -18,7 +18,7 @@ def test_header_symbols_all_exported():
 
 
 def test_abi_version_and_no_torch_in_signatures():
-    assert bbbp_b200.ABI_VERSION == 2
+    assert bbbp_b200.ABI_VERSION == 3
     header = open(_lib.HEADER_PATH).read()
     code = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
     assert "torch" not in code.lower() and "Tensor" not in code and "at::" not in code

@@ -70,6 +70,27 @@ def test_whole_model_pickles():
         assert torch.equal(a, b), k
 
 
+def test_pickle_and_deepcopy_drop_runtime_caches():
+    """The reference pickles the model right AFTER its eval loop (20250113.py:229-244), i.e. once CUDA graphs, streams and
+    staging buffers hang off the instance: those run-time caches must not travel (a CUDAGraph cannot be pickled)."""
+    import copy
+    model = bbbp_b200.MixedInputModel(167, 128)
+    unpicklable = lambda: None                                   # stands in for torch.cuda.CUDAGraph / Stream / Event
+    model._graphs = {"k": (unpicklable,)}
+    model._chunk_graphs = {"k": (unpicklable,)}
+    model._host_pipe = ("key", unpicklable)
+    model._side_stream = unpicklable
+    model._sig_tensors = list(model.parameters())
+    model.attention_fusion._stack_cache = ("key", unpicklable)
+    for clone in (pickle.loads(pickle.dumps(model)), copy.deepcopy(model)):
+        assert clone._graphs is None and clone._chunk_graphs is None and clone._side_stream is None
+        assert getattr(clone, "_host_pipe", None) is None and clone._sig_tensors is None
+        assert getattr(clone.attention_fusion, "_stack_cache", None) is None
+        for (k, a), (_, b) in zip(model.state_dict().items(), clone.state_dict().items()):
+            assert torch.equal(a, b), k
+    assert model._graphs is not None                             # the original keeps its caches
+
+
 def test_cpu_tensors_are_refused_loudly():
     model = bbbp_b200.MixedInputModelMLP(64, 128)
     with pytest.raises(RuntimeError, match="no CPU fallback"):

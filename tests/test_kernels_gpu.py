@@ -314,6 +314,31 @@ def test_dropout_mask_statistics_and_determinism(ops):
     assert torch.equal(ops.dropout(x[:1001], 0.0, 7), x[:1001])
 
 
+def test_dropout_masks_differ_across_sites_and_replay_steps(ops):
+    """Graph replay: every dropout site bakes seed_site = a + i*C into the capture and reads seed_step = b + s*C from device
+    memory.  The two must be combined so that (site i, step s) and (site i+1, step s-1) do NOT share a mask (an additive
+    combination did: the same mask travelled down the layer stack on successive steps)."""
+    C = 0xD1B54A32D192ED03
+    mask = (1 << 64) - 1
+    x = torch.ones(1 << 16).cuda()
+    site = lambda i: (12345 + i * C) & mask
+    def step(s):
+        v = (777 + s * C) & mask
+        return torch.tensor([v - (1 << 64) if v >= (1 << 63) else v], dtype=torch.int64).cuda()
+    m = {(i, s): ops.dropout(x, 0.5, site(i), seed_dev=step(s)) for i in range(3) for s in range(3)}
+    assert torch.equal(m[(1, 1)], ops.dropout(x, 0.5, site(1), seed_dev=step(1)))          # deterministic
+    keys = list(m)
+    for a in range(len(keys)):
+        for b in range(a + 1, len(keys)):
+            same = float((m[keys[a]] == m[keys[b]]).float().mean())
+            assert 0.45 < same < 0.55, (keys[a], keys[b], same)                            # independent fair coins agree half the time
+    # the attention kernels use the same combination
+    qkv = rnd(64, 3 * 24, seed=5).cuda()
+    o1, _ = ops.attention_fwd(qkv, 2, 32, 3, 8, 0.3, site(0), seed_dev=step(1))
+    o2, _ = ops.attention_fwd(qkv, 2, 32, 3, 8, 0.3, site(1), seed_dev=step(0))
+    assert not torch.equal(o1, o2)
+
+
 # ---- losses ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 32, 257, 5000])
 def test_mse_and_bce_losses(ops, n):
@@ -354,6 +379,41 @@ def test_fused_adamw_matches_torch_adamw_trajectory(cuda_device):
         close(b, a, 1e-7, rtol=1e-6, what="adamw params")
     for a, b in zip(ref_p, our_p):
         close(our_opt.state[b]["exp_avg_sq"], ref_opt.state[a]["exp_avg_sq"], 1e-10, rtol=2e-6, what="v")
+
+
+def test_adamw_state_interchanges_with_torch_adamw(cuda_device):
+    """Checkpoints move between torch.optim.AdamW and the fused optimizer in both directions: the per-parameter ``step``
+    of torch's state layout is honoured on load (bias correction resumes where it stopped) and mirrored on save."""
+    import bbbp_b200
+    shapes = [(40, 17), (9,)]
+    mk = lambda: [torch.nn.Parameter(rnd(*s, seed=300 + i).cuda()) for i, s in enumerate(shapes)]
+    grads = lambda k, ps: [rnd(*p.shape, seed=7000 + 10 * k + i).cuda() for i, p in enumerate(ps)]
+    ref_p, a_p = mk(), mk()
+    ref_opt = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-2)
+    a_opt = torch.optim.AdamW(a_p, lr=1e-3, weight_decay=1e-2)
+    for k in range(3):                                   # three stock steps on both
+        for opt, ps in ((ref_opt, ref_p), (a_opt, a_p)):
+            for p, g in zip(ps, grads(k, ps)):
+                p.grad = g
+            opt.step()
+    ours = bbbp_b200.AdamW(a_p, lr=1e-3, weight_decay=1e-2)
+    ours.load_state_dict(a_opt.state_dict())             # torch -> ours
+    for k in range(3, 5):
+        for opt, ps in ((ref_opt, ref_p), (ours, a_p)):
+            for p, g in zip(ps, grads(k, ps)):
+                p.grad = g
+            opt.step()
+    for a, b in zip(ref_p, a_p):
+        close(b, a, 1e-7, rtol=2e-6, what="torch -> bbbp resume")
+    assert float(ours.state[a_p[0]]["step"]) == 5.0
+    back = torch.optim.AdamW(a_p, lr=1e-3, weight_decay=1e-2)
+    back.load_state_dict(ours.state_dict())              # ours -> torch
+    for opt, ps in ((ref_opt, ref_p), (back, a_p)):
+        for p, g in zip(ps, grads(5, ps)):
+            p.grad = g
+        opt.step()
+    for a, b in zip(ref_p, a_p):
+        close(b, a, 1e-7, rtol=2e-6, what="bbbp -> torch resume")
 
 
 # ---- packed input contracts (bit-exact) ----------------------------------------------------------------------------------------
@@ -540,3 +600,136 @@ def test_gather_rows_and_device_feeder(ops):
     gpu = list(bbbp_b200.DeviceBatchFeeder(odd.repeat(6, 1)[:50], src, y, batch_size=16, shuffle=True, device="cuda"))
     for (a, b, c), (x, yy, z) in zip(gpu, cpu):
         assert torch.equal(a.cpu(), x) and torch.equal(b.cpu(), yy) and torch.equal(c.cpu(), z)
+
+
+# ---- 16-bit operand formats and split passes (fp16 / strict modes) ---------------------------------------------------------
+def _rn16(t, fmt):
+    return (t.half() if fmt == 1 else t.bfloat16()).float()
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_cast16_hi_lo_pairs(ops, fmt):
+    x = rnd(37, 167, seed=200) * 3
+    hi, lo = ops.cast16(x.cuda(), fmt, want_lo=True)
+    assert hi.shape == (37, 168) and hi.dtype == (torch.float16 if fmt else torch.bfloat16)
+    want_hi = _rn16(x, fmt)
+    assert torch.equal(hi[:, :167].float().cpu(), want_hi)                           # round to nearest: exact
+    assert torch.equal(lo[:, :167].float().cpu(), _rn16(x - want_hi, fmt))           # lo = rn(x - hi): exact
+    assert float(hi[:, 167:].float().abs().sum()) == 0 and float(lo[:, 167:].float().abs().sum()) == 0
+    err1 = float((hi.float().cpu()[:, :167] - x).abs().max())
+    err2 = float(((hi.float() + lo.float()).cpu()[:, :167] - x).abs().max())
+    assert err2 < err1 * 2e-2                                                         # the pair carries ~2x the mantissa
+    # fp16 saturates instead of overflowing to inf
+    if fmt == 1:
+        big, _ = ops.cast16(torch.tensor([[1e6, -1e6, 3.0, 0, 0, 0, 0, 0]]).cuda(), 1)
+        assert big.float().cpu().tolist()[0][:3] == [65504.0, -65504.0, 3.0]
+    # pitched destination view (the padded in_proj weight image)
+    dst = torch.zeros(10, 176, dtype=hi.dtype).cuda()
+    ops.cast16(x[:4].cuda(), fmt, out=dst[3:7, :168])
+    assert torch.equal(dst[3:7, :167].float().cpu(), want_hi[:4]) and float(dst[:3].float().abs().sum()) == 0
+
+
+@pytest.mark.parametrize("M,N,K,split", [(37, 501, 167, 1), (256, 64, 2048, 1), (33, 128, 65536, 8), (130, 300, 264, 1)])
+@pytest.mark.parametrize("mode", ["fp16", "a_split", "x3"])
+def test_gemm16_fp16_and_split_passes(ops, M, N, K, split, mode):
+    """fp16 operands, and the split passes of the strict mode: (A_hi + A_lo) W_hi^T [+ A_hi W_lo^T], all accumulated in
+    fp32 in the same TMEM accumulator.  Reference: fp64 product of exactly the operand parts the kernel multiplies."""
+    x, w, b = rnd(M, K, seed=210), rnd(N, K, seed=211, scale=1 / math.sqrt(K)), rnd(N, seed=212)
+    a_hi, a_lo = ops.cast16(x.cuda(), 1, want_lo=mode != "fp16")
+    w_hi, w_lo = ops.cast16(w.cuda(), 1, want_lo=mode == "x3")
+    y, _ = ops.gemm_bf16(a_hi, K, w_hi, N, bias=b.cuda(), split_k=split, fmt=1, a_lo=a_lo, w_lo=w_lo)
+    xh, wh = x.half().double(), w.half().double()
+    ref = xh @ wh.T + b.double()
+    if mode != "fp16":
+        xl = (x - x.half().float()).half().double()
+        ref = ref + xl @ wh.T
+    if mode == "x3":
+        ref = ref + xh @ (w - w.half().float()).half().double().T
+    close(y, ref.float(), atol=2e-5 * max(1.0, math.sqrt(K) / 8), what=f"gemm16 {mode} {M}x{N}x{K}")
+    exact = (x.double() @ w.double().T + b.double()).float()
+    err = float((y.cpu() - exact).abs().max())
+    if mode == "x3":
+        assert err <= 2e-5 * max(1.0, math.sqrt(K) / 8), err       # fp32-class product
+
+
+def test_gemm16_emits_hi_lo_output_pairs(ops):
+    M, N, K = 200, 167, 300
+    x, w, b = rnd(M, K, seed=220), rnd(N, K, seed=221, scale=0.1), rnd(N, seed=222)
+    a_hi, a_lo = ops.cast16(x.cuda(), 1, want_lo=True)
+    w_hi, _ = ops.cast16(w.cuda(), 1)
+    o32, hi, lo = ops.gemm_bf16(a_hi, K, w_hi, N, bias=b.cuda(), act="relu", out_bf16=True, fmt=1, a_lo=a_lo, out16_lo=True,
+                                ld_out16=176)
+    assert hi.dtype == torch.float16 and hi.shape == lo.shape == (M, 176)
+    assert torch.equal(hi[:, :N].float().cpu(), o32.cpu().half().float())
+    assert torch.equal(lo[:, :N].float().cpu(), (o32.cpu() - o32.cpu().half().float()).half().float())
+    assert float(hi[:, N:].float().abs().sum()) == 0 and float(lo[:, N:].float().abs().sum()) == 0
+    # split-K finish kernel writes the pair too
+    o32b, hib, lob = ops.gemm_bf16(a_hi, K, w_hi, N, bias=b.cuda(), act="relu", out_bf16=True, fmt=1, a_lo=a_lo, out16_lo=True,
+                                   split_k=2)
+    close(o32b, o32, 1e-5, what="split-K vs one pass")
+    assert torch.equal(hib[:, :N].float().cpu(), o32b.cpu().half().float())
+    assert torch.equal(lob[:, :N].float().cpu(), (o32b.cpu() - o32b.cpu().half().float()).half().float())
+
+
+@pytest.mark.parametrize("N", [1, 3, 37])
+@pytest.mark.parametrize("source", ["fp32", "uint8"])
+def test_conv_stack_tcgen05_fp16_and_strict(ops, N, source):
+    """conv1 (from the planar image) -> conv2 in the fp16 one-pass mode and in the strict mode (hi + lo activations, split
+    first-layer weights) against the fp32 convolution of the UNROUNDED operands: the strict stack must sit at fp32-class
+    error (weights of conv2 are the only once-rounded operand), the one-pass stack at fp16 round-off."""
+    from oracle import preprocess
+    rng = np.random.default_rng(N)
+    if source == "uint8":
+        img8 = np.full((N, 3, 128, 128), 255, dtype=np.uint8)             # mostly-white depictions with strokes
+        strokes = rng.random((N, 1, 128, 128)) < 0.07
+        img8[np.broadcast_to(strokes, img8.shape)] = rng.integers(0, 200, size=int(strokes.sum()) * 3, dtype=np.uint8)
+        dev = torch.from_numpy(img8).cuda()
+        stats = ops.u8_image_stats(dev)
+        img = torch.from_numpy(preprocess.u8_image_zscore(img8)).view(N, 3, 128, 128)
+    else:
+        img = rnd(N, 3, 128, 128, seed=230)
+        dev, stats = img.cuda(), None
+    w1, b1 = rnd(32, 3, 3, 3, seed=231, scale=0.2), rnd(32, seed=232, scale=0.1)
+    w2, b2 = rnd(64, 32, 3, 3, seed=233, scale=0.06), rnd(64, seed=234, scale=0.1)
+    ref1 = F.max_pool2d(F.relu(F.conv2d(img.double(), w1.double(), b1.double(), padding=1)), 2)
+    ref2 = F.max_pool2d(F.relu(F.conv2d(ref1, w2.double(), b2.double(), padding=1)), 2)
+    ref1, ref2 = ref1.float().permute(0, 2, 3, 1), ref2.float().permute(0, 2, 3, 1)
+    wp1, wp2 = ops.conv3x3_prepare_bf16(w1.cuda(), 1), ops.conv3x3_prepare_bf16(w2.cuda(), 1)
+    # one pass, fp16 operands
+    y1 = ops.conv1_from_image_bf16(dev, wp1, b1.cuda(), stats, fmt=1)
+    y2 = ops.conv3x3_relu_pool_bf16(y1, wp2, b2.cuda(), 64, fmt=1)
+    assert y1.dtype == torch.float16 and y2.shape == (N, 32, 32, 64)
+    close(y1, ref1, atol=4e-3, rtol=2e-3, what="conv1 fp16")
+    close(y2, ref2, atol=6e-3, rtol=2e-3, what="conv2 fp16")
+    # strict: (hi, lo) pairs all the way
+    s1, s1_lo = ops.conv1_from_image_bf16(dev, wp1, b1.cuda(), stats, fmt=1, split=True)
+    s2, s2_lo = ops.conv3x3_relu_pool_bf16(s1, wp2, b2.cuda(), 64, fmt=1, x_lo=s1_lo)
+    got1, got2 = s1.float() + s1_lo.float(), s2.float() + s2_lo.float()
+    e1, e2 = float((got1.cpu() - ref1).abs().max()), float((got2.cpu() - ref2).abs().max())
+    f1, f2 = float((y1.float().cpu() - ref1).abs().max()), float((y2.float().cpu() - ref2).abs().max())
+    print(f"[conv strict] N={N} {source}: conv1 {e1:.2e} (one pass {f1:.2e}), conv2 {e2:.2e} (one pass {f2:.2e})")
+    assert e1 <= 3e-5 * max(1.0, float(ref1.abs().max())), e1          # both operands split: fp32-class
+    assert e2 <= 5e-4 * max(1.0, float(ref2.abs().max())) and e2 < 0.35 * f2, (e2, f2)
+    assert torch.equal(s1.float(), (s1.float() + s1_lo.float()).half().float())       # hi IS the rounding of the pair's sum
+
+
+def test_attention_many_small_heads_fp16(ops):
+    groups, seq, heads, d = 2, 100, 32, 8
+    E = heads * d
+    qkv = rnd(groups * seq, 3 * E, seed=240, scale=0.7)
+    q16, _ = ops.cast16(qkv.cuda(), 1)
+    out = ops.attention_heads_bf16(q16, E, 2 * E, groups, seq, heads, d, fmt=1)
+    qh = qkv.half().double().view(groups, seq, 3, heads, d).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(qh[0], qh[1], qh[2]).permute(0, 2, 1, 3).reshape(groups * seq, E).float()
+    close(out, ref, atol=3e-3, rtol=2e-3, what="fp16 small-head attention")
+
+
+def test_fill_zero_any_alignment(ops):
+    t = torch.ones(7, 50, dtype=torch.bfloat16).cuda()
+    ops.fill_zero(t[:, 3:10])
+    want = torch.ones(7, 50)
+    want[:, 3:10] = 0
+    assert torch.equal(t.float().cpu(), want)
+    u = torch.ones(1000).cuda()
+    ops.fill_zero(u)
+    assert float(u.abs().sum()) == 0
