@@ -173,8 +173,9 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int ld_src, float* 
 // fp32 rows -> 16-bit rows (bf16 or fp16), optional lo part (hi + lo carries ~2x the mantissa), zero fill of the pad columns.
 // One thread = 8 output columns = one 16-byte store per output (the scalar version sat at 0.28 of the HBM roofline).
 template <int FMT>
-__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ src, int ld_src, uint16_t* __restrict__ hi,
-                                                     uint16_t* __restrict__ lo, int ld_dst, int rows, int cols, int cols_pad) {
+__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ src, int ld_src, const float* __restrict__ col_sub,
+                                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int ld_dst, int rows,
+                                                     int cols, int cols_pad) {
   const int groups = cols_pad / 8;            // cols_pad is a multiple of 8 on this path
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * groups) return;
@@ -187,6 +188,10 @@ __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ s
   } else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = c0 + k < cols ? s[k] : 0.0f;
+  }
+  if (col_sub) {       // fused centring (PCA.transform: X - mean_), in fp32 before the split
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = c0 + k < cols ? v[k] - col_sub[c0 + k] : 0.0f;
   }
   uint32_t h[4], l[4];
 #pragma unroll
@@ -565,8 +570,8 @@ extern "C" int bbbp_fill_zero(void* dst, long long rows, long long row_bytes, lo
   return launch_status("fill_zero");
 }
 
-extern "C" int bbbp_cast16(int fmt, const float* src, int ld_src, void* dst_hi, void* dst_lo, int ld_dst, int rows, int cols,
-                           int cols_pad, bbbp_stream_t stream) {
+extern "C" int bbbp_cast16(int fmt, const float* src, int ld_src, const float* col_sub, void* dst_hi, void* dst_lo, int ld_dst,
+                           int rows, int cols, int cols_pad, bbbp_stream_t stream) {
   BBBP_CHECK_ARG(fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "cast16: bad fmt %d", fmt);
   BBBP_CHECK_ARG(src && dst_hi && rows >= 0 && cols >= 0 && cols_pad >= cols && ld_dst >= cols_pad, "cast16: bad argument");
   BBBP_CHECK_ARG(cols_pad % 8 == 0 && ld_dst % 8 == 0 && ((uintptr_t)dst_hi % 16) == 0 && ((uintptr_t)dst_lo % 16) == 0,
@@ -575,10 +580,10 @@ extern "C" int bbbp_cast16(int fmt, const float* src, int ld_src, void* dst_hi, 
   if (total == 0) return BBBP_OK;
   const unsigned blocks = (unsigned)ceil_div(total, (size_t)256);
   if (fmt == BBBP_FMT_F16)
-    cast16_kernel<BBBP_FMT_F16><<<blocks, 256, 0, as_stream(stream)>>>(src, ld_src, static_cast<uint16_t*>(dst_hi),
+    cast16_kernel<BBBP_FMT_F16><<<blocks, 256, 0, as_stream(stream)>>>(src, ld_src, col_sub, static_cast<uint16_t*>(dst_hi),
                                                                        static_cast<uint16_t*>(dst_lo), ld_dst, rows, cols, cols_pad);
   else
-    cast16_kernel<BBBP_FMT_BF16><<<blocks, 256, 0, as_stream(stream)>>>(src, ld_src, static_cast<uint16_t*>(dst_hi),
+    cast16_kernel<BBBP_FMT_BF16><<<blocks, 256, 0, as_stream(stream)>>>(src, ld_src, col_sub, static_cast<uint16_t*>(dst_hi),
                                                                         static_cast<uint16_t*>(dst_lo), ld_dst, rows, cols, cols_pad);
   return launch_status("cast16");
 }

@@ -259,7 +259,53 @@ __global__ void __launch_bounds__(256) batchnorm_bwd_kernel(const float* __restr
   }
 }
 
+// Per-FEATURE standardisation inside chunks of ``chunk`` rows: the preprocessing that produces the ``lso_fixed_1`` pickle the
+// canonical script trains on (Descriptors/multi_input_data_preprocess_maccs_opt_IsolationForest_fixed_1.py:86-101:
+// ``StandardScaler().fit_transform`` on every block of 100 molecules, MACCS and pixel columns side by side).  One thread =
+// one column of one chunk; adjacent threads read adjacent columns (coalesced), the 2nd / 3rd pass over the chunk's slab
+// (100 x 49 319 floats = 19.7 MB) comes from L2.  The arithmetic restates sklearn's: float64 accumulators, the corrected
+// two-pass variance of _incremental_mean_and_var, the near-constant test of _is_constant_feature (scale -> 1), and the
+// float32 transform X -= float32(mean); X /= float32(scale).
+__global__ void __launch_bounds__(256) standardize_chunks_kernel(const float* __restrict__ x, size_t ld_x,
+                                                                 float* __restrict__ out, size_t ld_out, long long rows,
+                                                                 int cols, int chunk) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= cols) return;
+  const long long r0 = (long long)blockIdx.y * chunk;
+  const int n = (int)min((long long)chunk, rows - r0);
+  const float* xc = x + (size_t)r0 * ld_x + col;
+  double sum = 0.0;
+  for (int r = 0; r < n; ++r) sum += (double)xc[(size_t)r * ld_x];
+  const double mean = sum / n;
+  double corr = 0.0, sq = 0.0;
+  for (int r = 0; r < n; ++r) {
+    const double d = (double)xc[(size_t)r * ld_x] - mean;
+    corr += d;
+    sq += d * d;
+  }
+  const double var = (sq - corr * corr / n) / n;
+  const double eps = 2.220446049250313e-16;
+  const double t = (double)n * mean * eps;
+  const double scale = var <= (double)n * eps * var + t * t ? 1.0 : sqrt(var);
+  float* oc = out + (size_t)r0 * ld_out + col;
+  const float mean32 = (float)mean, scale32 = (float)scale;     // sklearn 1.9: statistics cast to X's dtype, float32 arithmetic
+  for (int r = 0; r < n; ++r) oc[(size_t)r * ld_out] = __fdiv_rn(__fsub_rn(xc[(size_t)r * ld_x], mean32), scale32);
+}
+
 }  // namespace bbbp
+
+extern "C" int bbbp_standardize_chunks_f32(const float* x, long long ld_x, float* out, long long ld_out, long long rows, int cols,
+                                           int chunk_rows, bbbp_stream_t stream) {
+  using namespace bbbp;
+  BBBP_CHECK_ARG(x && out && rows >= 0 && cols > 0 && chunk_rows > 0 && ld_x >= cols && ld_out >= cols,
+                 "standardize_chunks: bad argument");
+  if (rows == 0) return BBBP_OK;
+  const long long chunks = (rows + chunk_rows - 1) / chunk_rows;
+  BBBP_CHECK_ARG(chunks <= 65535, "standardize_chunks: %lld chunks exceed 65535 per launch", chunks);
+  standardize_chunks_kernel<<<dim3(ceil_div(cols, 256), (unsigned)chunks), 256, 0, as_stream(stream)>>>(
+      x, (size_t)ld_x, out, (size_t)ld_out, rows, cols, chunk_rows);
+  return launch_status("standardize_chunks");
+}
 
 extern "C" int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, const float* gamma, const float* beta,
                                           float* y, float* sum_out, float* mean, float* rstd, void* y_bf16, int ld_bf16,

@@ -140,21 +140,33 @@ def cast_bf16(x: torch.Tensor, ld: int | None = None, out: torch.Tensor | None =
     return out
 
 
-def cast16(x: torch.Tensor, fmt: int = FMT_BF16, ld: int | None = None, want_lo: bool = False, out: torch.Tensor | None = None):
+def cast16(x: torch.Tensor, fmt: int = FMT_BF16, ld: int | None = None, want_lo: bool = False, out: torch.Tensor | None = None,
+           sub: torch.Tensor | None = None):
     """(rows, cols) float32 -> (rows, ld) 16-bit rows in format ``fmt`` (pad columns zero, ld a multiple of 8).  With
     ``want_lo`` also the low part ``rn(x - hi)``: returns (hi, lo | None).  128-bit stores (one thread = 8 columns).
-    ``out``: a pitched 2-D destination view for hi (row stride = pitch, width = pad-to, both multiples of 8)."""
+    ``out``: a pitched 2-D destination view for hi (row stride = pitch, width = pad-to, both multiples of 8).
+    ``sub``: a (cols,) float32 row subtracted from every row before the split (fused centring)."""
     rows, cols = x.shape
     if out is not None:
         assert not want_lo and out.shape[0] == rows
-        check(lib.bbbp_cast16(fmt, x.data_ptr(), x.stride(0), out.data_ptr(), None, out.stride(0), rows, cols, out.shape[1],
-                              _stream()), "cast16")
+        check(lib.bbbp_cast16(fmt, x.data_ptr(), x.stride(0), _ptr(sub), out.data_ptr(), None, out.stride(0), rows, cols,
+                              out.shape[1], _stream()), "cast16")
         return out, None
     ld = -(-cols // 8) * 8 if ld is None else ld
     hi = torch.empty((rows, ld), device=x.device, dtype=_DT16[fmt])
     lo = torch.empty((rows, ld), device=x.device, dtype=_DT16[fmt]) if want_lo else None
-    check(lib.bbbp_cast16(fmt, x.data_ptr(), x.stride(0), hi.data_ptr(), _ptr(lo), ld, rows, cols, ld, _stream()), "cast16")
+    check(lib.bbbp_cast16(fmt, x.data_ptr(), x.stride(0), _ptr(sub), hi.data_ptr(), _ptr(lo), ld, rows, cols, ld, _stream()),
+          "cast16")
     return hi, lo
+
+
+def standardize_chunks(x: torch.Tensor, chunk_rows: int = 100, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-feature z-score inside consecutive blocks of ``chunk_rows`` rows (StandardScaler().fit_transform per block)."""
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    out = torch.empty_like(x) if out is None else out
+    check(lib.bbbp_standardize_chunks_f32(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                                          int(chunk_rows), _stream()), "standardize_chunks")
+    return out
 
 
 def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, out_bf16=False, split_k=1,

@@ -46,6 +46,15 @@ class AdamW(torch.optim.Optimizer):
             if st.get("step") is not shared:
                 st["step"] = shared
 
+    def state_dict(self):
+        """torch's layout: every parameter gets its OWN ``step`` tensor (the in-memory mirror is one shared scalar per group;
+        stock AdamW increments ``state[p]["step"]`` in place per parameter, so a shared object would be bumped N times)."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if torch.is_tensor(st.get("step")):
+                st["step"] = st["step"].clone()
+        return sd
+
     @staticmethod
     def _to_device(values, dtype, dev):
         """Small host table -> device through pinned memory (no synchronous pageable copy in the middle of training)."""

@@ -81,8 +81,9 @@ int bbbp_fill_zero(void* dst, long long rows, long long row_bytes, long long pit
 /* fp32 rows -> 16-bit rows in format fmt: dst_hi = rn(src), optional dst_lo = rn(src - dst_hi) (NULL to skip), zero fill of
  * [cols, cols_pad).  cols_pad and ld_dst multiples of 8, destinations 16-byte aligned.  A (hi, lo) pair carries ~2x the
  * mantissa of one 16-bit operand; the strict inference mode feeds both through the same weights. */
-int bbbp_cast16(int fmt, const float* src, int ld_src, void* dst_hi, void* dst_lo, int ld_dst, int rows, int cols, int cols_pad,
-                bbbp_stream_t stream);
+/* col_sub (may be NULL): a row vector subtracted from every row in fp32 before the split (PCA.transform's X - mean_). */
+int bbbp_cast16(int fmt, const float* src, int ld_src, const float* col_sub, void* dst_hi, void* dst_lo, int ld_dst, int rows,
+                int cols, int cols_pad, bbbp_stream_t stream);
 
 /* tcgen05 / TMEM / TMA GEMM: out = act( A[M,K] * W[N,K]^T + bias ) (+ residual), bf16 operands, fp32
  * accumulate.  A and W are bf16 row-major with K contiguous; lda/ldw in elements, multiples of 8, 16-byte
@@ -233,6 +234,13 @@ int bbbp_attention_heads_bf16(const void* qkv_bf16, int ld, int k_offset, int v_
 
 int bbbp_attention_heads16(int fmt, const void* qkv, int ld, int k_offset, int v_offset, void* out, int ld_out, int groups,
                            int seq, int heads, int head_dim, bbbp_stream_t stream);
+
+/* out[r, c] = (x[r, c] - mean_c) / std_c with the statistics of column c taken over the rows of r's CHUNK (chunk_rows
+ * consecutive rows; the last chunk may be shorter): StandardScaler().fit_transform per block of 100 molecules,
+ * Descriptors/multi_input_data_preprocess_maccs_opt_IsolationForest_fixed_1.py:86-101.  float64 statistics, sklearn's
+ * near-constant rule (scale 1), float32 transform (x - float32(mean)) / float32(std) as sklearn 1.9.  In place allowed. */
+int bbbp_standardize_chunks_f32(const float* x, long long ld_x, float* out, long long ld_out, long long rows, int cols,
+                                int chunk_rows, bbbp_stream_t stream);
 
 /* ---- normalisation: nn.LayerNorm (post-norm residual, eps 1e-5) and nn.BatchNorm1d C:101 ------- */
 

@@ -44,6 +44,33 @@ def u8_image_zscore(images_u8: np.ndarray) -> np.ndarray:
     return zscore_rows(x)
 
 
+def standardize_chunks(x: np.ndarray, chunk: int = 100) -> np.ndarray:
+    """Per-FEATURE z-score inside consecutive blocks of ``chunk`` molecules: the reference's ``standardize_features``
+    (/root/reference/Descriptors/multi_input_data_preprocess_maccs_opt_IsolationForest_fixed_1.py:86-101,
+    ``scaler.fit_transform(batch_features)`` per block; ``fit`` resets the scaler, so blocks are independent).  Restates
+    sklearn 1.9 StandardScaler on a float32 matrix: float64 sums, the corrected two-pass variance of
+    ``_incremental_mean_and_var``, ``_is_constant_feature`` -> scale 1, and the in-place float32 transform
+    ``X -= float32(mean_); X /= float32(scale_)``.  Checked against sklearn itself in tests/test_oracle_pinning.py."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    eps = np.finfo(np.float64).eps
+    for a in range(0, x.shape[0], chunk):
+        blk = x[a:a + chunk]
+        n = blk.shape[0]
+        total = blk.sum(axis=0, dtype=np.float64)
+        mean = total / n
+        dev = blk - mean                                   # float64
+        corr = dev.sum(axis=0)
+        var = ((dev ** 2).sum(axis=0) - corr ** 2 / n) / n
+        scale = np.sqrt(var)
+        scale[var <= n * eps * var + (n * mean * eps) ** 2] = 1.0
+        # sklearn 1.9 transform: X -= astype(mean_, X.dtype); X /= astype(scale_, X.dtype)  -> float32 arithmetic
+        # (releases before the array-API port subtracted the float64 statistics instead: a 1-ulp difference; the reference
+        # pins no sklearn version, the oracle is "sklearn as installed in this image", like torch)
+        out[a:a + chunk] = (blk - mean.astype(np.float32)) / scale.astype(np.float32)
+    return out
+
+
 def pca_transform(x: np.ndarray, mean: np.ndarray, components: np.ndarray) -> np.ndarray:
     """(N, D) -> (N, k) in float32, ``(x - mean) @ components.T``."""
     x = np.asarray(x, dtype=np.float32)

@@ -120,7 +120,7 @@ def uniform(mode):
     return {k: mode for k in BRANCHES}
 
 
-STRICT = dict(uniform("fp16"), conv1="fp16+a", conv2="fp16+a", imfc="fp16+a", head="fp16x3", fpfc="fp16x3")
+STRICT = dict(uniform("fp16"), conv1="fp16x3", conv2="fp16+a", imfc="fp16+a", head="fp16x3", fpfc="fp16x3")
 
 
 def trained_state(steps=200):

@@ -151,3 +151,26 @@ def test_input_contract_oracle():
     for r in (0, 3, 5):   # the reference's exact call: Descriptors/multi_input_data_preprocess_maccs_opt.py:121-124
         ref = StandardScaler().fit_transform(bits[r].astype(np.float64).reshape(-1, 1)).ravel().astype(np.float32)
         np.testing.assert_array_equal(z[r], ref)
+
+
+def test_chunked_standardisation_oracle_equals_sklearn():
+    """N3: oracle/preprocess.standardize_chunks restates ``scaler.fit_transform`` per block of 100 molecules
+    (Descriptors/multi_input_data_preprocess_maccs_opt_IsolationForest_fixed_1.py:86-101); checked here against sklearn's
+    StandardScaler itself, driven exactly as the reference drives it (one scaler object, fit_transform per block, MACCS and
+    pixel columns side by side), including constant columns (MACCS bit 0, white border pixels) and a ragged last block."""
+    from sklearn.preprocessing import StandardScaler
+    rng = np.random.default_rng(3)
+    n = 257
+    maccs = (rng.random((n, 167)) < 0.25).astype(np.uint8)
+    maccs[:, 0] = 0
+    pixels = rng.random((n, 600)).astype(np.float32)
+    pixels[:, :40] = 1.0                                        # constant (white) pixels
+    pixels[:, 40:60] = np.float32(1.0) - (rng.random((n, 20)) < 0.01) * np.float32(0.37)   # almost constant
+    scaler = StandardScaler()
+    want = []
+    for i in range(0, n, 100):
+        block = np.hstack([maccs[i:i + 100], pixels[i:i + 100]])
+        want.extend(scaler.fit_transform(block))
+    want = np.array(want, dtype=np.float32)
+    got = preprocess.standardize_chunks(np.hstack([maccs, pixels]).astype(np.float32), 100)
+    np.testing.assert_array_equal(got, want)
