@@ -574,13 +574,26 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
 
 // ---- weight / input re-layout (prepare-time and per-call helpers) --------------------------------------------------
 // conv2-style (KC >= 2): wp[kc][8 - tap][n][8] = w[n][kc*8 + c][kh][kw]; taps are stored in REVERSE order so that the
-// weights of taps (kh, kw) and (kh, kw-1) -- the two B halves of a paired MMA -- are adjacent 64-row blocks
+// weights of taps (kh, kw) and (kh, kw-1) -- the two B halves of a paired MMA -- are adjacent 64-row blocks.
+// One thread = one 3x3 filter (n, ci).  fp16 weights are rounded with ERROR DIFFUSION over the nine taps (tap order 0..8,
+// float32 carry), so the filter's SUM -- its response to a locally constant input, which is what the background of a
+// depiction is after the first layer -- keeps full precision: plain round-to-nearest leaves every filter a random DC error
+// of ~0.9 ulp, and the same DC error at every background pixel adds up coherently in the Linear(65536, 128) that follows
+// (tests/precision_study.py: the strict mode's largest remaining term, 7e-4 -> 2.6e-4).  bf16 weights keep plain
+// round-to-nearest (the fast mode's results stay bit-identical to earlier releases).
 __global__ void prep_weights_kc_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Cin, int Cout, int fmt) {
   const int KC = Cin / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 9 * KC * Cout * 8) return;
-  const int c = i % 8, n = (i / 8) % Cout, u = (i / (8 * Cout)) % 9, kc = i / (8 * Cout * 9);
-  wp[i] = cvt16_rt(w[((size_t)n * Cin + kc * 8 + c) * 9 + (8 - u)], fmt);
+  if (i >= KC * Cout * 8) return;
+  const int c = i % 8, n = (i / 8) % Cout, kc = i / (8 * Cout);
+  const float* f = w + ((size_t)n * Cin + kc * 8 + c) * 9;
+  float carry = 0.0f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const float target = f[tap] + carry;
+    const uint16_t r = cvt16_rt(target, fmt);
+    if (fmt == BBBP_FMT_F16) carry = target - round16<BBBP_FMT_F16>(target);
+    wp[((size_t)(kc * 9 + (8 - tap)) * Cout + n) * 8 + c] = r;
+  }
 }
 // conv1-style (Cin <= 8, one chunk): wp[dx][pair][chunk][n][8]
 __global__ void prep_weights_c8_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Cin, int Cout, int fmt) {
@@ -754,7 +767,7 @@ extern "C" int bbbp_conv3x3_prepare16(int fmt, const float* w, void* wprep, int 
     conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(w, wp + n8 + n4, Cin, Cout, fmt, 1);
     note_launches(2);
   } else
-    conv::prep_weights_kc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, wp, Cin, Cout, fmt);
+    conv::prep_weights_kc_kernel<<<ceil_div(total / 9, 256), 256, 0, as_stream(stream)>>>(w, wp, Cin, Cout, fmt);
   return launch_status("conv3x3_prepare");
 }
 extern "C" int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream) {

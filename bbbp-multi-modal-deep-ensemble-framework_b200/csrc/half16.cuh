@@ -12,13 +12,23 @@
 
 namespace bbbp {
 
-__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+// fp16 conversions saturate at +-65504 in the conversion instruction itself (F2FP.SATFINITE: no extra clamp instructions
+// in the latency-bound epilogues)
+__device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ uint16_t f16_sat(float v) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return r;
+}
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack16(float a, float b) {
   if constexpr (FMT == BBBP_FMT_F16) {
-    __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
-    return *reinterpret_cast<uint32_t*>(&h);
+    return f16x2_sat(a, b);
   } else {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -26,8 +36,12 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
 }
 template <int FMT>
 __device__ __forceinline__ float round16(float a) {
-  if constexpr (FMT == BBBP_FMT_F16) return __half2float(__float2half_rn(sat_f16(a)));
-  else return __bfloat162float(__float2bfloat16(a));
+  if constexpr (FMT == BBBP_FMT_F16) {
+    const uint16_t h = f16_sat(a);
+    return __half2float(*reinterpret_cast<const __half*>(&h));
+  } else {
+    return __bfloat162float(__float2bfloat16(a));
+  }
 }
 // hi = rn(a, b), lo = rn(a - hi_a, b - hi_b)
 template <int FMT>
@@ -38,8 +52,7 @@ __device__ __forceinline__ void split16(float a, float b, uint32_t& hi, uint32_t
 template <int FMT>
 __device__ __forceinline__ uint16_t cvt16(float a) {
   if constexpr (FMT == BBBP_FMT_F16) {
-    __half h = __float2half_rn(sat_f16(a));
-    return *reinterpret_cast<uint16_t*>(&h);
+    return f16_sat(a);
   } else {
     __nv_bfloat16 h = __float2bfloat16(a);
     return *reinterpret_cast<uint16_t*>(&h);

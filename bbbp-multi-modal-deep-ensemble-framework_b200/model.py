@@ -303,7 +303,12 @@ class TransformerCnnModel(_KernelModule):
             w_in = ag.derived_weight(attn.in_proj_weight, f"qkv_pad16_{fmt}", padded_in_proj)
             b_in = ag.derived_weight(attn.in_proj_bias, "qkv_pad", padded_in_bias)
             _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True, fmt=fmt)
-            if attn.num_heads == 1:
+            if attn.num_heads == 1 and seq > 256 and F_ <= 192:
+                # scopes wider than one score tile: streaming-softmax kernel, the seq x seq logits stay in TMEM / shared memory
+                ldp = -(-seq // 8) * 8
+                vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
+                a16 = ops.attention_flash16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, vt, ldp, fmt=fmt, ld_out=Fq)
+            elif attn.num_heads == 1:
                 p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, fmt=fmt)
                 ldp = p16.shape[1]
                 vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)

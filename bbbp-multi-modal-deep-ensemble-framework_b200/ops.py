@@ -247,6 +247,22 @@ def attention_scores_softmax_bf16(q16, k16, ld, groups, seq, head_dim, scale, fm
     return p
 
 
+def attention_flash16(q16, k16, ld, groups, seq, head_dim, scale, vt, ld_vt, fmt=FMT_BF16, ld_out=None):
+    """softmax(scale * Q K^T) V per group with the streaming tcgen05 kernel (any seq; one head, head_dim <= 192).  q16 / k16:
+    views into the packed qkv buffer (row pitch ``ld``); vt: (groups, head_dim, ld_vt) transposed values.  Returns
+    (groups*seq, ld_out) 16-bit rows, pad columns zero."""
+    ld_out = -(-head_dim // 8) * 8 if ld_out is None else ld_out
+    out = torch.empty((groups * seq, ld_out), device=q16.device, dtype=_DT16[fmt])
+    if ld_out > -(-head_dim // 16) * 16:
+        fill_zero(out[:, -(-head_dim // 16) * 16:])
+    t0 = KERNEL_TIMER.start("attn_flash")
+    check(lib.bbbp_attention_flash16(fmt, groups, seq, head_dim, q16.data_ptr(), ld, k16.data_ptr(), ld, seq * ld, vt.data_ptr(),
+                                     ld_vt, head_dim * ld_vt, float(scale), out.data_ptr(), ld_out, seq * ld_out, _stream()),
+          "attention_flash16")
+    KERNEL_TIMER.stop("attn_flash", t0, groups * seq)
+    return out
+
+
 def transpose_bf16(src, batches, rows, cols, ld_src, src_bs, ld_dst):
     """(batches, rows, cols) pitched bf16 -> (batches, cols, ld_dst) with zero fill of columns >= rows."""
     dst = torch.empty((batches, cols, ld_dst), device=src.device, dtype=src.dtype)

@@ -232,6 +232,15 @@ int bbbp_attn_softmax_bwd_f32(const float* p, const float* dp_dropped, float* ds
 int bbbp_attention_heads_bf16(const void* qkv_bf16, int ld, int k_offset, int v_offset, void* out_bf16, int ld_out, int groups,
                               int seq, int heads, int head_dim, bbbp_stream_t stream);
 
+/* Streaming-softmax attention for ONE head (head_dim <= 192) and ANY scope length on tcgen05 / TMEM / TMA: a CTA owns 128
+ * queries and walks the keys in blocks of 128 (S = Q K^T -> TMEM, P = exp2(S - m) -> shared memory, O += P V -> TMEM) with a
+ * lazily moved running maximum; the seq x seq logits never reach HBM (at seq = 65 536 they would be 17 GB per layer).
+ * q / k: 16-bit rows (pitches ldq / ldk, group g starts group_stride elements after g - 1); v_t: the TRANSPOSED values
+ * [groups][head_dim][ld_vt] (bbbp_transpose_bf16), ld_vt >= seq; out: [groups*seq][ld_out] 16-bit, columns >= head_dim of a
+ * row are written as zeros up to ld_out.  All pitches / strides multiples of 8 elements. */
+int bbbp_attention_flash16(int fmt, int groups, int seq, int head_dim, const void* q, int ldq, const void* k, int ldk,
+                           long long group_stride, const void* v_t, int ld_vt, long long vt_group_stride, float scale, void* out,
+                           int ld_out, long long out_group_stride, bbbp_stream_t stream);
 int bbbp_attention_heads16(int fmt, const void* qkv, int ld, int k_offset, int v_offset, void* out, int ld_out, int groups,
                            int seq, int heads, int head_dim, bbbp_stream_t stream);
 

@@ -778,3 +778,73 @@ def test_pca_projection_on_the_tensor_cores(cuda_device, precision, tol):
     got = bbbp_b200.pca_transform(x.cuda(), mu.cuda(), comp.cuda(), precision=precision).cpu().double()
     assert got.shape == (300, 128)
     assert float((got - want).abs().max()) <= tol * max(1.0, float(want.abs().max()))
+
+
+def test_conv2_fp16_weights_preserve_every_filters_sum(ops):
+    """The fp16 weight image of the second layer is rounded with error diffusion over the nine taps of each 3x3 filter, so the
+    filter's SUM (its response to a locally constant input: the background of a depiction after the first layer) keeps full
+    precision.  On a constant input every interior pre-pool output is sum_ci c[ci] * sum_taps w[co, ci, :] + b: the device
+    result must match that to fp32-class error, far below what round-to-nearest weights give."""
+    g = torch.Generator().manual_seed(7)
+    w = torch.randn(64, 32, 3, 3, generator=g) * 0.06
+    b = torch.randn(64, generator=g) * 0.1
+    c = (torch.rand(32, generator=g) * 2).half().float()                 # fp16-exact background activations
+    x = c.view(1, 1, 1, 32).expand(2, 64, 64, 32).contiguous().half().cuda()
+    y = ops.conv3x3_relu_pool_bf16(x, ops.conv3x3_prepare_bf16(w.cuda(), 1), b.cuda(), 64, fmt=1).float().cpu()
+    exact = torch.relu((w.double().sum((2, 3)) @ c.double()) + b.double()).float()             # interior response
+    plain = torch.relu((w.half().double().sum((2, 3)) @ c.double()) + b.double()).float()       # round-to-nearest weights
+    got = y[:, 4:28, 4:28, :]                                             # pooled pixels away from the zero padding
+    err_dev = float((got - exact).abs().max())
+    err_rn = float((plain - exact).abs().max())
+    out_rounding = float(exact.abs().max()) * 2 ** -11                    # the fp16 output itself
+    assert err_dev <= out_rounding + 0.25 * err_rn, (err_dev, err_rn, out_rounding)
+    # bf16 weights keep plain round-to-nearest (bit-compatible with the round-1 fast mode)
+    yb = ops.conv3x3_relu_pool_bf16(x.bfloat16(), ops.conv3x3_prepare_bf16(w.cuda(), 0), b.cuda(), 64, fmt=0).float().cpu()
+    plain_b = torch.relu((w.bfloat16().double().sum((2, 3)) @ c.bfloat16().double()) + b.double()).float()
+    close(yb[:, 4:28, 4:28, :], plain_b.view(1, 1, 1, 64).expand(2, 24, 24, 64), atol=1e-3, rtol=1e-2, what="bf16 plain RN")
+
+
+# ---- streaming-softmax attention on tcgen05 (any scope length) -----------------------------------------------------------------
+def _flash_case(ops, groups, seq, d, fmt, q, k, v):
+    """q, k, v: (groups*seq, d) fp32 -> device result and the fp64 reference on the 16-bit-rounded operands."""
+    dq = -(-d // 8) * 8
+    qkv = torch.zeros(groups * seq, 3 * dq)
+    qkv[:, :d], qkv[:, dq:dq + d], qkv[:, 2 * dq:2 * dq + d] = q, k, v
+    q16, _ = ops.cast16(qkv.cuda(), fmt)
+    ldp = -(-seq // 8) * 8
+    vt = ops.transpose_bf16(q16[:, 2 * dq:], groups, seq, d, 3 * dq, seq * 3 * dq, ldp)
+    out = ops.attention_flash16(q16, q16[:, dq:], 3 * dq, groups, seq, d, d ** -0.5, vt, ldp, fmt=fmt, ld_out=dq)
+    r = lambda t: _rn16(t, fmt).double().view(groups, 1, seq, d)
+    ref = F.scaled_dot_product_attention(r(q), r(k), r(v)).reshape(groups * seq, d).float()
+    return out, ref, dq
+
+
+@pytest.mark.parametrize("groups,seq,d", [(1, 300, 167), (2, 129, 64), (3, 128, 16), (1, 1000, 167), (1, 257, 192), (2, 1, 8),
+                                          (1, 4096, 167), (1, 513, 40)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_attention_flash_tcgen05(ops, groups, seq, d, fmt):
+    g = torch.Generator().manual_seed(seq + d)
+    q, k, v = (torch.randn(groups * seq, d, generator=g) * s for s in (1.0, 1.0, 0.7))
+    out, ref, dq = _flash_case(ops, groups, seq, d, fmt, q, k, v)
+    assert out.shape == (groups * seq, dq)
+    tol = 4e-3 if fmt == 1 else 2e-2                      # P and the output are rounded to 16 bits
+    close(out[:, :d], ref, atol=tol, rtol=tol, what=f"flash attention {groups}x{seq}x{d} fmt {fmt}")
+    assert float(out[:, d:].float().abs().sum()) == 0.0   # pad columns
+
+
+def test_attention_flash_rescales_when_the_running_maximum_moves(ops):
+    """Keys whose logits keep growing along the scope force the lazy running maximum to move (by more than the threshold of
+    2^8) many times: the O accumulator is rescaled in TMEM each time, and rows whose reference does NOT move share the warp
+    with rows whose reference does."""
+    groups, seq, d = 1, 1500, 167
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(seq, d, generator=g)
+    q[::3] *= 0.05                                          # rows with tiny logits: their maximum barely moves
+    k = torch.randn(seq, d, generator=g) * torch.linspace(0.2, 6.0, seq).view(-1, 1)    # logits grow along the keys
+    v = torch.randn(seq, d, generator=g)
+    out, ref, _ = _flash_case(ops, groups, seq, d, 1, q, k, v)
+    close(out[:, :d], ref, atol=6e-3, rtol=6e-3, what="flash attention with a moving maximum")
+    # and the opposite order (maximum found in the first block, never moves again)
+    out2, ref2, _ = _flash_case(ops, groups, seq, d, 1, q, k.flip(0), v.flip(0))
+    close(out2[:, :d], ref2, atol=6e-3, rtol=6e-3, what="flash attention with an early maximum")
+    close(out2[:, :d], out[:, :d].float(), atol=1.2e-2, rtol=1.2e-2, what="key order invariance")

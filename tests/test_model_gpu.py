@@ -650,3 +650,24 @@ def test_morgan_classification_auc_matches_to_three_decimals(cuda_device):
     assert 0.2 < y.mean() < 0.8
     auc_want, auc_got = roc_auc_score(y, want.numpy()), roc_auc_score(y, got.numpy())
     assert round(auc_got, 3) == round(auc_want, 3), (auc_got, auc_want)
+
+
+@pytest.mark.parametrize("seq,mode", [(4096, "bf16"), (4096, "strict"), (16384, "bf16")])
+def test_wide_attention_scopes_on_the_streaming_kernel(cuda_device, seq, mode):
+    """BASELINE configs[4] (batch sweep to 65 536): ONE reference batch of ``seq`` molecules, i.e. self-attention over
+    S = seq.  The tensor-core path streams the softmax (attention_flash_umma.cu); the fp32 reference is the
+    oracle net on the CPU.  Depictions repeat a small set (the conv branch is per molecule) so the CPU side stays short."""
+    ref, ours = make_pair("tcnn", 167, 128, 17, cuda_device)
+    ref.eval(), ours.eval().set_precision(mode)
+    g = torch.Generator().manual_seed(seq)
+    fp = torch.randn(seq, 167, generator=g)
+    base_img = torch.randn(64, IMG, generator=g)
+    idx = torch.arange(seq) % 64
+    with torch.no_grad():
+        x = ref.fingerprint_transformer(fp.unsqueeze(1)).squeeze(1)
+        fp_feat = ref.fingerprint_fc(x)
+        im_feat = ref.image_cnn(base_img.view(-1, 3, 128, 128))[idx]
+        want = ref.fc(ref.attention_fusion(fp_feat, im_feat))
+        got = ours(fp.cuda(), base_img[idx].cuda()).cpu()
+    tol = BF16_TOL if mode == "bf16" else 1e-3
+    assert float((got - want).abs().max()) <= tol, float((got - want).abs().max())
