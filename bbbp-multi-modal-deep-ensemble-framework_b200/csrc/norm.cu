@@ -42,6 +42,173 @@ __global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_kernel(
   }
 }
 
+// The same kernel with the row held in registers (VPL values per lane, dim <= 32 * VPL): x and res are read ONCE instead of
+// three times and every lane has VPL (x2) independent loads in flight -- the three-pass version sat at 0.59 of the HBM
+// roofline.  Per-lane summation order is unchanged (k ascending = i ascending), so results are bit-identical to it.
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32) add_layernorm_fwd_reg_kernel(
+    const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ sum_out, float* __restrict__ mean_out,
+    float* __restrict__ rstd_out, uint16_t* __restrict__ y16, int ld16, int rows, int dim, float eps, int ld_x,
+    int ld_res, int ld_y, int fmt) {
+  const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ld_x;
+  const float* rr = res ? res + (size_t)row * ld_res : nullptr;
+  float v[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < dim ? xr[i] : 0.0f;
+  }
+  if (rr) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < dim) v[k] += rr[i];
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) s += v[k];            // lanes beyond dim hold zeros
+  const float mean = warp_sum(s) / dim;
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float t = v[k] - mean;
+    q = (lane + 32 * k) < dim ? fmaf(t, t, q) : q;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < dim) {
+      const float o = (v[k] - mean) * rstd * gamma[i] + beta[i];
+      y[(size_t)row * ld_y + i] = o;
+      if (sum_out) sum_out[(size_t)row * dim + i] = v[k];
+      if (y16) y16[(size_t)row * ld16 + i] = cvt16_rt(o, fmt);
+    }
+  }
+  if (y16)
+    for (int i = dim + lane; i < ld16; i += 32) y16[(size_t)row * ld16 + i] = 0;
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+template <typename... Args>
+static void launch_add_layernorm_fwd(int rows, int dim, cudaStream_t stream, Args... args) {
+  const dim3 grid(ceil_div(rows, LN_WARPS)), block(LN_WARPS * 32);
+  if (dim <= 192) add_layernorm_fwd_reg_kernel<6><<<grid, block, 0, stream>>>(args...);
+  else if (dim <= 512) add_layernorm_fwd_reg_kernel<16><<<grid, block, 0, stream>>>(args...);
+  else if (dim <= 2048) add_layernorm_fwd_reg_kernel<64><<<grid, block, 0, stream>>>(args...);
+  else add_layernorm_fwd_kernel<<<grid, block, 0, stream>>>(args...);
+}
+
+// dx with dy * gamma and the normalised row held in registers (same per-lane summation order as the two-pass kernel below)
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_dx_reg_kernel(const float* __restrict__ dy,
+                                                                             const float* __restrict__ s,
+                                                                             const float* __restrict__ mean,
+                                                                             const float* __restrict__ rstd,
+                                                                             const float* __restrict__ gamma,
+                                                                             float* __restrict__ dx, int rows, int dim) {
+  const int row = blockIdx.x * LN_WARPS + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  const float* dyr = dy + (size_t)row * dim;
+  const float* sr = s + (size_t)row * dim;
+  float g[VPL], xh[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    g[k] = i < dim ? dyr[i] : 0.0f;
+    xh[k] = i < dim ? sr[i] : mu;
+  }
+  float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < dim) {
+      g[k] *= gamma[i];
+      xh[k] = (xh[k] - mu) * rs;
+      c1 += g[k];
+      c2 = fmaf(g[k], xh[k], c2);
+    }
+  }
+  c1 = warp_sum(c1) / dim;
+  c2 = warp_sum(c2) / dim;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < dim) dx[(size_t)row * dim + i] = rs * (g[k] - c1 - xh[k] * c2);
+  }
+}
+
+// Many rows: dx AND the parameter-gradient partials in ONE pass over dy and s (the separate partial kernel re-read both:
+// 5 array passes for 3 algorithmic ones).  A warp is a row class (rows c, c + classes, ...): it keeps dy * gamma and the
+// normalised row in registers for dx and accumulates its class's dgamma / dbeta per lane; partial row c of the workspace
+// is summed over the classes in a fixed order by layernorm_bwd_param_final_kernel (deterministic).
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_fused_kernel(const float* __restrict__ dy,
+                                                                            const float* __restrict__ s,
+                                                                            const float* __restrict__ mean,
+                                                                            const float* __restrict__ rstd,
+                                                                            const float* __restrict__ gamma,
+                                                                            float* __restrict__ dx, float* __restrict__ part,
+                                                                            int rows, int dim, int classes) {
+  const int cls = blockIdx.x * LN_WARPS + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (cls >= classes) return;
+  float gam[VPL], dg[VPL], db[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    gam[k] = i < dim ? gamma[i] : 0.0f;
+    dg[k] = db[k] = 0.0f;
+  }
+  for (int row = cls; row < rows; row += classes) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* dyr = dy + (size_t)row * dim;
+    const float* sr = s + (size_t)row * dim;
+    float d[VPL], xh[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      d[k] = i < dim ? dyr[i] : 0.0f;
+      xh[k] = i < dim ? sr[i] : mu;
+    }
+    float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      xh[k] = (xh[k] - mu) * rs;
+      dg[k] = fmaf(d[k], xh[k], dg[k]);
+      db[k] += d[k];
+      d[k] *= gam[k];
+      c1 += d[k];
+      c2 = fmaf(d[k], xh[k], c2);
+    }
+    c1 = warp_sum(c1) / dim;
+    c2 = warp_sum(c2) / dim;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < dim) dx[(size_t)row * dim + i] = rs * (d[k] - c1 - xh[k] * c2);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < dim) {
+      part[(size_t)cls * dim + i] = dg[k];
+      part[(size_t)(classes + cls) * dim + i] = db[k];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_dx_kernel(const float* __restrict__ dy,
                                                                          const float* __restrict__ s,
                                                                          const float* __restrict__ mean,
@@ -69,7 +236,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_dx_kernel(const f
 }
 
 // parts = gridDim.x row classes (rows r = part, part + parts, ...): enough of them to fill the GPU at any row count
-__host__ __device__ inline int ln_parts(int rows) { return rows <= 8192 ? 64 : (rows / 128 < 2048 ? rows / 128 : 2048); }
+__host__ __device__ inline int ln_parts(int rows) { return rows / 8 < 64 ? 64 : (rows / 8 < 4736 ? rows / 8 : 4736); }
 __global__ void layernorm_bwd_param_partial_kernel(const float* __restrict__ dy, const float* __restrict__ s,
                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                    float* __restrict__ part, int rows, int dim) {
@@ -314,9 +481,8 @@ extern "C" int bbbp_add_layernorm_fwd_f32(const float* x, const float* res, cons
   BBBP_CHECK_ARG(x && gamma && beta && y && rows >= 0 && dim > 0, "add_layernorm_fwd: bad argument");
   BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd: ld_bf16 < dim");
   if (rows == 0) return BBBP_OK;
-  add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
-      x, res, gamma, beta, y, sum_out, mean, rstd, reinterpret_cast<uint16_t*>(y_bf16), ld_bf16, rows, dim, eps, dim, dim,
-      dim, BBBP_FMT_BF16);
+  launch_add_layernorm_fwd(rows, dim, as_stream(stream), x, res, gamma, beta, y, sum_out, mean, rstd,
+                           reinterpret_cast<uint16_t*>(y_bf16), ld_bf16, rows, dim, eps, dim, dim, dim, (int)BBBP_FMT_BF16);
   return launch_status("add_layernorm_fwd");
 }
 
@@ -336,9 +502,8 @@ extern "C" int bbbp_add_layernorm_fwd_pitched16(int fmt, const float* x, int ld_
                  "add_layernorm_fwd_pitched: bad argument");
   BBBP_CHECK_ARG(!y_bf16 || ld_bf16 >= dim, "add_layernorm_fwd_pitched: ld_bf16 < dim");
   if (rows == 0) return BBBP_OK;
-  add_layernorm_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, as_stream(stream)>>>(
-      x, res, gamma, beta, y, nullptr, nullptr, nullptr, reinterpret_cast<uint16_t*>(y_bf16), ld_bf16, rows, dim, eps, ld_x,
-      ld_res, ld_y, fmt);
+  launch_add_layernorm_fwd(rows, dim, as_stream(stream), x, res, gamma, beta, y, (float*)nullptr, (float*)nullptr,
+                           (float*)nullptr, reinterpret_cast<uint16_t*>(y_bf16), ld_bf16, rows, dim, eps, ld_x, ld_res, ld_y, fmt);
   return launch_status("add_layernorm_fwd_pitched");
 }
 
@@ -364,6 +529,14 @@ extern "C" int bbbp_layernorm_bwd_f32(const float* dy, const float* s, const flo
     layernorm_bwd_small_kernel<<<row_blocks + ceil_div(dim, 32), LN_WARPS * 32, 0, st>>>(
         dy, s, mean, rstd, gamma, dx, dgamma, dbeta, rows, dim, row_blocks);
     return launch_status("layernorm_bwd (small)");
+  }
+  if (dim <= 512) {
+    const dim3 grid(ceil_div(parts, LN_WARPS)), block(LN_WARPS * 32);
+    if (dim <= 192) layernorm_bwd_fused_kernel<6><<<grid, block, 0, st>>>(dy, s, mean, rstd, gamma, dx, workspace, rows, dim, parts);
+    else layernorm_bwd_fused_kernel<16><<<grid, block, 0, st>>>(dy, s, mean, rstd, gamma, dx, workspace, rows, dim, parts);
+    layernorm_bwd_param_final_kernel<<<ceil_div(dim, 128), 128, 0, st>>>(workspace, dgamma, dbeta, dim, parts);
+    note_launches(1);
+    return launch_status("layernorm_bwd (fused)");
   }
   layernorm_bwd_dx_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, st>>>(dy, s, mean, rstd, gamma, dx, rows, dim);
   layernorm_bwd_param_partial_kernel<<<dim3(parts, ceil_div(dim, 128)), 128, 0, st>>>(dy, s, mean, rstd, workspace, rows, dim);

@@ -182,6 +182,10 @@ int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, b
 /* Diagnostics: probe = DEVICE array of 16 uint64 cycle counters that CTA 0 of the tcgen05 conv kernels accumulates
  * per pipeline role (see conv_umma.cu), or NULL to switch the probe off (default). */
 int bbbp_debug_conv_probe(void* probe);
+/* Diagnostics: TMEM -> register read rate of one SM (tcgen05.ld 32x32b.x32 in a loop, `warps` = 4 or 8 reading warps).
+ * out: DEVICE uint64[3] = {cycles, bytes read, checksum}.  The pooled convolutions read four pre-pool accumulators per
+ * output value, so this rate is the first layer's floor. */
+int bbbp_debug_tmem_read_probe(void* out, int warps, int reps, bbbp_stream_t stream);
 /* fp32 NCHW image with C <= 8 planes (the reference's (B,3*128*128) input viewed as (B,3,128,128), 20250113.py:114)
  * -> bf16 NHWC with 8 channels per pixel, channels >= C zero */
 int bbbp_image_to_nhwc8_bf16(const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W, bbbp_stream_t stream);

@@ -64,6 +64,20 @@ def main():
             a_hi, a_lo = ops.cast16(a, fmt, want_lo=split)
             o2, _ = ops.gemm_bf16(a_hi, 65536, wfc, 128, bias=fc.bias, act="relu", split_k=8, fmt=fmt, a_lo=a_lo)
             rep(f"[{mode}] Linear(65536,128) alone, exact input", o2, r3)
+            if split:
+                # is the rest weight rounding, or the tensor core's accumulation over a long K?  more split-K partials
+                # (summed in fp32 by the finish kernel) shorten every accumulation chain; split weights remove their rounding
+                for sk in (1, 8, 32, 128):
+                    o3, _ = ops.gemm_bf16(a_hi, 65536, wfc, 128, bias=fc.bias, act="relu", split_k=sk, fmt=fmt, a_lo=a_lo)
+                    rep(f"[{mode}]   ... split_k = {sk}", o3, r3)
+                w_hi, w_lo = ops.cast16(wfc.float(), fmt, want_lo=False)[0], None
+                wexact = ops.fc_weight_to_hwc_bf16(fc.weight.detach(), 64, 1024, fmt)
+                w32 = torch.empty((128, 65536), device=dev)
+                w32.copy_(fc.weight.detach().view(128, 64, 1024).permute(0, 2, 1).reshape(128, 65536))
+                wh, wl = ops.cast16(w32, fmt, want_lo=True)
+                for sk in (8, 128):
+                    o4, _ = ops.gemm_bf16(a_hi, 65536, wh, 128, bias=fc.bias, act="relu", split_k=sk, fmt=fmt, a_lo=a_lo, w_lo=wl)
+                    rep(f"[{mode}]   ... split weights too (x3), split_k = {sk}", o4, r3)
         want = torch.cat([model(fp[i:i + 256], img[i:i + 256]).reshape(-1) for i in range(0, fp.shape[0], 256)])
         for mode in ("strict", "fp16", "bf16"):
             ours.set_precision(mode)

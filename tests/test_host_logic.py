@@ -182,6 +182,56 @@ def test_gradient_averaging_world2_gloo(tmp_path):
         np.testing.assert_array_equal(np.load(tmp_path / f"g{r}.npy"), want)
 
 
+def _flat_grad_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                                    # identical replicas
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 1))
+        unused = torch.nn.Parameter(torch.ones(4))              # never reached by backward: its bucket is reduced as zeros
+        flat = bbbp_b200.FlatGradients(list(net.parameters()) + [unused], bucket_bytes=32)      # several tiny buckets
+        assert len(flat.buckets) >= 3 and all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())
+        out = []
+        for step in range(2):
+            g = torch.Generator().manual_seed(10 * step + rank)         # a different micro-batch per rank
+            x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+            flat.zero()
+            torch.nn.functional.mse_loss(net(x), y).backward()          # hooks launch the bucket all-reduces during backward
+            flat.synchronize()
+            out.append(flat.flat.clone())
+        np.save(os.path.join(out_dir, f"f{rank}.npy"), torch.stack(out).numpy())
+        flat.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_buckets_average_during_backward_world2_gloo(tmp_path):
+    """SURVEY 8e data-parallel training: every p.grad is a view into ONE persistent buffer, buckets are all-reduced as
+    backward completes them; the result equals the mean of the two replicas' micro-batch gradients."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_flat_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(tmp_path / f"f{r}.npy") for r in range(2)]
+    np.testing.assert_array_equal(got[0], got[1])
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 1))
+    for step in range(2):
+        grads = []
+        for rank in range(2):
+            g = torch.Generator().manual_seed(10 * step + rank)
+            x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+            net.zero_grad()
+            torch.nn.functional.mse_loss(net(x), y).backward()
+            grads.append(torch.cat([p.grad.reshape(-1) for p in reversed(list(net.parameters()))]))
+        want = torch.cat([torch.zeros(4), (grads[0] + grads[1]) / 2])       # buffer layout: reverse parameter order
+        np.testing.assert_allclose(got[0][step], want.numpy(), rtol=1e-6, atol=1e-7)
+
+
 def test_device_batch_feeder_reproduces_dataloader_order():
     """same batches, same order as the reference's MixedDataset + DataLoader(shuffle=True) under the same
     torch seed, for several epochs (the DataLoader draws one seed per epoch from the global generator)."""

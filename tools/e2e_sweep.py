@@ -3,7 +3,7 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bbbp_b200
 dev = torch.device("cuda:0"); torch.manual_seed(0)
-m = bbbp_b200.MixedInputModel(167, 128).to(dev).eval().set_precision("bf16")
+m = bbbp_b200.MixedInputModel(167, 128).to(dev).eval().set_precision(os.environ.get("PRECISION", "bf16"))
 n = int(os.environ.get("N", 8192))
 packed = torch.randint(0, 256, (n, 21), dtype=torch.uint8).pin_memory()
 img8 = torch.randint(0, 256, (n, 3, 128, 128), dtype=torch.uint8).pin_memory()
