@@ -112,8 +112,8 @@ class Linear(Function):
             fmt, split = TENSOR_CORE[precision]
             a_hi, a_lo = ops.cast16(x, fmt, want_lo=split)
             w_hi, w_lo = weight16(weight, fmt, split)
-            y, _ = ops.gemm_bf16(a_hi, K, w_hi, N, bias=bias, act=act, split_k=ops.fixed_split_k(K), fmt=fmt, a_lo=a_lo,
-                                 w_lo=w_lo)
+            y, _ = ops.gemm_bf16(a_hi, K, w_hi, N, bias=bias, act=act, fmt=fmt, a_lo=a_lo, w_lo=w_lo,
+                                 split_k=ops.fixed_split_k_strict(K) if split else ops.fixed_split_k(K))
         else:
             # inference keeps a K-only split (bit-identical scores however batches are grouped); a training forward
             # has no such contract and takes the latency mode (one-shot kernel at M <= 32)

@@ -174,8 +174,19 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
   float s = 0.0f;
-  if (c < cols)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += x[(size_t)r * ldx + c];
+  if (c < cols) {
+    // four independent row streams per thread: four loads in flight instead of one (0.61 -> of the HBM roofline before)
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      s0 += x[(size_t)r * ldx + c];
+      s1 += x[(size_t)(r + 8) * ldx + c];
+      s2 += x[(size_t)(r + 16) * ldx + c];
+      s3 += x[(size_t)(r + 24) * ldx + c];
+    }
+    for (; r < r1; r += 8) s0 += x[(size_t)r * ldx + c];
+    s = (s0 + s1) + (s2 + s3);
+  }
   s = strip_reduce(s, red);
   if (c < cols && threadIdx.y == 0) part[(size_t)blockIdx.y * cols + c] = s;
 }
@@ -391,6 +402,49 @@ __global__ void __launch_bounds__(128) unpack_zscore_kernel(const uint8_t* __res
   if (sd == 0.0) sd = 1.0;
   const float v0 = (float)((0.0 - mean) / sd), v1 = (float)((1.0 - mean) / sd);
   for (int i = lane; i < n_bits; i += 32) out[(size_t)row * ld_out + i] = ((pr[i >> 3] >> (i & 7)) & 1) ? v1 : v0;
+}
+
+// Contiguous output (ld_out == n_bits, 16-byte aligned base): a block owns FOUR consecutive rows, whose 4 * n_bits floats
+// start on a 16-byte boundary whatever n_bits is, and writes them as 128-bit stores (the warp-per-row kernel above writes
+// rows of 167 floats with scalar stores: 0.27 of the HBM roofline).  Same float64 statistics, same two values per row.
+__global__ void __launch_bounds__(128) unpack_zscore_vec_kernel(const uint8_t* __restrict__ packed, int bytes_per_row,
+                                                                float* __restrict__ out, int rows, int n_bits) {
+  extern __shared__ uint8_t sm_bits[];                 // 4 rows of packed bytes
+  __shared__ float2 sval[4];
+  const int row0 = blockIdx.x * 4, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = row0 + warp;
+  int pop = 0;
+  if (row < rows) {
+    const uint8_t* pr = packed + (size_t)row * bytes_per_row;
+    for (int b = lane; b < bytes_per_row; b += 32) {
+      uint32_t byte = pr[b];
+      sm_bits[warp * bytes_per_row + b] = (uint8_t)byte;
+      int valid = n_bits - b * 8;
+      if (valid < 8) byte &= (1u << (valid > 0 ? valid : 0)) - 1u;
+      pop += __popc(byte);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
+  if (lane == 0) {
+    const double mean = (double)pop / n_bits;
+    const double var = ((double)pop * (1.0 - mean) * (1.0 - mean) + (double)(n_bits - pop) * mean * mean) / n_bits;
+    double sd = sqrt(var);
+    if (sd == 0.0) sd = 1.0;
+    sval[warp] = make_float2((float)((0.0 - mean) / sd), (float)((1.0 - mean) / sd));
+  }
+  __syncthreads();
+  const int nrows = min(4, rows - row0);
+  const int total4 = nrows * n_bits / 4, tail = nrows * n_bits % 4;       // tail != 0 only for the last, ragged block
+  float* obase = out + (size_t)row0 * n_bits;
+  auto value = [&](int e) {
+    const int r = e / n_bits, i = e - r * n_bits;
+    const float2 v = sval[r];
+    return ((sm_bits[r * bytes_per_row + (i >> 3)] >> (i & 7)) & 1) ? v.y : v.x;
+  };
+  for (int g = threadIdx.x; g < total4; g += 128)
+    reinterpret_cast<float4*>(obase)[g] = make_float4(value(4 * g), value(4 * g + 1), value(4 * g + 2), value(4 * g + 3));
+  if ((int)threadIdx.x < tail) obase[total4 * 4 + threadIdx.x] = value(total4 * 4 + threadIdx.x);
 }
 
 __device__ __forceinline__ double block_sum_double(double v, double* red) {
@@ -711,7 +765,10 @@ extern "C" int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, 
   BBBP_CHECK_ARG(packed && out && rows >= 0 && n_bits > 0 && bytes_per_row * 8 >= n_bits && ld_out >= n_bits,
                  "unpack_zscore: bad argument");
   if (rows == 0) return BBBP_OK;
-  unpack_zscore_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(packed, bytes_per_row, out, ld_out, rows, n_bits);
+  if (ld_out == n_bits && ((uintptr_t)out & 15) == 0 && bytes_per_row <= 2048)
+    unpack_zscore_vec_kernel<<<ceil_div(rows, 4), 128, 4 * bytes_per_row, as_stream(stream)>>>(packed, bytes_per_row, out, rows, n_bits);
+  else
+    unpack_zscore_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(packed, bytes_per_row, out, ld_out, rows, n_bits);
   return launch_status("unpack_zscore");
 }
 

@@ -438,7 +438,7 @@ class TransformerCnnModel(_KernelModule):
                 y1, y1_lo = ops.conv1_from_image_bf16(part, w1, conv1.bias, stats, fmt=fmt, split=True)
                 y2, y2_lo = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64, fmt=fmt, x_lo=y1_lo)
                 o, _ = ops.gemm_bf16(y2.view(y2.shape[0], 65536), 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
-                                     split_k=ops.fixed_split_k(65536), fmt=fmt, a_lo=y2_lo.view(y2.shape[0], 65536))
+                                     split_k=ops.fixed_split_k_strict(65536), fmt=fmt, a_lo=y2_lo.view(y2.shape[0], 65536))
             else:
                 y1 = ops.conv1_from_image_bf16(part, w1, conv1.bias, stats, fmt=fmt)
                 y2 = ops.conv3x3_relu_pool_bf16(y1, w2, conv2.bias, 64, fmt=fmt)

@@ -114,6 +114,14 @@ def fixed_split_k(K: int) -> int:
     return 1 if K < 8192 else min(8, K // 2048)
 
 
+def fixed_split_k_strict(K: int) -> int:
+    """Strict mode: the tensor core's fp32 accumulator is not a round-to-nearest one, and its error grows with the length
+    of an accumulation chain (measured on Linear(65536, 128), tests/strict_error_budget.py: relative error 2.6e-4 with one
+    chain of 1 024 K-blocks, 3.7e-5 with 8 chains, 1.2e-5 with 32, 8e-6 with 128).  More split-K partials -- summed in fp32
+    by the finish kernel -- shorten every chain: 32 K-blocks of 64 at most.  Still a function of K only."""
+    return 1 if K < 4096 else min(64, K // 2048)
+
+
 def fixed_split_k_f32(K: int) -> int:
     """Same contract for the CUDA-core fp32 GEMM (64-wide tiles, used at small batch where tiles are few)."""
     return 1 if K < 1024 else min(64, K // 256)

@@ -47,7 +47,8 @@ def pca_transform(x: torch.Tensor, mean: torch.Tensor, components: torch.Tensor,
         K, k = x.shape[1], comp.shape[0]
         a_hi, a_lo = ops.cast16(x, fmt, want_lo=split, sub=mean.contiguous())
         w_hi, w_lo = ops.cast16(comp, fmt, want_lo=split)
-        y, _ = ops.gemm_bf16(a_hi, K, w_hi, k, split_k=ops.fixed_split_k(K), fmt=fmt, a_lo=a_lo, w_lo=w_lo)
+        y, _ = ops.gemm_bf16(a_hi, K, w_hi, k, fmt=fmt, a_lo=a_lo, w_lo=w_lo,
+                             split_k=ops.fixed_split_k_strict(K) if split else ops.fixed_split_k(K))
         return y
     shift = ops.gemm_f32(mean.reshape(1, -1).contiguous(), comp, trans_b=True)          # (1, k) = mean @ C^T
     neg = ops.scale_by_device_scalar(shift.reshape(-1), torch.full((1,), -1.0, device=x.device))

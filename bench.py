@@ -44,6 +44,9 @@ IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
 # the workload both arms run (identical dict in both JSON lines; per-arm sample sizes live outside it)
 CONFIG = {"workload": "screen_maccs_b256", "model": "MixedInputModel(167,128) 20250113 (13.46M params)", "batch": BATCH,
           "inputs": "MACCS-167 fingerprint + 3x128x128 depiction per molecule"}
+# molecules per staged chunk of the host pipeline: a chunk's replay costs ~0.55 ms + its compute, its copy 0.94 ms per 1 024
+# (tools/e2e_sweep.py on B200, strict mode, 16 384 molecules: 1 024 -> 20.0 ms, 2 048 -> 16.4 ms, 4 096 -> 17.5 ms)
+E2E_CHUNK = 2048
 DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (hi+lo pairs, fp32 accumulate)"}
 
 
@@ -331,7 +334,7 @@ def main():
     def step_e2e_compact():
         # the user-facing host API: chunked H2D on a copy stream overlapped with scoring, D2H of the scores, and a wait
         # for that copy -- every step ends with its scores readable in host memory
-        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=1024, packed=True, out_host=scores_host,
+        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=E2E_CHUNK, packed=True, out_host=scores_host,
                                        return_device=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
@@ -344,7 +347,7 @@ def main():
         # the first H2D chunks of step k+1 fly while the last chunk of step k is scored; results are complete at the
         # synchronisation that closes the timed region
         stream_state[0] ^= 1
-        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=1024, packed=True,
+        _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=E2E_CHUNK, packed=True,
                                        out_host=scores_host2 if stream_state[0] else scores_host, return_device=True,
                                        synchronize=False)
         if world > 1:

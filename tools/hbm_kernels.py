@@ -29,8 +29,11 @@ y, s_, mean, rstd, _ = ops.add_layernorm_fwd(x, res, g, b, save=True)
 dy = torch.randn_like(x)
 report("LayerNorm bwd (dy, s -> dx, dgamma, dbeta)", 3 * x.numel() * 4 + 2 * x.numel() * 4, t(lambda: ops.layernorm_bwd(dy, s_, mean, rstd, g)))
 del y, s_, dy, res
-report("cast fp32 -> bf16 (pitch 168)", x.numel() * 4 + R * 168 * 2, t(lambda: ops.cast_bf16(x)))
-report("ReLU backward (dy, y -> dx)", 3 * x.numel() * 4, t(lambda: ops.act_bwd(x, x, "relu")))
+report("cast fp32 -> bf16 (pitch 168)", x.numel() * 4 + R * 168 * 2, t(lambda: ops.cast16(x, 0)))
+report("cast fp32 -> fp16 hi + lo pair (pitch 168)", x.numel() * 4 + 2 * R * 168 * 2, t(lambda: ops.cast16(x, 1, want_lo=True)))
+x2 = torch.randn(R, 167, device=dev)
+report("ReLU backward (dy, y -> dx)", 3 * x.numel() * 4, t(lambda: ops.act_bwd(x2, x, "relu")))
+del x2
 report("dropout (x -> y)", 2 * x.numel() * 4, t(lambda: ops.dropout(x, 0.1, 7)))
 report("column sum (bias gradient)", x.numel() * 4, t(lambda: ops.colsum(x)))
 del x
