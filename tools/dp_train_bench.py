@@ -82,6 +82,14 @@ if world > 1:
     res["allreduce_ms_alone"] = timed(lambda: dist.all_reduce(flat.flat, op=dist.ReduceOp.AVG), 20)
     res["allreduce_bus_GBs"] = 2 * (world - 1) / world * flat.flat.numel() * 4 / (res["allreduce_ms_alone"] * 1e-3) / 1e9
 flat._hooks = [p.register_post_accumulate_grad_hook(flat._on_grad) for p in flat.params] if world > 1 else []
+if world > 1:      # the un-synchronised variant above let the replicas drift apart: start the DP phase from rank 0's state
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, 0)
+    for st in opt.state.values():
+        for v in st.values():
+            if torch.is_tensor(v) and v.is_cuda:
+                dist.broadcast(v, 0)
+    bbbp_b200.autograd.clear_weight_cache()
 res["step_ms_bucketed_overlapped"] = timed(step_overlapped)
 chk = torch.tensor([float(sum(p.double().sum() for p in model.parameters()))], device=dev, dtype=torch.float64)
 if world > 1:
