@@ -175,6 +175,82 @@ class ConvReluPool(Function):
         return dx, dw, db
 
 
+class ImageBranchTensorCore(Function):
+    """The whole image branch of the canonical network (20250113.py:85-93: two conv + ReLU + max-pool blocks, Flatten,
+    Linear(65536, 128) + ReLU) for TRAINING in a tensor-core precision mode, forward and backward, with every contraction
+    on the tcgen05 GEMM and NHWC 16-bit activations in between (see csrc/conv_train.cu):
+
+      forward   x0 = NHWC8(image); per block: cols = im2col(x) -> a = relu(cols W^T + b) -> (y, argmax) = pool(a);
+                out = relu(flat(y2) Wfc_hwc^T + bfc)
+      backward  Linear: dWfc = dpre^T flat, dflat = dpre Wfc_hwc (operands read in place, MN-major);
+                per block: dpre = unpool(dy, argmax, y > 0); dW = dpre^T cols (MN-major both, split-K over the pixels);
+                db = column sum of the masked pooled gradient; dy_prev = im2col(dpre) Wflip^T.
+
+    The im2col rows of the forward pass are kept for the weight gradients (0.6 GB per block at batch 256).  Gradients leave
+    in fp32; operands are rounded to the mode's 16-bit format once, as in the forward pass."""
+
+    @staticmethod
+    def forward(ctx, image, w1, b1, w2, b2, wfc, bfc, fmt):
+        img = image if image.is_contiguous() else image.contiguous()
+        n = img.numel() // (3 * 128 * 128)
+        x0 = ops.image_to_nhwc8_16(img, fmt)
+        saved_blocks = []
+        x = x0
+        for w, b in ((w1, b1), (w2, b2)):
+            nb, H, W, C = x.shape
+            cout = w.shape[0]
+            w16 = derived_weight(w, f"im2col16_{fmt}_{C}", lambda d, C=C: ops.conv3x3_weight_im2col16(d, C, fmt))
+            cols = ops.im2col3x3_16(x)
+            _, a = ops.gemm_bf16(cols, 9 * C, w16, cout, bias=b, act="relu", out_f32=False, out_bf16=True, fmt=fmt)
+            y, arg = ops.maxpool2x2_argmax_nhwc16(a.view(nb, H, W, cout), fmt)
+            saved_blocks.append((cols, y, arg))
+            x = y
+        flat = x.view(n, -1)
+        K = flat.shape[1]
+        c_last, hw_last = x.shape[3], x.shape[1] * x.shape[2]
+        wfc16 = derived_weight(wfc, f"hwc_{fmt}", lambda d: ops.fc_weight_to_hwc_bf16(d, c_last, hw_last, fmt))
+        out, _ = ops.gemm_bf16(flat, K, wfc16, wfc.shape[0], bias=bfc, act="relu", split_k=ops.fixed_split_k(K), fmt=fmt)
+        ctx.fmt, ctx.dims = fmt, (c_last, hw_last)
+        (c1, y1, a1), (c2, y2, a2) = saved_blocks
+        ctx.save_for_backward(c1, y1, a1, c2, y2, a2, out, w1, w2, wfc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        c1, y1, a1, c2, y2, a2, out, w1, w2, wfc = ctx.saved_tensors
+        fmt = ctx.fmt
+        c_last, hw_last = ctx.dims
+        n = out.shape[0]
+        sms = ops.sm_count(dout.device)
+        # Linear(65536, 128) + ReLU
+        dpre = ops.act_bwd(contig(dout), out, "relu")
+        dbfc = ops.colsum(dpre)
+        dp16, _ = ops.cast16(dpre, fmt)                                        # (n, 128)
+        flat = y2.view(n, -1)
+        K = flat.shape[1]
+        g_hwc, _ = ops.gemm16_tn(dp16, flat, wfc.shape[0], K, n, trans_a=True, trans_w=True, fmt=fmt)       # dpre^T flat
+        dwfc = ops.fc_grad_hwc_to_chw(g_hwc, c_last, hw_last)
+        wfc16 = derived_weight(wfc, f"hwc_{fmt}", lambda d: ops.fc_weight_to_hwc_bf16(d, c_last, hw_last, fmt))
+        dy, _ = ops.gemm16_tn(dp16, wfc16, n, K, wfc.shape[0], trans_w=True, fmt=fmt)                         # dpre Wfc_hwc
+        grads = []
+        for cols, y, arg, w, last in ((c2, y2, a2, w2, False), (c1, y1, a1, w1, True)):
+            nb, OH, OW, cout = y.shape
+            cin, cpad = w.shape[1], cols.shape[1] // 9
+            dp, dym = ops.unpool_relu_nhwc16(dy.view(nb, OH, OW, cout), y, arg, fmt)
+            db = ops.colsum(dym.view(-1, cout))
+            pix = nb * 4 * OH * OW
+            split = max(1, min(2 * sms, pix // 64 // 8))
+            g, _ = ops.gemm16_tn(dp.view(pix, cout), cols, cout, 9 * cpad, pix, trans_a=True, trans_w=True, split_k=split, fmt=fmt)
+            grads.append((ops.conv3x3_wgrad_from_im2col(g, cin, cpad), db))
+            if not last:                                                       # gradient wrt the previous block's pooled output
+                wd = derived_weight(w, f"dgrad16_{fmt}", lambda d: ops.conv3x3_weight_dgrad16(d, cin, fmt))
+                dcols = ops.im2col3x3_16(dp)
+                dy, _ = ops.gemm_bf16(dcols, 9 * cout, wd, cin, fmt=fmt)       # (pix, cin) fp32 = NHWC gradient of y_prev
+                del dcols
+        (dw2, db2), (dw1, db1) = grads
+        return None, dw1, db1, dw2, db2, dwfc, dbfc, None
+
+
 class Attention(Function):
     """Self-attention over the molecules of each reference batch; qkv rows = groups*seq.
 

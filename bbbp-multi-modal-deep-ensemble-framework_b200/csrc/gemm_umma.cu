@@ -107,6 +107,12 @@ struct Params {
   int n_a, n_w; // 1, or 2 when a "lo" tile of A / W rides along (split passes)
   int stages;   // ring depth chosen by the host for this (n_a, n_w)
   uint16_t* out16_lo;   // optional lo part of the 16-bit output (same pitch / batch stride as out16)
+  // MN-major operands (the backward products read activations / weights in place, no transposed copies):
+  //   a_mn: A is stored [K][M] (M contiguous), b_mn: W is stored [K][N] (N contiguous).  The TMA box is then 64 elements of
+  //   M (N) x 64 rows of K, one box per 64-wide block of the tile; in shared memory a block is 64 K-rows of 128 bytes
+  //   (128B swizzle), the canonical MN-major layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) with SBO = 1024 (8 K-rows) and
+  //   LBO = 8192 (next 64-wide block); a K = 16 MMA step advances the start address by 16 rows = 2048 bytes.
+  int a_mn, b_mn;
 };
 
 // 32 fp32 values -> 32 16-bit values as four 16-byte stores (and the matching lo parts when lo != nullptr)
@@ -186,16 +192,24 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         uint8_t* st = tiles + s * stage_bytes;
         const int kc = (kb_begin + i) * BK;
-        tma_load_3d(&tmA, &full[s], st, kc, m0, batch);
-        if (p.n_a == 2) tma_load_3d(&tmA2, &full[s], st + C::A_BYTES, kc, m0, batch);
-        tma_load_3d(&tmB, &full[s], st + b_off, kc, n0, batch);
-        if (p.n_w == 2) tma_load_3d(&tmB2, &full[s], st + b_off + C::B_BYTES, kc, n0, batch);
+        if (p.a_mn) {
+          for (int mb = 0; mb < BM / 64; ++mb) tma_load_3d(&tmA, &full[s], st + mb * 8192, m0 + mb * 64, kc, batch);
+        } else {
+          tma_load_3d(&tmA, &full[s], st, kc, m0, batch);
+          if (p.n_a == 2) tma_load_3d(&tmA2, &full[s], st + C::A_BYTES, kc, m0, batch);
+        }
+        if (p.b_mn) {
+          for (int nb = 0; nb < BN / 64; ++nb) tma_load_3d(&tmB, &full[s], st + b_off + nb * 8192, n0 + nb * 64, kc, batch);
+        } else {
+          tma_load_3d(&tmB, &full[s], st + b_off, kc, n0, batch);
+          if (p.n_w == 2) tma_load_3d(&tmB2, &full[s], st + b_off + C::B_BYTES, kc, n0, batch);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_16(BM, BN, p.fmt);
+      const uint32_t idesc = make_idesc_16(BM, BN, p.fmt) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -205,8 +219,10 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // K-major, 128B swizzle: 8-row atoms 1024 B apart (SBO); one atom along K, advance 32 B per UMMA_K
-          const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSw128);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSw128);
+          const uint64_t ad = p.a_mn ? make_smem_desc(a_addr + k * 2048, 8192, 1024, kLayoutSw128)
+                                     : make_smem_desc(a_addr + k * 32, 0, 1024, kLayoutSw128);
+          const uint64_t bd = p.b_mn ? make_smem_desc(b_addr + k * 2048, 8192, 1024, kLayoutSw128)
+                                     : make_smem_desc(b_addr + k * 32, 0, 1024, kLayoutSw128);
           umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0);
           if (p.n_a == 2)      // + A_lo W_hi^T
             umma_bf16(tmem_base, make_smem_desc(a_addr + C::A_BYTES + k * 32, 0, 1024, kLayoutSw128), bd, idesc, true);
@@ -405,6 +421,7 @@ struct Problem {
   Params p;
   const void* A_lo = nullptr;   // optional lo parts (same pitch / batch stride as the hi parts)
   const void* W_lo = nullptr;
+  bool a_mn = false, b_mn = false;   // A stored [K][M] / W stored [K][N]
 };
 
 template <int BN, int EPI>
@@ -412,11 +429,16 @@ int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   using C = Cfg<BN>;
   // (fp16 tiles go through the same 2-byte tensor maps: the element type only selects the out-of-bounds fill, zero in both)
   CUtensorMap tmA, tmB, tmA2, tmB2;
-  int st = make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
-                             (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  // K-major: rows = M (N), cols = K, box = tile rows x 64.  MN-major: rows = K, cols = M (N), box = 64 K-rows x 64 columns.
+  int st = pr.a_mn ? make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.K, (uint64_t)pr.M, (uint64_t)pr.lda, (uint64_t)pr.batches,
+                                       (uint64_t)pr.a_bs, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+                   : make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
+                                       (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != BBBP_OK) return st;
-  st = make_tmap_bf16_3d(&tmB, pr.W, (uint64_t)pr.N, (uint64_t)pr.K, (uint64_t)pr.ldw, (uint64_t)pr.batches,
-                         (uint64_t)pr.w_bs, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  st = pr.b_mn ? make_tmap_bf16_3d(&tmB, pr.W, (uint64_t)pr.K, (uint64_t)pr.N, (uint64_t)pr.ldw, (uint64_t)pr.batches,
+                                   (uint64_t)pr.w_bs, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+               : make_tmap_bf16_3d(&tmB, pr.W, (uint64_t)pr.N, (uint64_t)pr.K, (uint64_t)pr.ldw, (uint64_t)pr.batches,
+                                   (uint64_t)pr.w_bs, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (st != BBBP_OK) return st;
   tmA2 = tmA, tmB2 = tmB;
   if (pr.A_lo) {
@@ -432,6 +454,7 @@ int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   Params p = pr.p;
   p.n_a = pr.A_lo ? 2 : 1;
   p.n_w = pr.W_lo ? 2 : 1;
+  p.a_mn = pr.a_mn, p.b_mn = pr.b_mn;
   p.stages = C::stages(p.n_a, p.n_w);
   const int smem_bytes = C::smem_bytes(p.n_a, p.n_w);
   p.M = pr.M;
@@ -591,6 +614,44 @@ extern "C" int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const
   pr.p.bias = bias, pr.p.residual = residual, pr.p.ld_res = ld_res;
   pr.p.out = out_f32, pr.p.ld_out = ld_out;
   pr.p.out16 = static_cast<uint16_t*>(out16_hi), pr.p.out16_lo = static_cast<uint16_t*>(out16_lo), pr.p.ld_out16 = ld_out16;
+  pr.p.act = act, pr.p.partial = static_cast<float*>(workspace), pr.p.fmt = fmt;
+  cudaStream_t s = as_stream(stream);
+  if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, split_k, s);
+  if (N >= 512 && split_k == 1) return gemm::launch<256, gemm::EPI_LINEAR>(pr, split_k, s);
+  return gemm::launch<128, gemm::EPI_LINEAR>(pr, split_k, s);
+}
+
+// out[M,N] = opA(A) opW(W)^T with either operand read in place in its MN-major storage (see Params::a_mn).
+extern "C" int bbbp_gemm16_tn(int fmt, int trans_a, int trans_w, int M, int N, int K, const void* A, int lda, const void* W,
+                              int ldw, const float* bias, float* out_f32, int ld_out, void* out16, int ld_out16, int act,
+                              int split_k, void* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
+  using namespace bbbp;
+  int st = check_fmt("gemm16_tn", fmt);
+  if (st != BBBP_OK) return st;
+  BBBP_CHECK_ARG(M >= 0 && N >= 0 && K > 0 && A && W, "gemm16_tn: bad argument");
+  BBBP_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && lda >= (trans_a ? M : K) && ldw >= (trans_w ? N : K),
+                 "gemm16_tn: pitches must be multiples of 8 and cover the contiguous dimension");
+  BBBP_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm16_tn: operands must be 16-byte aligned");
+  BBBP_CHECK_ARG(out_f32 || out16, "gemm16_tn: no output given");
+  BBBP_CHECK_ARG((!out_f32 || ld_out >= N) && (!out16 || ld_out16 >= N), "gemm16_tn: output pitch < N");
+  if (M == 0 || N == 0) return BBBP_OK;
+  if (split_k < 1) split_k = 1;
+  const int total_kb = ceil_div(K, gemm::BK);
+  if (split_k > total_kb) split_k = total_kb;
+  if (split_k > 1) {
+    const size_t need = bbbp_gemm_bf16_workspace(M, N, split_k);
+    if (!workspace || workspace_bytes < need) {
+      set_error("gemm16_tn: split_k=%d needs %zu workspace bytes, got %zu", split_k, need, workspace_bytes);
+      return BBBP_EWORKSPACE;
+    }
+  }
+  gemm::Problem pr{};
+  pr.M = M, pr.N = N, pr.K = K, pr.batches = 1;
+  pr.A = A, pr.lda = lda, pr.W = W, pr.ldw = ldw;
+  pr.a_mn = trans_a != 0, pr.b_mn = trans_w != 0;
+  pr.p.bias = bias;
+  pr.p.out = out_f32, pr.p.ld_out = ld_out;
+  pr.p.out16 = static_cast<uint16_t*>(out16), pr.p.ld_out16 = ld_out16;
   pr.p.act = act, pr.p.partial = static_cast<float*>(workspace), pr.p.fmt = fmt;
   cudaStream_t s = as_stream(stream);
   if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, split_k, s);

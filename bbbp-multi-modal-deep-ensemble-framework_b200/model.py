@@ -364,6 +364,12 @@ class TransformerCnnModel(_KernelModule):
                 x = self._image_branch_im2col(image, mods)
                 return self._drop(x, mods[-1]) if isinstance(mods[-1], nn.Dropout) else x
             return self._image_branch_tensor_core(image, mods)
+        if (self.precision in ag.TENSOR_CORE and side == 128 and self.kind != "big" and image.dtype == torch.float32
+                and image.shape[0] >= self.tensor_core_train_min_batch and torch.is_grad_enabled()):
+            # training in a tensor-core mode: forward AND backward of the branch on the tcgen05 GEMM (autograd.ImageBranchTensorCore)
+            fmt, _ = ag.TENSOR_CORE[self.precision]
+            return ag.ImageBranchTensorCore.apply(image, mods[0].weight, mods[0].bias, mods[3].weight, mods[3].bias,
+                                                  mods[7].weight, mods[7].bias, fmt)
         x = image.reshape(-1, 3, side, side)
         i = 0
         while isinstance(mods[i], nn.Conv2d):
@@ -376,6 +382,7 @@ class TransformerCnnModel(_KernelModule):
         return x
 
     tensor_core_chunk = 0   # images per pass of the tcgen05 image branch (0 = all at once)
+    tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
     im2col_chunk = 256      # images per pass of the im2col route (bounds the im2col buffer: 4.7 MB per image at 64 -> 128)
 
     def _image_branch_im2col(self, image, mods):

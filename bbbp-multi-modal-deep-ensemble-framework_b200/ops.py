@@ -201,6 +201,23 @@ def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, 
     return (o32, o16, o16lo) if out16_lo is not None else (o32, o16)
 
 
+def gemm16_tn(a16, w16, M, N, K, trans_a=False, trans_w=False, bias=None, act=None, split_k=1, fmt=FMT_BF16, out16=False,
+              out_f32=True):
+    """act(opA(a16) @ opW(w16)^T + bias) with operands read in place: trans_a -> a16 is stored (K, M); trans_w -> w16 is
+    stored (K, N) (row pitches = tensor strides).  Returns (f32 | None, 16-bit | None)."""
+    o32 = torch.empty((M, N), device=a16.device, dtype=torch.float32) if out_f32 else None
+    ld16 = -(-N // 8) * 8
+    o16 = torch.empty((M, ld16), device=a16.device, dtype=_DT16[fmt]) if out16 else None
+    ws_bytes = lib.bbbp_gemm_bf16_workspace(M, N, split_k)
+    ws = torch.empty((ws_bytes,), device=a16.device, dtype=torch.uint8) if ws_bytes else None
+    if o16 is not None and ws_bytes and ld16 > N:
+        fill_zero(o16[:, N:])
+    check(lib.bbbp_gemm16_tn(fmt, int(trans_a), int(trans_w), M, N, K, a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0),
+                             _ptr(bias), _ptr(o32), N, _ptr(o16), ld16, _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()),
+          "gemm16_tn")
+    return o32, o16
+
+
 def fill_zero(t: torch.Tensor) -> torch.Tensor:
     """Zero a (possibly pitched) 2-D view or a contiguous tensor with the library's fill kernel."""
     if t.numel() == 0:
@@ -407,6 +424,68 @@ def conv3x3_weight_im2col_bf16(w: torch.Tensor, c_pad: int | None = None) -> tor
     out = torch.empty((Cout, 9 * c_pad), device=w.device, dtype=torch.bfloat16)
     check(lib.bbbp_conv3x3_weight_im2col_bf16(w.data_ptr(), out.data_ptr(), Cin, c_pad, Cout, _stream()), "conv3x3_weight_im2col")
     return out
+
+
+# ---- mixed-precision training path of the image branch (conv_train.cu) ---------------------------------------------------
+def image_to_nhwc8_16(img: torch.Tensor, fmt=FMT_BF16, C=3, H=128, W=128) -> torch.Tensor:
+    N = img.numel() // (C * H * W)
+    out = torch.empty((N, H, W, 8), device=img.device, dtype=_DT16[fmt])
+    check(lib.bbbp_image_to_nhwc8_16(fmt, img.data_ptr(), out.data_ptr(), N, C, H, W, _stream()), "image_to_nhwc8_16")
+    return out
+
+
+def im2col3x3_16(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """(N, H, W, C) 16-bit (either format) -> (N*H*W, 9*C) rows in (tap, channel) order, zero padding at the border."""
+    N, H, W, C = x_nhwc.shape
+    out = torch.empty((N * H * W, 9 * C), device=x_nhwc.device, dtype=x_nhwc.dtype)
+    check(lib.bbbp_im2col3x3_bf16(x_nhwc.data_ptr(), out.data_ptr(), N, H, W, C, _stream()), "im2col3x3")
+    return out
+
+
+def maxpool2x2_argmax_nhwc16(x_nhwc: torch.Tensor, fmt=FMT_BF16):
+    N, H, W, C = x_nhwc.shape
+    y = torch.empty((N, H // 2, W // 2, C), device=x_nhwc.device, dtype=x_nhwc.dtype)
+    arg = torch.empty((N, H // 2, W // 2, C), device=x_nhwc.device, dtype=torch.uint8)
+    check(lib.bbbp_maxpool2x2_argmax_nhwc16(fmt, x_nhwc.data_ptr(), y.data_ptr(), arg.data_ptr(), N, H, W, C, _stream()),
+          "maxpool2x2_argmax_nhwc16")
+    return y, arg
+
+
+def unpool_relu_nhwc16(dy: torch.Tensor, y: torch.Tensor, arg: torch.Tensor, fmt=FMT_BF16, want_masked=True):
+    """dy: fp32 (N, H/2, W/2, C) contiguous; returns (dpre 16-bit (N, H, W, C), dy * (y > 0) fp32 | None)."""
+    N, OH, OW, C = y.shape
+    dpre = torch.empty((N, 2 * OH, 2 * OW, C), device=y.device, dtype=y.dtype)
+    dym = torch.empty((N, OH, OW, C), device=y.device, dtype=torch.float32) if want_masked else None
+    check(lib.bbbp_unpool_relu_nhwc16(fmt, dy.data_ptr(), y.data_ptr(), arg.data_ptr(), dpre.data_ptr(), _ptr(dym), N, 2 * OH, 2 * OW,
+                                      C, _stream()), "unpool_relu_nhwc16")
+    return dpre, dym
+
+
+def conv3x3_weight_im2col16(w: torch.Tensor, c_pad: int, fmt=FMT_BF16) -> torch.Tensor:
+    Cout, Cin = w.shape[:2]
+    out = torch.empty((Cout, 9 * c_pad), device=w.device, dtype=_DT16[fmt])
+    check(lib.bbbp_conv3x3_weight_im2col16(fmt, w.data_ptr(), out.data_ptr(), Cin, c_pad, Cout, _stream()), "conv3x3_weight_im2col16")
+    return out
+
+
+def conv3x3_wgrad_from_im2col(g: torch.Tensor, Cin: int, c_pad: int) -> torch.Tensor:
+    Cout = g.shape[0]
+    dw = torch.empty((Cout, Cin, 3, 3), device=g.device, dtype=torch.float32)
+    check(lib.bbbp_conv3x3_wgrad_from_im2col_f32(g.data_ptr(), dw.data_ptr(), Cin, c_pad, Cout, _stream()), "wgrad_from_im2col")
+    return dw
+
+
+def conv3x3_weight_dgrad16(w: torch.Tensor, cin_pad: int, fmt=FMT_BF16) -> torch.Tensor:
+    Cout, Cin = w.shape[:2]
+    out = torch.empty((cin_pad, 9 * Cout), device=w.device, dtype=_DT16[fmt])
+    check(lib.bbbp_conv3x3_weight_dgrad16(fmt, w.data_ptr(), out.data_ptr(), Cin, cin_pad, Cout, _stream()), "conv3x3_weight_dgrad16")
+    return out
+
+
+def fc_grad_hwc_to_chw(g: torch.Tensor, C: int, HW: int) -> torch.Tensor:
+    dw = torch.empty_like(g)
+    check(lib.bbbp_fc_grad_hwc_to_chw_f32(g.data_ptr(), dw.data_ptr(), g.shape[0], C, HW, _stream()), "fc_grad_hwc_to_chw")
+    return dw
 
 
 # ---- attention --------------------------------------------------------------------------------------------------------

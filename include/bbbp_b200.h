@@ -103,6 +103,13 @@ int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo
                 int ldw, const float* bias, const float* residual, int ld_res, float* out_f32, int ld_out, void* out16_hi,
                 void* out16_lo, int ld_out16, int act, int split_k, void* workspace, size_t workspace_bytes,
                 bbbp_stream_t stream);
+/* Operands read in place in their TRANSPOSED storage (the backward products of a Linear layer and the convolution weight
+ * gradient over im2col rows need no transposed copies): trans_a != 0: A is stored [K][M] (M contiguous, lda >= M);
+ * trans_w != 0: W is stored [K][N] (N contiguous, ldw >= N).  out = act(opA(A) opW(W)^T + bias).  UMMA MN-major operand
+ * descriptors; split_k as bbbp_gemm_bf16. */
+int bbbp_gemm16_tn(int fmt, int trans_a, int trans_w, int M, int N, int K, const void* A, int lda, const void* W, int ldw,
+                   const float* bias, float* out_f32, int ld_out, void* out16, int ld_out16, int act, int split_k,
+                   void* workspace, size_t workspace_bytes, bbbp_stream_t stream);
 int bbbp_gemm16_batched(int fmt, int batches, int M, int N, int K, const void* A, int lda, long long a_batch_stride,
                         const void* W, int ldw, long long w_batch_stride, float* out_f32, int ld_out,
                         long long out_batch_stride, void* out16, int ld_out16, long long out16_batch_stride,
@@ -202,6 +209,26 @@ int bbbp_maxpool2x2_nhwc_bf16(const void* x_nhwc, void* y_nhwc, int N, int H, in
 /* out[Cout][9*Cpad] bf16 with out[co][tap*Cpad + c] = w[co][c][tap] (zero for c >= Cin): the W operand matching the
  * im2col row order */
 int bbbp_conv3x3_weight_im2col_bf16(const float* w, void* out_bf16, int Cin, int Cpad, int Cout, bbbp_stream_t stream);
+
+/* Mixed-precision TRAINING path of the image branch (conv_train.cu): every contraction runs on the tcgen05 GEMM -- the
+ * convolutions as im2col rows x weights (bbbp_im2col3x3_bf16 is format-agnostic), their weight gradients as
+ * dpre^T x im2col rows through bbbp_gemm16_tn (both operands MN-major, no transposes), their data gradient as
+ * im2col(dpre) x flipped weights -- and these are the memory-bound pieces in between, NHWC, 16-bit format fmt. */
+/* y[N,H/2,W/2,C] = 2x2 max-pool of x[N,H,W,C]; argmax[N,H/2,W/2,C] (uint8) = 2*i + j of the first maximum (torch order) */
+int bbbp_maxpool2x2_argmax_nhwc16(int fmt, const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C,
+                                  bbbp_stream_t stream);
+/* dpre[N,H,W,C] (16-bit) = dy[N,H/2,W/2,C] (fp32) routed to the arg-max member where y > 0 (ReLU), zeros elsewhere;
+ * dy_masked (fp32, may be NULL) = dy * (y > 0): its column sum is the bias gradient */
+int bbbp_unpool_relu_nhwc16(int fmt, const float* dy, const void* y, const uint8_t* argmax, void* dpre, float* dy_masked, int N,
+                            int H, int W, int C, bbbp_stream_t stream);
+int bbbp_image_to_nhwc8_16(int fmt, const float* img_nchw, void* out_nhwc8, int N, int C, int H, int W, bbbp_stream_t stream);
+/* out[Cout][9*Cpad] with out[co][tap*Cpad + c] = w[co][c][tap]; and its inverse for the fp32 gradient */
+int bbbp_conv3x3_weight_im2col16(int fmt, const float* w, void* out16, int Cin, int Cpad, int Cout, bbbp_stream_t stream);
+int bbbp_conv3x3_wgrad_from_im2col_f32(const float* g, float* dw, int Cin, int Cpad, int Cout, bbbp_stream_t stream);
+/* out[CinPad][9*Cout] with out[ci][tap*Cout + co] = w[co][ci][8 - tap]: the W operand of the data-gradient GEMM */
+int bbbp_conv3x3_weight_dgrad16(int fmt, const float* w, void* out16, int Cin, int CinPad, int Cout, bbbp_stream_t stream);
+/* dw[o][c*HW + hw] = g[o][hw*C + c]: Linear weight gradient computed over the NHWC flattening -> nn.Flatten's order */
+int bbbp_fc_grad_hwc_to_chw_f32(const float* g, float* dw, int rows, int C, int HW, bbbp_stream_t stream);
 
 /* ---- encoder self-attention across the molecules of a reference batch: the (B,1,F)
  *      input of C:110-111 is read by nn.TransformerEncoder as seq_len = B, batch = 1.  ``groups``

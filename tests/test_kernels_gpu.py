@@ -848,3 +848,18 @@ def test_attention_flash_rescales_when_the_running_maximum_moves(ops):
     out2, ref2, _ = _flash_case(ops, groups, seq, d, 1, q, k.flip(0), v.flip(0))
     close(out2[:, :d], ref2, atol=6e-3, rtol=6e-3, what="flash attention with an early maximum")
     close(out2[:, :d], out[:, :d].float(), atol=1.2e-2, rtol=1.2e-2, what="key order invariance")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (167, 300, 256), (64, 288, 5000), (200, 40, 130), (2048, 167, 256)])
+@pytest.mark.parametrize("trans_a,trans_w", [(False, True), (True, False), (True, True)])
+def test_gemm16_operands_in_transposed_storage(ops, M, N, K, trans_a, trans_w):
+    """MN-major UMMA operands: the backward products dX = dY W (W read as stored, (N_w, K_w) = [K][N] of the product) and
+    dW = dY^T X (both operands stored with the contraction index as ROWS) without transposed copies."""
+    x, w = rnd(M, K, seed=250), rnd(N, K, seed=251, scale=1 / math.sqrt(K))
+    ref = (x.bfloat16().double() @ w.bfloat16().double().T).float()
+    pad = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 8))         # pitches multiples of 8 elements
+    a16 = pad(x.T.contiguous() if trans_a else x).bfloat16().cuda()
+    w16 = pad(w.T.contiguous() if trans_w else w).bfloat16().cuda()
+    split = 4 if K >= 2048 else 1
+    y, _ = ops.gemm16_tn(a16, w16, M, N, K, trans_a=trans_a, trans_w=trans_w, split_k=split)
+    close(y, ref, atol=2e-5 * max(1.0, math.sqrt(K) / 8), what=f"gemm16_tn {M}x{N}x{K} tA={trans_a} tW={trans_w}")

@@ -671,3 +671,74 @@ def test_wide_attention_scopes_on_the_streaming_kernel(cuda_device, seq, mode):
         got = ours(fp.cuda(), base_img[idx].cuda()).cpu()
     tol = BF16_TOL if mode == "bf16" else 1e-3
     assert float((got - want).abs().max()) <= tol, float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16", 4e-2), ("fp16", 6e-3)])
+def test_tensor_core_training_gradients_of_the_image_branch(cuda_device, mode, tol):
+    """P13 on the tensor cores: at batch >= 64 a tensor-core precision mode runs forward AND backward of the image branch on
+    the tcgen05 GEMM (convolutions as im2col rows, weight gradients with MN-major operands read in place, data gradient
+    through the flipped filters).  Every gradient of the network against the fp32 oracle: relative L2 error at the
+    operand format's round-off level (bf16 2^-9, fp16 2^-12, amplified by the depth), loss to 1e-3."""
+    import bbbp_b200
+    ref, ours = make_pair("tcnn", 167, 128, 21, cuda_device)
+    nets.zero_dropout(ref), nets.zero_dropout(ours)
+    ref.train(), ours.train().set_precision(mode)
+    fp, img, y = seeded_inputs(41, 64, 167, IMG)
+    loss_ref = torch.nn.functional.mse_loss(ref(fp, img).squeeze(), y)
+    loss_ref.backward()
+    loss = bbbp_b200.MSELoss()(ours(fp.cuda(), img.cuda()).squeeze(), y.cuda())
+    assert loss.grad_fn is not None
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-3 * max(1.0, abs(float(loss_ref.detach())))
+    worst = {}
+    for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        a, b = p.grad.cpu().double(), q.grad.double()
+        if float(b.abs().max()) < 1e-7:
+            continue
+        worst[k] = float((a - b).norm() / b.norm())
+    bad = {k: v for k, v in worst.items() if v > tol}
+    print(f"[tc training] {mode}: worst rel-L2 gradient errors", sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+    assert not bad, bad
+    for k in ("image_cnn.0.weight", "image_cnn.0.bias", "image_cnn.3.weight", "image_cnn.3.bias", "image_cnn.7.weight", "image_cnn.7.bias"):
+        assert k in worst, k
+
+
+def test_tensor_core_training_trajectory_tracks_fp32(cuda_device):
+    """BASELINE configs[1]: 100 AdamW steps at batch 64 on real depictions, bf16 tensor-core training (forward and backward
+    of the image branch + the forward of every Linear on tcgen05) against the all-fp32 run from the same initial weights:
+    the smoothed loss curves stay within 10 % of each other and both fall."""
+    import os
+    import bbbp_b200
+    from conftest import GOLDEN
+    from oracle import preprocess
+    g = np.load(os.path.join(GOLDEN, "b3db_depictions_u8.npz"))
+    img_u8, logbb = g["img"][:512], g["logBB"][:512]
+    rng = np.random.default_rng(5)
+    bits = (rng.random((512, 167)) < 0.25).astype(np.uint8)
+    bits[:, 0] = 0
+    fp = torch.from_numpy(preprocess.zscore_rows(bits)).cuda()
+    img = torch.from_numpy(preprocess.u8_image_zscore(img_u8)).cuda()
+    ink = (img_u8 < 255).reshape(512, -1).mean(1)
+    s = bits.astype(np.float64) @ rng.normal(size=167)
+    raw = (s - s.mean()) / s.std() + 0.7 * (ink - ink.mean()) / ink.std()
+    y = torch.from_numpy((logbb.mean() + logbb.std() * (raw - raw.mean()) / raw.std()).astype(np.float32)).cuda()
+    curves = {}
+    for mode in ("fp32", "bf16"):
+        _, model = make_pair("tcnn", 167, 128, 3, cuda_device)
+        nets.zero_dropout(model)
+        model.train().set_precision(mode)
+        opt = bbbp_b200.AdamW(model.parameters(), lr=3e-4, weight_decay=1e-5)
+        step = bbbp_b200.GraphedTrainStep(model, opt, bbbp_b200.MSELoss())
+        gen = torch.Generator().manual_seed(1)
+        losses = []
+        while len(losses) < 100:
+            perm = torch.randperm(512, generator=gen).cuda()
+            for a in range(0, 512, 64):
+                idx = perm[a:a + 64]
+                losses.append(float(step(fp[idx], img[idx], y[idx])))
+        curves[mode] = np.array(losses[:100])
+    smooth = lambda c: np.convolve(c, np.ones(10) / 10, mode="valid")
+    a, b = smooth(curves["fp32"]), smooth(curves["bf16"])
+    print(f"[tc training] loss fp32 {a[0]:.4f} -> {a[-1]:.4f}, bf16 {b[0]:.4f} -> {b[-1]:.4f}, max rel gap {np.abs(a - b).max() / a.mean():.3f}")
+    assert a[-1] < 0.8 * a[0] and b[-1] < 0.8 * b[0]
+    assert np.abs(a - b).max() <= 0.10 * a.mean() + 0.02
