@@ -215,6 +215,13 @@ def train_step_ms(torch, bbbp_b200, nets, dev, with_cpu=True):
             opt.step()
         out[f"eager_ms_batch{batch}"] = timed(eager, 10)
         out[f"ms_batch{batch}"] = timed(lambda: graphed(fp, img, y), 20)
+    # tensor-core training mode (bf16 operands): every nn.Linear forward and, at batch >= 64, forward AND backward of the
+    # image branch on tcgen05 (autograd.ImageBranchTensorCore); the reference's batch 32 stays latency-bound either way
+    model.set_precision("bf16")
+    fp, img = synthetic_inputs(256, 3, dev)
+    y = torch.randn(256, device=dev) * 0.75 - 0.1
+    out["ms_batch256_tensor_core_bf16"] = timed(lambda: graphed(fp, img, y), 20)
+    model.set_precision("fp32")
     if with_cpu:
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
