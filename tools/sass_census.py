@@ -1,5 +1,5 @@
 """SASS opcode census of libbbbp_b200.so: which kernels carry tcgen05 (UTC*MMA), TMEM loads / stores (LDTM / STTM), TMA
-(UTMALDG / UTMASTG / UBLKCP), legacy warp MMA (HMMA), cp.async (LDGSTS).  Writes profiles/r2_sass_census.txt.
+(UTMALDG / UTMASTG / UBLKCP), legacy warp MMA (HMMA), cp.async (LDGSTS).  Writes profiles/r02_sass_census.txt.
 
     python tools/sass_census.py
 """
@@ -29,5 +29,5 @@ for k, c in sorted(rows, key=lambda kc: (-kc[1]['UTCHMMA'], kc[0])):
     out.append(f"{k[:78]:78s} " + " ".join(f"{c[o]:8d}" for o in OPS))
 text = "\n".join(out) + "\n"
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-open(os.path.join(ROOT, "profiles", "r2_sass_census.txt"), "w").write(text)
+open(os.path.join(ROOT, "profiles", "r02_sass_census.txt"), "w").write(text)
 print(text)
