@@ -40,6 +40,19 @@ def encoder_heads(fingerprint_size: int, start: int | None = None) -> int:
     return nhead
 
 
+def _stack_rows(parts):
+    """cat(parts, dim=0) of 2-D float32 tensors through the library's pitched copy kernel (no ATen kernels on the path)."""
+    if any(p.requires_grad for p in parts):
+        return torch.cat(parts, dim=0)                 # autograd needs the graph edge (training of the big variant only)
+    from . import ops
+    out = torch.empty((sum(p.shape[0] for p in parts), parts[0].shape[1]), device=parts[0].device, dtype=torch.float32)
+    row = 0
+    for p in parts:
+        ops.copy2d(p if p.stride(1) == 1 else p.contiguous(), out[row:row + p.shape[0]])
+        row += p.shape[0]
+    return out
+
+
 def _encoder(fingerprint_size: int, nhead: int, layers: int) -> nn.TransformerEncoder:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # "enable_nested_tensor is True, but ... batch_first was not True"
@@ -197,7 +210,7 @@ class MultiModalAttentionFusion(_KernelModule):
             fp_w = ag.ScaledColmean.apply(fingerprint[rows], w[rows, 0])
             im_w = ag.ScaledColmean.apply(image[rows], w[rows, 1])
             parts.append(ag.concat_cols(fp_w, im_w, cross[rows]))
-        return parts[0] if groups == 1 else torch.cat(parts, dim=0)
+        return parts[0] if groups == 1 else _stack_rows(parts)
 
 
 # ---- transformer-CNN family --------------------------------------------------------------------------------------------
@@ -417,7 +430,7 @@ class TransformerCnnModel(_KernelModule):
             K = flat.shape[1]
             o, _ = ops.gemm_bf16(flat, K, wfc, fc.out_features, bias=fc.bias, act="relu", split_k=ops.fixed_split_k(K))
             outs.append(o)
-        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        return outs[0] if len(outs) == 1 else _stack_rows(outs)
 
     def _image_branch_tensor_core(self, image, mods):
         """Inference path: planar CHW image (fp32 standardised, or raw uint8 normalised in the producer) -> tcgen05
@@ -452,7 +465,7 @@ class TransformerCnnModel(_KernelModule):
                 o, _ = ops.gemm_bf16(y2.view(y2.shape[0], 65536), 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
                                      split_k=ops.fixed_split_k(65536), fmt=fmt)
             outs.append(o)
-        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        return outs[0] if len(outs) == 1 else _stack_rows(outs)
 
     # Set while a CUDA graph is being captured (train.GraphedTrainStep, the inference graphs below): the conv branch is
     # forked onto a second stream so the graph keeps it parallel to the encoder chain.  Forking EAGER launches of a large
@@ -528,7 +541,9 @@ class TransformerCnnModel(_KernelModule):
         s_fp.copy_(fingerprint)
         s_img.copy_(image)
         graph.replay()
-        return s_out.clone()
+        from . import ops
+        out = torch.empty_like(s_out)                  # the caller owns its result: copy out of the graph's static buffer
+        return ops.copy2d(s_out, out)
 
     def forward_groups(self, fingerprint, image, groups: int = 1):
         """``groups`` independent reference batches of equal size stacked along dim 0 (see _forward_groups_eager)."""
@@ -657,12 +672,23 @@ class TransformerCnnModel(_KernelModule):
         compute = torch.cuda.current_stream(dev)
         # the copy stream and the two staging slots are created once and reused: a fresh stream per call would defeat
         # the caching allocator (per-stream pools) and turn every chunk into a cudaMalloc
+        sparse = hasattr(image_host, "mask") and hasattr(image_host, "offsets")      # screening.SparseDepictions
+        if sparse and not packed:
+            raise ValueError("sparse depictions are uint8 images: use packed=True (packed fingerprint bits + uint8 depictions)")
         key = (chunk, tuple(fingerprint_host.shape[1:]), fingerprint_host.dtype, tuple(image_host.shape[1:]), image_host.dtype,
-               dev.index)
+               dev.index, sparse)
         pipe = getattr(self, "_host_pipe", None)
         if pipe is None or pipe[0] != key:
-            slots = [(torch.empty((chunk,) + tuple(fingerprint_host.shape[1:]), device=dev, dtype=fingerprint_host.dtype),
-                      torch.empty((chunk,) + tuple(image_host.shape[1:]), device=dev, dtype=image_host.dtype)) for _ in range(2)]
+            def make_slot():
+                fp_slot = torch.empty((chunk,) + tuple(fingerprint_host.shape[1:]), device=dev, dtype=fingerprint_host.dtype)
+                img_slot = torch.empty((chunk,) + tuple(image_host.shape[1:]), device=dev, dtype=image_host.dtype)
+                if not sparse:
+                    return (fp_slot, img_slot)
+                # staging for the encoded chunk (values sized for the worst case: every pixel marked) + the decode target
+                return (fp_slot, img_slot, torch.empty((chunk, 2048), device=dev, dtype=torch.uint8),
+                        torch.empty((chunk * 3 * 128 * 128 + 16,), device=dev, dtype=torch.uint8),
+                        torch.empty((chunk + 1,), device=dev, dtype=torch.int64))
+            slots = [make_slot() for _ in range(2)]
             pipe = (key, torch.cuda.Stream(dev), slots, [None, None])
             self._host_pipe = pipe
             pipe[1].wait_stream(compute)
@@ -677,7 +703,14 @@ class TransformerCnnModel(_KernelModule):
                 if freed[slot] is not None:
                     copier.wait_event(freed[slot])        # the compute stream is done with this slot's old contents
                 slots[slot][0][: b - a].copy_(fingerprint_host[a:b], non_blocking=True)
-                slots[slot][1][: b - a].copy_(image_host[a:b], non_blocking=True)
+                if sparse:
+                    v0, v1 = 3 * int(image_host.offsets[a]), 3 * int(image_host.offsets[b])
+                    slots[slot][2][: b - a].copy_(image_host.mask[a:b], non_blocking=True)
+                    if v1 > v0:
+                        slots[slot][3][: v1 - v0].copy_(image_host.values[v0:v1], non_blocking=True)
+                    slots[slot][4][: b - a + 1].copy_(image_host.offsets[a:b + 1], non_blocking=True)
+                else:
+                    slots[slot][1][: b - a].copy_(image_host[a:b], non_blocking=True)
                 ready[slot] = torch.cuda.Event()
                 ready[slot].record(copier)
 
@@ -689,7 +722,8 @@ class TransformerCnnModel(_KernelModule):
             slot = i % 2
             compute.wait_event(ready[slot])
             fp, img = slots[slot][0][: b - a], slots[slot][1][: b - a]
-            part = self._score_staged_chunk(slot, fp, img, batch_size, chunk, packed)
+            encoded = (slots[slot][2][: b - a], slots[slot][3], slots[slot][4][: b - a + 1]) if sparse else None
+            part = self._score_staged_chunk(slot, fp, img, batch_size, chunk, packed, encoded)
             scores[a:b].copy_(part)
             freed[slot] = torch.cuda.Event()
             freed[slot].record(compute)
@@ -704,19 +738,27 @@ class TransformerCnnModel(_KernelModule):
 
     _chunk_graphs = None
 
-    def _score_staged_chunk(self, slot, fp, img, batch_size, chunk, packed):
+    def _score_staged_chunk(self, slot, fp, img, batch_size, chunk, packed, encoded=None):
         """Scores of one staged chunk.  The staging slots are persistent buffers, so the whole chunk computation (unpack +
         z-score + forward of every reference batch, conv branch forked beside the encoder) is captured ONCE per (slot,
         chunk length) into a CUDA graph that reads the slot in place -- no copy into graph-private inputs, one launch per
         chunk instead of ~90, which is what lets the short first / last chunks of the ramped schedule cost less than
         their own H2D copy."""
-        fn = self.predict_batches_packed if packed else self.predict_batches
+        score = self.predict_batches_packed if packed else self.predict_batches
+        if encoded is None:
+            fn = score
+        else:
+            from . import ops
+
+            def fn(fp_, img_, bs_, max_rows_per_pass):      # sparse depictions: rebuild the uint8 images in the slot, then score
+                ops.decode_sparse_depictions(encoded[0], encoded[1], encoded[2], out=img_)
+                return score(fp_, img_, bs_, max_rows_per_pass=max_rows_per_pass)
         if not self.use_cuda_graphs or self._chunk_graphs is False or torch.cuda.is_current_stream_capturing():
             return fn(fp, img, batch_size, max_rows_per_pass=chunk)
         if self._chunk_graphs is None:
             self._chunk_graphs = {}
         key = (fp.data_ptr(), img.data_ptr(), fp.shape[0], fp.dtype, img.dtype, batch_size, chunk, packed, self.precision,
-               self._weight_signature())
+               self._weight_signature(), None if encoded is None else encoded[0].data_ptr())
         entry = self._chunk_graphs.get(key)
         if entry is None:
             if len(self._chunk_graphs) >= 24:
@@ -735,7 +777,7 @@ class TransformerCnnModel(_KernelModule):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     out = fn(fp, img, batch_size, max_rows_per_pass=chunk)
-                entry = (graph, out, fp, img)            # fp / img keep the slot views alive
+                entry = (graph, out, fp, img, encoded)   # fp / img / encoded keep the slot views alive
                 self._chunk_graphs[key] = entry
             except Exception as e:      # capture is an optimisation: fall back to plain launches of the same kernels
                 warnings.warn(f"bbbp_b200: chunk-graph capture disabled for this model ({e})")

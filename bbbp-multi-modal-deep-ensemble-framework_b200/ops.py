@@ -371,6 +371,17 @@ def conv3x3_relu_pool_bf16(x_nhwc: torch.Tensor, wprep: torch.Tensor, bias: torc
     return y if x_lo is None else (y, y_lo)
 
 
+def decode_sparse_depictions(mask: torch.Tensor, values: torch.Tensor, offsets: torch.Tensor, out: torch.Tensor | None = None):
+    """(n, 2048) uint8 bit masks + RGB triples of the non-white pixels + (n + 1,) int64 running counts -> (n, 3, 128, 128) uint8."""
+    n = mask.shape[0]
+    assert mask.dtype == torch.uint8 and mask.shape[1] == 2048 and mask.is_contiguous() and offsets.dtype == torch.int64
+    if out is None:
+        out = torch.empty((n, 3, 128, 128), device=mask.device, dtype=torch.uint8)
+    check(lib.bbbp_decode_sparse_depictions_u8(mask.data_ptr(), values.data_ptr(), offsets.data_ptr(), out.data_ptr(), n, _stream()),
+          "decode_sparse_depictions")
+    return out
+
+
 def u8_image_stats(img_u8: torch.Tensor) -> torch.Tensor:
     rows = img_u8.shape[0]
     flat = img_u8.reshape(rows, -1)

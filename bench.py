@@ -321,6 +321,8 @@ def main():
     strokes = torch.rand(n, 1, 128, 128, generator=g) < 0.06
     img8_host[strokes.expand(-1, 3, -1, -1)] = 40
     img8_host = img8_host.pin_memory()
+    # the same depictions in the lossless sparse encoding (bit mask of the non-white pixels + their RGB triples)
+    sparse_host = bbbp_b200.SparseDepictions.encode(img8_host.numpy())
     gathered = torch.empty(world * n, device=dev, dtype=torch.float32) if world > 1 else None
 
     def step_resident():
@@ -342,6 +344,12 @@ def main():
         # the user-facing host API: chunked H2D on a copy stream overlapped with scoring, D2H of the scores, and a wait
         # for that copy -- every step ends with its scores readable in host memory
         _, s = model.predict_from_host(packed_host, img8_host, BATCH, chunk_molecules=E2E_CHUNK, packed=True, out_host=scores_host,
+                                       return_device=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, s)
+
+    def step_e2e_sparse():
+        _, s = model.predict_from_host(packed_host, sparse_host, BATCH, chunk_molecules=E2E_CHUNK, packed=True, out_host=scores_host,
                                        return_device=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
@@ -398,6 +406,9 @@ def main():
         for _ in range(2):
             step_e2e_streaming()
         ms_e2e_stream = timed(step_e2e_streaming, args.steps)
+        for _ in range(2):
+            step_e2e_sparse()
+        ms_e2e_sparse = timed(step_e2e_sparse, args.steps)
         by_precision = {}
         for mode in [m for m in args.also.split(",") if m and m != args.precision]:
             model.set_precision(mode)
@@ -406,15 +417,17 @@ def main():
             m_res = timed(step_resident, args.steps)
             for _ in range(2):
                 step_e2e_compact()
-            m_e2e = timed(step_e2e_compact, args.steps)
+            m_e2e = timed(step_e2e_sparse, args.steps)
             by_precision[mode] = {"value": world * n * args.steps / (m_res * 1e-3), "e2e": world * n * args.steps / (m_e2e * 1e-3),
                                   "unit": UNIT, "dtype": DTYPE[mode], "ms_per_step": m_res / args.steps}
         model.set_precision(args.precision)
 
     total_mols = world * n * args.steps
     value = total_mols / (ms * 1e-3)
-    e2e = total_mols / (ms_e2e * 1e-3)
+    e2e_dense = total_mols / (ms_e2e * 1e-3)
+    e2e = total_mols / (ms_e2e_sparse * 1e-3)
     e2e32 = total_mols / (ms_e2e32 * 1e-3)
+    sparse_bytes = sparse_host.nbytes() + packed_host.numel()
     pk = peaks()
     roof = None
     if conv2_ms:
@@ -444,10 +457,16 @@ def main():
                       "spread (tests/test_trained_parity_gpu.py)",
             "by_precision": by_precision,
             "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * ((F_BITS + 7) // 8 + IMG), "d2h_bytes_per_step": n * 4,
-                    "ms_per_step": ms_e2e / args.steps,
-                    "api": "model.predict_from_host(packed MACCS bits uint8, depictions uint8 CHW, packed=True): pinned host -> "
-                           "chunked H2D overlapped with [unpack + z-score + in-kernel image normalisation + forward] -> D2H scores"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(sparse_bytes), "d2h_bytes_per_step": n * 4,
+                    "ms_per_step": ms_e2e_sparse / args.steps,
+                    "api": "model.predict_from_host(packed MACCS bits uint8, bbbp_b200.SparseDepictions, packed=True): pinned host -> "
+                           "chunked H2D overlapped with [sparse decode to uint8 CHW + unpack + z-score + in-kernel image "
+                           "normalisation + forward] -> D2H scores, readable in host memory when the call returns",
+                    "input_format": "lossless sparse depictions: 2 048-byte bit mask of the non-white pixels + their RGB triples "
+                                    f"({sparse_bytes / n:.0f} B per molecule here, 6 084 B on the real B3DB depictions; dense uint8 = 49 152 B)"},
+            "e2e_dense_u8": {"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": n * ((F_BITS + 7) // 8 + IMG), "d2h_bytes_per_step": n * 4,
+                             "ms_per_step": ms_e2e / args.steps,
+                             "api": "the same call with dense uint8 CHW depictions (round 1's e2e format): PCIe-bound at 55 GB/s"},
             "e2e_streaming": {"value": total_mols / (ms_e2e_stream * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * ((F_BITS + 7) // 8 + IMG),
                               "d2h_bytes_per_step": n * 4, "ms_per_step": ms_e2e_stream / args.steps,
                               "api": "the same call with synchronize=False on consecutive shards (per-slot events carry across calls; "

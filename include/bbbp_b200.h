@@ -184,6 +184,11 @@ int bbbp_conv3x3_relu_pool16(int fmt, int split, const void* x_nhwc, const void*
 int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
                             const float* bias, void* y_nhwc, void* y_lo, int N, int H, int W, bbbp_stream_t stream);
 int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int C, int HW, bbbp_stream_t stream);
+/* Lossless sparse depictions (extension, sparse_depictions.cu): rebuilds out[n][3][128][128] uint8 from mask[n][2048]
+ * (bit p, little-endian, set where pixel p is not white), values (the RGB triples of the marked pixels in scan order) and
+ * offsets[n + 1] (running pixel counts; only differences to offsets[0] are used).  ~5.5 KB per molecule instead of 49 152. */
+int bbbp_decode_sparse_depictions_u8(const uint8_t* mask, const uint8_t* values, const int64_t* offsets, uint8_t* out, int n,
+                                     bbbp_stream_t stream);
 /* stats[r] = {mean, 1/std} of img[r, 0:n] / 255 (population std, 0 -> 1), exact integer sums, fp64 finish */
 int bbbp_u8_image_stats_f32(const uint8_t* img, float* stats, int rows, int n, bbbp_stream_t stream);
 /* Diagnostics: probe = DEVICE array of 16 uint64 cycle counters that CTA 0 of the tcgen05 conv kernels accumulates

@@ -773,3 +773,36 @@ def test_tensor_core_training_trajectory_tracks_fp32(cuda_device):
     print(f"[tc training] loss fp32 {a[0]:.4f} -> {a[-1]:.4f}, bf16 {b[0]:.4f} -> {b[-1]:.4f}, max rel gap {np.abs(a - b).max() / a.mean():.3f}")
     assert a[-1] < 0.8 * a[0] and b[-1] < 0.8 * b[0]
     assert np.abs(a - b).max() <= 0.25 * a.mean() + 0.02          # chaotic early phase: observed 0.17
+
+
+def test_sparse_depictions_decode_and_host_pipeline(cuda_device):
+    """Lossless sparse depiction encoding (csrc/sparse_depictions.cu): the device decode of real B3DB depictions equals the
+    original uint8 images bit for bit, for whole tables and for slices of a longer table (running offsets), and
+    predict_from_host on the encoded library returns exactly the scores of the dense uint8 call."""
+    import os
+    import bbbp_b200
+    from bbbp_b200 import ops
+    from conftest import GOLDEN
+    img = np.load(os.path.join(GOLDEN, "b3db_depictions_u8.npz"))["img"][:300].copy()
+    img[7] = 255                                           # a blank depiction (no marked pixel)
+    img[8, :, 5:9, :] = 0                                  # dense runs
+    sd = bbbp_b200.SparseDepictions.encode(img)
+    assert np.array_equal(sd.decode_host(), img)
+    assert sd.nbytes() < img.size / 5
+    dev = lambda t: t.cuda()
+    full = ops.decode_sparse_depictions(dev(sd.mask), dev(sd.values), dev(sd.offsets))
+    assert torch.equal(full.cpu(), torch.from_numpy(img))
+    a, b = 100, 237                                        # a chunk of the table: offsets are used relative to their first entry
+    v0, v1 = 3 * int(sd.offsets[a]), 3 * int(sd.offsets[b])
+    part = ops.decode_sparse_depictions(dev(sd.mask[a:b].contiguous()), dev(sd.values[v0:v1].contiguous()), dev(sd.offsets[a:b + 1].contiguous()))
+    assert torch.equal(part.cpu(), torch.from_numpy(img[a:b]))
+    _, ours = make_pair("tcnn", 167, 128, 3, cuda_device)
+    ours.eval().set_precision("strict")
+    rng = np.random.default_rng(2)
+    packed = torch.from_numpy(rng.integers(0, 256, size=(300, 21), dtype=np.uint8)).pin_memory()
+    dense = torch.from_numpy(img).pin_memory()
+    want = ours.predict_from_host(packed, dense, 32, chunk_molecules=96, packed=True).clone()
+    got = ours.predict_from_host(packed, sd, 32, chunk_molecules=96, packed=True)
+    assert torch.equal(got, want)
+    got2 = ours.predict_from_host(packed, sd, 32, chunk_molecules=128, packed=True)      # another chunking, graphs re-captured
+    assert torch.equal(got2, want)
