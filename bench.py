@@ -39,6 +39,9 @@ CONV2_FLOP_PER_MOL = 2 * 64 * 64 * 64 * 288
 # (profiles/r01_ncu_conv_umma_full.txt: dram__bytes_read 2.186054 GB + dram__bytes_write 1.046418 GB per 8192-molecule
 # launch); the algorithmic figure is 256 KiB in + 128 KiB out = 393 216 B, i.e. no re-reads
 CONV2_DRAM_BYTES_PER_MOL = (2.186054e9 + 1.046418e9) / 8192
+# ... and of its strict-mode instantiation (profiles/r02_ncu_conv.txt: 2.148330 GB + 1.042366 GB per 4 096-molecule launch);
+# algorithmic: (hi, lo) pairs in and out = 2 x (256 KiB + 128 KiB) = 786 432 B, i.e. no re-reads either
+CONV2_STRICT_DRAM_BYTES_PER_MOL = (2.148330e9 + 1.042366e9) / 4096
 FWD_FLOP_PER_MOL = 207.2e6
 IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
 # the workload both arms run (identical dict in both JSON lines; per-arm sample sizes live outside it)
@@ -435,12 +438,13 @@ def main():
         flop = CONV2_FLOP_PER_MOL * statistics.mean(conv2_mols)
         ach = flop / (per_launch_ms * 1e-3) / 1e12
         passes = 2 if args.precision == "strict" else 1        # strict: hi and lo activation parts, two MMAs per K step
-        traffic = CONV2_DRAM_BYTES_PER_MOL * statistics.mean(conv2_mols) * passes
+        traffic = (CONV2_STRICT_DRAM_BYTES_PER_MOL if passes == 2 else CONV2_DRAM_BYTES_PER_MOL) * statistics.mean(conv2_mols)
         roof = {"kernel": "conv2 (3x3, 32->64, +bias+ReLU+maxpool) implicit GEMM", "bound": "tensor", "achieved": ach,
                 "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                 "traffic": traffic, "traffic_unit": "bytes/launch",
-                "traffic_source": "ncu --set full of the bf16 launch (profiles/r01_ncu_conv_umma_full.txt) scaled to this launch's "
-                                  "molecules" + (" x2: the strict mode reads and writes every activation as a (hi, lo) pair" if passes == 2 else ""),
+                "traffic_source": ("ncu --set full of the strict-mode kernel (profiles/r02_ncu_conv.txt: tensor pipe 59 %, DRAM = the "
+                                   "algorithmic bytes of the (hi, lo) pairs)" if passes == 2 else
+                                   "ncu --set full of the bf16 launch (profiles/r01_ncu_conv_umma_full.txt)") + ", scaled to this launch's molecules",
                 "peak_source": pk["src"] + " bf16_tflops_sustained", "launch_ms": per_launch_ms,
                 "mma_passes": passes, "executed_tflops": ach * passes, "executed_frac": ach * passes / pk["tensor"],
                 "note": "achieved = ALGORITHMIC flops (151.0 MFLOP per molecule, SURVEY 8d) / CUDA-event time; the strict mode issues "

@@ -8,8 +8,14 @@ n = int(os.environ.get("N", 8192))
 packed = torch.randint(0, 256, (n, 21), dtype=torch.uint8).pin_memory()
 img8 = torch.randint(0, 256, (n, 3, 128, 128), dtype=torch.uint8).pin_memory()
 out_host = torch.empty(n, dtype=torch.float32).pin_memory()
+if os.environ.get("SPARSE", "0") == "1":            # mostly-white depictions in the lossless sparse encoding
+    img8 = torch.full((n, 3, 128, 128), 255, dtype=torch.uint8)
+    strokes = torch.rand(n, 1, 128, 128) < 0.06
+    img8[strokes.expand(-1, 3, -1, -1)] = 40
+    img8 = bbbp_b200.SparseDepictions.encode(img8.numpy())
 res = {}
-for chunk in (256, 512, 1024, 2048, 4096):
+for chunk in (256, 512, 1024, 2048, 4096, 8192, 16384):
+    if chunk > n: continue
     fn = lambda: m.predict_from_host(packed, img8, 256, chunk_molecules=chunk, packed=True, out_host=out_host)
     for _ in range(3): fn()
     torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -19,6 +25,7 @@ for chunk in (256, 512, 1024, 2048, 4096):
     res[chunk] = e0.elapsed_time(e1) / 8
     print(chunk, res[chunk], n / res[chunk] * 1e3, flush=True)
 # H2D alone
+if not torch.is_tensor(img8): sys.exit(0)
 d = torch.empty_like(img8, device=dev)
 torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record()

@@ -41,6 +41,12 @@ n = 16384
 img8 = torch.randint(0, 256, (n, 3, 128, 128), device=dev, dtype=torch.uint8)
 report("uint8 depiction -> z-scored fp32", img8.numel() * 5, t(lambda: ops.u8_zscore(img8.reshape(n, -1))))
 report("uint8 depiction statistics", img8.numel(), t(lambda: ops.u8_image_stats(img8)))
+white = torch.full((n, 3, 128, 128), 255, dtype=torch.uint8)
+white[(torch.rand(n, 1, 128, 128) < 0.07).expand(-1, 3, -1, -1)] = 40
+sd = bbbp_b200.SparseDepictions.encode(white.numpy(), pin=False)
+m_, v_, o_ = sd.mask.to(dev), sd.values.to(dev), sd.offsets.to(dev)
+report("sparse depictions -> uint8 CHW (7 % marked)", sd.nbytes() + white.numel(), t(lambda: ops.decode_sparse_depictions(m_, v_, o_)))
+del white, m_, v_, o_
 packed = torch.randint(0, 256, (1 << 22, 21), device=dev, dtype=torch.uint8)
 report("packed bits -> z-scored fp32 (167 bits)", packed.numel() + (1 << 22) * 167 * 4, t(lambda: ops.unpack_zscore(packed, 167)))
 del img8, packed
