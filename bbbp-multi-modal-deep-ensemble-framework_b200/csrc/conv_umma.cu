@@ -55,7 +55,7 @@ constexpr int ROW_B = XH * 16;                 // 144 bytes per (parity, y) row
 constexpr int PAR_B = HALO_H * ROW_B + 32;     // 4928 = 64 (mod 128)
 constexpr int KC_B = 2 * PAR_B + 16;           // 9872 = 16 (mod 128) bytes per 8-channel chunk plane
 
-template <int KC, int COUT, int SRC = 0, int FMT = BBBP_FMT_BF16, int SPLIT = 1>
+template <int KC, int COUT, int SRC = 0, int FMT = BBBP_FMT_BF16, int SPLIT = 1, int BG = 0>
 struct Cfg {
   // conv2's epilogue (64 channels) gets two warps per TMEM lane quadrant; conv1's (32 channels) one, which also keeps
   // its CTA small enough for two CTAs per SM
@@ -77,6 +77,10 @@ struct Cfg {
   // 1.65 ms vs 1.42 ms per 8 192 images)
   static constexpr int MIN_CTAS = KC == 1 ? 2 : 1;
   static constexpr int A_BYTES = KC * KC_B;
+  // planar first-layer sources in two parts: BOTH parts of a tile's halo share one ring slot (hi image, then lo image), so
+  // the producers pay one wait / fence / arrive round per tile instead of two (they, not the MMAs, bound that kernel)
+  static constexpr bool MERGED = PACK4 && SPLIT == 2;
+  static constexpr int STAGE_BYTES = (MERGED ? 2 : 1) * A_BYTES;
   static constexpr int NMMA = KC == 1 ? 5 : 9 * (KC / 2);  // K=16 steps per window member
   // instructions per tile: conv1 issues one N=COUT MMA per (member, step); conv2 pairs the two members of a pooling
   // row that read the SAME halo view (dx=0 with tap kw+1, dx=1 with tap kw) into one N=2*COUT MMA: 24 per K-chunk pair
@@ -94,12 +98,17 @@ struct Cfg {
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int OUT_ROW_B = COUT * 2;            // bytes of one pooled pixel (= the TMA store's swizzle span)
   static constexpr int OUT_BYTES = 128 * OUT_ROW_B;     // one output tile: 128 pooled pixels x COUT bf16
-  static constexpr int OUT_BUFS = 2 * SPLIT;            // double-buffered hi (and lo) output tiles
+  // BG (background-referenced activations, see the kernel comment): the input may still arrive as a (hi, lo) pair, the
+  // output is ONE 16-bit tensor (values relative to the layer's per-image background response)
+  static constexpr int OSPLIT = BG ? 1 : SPLIT;
+  static constexpr int OUT_BUFS = 2 * OSPLIT;           // double-buffered hi (and lo) output tiles
   // strict mode, first layer: the WEIGHTS are split as well (w = hi + lo, the lo image follows the hi image in the prepared
   // blob and in shared memory) -- K is tiny there, so the third pass costs little, and the first layer's weight rounding
   // is the largest remaining term of the strict mode's error budget (tests/precision_study.py: 6e-4 of 8e-4)
-  static constexpr int W_PARTS = (SPLIT == 2 && PACK4) ? 2 : 1;
-  static constexpr int SMEM_BYTES = 1024 + OUT_BUFS * OUT_BYTES + STAGES * A_BYTES + W_PARTS * W_BYTES + COUT * 4 + BAR_BYTES;
+  static constexpr int W_PARTS = (SPLIT == 2 && PACK4 && !BG) ? 2 : 1;
+  // BG: the current and the next tile's per-image table rows (T and bg_out), double-buffered
+  static constexpr int TAB_FLOATS = 2 * COUT, TAB_BYTES = BG ? 2 * TAB_FLOATS * 4 : 0;
+  static constexpr int SMEM_BYTES = 1024 + OUT_BUFS * OUT_BYTES + STAGES * STAGE_BYTES + W_PARTS * W_BYTES + COUT * 4 + BAR_BYTES + TAB_BYTES;
 };
 
 __host__ __device__ constexpr int halo_offset(int dy, int dx, int tap) {
@@ -195,12 +204,26 @@ __device__ unsigned long long* g_conv_probe = nullptr;
 // per-image (mean, 1/std) pair (ToTensor + per-molecule StandardScaler, Descriptors/..._preprocess_maccs_opt.py:52-67,
 // 121-124).  In both planar cases the 3 channels are packed to one 16-byte bf16 chunk per pixel in registers, so the
 // NHWC8 image never exists in HBM.
-template <int KC, int COUT, int SRC, int FMT, int SPLIT>
-__global__ void __launch_bounds__(Cfg<KC, COUT, SRC, FMT, SPLIT>::THREADS, Cfg<KC, COUT, SRC, FMT, SPLIT>::MIN_CTAS)
+//
+// BG = 1, background-referenced activations (the strict mode since round 2): a depiction is mostly ONE
+// value per channel (the white canvas), and so is every activation map computed from it away from the strokes.  The layer
+// therefore works on  x' = x - bg  (bg = this image's background per input channel: x' is exactly 0 on the canvas, so nothing
+// is lost there when x' is rounded to 16 bits), and the epilogue adds back what the constant part contributes, in fp32 and
+// from the fp32 weights:   conv(x)[p] = conv(x')[p] + T[co],   T[co] = bias[co] + sum over ALL nine taps of w[co][ci][tap] * bg[ci].
+// For that to hold at the image border the zero padding of x must read as -bg in the shifted space: the first layer's
+// producers stage it as such (hi + lo, exact); later layers receive a background that IS a 16-bit number (the previous
+// layer subtracts bg_out = rn16(relu(T)), which leaves a residue of at most half an ulp of bg on the canvas -- itself
+// rounded with negligible error), so their producers write the exact -bg into the out-of-image halo chunks instead of
+// letting cp.async zero-fill them.  bg_tab[image] = {T[COUT], bg_out[COUT]} (bbbp_bg_layer); after ReLU + pooling the
+// epilogue subtracts bg_out before rounding.  bg_in: first layer float[image][4]; later layers the NEGATED background of the
+// input in the operand format, [image][8 * KC].
+template <int KC, int COUT, int SRC, int FMT, int SPLIT, int BG>
+__global__ void __launch_bounds__(Cfg<KC, COUT, SRC, FMT, SPLIT, BG>::THREADS, Cfg<KC, COUT, SRC, FMT, SPLIT, BG>::MIN_CTAS)
 conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ src_lo_any, const float2* __restrict__ stats,
                     const uint4* __restrict__ wprep, const float* __restrict__ bias, const __grid_constant__ CUtensorMap tmOut,
-                    const __grid_constant__ CUtensorMap tmOutLo, int n_img, int H, int W) {
-  using C = Cfg<KC, COUT, SRC, FMT, SPLIT>;
+                    const __grid_constant__ CUtensorMap tmOutLo, int n_img, int H, int W, const void* __restrict__ bg_in,
+                    const float* __restrict__ bg_tab) {
+  using C = Cfg<KC, COUT, SRC, FMT, SPLIT, BG>;
   static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
     constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
   constexpr int PROD_THREADS = C::PROD_THREADS, STAGES = C::STAGES;
@@ -208,13 +231,14 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sOut = base;                     // 2 (x2 with a lo part) swizzled output tiles (1024-byte aligned) for the TMA stores
   uint8_t* sA = sOut + C::OUT_BUFS * C::OUT_BYTES;
-  uint8_t* sW = sA + STAGES * C::A_BYTES;
+  uint8_t* sW = sA + STAGES * C::STAGE_BYTES;
   float* sBias = reinterpret_cast<float*>(sW + C::W_PARTS * C::W_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sBias + COUT);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  [[maybe_unused]] float* sTab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + C::BAR_BYTES);   // 16-byte aligned
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int tiles_x = (W / 2) / TILE_PW, tiles_y = (H / 2) / TILE_PH;
@@ -226,8 +250,8 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
   for (int i = threadIdx.x; i < C::W_PARTS * C::W_BYTES / 16; i += THREADS)
     reinterpret_cast<uint4*>(sW)[i] = wprep[C::W_OFFSET / 16 + i];
   if constexpr (C::PACK4)   // pad bytes of the stage are never written by the producers: keep them finite
-    for (int i = threadIdx.x; i < STAGES * C::A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = threadIdx.x; i < COUT; i += THREADS) sBias[i] = bias[i];
+    for (int i = threadIdx.x; i < STAGES * C::STAGE_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < COUT; i += THREADS) sBias[i] = BG ? 0.0f : bias[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], PROD_THREADS);
@@ -266,9 +290,16 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
         long long tp = probe ? clock64() : 0;
         mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
         PROBE_ADD(8, tp);
-        const uint32_t stage = smem_u32(sA + s * C::A_BYTES);
+        const uint32_t stage = smem_u32(sA + s * C::STAGE_BYTES);
         const uint8_t* img = reinterpret_cast<const uint8_t*>((SPLIT == 2 && (i & 1)) ? src_lo_any : src_any) +
                              (size_t)n * H * W * PIX_B;
+        // BG: what an out-of-image chunk must hold, -bg of this thread's 8-channel chunk (kc = ji % KC for every chunk of
+        // the thread: the chunk stride PROD_THREADS and the row length are multiples of KC); copied like any other chunk
+        [[maybe_unused]] const uint8_t* padsrc = nullptr;    // this image's -bg row, chunk kc
+        if constexpr (BG) {
+          padsrc = static_cast<const uint8_t*>(bg_in) + (size_t)n * PIX_B + (ji % KC) * 16;
+          static_assert(PROD_THREADS % KC == 0 && ROWC % KC == 0, "a producer thread keeps one channel chunk");
+        }
         int Y = Yi, j = ji;
   #pragma unroll 4
         for (int c = ptid; c < CHUNKS; c += PROD_THREADS) {
@@ -276,7 +307,9 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
           const int y = y0 + Y, x = x0 + X;
           const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
           const int goff = ok ? (y * W + x) * PIX_B + kc * 16 : 0;
-          cp_async_16(stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16, img + goff, ok ? 16u : 0u);
+          const uint32_t dst = stage + kc * KC_B + (X & 1) * PAR_B + Y * ROW_B + (X >> 1) * 16;
+          if constexpr (BG) cp_async_16(dst, ok ? img + goff : padsrc, 16u);   // out of the image: -bg instead of zero fill
+          else cp_async_16(dst, img + goff, ok ? 16u : 0u);
           j += STEP_J;
           Y += STEP_Y;
           if (j >= ROWC) {
@@ -324,6 +357,10 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       auto load_tile = [&](int i, Vec (&v)[TPT][CH], uint32_t& okmask) {
         int n, y0, x0;
         tile_origin(i, n, y0, x0);
+        // the per-image scalars store_tile() will need (PF - 1 tiles later): into L1 now, so that they cost a hit then
+        // instead of an exposed L2 round trip per tile
+        if constexpr (SRC == SRC_CHW_U8) prefetch_l1(stats + n);
+        if constexpr (BG) prefetch_l1(static_cast<const float*>(bg_in) + 4 * (size_t)n);
         okmask = 0;
 #pragma unroll
         for (int k = 0; k < TPT; ++k) {
@@ -349,14 +386,20 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
           const float2 st = __ldg(stats + (blockIdx.x + i * gridDim.x) / tiles_per_img);
           scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
         }
+        [[maybe_unused]] float bgc[CH] = {0.0f, 0.0f, 0.0f};   // BG: this image's background value per channel
+        if constexpr (BG) {
+          const float* bp = static_cast<const float*>(bg_in) + 4 * (size_t)((blockIdx.x + i * gridDim.x) / tiles_per_img);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) bgc[c] = __ldg(bp + c);
+        }
+        // one ring slot per tile; part 1 (the lo halves x - rn16(x) of the same pixels) follows part 0 inside the slot
+        const int s = i % STAGES;
+        long long tp = probe ? clock64() : 0;
+        mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+        PROBE_ADD(8, tp);
 #pragma unroll
         for (int part = 0; part < SPLIT; ++part) {
-        const int u = i * SPLIT + part;       // ring unit: part 1 stages the lo halves (x - rn16(x)) of the same pixels
-        const int s = u % STAGES;
-        long long tp = probe ? clock64() : 0;
-        mbar_wait(&empty[s], ((u / STAGES) & 1) ^ 1);
-        PROBE_ADD(8, tp);
-        uint8_t* stage = sA + s * C::A_BYTES;
+        uint8_t* stage = sA + s * C::STAGE_BYTES + part * C::A_BYTES;
 #pragma unroll
         for (int k = 0; k < TPT; ++k) {
           if (ptid + k * PROD_THREADS < NTASK) {
@@ -366,10 +409,14 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
             for (int c = 0; c < CH; ++c) {
               if constexpr (SRC == SRC_CHW_F32) {
                 px[0][c] = v[k][c].x, px[1][c] = v[k][c].y, px[2][c] = v[k][c].z, px[3][c] = v[k][c].w;
+                if constexpr (BG) {           // the zero padding of x reads as -bg in the shifted space
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) px[e][c] = (ok ? px[e][c] : 0.0f) - bgc[c];
+                }
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)   // zero padding applies to the NORMALISED image
-                  px[e][c] = ok ? fmaf((float)((v[k][c] >> (8 * e)) & 255u), scale, shift) : 0.0f;
+                  px[e][c] = (ok ? fmaf((float)((v[k][c] >> (8 * e)) & 255u), scale, shift) : 0.0f) - bgc[c];
               }
             }
 #pragma unroll
@@ -390,10 +437,10 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
             }
           }
         }
+        }
         fence_proxy_async_smem();
         mbar_arrive(&full[s]);
         PROBE_ADD(10, tp);
-        }
       };
       // Register prefetch ring, PF tiles deep (loop unrolled by PF, no register copies): PF - 1 tile loads stay in flight
       // per CTA while tile i is converted and stored.  With the store warp in place the producers' global-load latency
@@ -408,7 +455,9 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
           if (i + q < my_tiles) {
+            long long tl = probe ? clock64() : 0;
             if (i + q + PF - 1 < my_tiles) load_tile(i + q + PF - 1, buf[(q + PF - 1) % PF], okm[(q + PF - 1) % PF]);
+            PROBE_ADD(9, tl);
             store_tile(i + q, buf[q], okm[q]);
           }
         }
@@ -428,7 +477,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       named_bar_sync(2, EPI_THREADS + 32);
       if (lane == 0) {
         tma_store_3d(&tmOut, sOut + (i & 1) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
-        if constexpr (SPLIT == 2)   // the lo tile travels in the same bulk group
+        if constexpr (C::OSPLIT == 2)   // the lo tile travels in the same bulk group
           tma_store_3d(&tmOutLo, sOut + (2 + (i & 1)) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
         bulk_store_commit();
       }
@@ -445,13 +494,20 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       long long tp = probe ? clock64() : 0;
       mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);
       PROBE_ADD(0, tp);
-      if constexpr (SPLIT == 1) {
+      if constexpr (SPLIT == 1 || C::MERGED) {
         mbar_wait(&full[s], (i / STAGES) & 1);
         PROBE_ADD(1, tp);
         tc_fence_after_sync();
         if (elect_one_sync()) {
-          issue_tile<KC, COUT, C::PACK4, FMT, false>(smem_u32(sA + s * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
-                                                     std::make_integer_sequence<int, C::NISSUE>{});
+          const uint32_t a_lo = smem_u32(sA + s * C::STAGE_BYTES) >> 4;
+          issue_tile<KC, COUT, C::PACK4, FMT, false>(a_lo, w_lo, tmem_base + b * C::ACC_COLS, std::make_integer_sequence<int, C::NISSUE>{});
+          if constexpr (C::MERGED) {
+            if constexpr (C::W_PARTS == 2)      // + x_hi * w_lo
+              issue_tile<KC, COUT, C::PACK4, FMT, true>(a_lo, w_lo + (C::W_BYTES >> 4), tmem_base + b * C::ACC_COLS,
+                                                        std::make_integer_sequence<int, C::NISSUE>{});
+            issue_tile<KC, COUT, C::PACK4, FMT, true>(a_lo + (C::A_BYTES >> 4), w_lo, tmem_base + b * C::ACC_COLS,   // + x_lo * w_hi
+                                                      std::make_integer_sequence<int, C::NISSUE>{});
+          }
           umma_commit(&empty[s]);      // halo slot reusable once these MMAs have read it
           umma_commit(&acc_full[b]);   // accumulators of this tile complete
         }
@@ -461,10 +517,10 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
         mbar_wait(&full[s0], (u0 / STAGES) & 1);
         tc_fence_after_sync();
         if (elect_one_sync()) {
-          issue_tile<KC, COUT, C::PACK4, FMT, false>(smem_u32(sA + s0 * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+          issue_tile<KC, COUT, C::PACK4, FMT, false>(smem_u32(sA + s0 * C::STAGE_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
                                                      std::make_integer_sequence<int, C::NISSUE>{});
           if constexpr (C::W_PARTS == 2)      // + x_hi * w_lo
-            issue_tile<KC, COUT, C::PACK4, FMT, true>(smem_u32(sA + s0 * C::A_BYTES) >> 4, w_lo + (C::W_BYTES >> 4),
+            issue_tile<KC, COUT, C::PACK4, FMT, true>(smem_u32(sA + s0 * C::STAGE_BYTES) >> 4, w_lo + (C::W_BYTES >> 4),
                                                       tmem_base + b * C::ACC_COLS, std::make_integer_sequence<int, C::NISSUE>{});
           umma_commit(&empty[s0]);
         }
@@ -473,7 +529,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
         PROBE_ADD(1, tp);
         tc_fence_after_sync();
         if (elect_one_sync()) {
-          issue_tile<KC, COUT, C::PACK4, FMT, true>(smem_u32(sA + s1 * C::A_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
+          issue_tile<KC, COUT, C::PACK4, FMT, true>(smem_u32(sA + s1 * C::STAGE_BYTES) >> 4, w_lo, tmem_base + b * C::ACC_COLS,
                                                     std::make_integer_sequence<int, C::NISSUE>{});
           umma_commit(&empty[s1]);
           umma_commit(&acc_full[b]);
@@ -490,7 +546,6 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
     // keep it hidden behind the next tile's MMAs.
     const int quad = warp & 3, half = warp >> 2;
     const int m = quad * 32 + lane;  // pooled pixel within the tile == TMEM lane == row of the output tile
-    const int PH = H / 2;
     constexpr int CH = COUT / (C::EPI_WARPS / 4);  // channels per epilogue warp
     // The tile is written to shared memory in the TMA store's swizzled layout (row = pixel, 16-byte chunk j of row r
     // at position j ^ swz(r)): conflict-free 16-byte stores here, and ONE bulk tensor store per tile instead of 32
@@ -498,11 +553,30 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
     // pipe this kernel is bound by).
     constexpr int SWZ_SHIFT = C::OUT_ROW_B == 128 ? 0 : 1, SWZ_MASK = C::OUT_ROW_B / 16 - 1;
     const int swz = (m >> SWZ_SHIFT) & SWZ_MASK;
+    // BG: the table rows of a tile's image (T and bg_out = 2 * COUT floats) are copied to shared memory one tile
+    // ahead by cp.async (thread e moves 16 bytes); the per-tile barrier below publishes them.  Reading them from global
+    // memory in the channel loop instead cost the (latency-bound) epilogue ~2x its time.
+    [[maybe_unused]] auto fetch_tab = [&](int it) {
+      if constexpr (BG) {
+        const int e = threadIdx.x;
+        if (it < my_tiles && e < C::TAB_FLOATS / 4) {
+          const int n = (blockIdx.x + it * gridDim.x) / tiles_per_img;
+          cp_async_16(smem_u32(sTab + (it & 1) * C::TAB_FLOATS + 4 * e), bg_tab + (size_t)n * C::TAB_FLOATS + 4 * e, 16u);
+        }
+        cp_async_commit();
+      }
+    };
+    if constexpr (BG) {
+      static_assert(C::TAB_FLOATS / 4 <= EPI_THREADS, "one 16-byte copy per epilogue thread");
+      fetch_tab(0);
+      cp_async_wait<0>();
+    }
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
       uint8_t* otile = sOut + b * C::OUT_BYTES;
       long long tp = probe ? clock64() : 0;
       named_bar_sync(1, EPI_THREADS + 32);     // the store warp: tile i-2 has been read out of this buffer
+      fetch_tab(i + 1);                        // (every epilogue thread is past tile i-1: its table buffer is free)
       PROBE_ADD(6, tp);
       mbar_wait(&acc_full[b], (i >> 1) & 1);
       PROBE_ADD(4, tp);
@@ -510,6 +584,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
       uint8_t* orow = otile + m * C::OUT_ROW_B;
       [[maybe_unused]] uint8_t* orow_lo = sOut + (2 + b) * C::OUT_BYTES + m * C::OUT_ROW_B;
+      [[maybe_unused]] const uint32_t tb_s = BG ? smem_u32(sTab + b * C::TAB_FLOATS + half * CH) : 0u;   // this tile's {T, bg_out}
       // CS channels per step (CS/8 output chunks): 4*CS live accumulator registers.  The first layer uses 8 so that its
       // variants fit the register cap of two CTAs per SM with eight producer warps; conv2 (no cap) uses 16.
       constexpr int CS = COUT >= 64 ? 16 : (C::PACK4 ? BBBP_CONV1_CS : 8);
@@ -532,6 +607,17 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
         [[maybe_unused]] uint32_t packed_lo[CS / 2];
 #pragma unroll
         for (int j = 0; j < CS; j += 4) {
+          if constexpr (BG) {
+            const float4 t = ld_shared_f4(tb_s + (c0 + j) * 4), bo = ld_shared_f4(tb_s + (COUT + c0 + j) * 4);
+            const float e[4] = {t.x, t.y, t.z, t.w}, o[4] = {bo.x, bo.y, bo.z, bo.w};
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              v[k] = fmaxf(fmaxf(fmaxf(__uint_as_float(r0[j + k]), __uint_as_float(r1[j + k])),
+                                 fmaxf(__uint_as_float(r2[j + k]), __uint_as_float(r3[j + k]))) + e[k], 0.0f) - o[k];
+            packed[j / 2] = pack16<FMT>(v[0], v[1]);
+            packed[j / 2 + 1] = pack16<FMT>(v[2], v[3]);
+          } else {
           const float4 bv = *reinterpret_cast<const float4*>(sBias + half * CH + c0 + j);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
@@ -542,8 +628,9 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
                              fmaxf(__uint_as_float(r2[j + k + 1]), __uint_as_float(r3[j + k + 1])));
             v0 = fmaxf(v0 + bb[k], 0.0f);
             v1 = fmaxf(v1 + bb[k + 1], 0.0f);
-            if constexpr (SPLIT == 2) split16<FMT>(v0, v1, packed[(j + k) / 2], packed_lo[(j + k) / 2]);
+            if constexpr (C::OSPLIT == 2) split16<FMT>(v0, v1, packed[(j + k) / 2], packed_lo[(j + k) / 2]);
             else packed[(j + k) / 2] = pack16<FMT>(v0, v1);
+          }
           }
         }
         const int chunk = (half * CH + c0) / 8;
@@ -551,13 +638,14 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
         for (int g = 0; g < CS / 8; ++g) {
           *reinterpret_cast<uint4*>(orow + (((chunk + g) ^ swz) << 4)) =
               make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
-          if constexpr (SPLIT == 2)
+          if constexpr (C::OSPLIT == 2)
             *reinterpret_cast<uint4*>(orow_lo + (((chunk + g) ^ swz) << 4)) =
                 make_uint4(packed_lo[4 * g], packed_lo[4 * g + 1], packed_lo[4 * g + 2], packed_lo[4 * g + 3]);
         }
       }
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[b]);   // TMEM reads done: the MMA warp may start the tile after next
+      if constexpr (BG) cp_async_wait<0>();   // the next tile's table has landed (published by the next per-tile barrier)
       PROBE_ADD(5, tp);
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA (async proxy)
       named_bar_arrive(2, EPI_THREADS + 32);   // tile written: the store warp takes it from here
@@ -692,13 +780,117 @@ __global__ void __launch_bounds__(256) u8_image_stats_kernel(const uint8_t* __re
   }
 }
 
-template <int KC, int COUT, int SRC, int FMT, int SPLIT>
+// ---- background-referenced strict mode: per-image tables (see the kernel comment, BG = 1) ------------------------------
+// Background value of an image per channel: the value most of the 8 probe pixels (4 corners, 4 edge midpoints) agree on,
+// compared as raw (R, G, B) triples; computed with the producers' own arithmetic, so x - bg is EXACTLY 0 on the canvas.
+// Any choice is mathematically exact (the tables below account for it); this one makes the background cost no precision.
+__global__ void __launch_bounds__(128) image_background_kernel(const void* __restrict__ img, int is_u8,
+                                                               const float2* __restrict__ stats, float* __restrict__ bg, int N,
+                                                               int H, int W) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int HW = H * W;
+  const int py[8] = {0, 0, H - 1, H - 1, 0, H / 2, H - 1, H / 2}, px[8] = {0, W - 1, 0, W - 1, W / 2, 0, W / 2, W - 1};
+  uint32_t key[8][3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t at = ((size_t)n * 3 + c) * HW + py[k] * W + px[k];
+      key[k][c] = is_u8 ? (uint32_t) static_cast<const uint8_t*>(img)[at] : __float_as_uint(static_cast<const float*>(img)[at]);
+    }
+  int best = 0, best_votes = -1;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int votes = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) votes += (key[j][0] == key[k][0]) & (key[j][1] == key[k][1]) & (key[j][2] == key[k][2]);
+    if (votes > best_votes) best_votes = votes, best = k;
+  }
+  float scale = 1.0f, shift = 0.0f;
+  if (is_u8) {
+    const float2 st = stats[n];
+    scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint32_t kv = key[0][c];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) kv = best == k ? key[k][c] : kv;
+    bg[4 * (size_t)n + c] = is_u8 ? fmaf((float)kv, scale, shift) : __uint_as_float(kv);
+  }
+  bg[4 * (size_t)n + 3] = 0.0f;
+}
+
+// One "layer" of the background chain:  T[n][co] = bias[co] + sum_ci wsum[co][ci] * in[n][ci]  (wsum = the layer's weights
+// summed over the taps / positions a constant input reaches: bbbp_fc_weight_channel_sums), written to out0; optionally
+// out1[n][co] = relu(T), rounded to the 16-bit operand format when fmt >= 0 (the next layer's background must be a 16-bit
+// number, see the kernel comment), and neg16[n][co] = -out1 in that format (the next layer's padding value).  fp32 FMAs in
+// a fixed order; weights transposed in shared memory, lane = output channel, 4 images per thread.
+constexpr int BGL_IMGS = 4;
+__global__ void __launch_bounds__(256) bg_layer_kernel(const float* __restrict__ wsum, const float* __restrict__ bias,
+                                                       const float* __restrict__ in, int ld_in, int Cin, int Cout,
+                                                       float* __restrict__ out0, int ld0, float* __restrict__ out1, int ld1,
+                                                       uint16_t* __restrict__ neg16, int fmt, int N, int imgs_per_block) {
+  extern __shared__ float sm_bgl[];
+  const int pitch = Cout + 1;
+  float* swT = sm_bgl;                         // [Cin][Cout + 1]
+  float* sin = sm_bgl + Cin * pitch;           // [imgs_per_block][Cin]
+  const int n0 = blockIdx.x * imgs_per_block, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int i = threadIdx.x; i < Cout * Cin; i += 256) swT[(i % Cin) * pitch + i / Cin] = wsum[i];
+  for (int i = threadIdx.x; i < imgs_per_block * Cin; i += 256) {
+    const int img = i / Cin, ci = i % Cin;
+    sin[i] = n0 + img < N ? in[(size_t)(n0 + img) * ld_in + ci] : 0.0f;
+  }
+  __syncthreads();
+  const int cogroups = Cout / 32, co = (warp % cogroups) * 32 + lane;
+  const float bs = bias ? bias[co] : 0.0f;
+  for (int q = warp / cogroups; q * BGL_IMGS < imgs_per_block; q += 8 / cogroups) {
+    float S[BGL_IMGS];
+#pragma unroll
+    for (int g = 0; g < BGL_IMGS; ++g) S[g] = bs;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float wv = swT[ci * pitch + co];
+#pragma unroll
+      for (int g = 0; g < BGL_IMGS; ++g) S[g] = fmaf(wv, sin[(q * BGL_IMGS + g) * Cin + ci], S[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < BGL_IMGS; ++g) {
+      const int n = n0 + q * BGL_IMGS + g;
+      if (n >= N) continue;
+      out0[(size_t)n * ld0 + co] = S[g];
+      float r = fmaxf(S[g], 0.0f);
+      if (fmt >= 0) r = round16_rt(r, fmt);
+      if (out1) out1[(size_t)n * ld1 + co] = r;
+      if (neg16) neg16[(size_t)n * Cout + co] = cvt16_rt(-r, fmt);
+    }
+  }
+}
+
+// out[o][c] = sum over hw of w[o][c*HW + hw]: what a Linear over the flattened (C, H, W) activation does to a per-channel
+// constant.  One warp per (o, c), fixed order.
+__global__ void __launch_bounds__(256) fc_weight_channel_sums_kernel(const float* __restrict__ w, float* __restrict__ out,
+                                                                     int rows_x_C, int HW) {
+  const int gw = (blockIdx.x * 256 + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (gw >= rows_x_C) return;
+  const float* src = w + (size_t)gw * HW;
+  float s = 0.0f;
+  for (int i = lane; i < HW; i += 32) s += src[i];
+  s = warp_sum(s);
+  if (lane == 0) out[gw] = s;
+}
+
+struct BgArgs {
+  const void* bg_in = nullptr;
+  const float* tab = nullptr;
+};
+template <int KC, int COUT, int SRC, int FMT, int SPLIT, int BG = 0>
 int launch(const void* x, const void* x_lo, const float* stats, const void* wprep, const float* bias, void* y, void* y_lo, int N,
-           int H, int W, cudaStream_t stream) {
-  using C = Cfg<KC, COUT, SRC, FMT, SPLIT>;
+           int H, int W, cudaStream_t stream, BgArgs bg = BgArgs{}) {
+  using C = Cfg<KC, COUT, SRC, FMT, SPLIT, BG>;
   static PerDeviceOnce attr_once;
   if (attr_once.first())
-    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   const int sms = current_sm_count();
   // NHWC output as a 3-D tensor {COUT, PW, N*PH}; one box = one tile (COUT x 8 x 16), swizzle span = one pixel row
   CUtensorMap tmOut, tmOutLo;
@@ -710,7 +902,7 @@ int launch(const void* x, const void* x_lo, const float* stats, const void* wpre
     cuuint64_t strides[2] = {(cuuint64_t)COUT * 2, (cuuint64_t)PW * COUT * 2};
     cuuint32_t box[3] = {(cuuint32_t)COUT, TILE_PW, TILE_PH};
     cuuint32_t estr[3] = {1, 1, 1};
-    for (int part = 0; part < SPLIT; ++part) {
+    for (int part = 0; part < C::OSPLIT; ++part) {
       CUresult r = enc(part ? &tmOutLo : &tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, part ? y_lo : y, dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, COUT * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -719,13 +911,14 @@ int launch(const void* x, const void* x_lo, const float* stats, const void* wpre
         return BBBP_ECUDA;
       }
     }
-    if (SPLIT == 1) tmOutLo = tmOut;
+    if (C::OSPLIT == 1) tmOutLo = tmOut;
   }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
   const int per_sm = C::MIN_CTAS;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
-  conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
-      x, x_lo, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, tmOut, tmOutLo, N, H, W);
+  conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT, BG><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(
+      x, x_lo, reinterpret_cast<const float2*>(stats), static_cast<const uint4*>(wprep), bias, tmOut, tmOutLo, N, H, W, bg.bg_in,
+      bg.tab);
   return launch_status("conv3x3_relu_pool16");
 }
 
@@ -844,6 +1037,80 @@ extern "C" int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, 
 extern "C" int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
                                           const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream) {
   return bbbp_conv1_from_image16(BBBP_FMT_BF16, 1, img_chw, img_is_u8, stats, wprep, bias, y_nhwc, nullptr, N, H, W, stream);
+}
+
+// ---- background-referenced strict mode (BG = 1) -------------------------------------------------------------------
+extern "C" int bbbp_image_background(const void* img_chw, int img_is_u8, const float* stats, float* bg, int N, int H, int W,
+                                     bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img_chw && bg && N >= 0 && H >= 2 && W >= 2, "image_background: bad argument");
+  BBBP_CHECK_ARG(!img_is_u8 || stats, "image_background: uint8 input needs the per-image (mean, 1/std) table");
+  if (N == 0) return BBBP_OK;
+  conv::image_background_kernel<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(img_chw, img_is_u8,
+                                                                                reinterpret_cast<const float2*>(stats), bg, N, H, W);
+  return launch_status("image_background");
+}
+
+extern "C" int bbbp_bg_layer(const float* wsum, const float* bias, const float* in, int ld_in, int Cin, int Cout, float* out0,
+                             int ld0, float* out1, int ld1, void* neg16, int fmt, int N, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(wsum && in && out0 && N >= 0, "bg_layer: null operand");
+  BBBP_CHECK_ARG(Cin >= 1 && Cin <= 256 && ld_in >= Cin && Cout >= 32 && Cout <= 256 && Cout % 32 == 0 && (256 / 32) % (Cout / 32) == 0,
+                 "bg_layer: Cin=%d (1..256), ld_in=%d, Cout=%d (32, 64, 128 or 256)", Cin, ld_in, Cout);
+  BBBP_CHECK_ARG(ld0 >= Cout && (!out1 || ld1 >= Cout), "bg_layer: output pitch < Cout");
+  BBBP_CHECK_ARG(fmt == -1 || fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "bg_layer: fmt %d (-1 = no rounding)", fmt);
+  BBBP_CHECK_ARG(!neg16 || fmt >= 0, "bg_layer: neg16 needs a 16-bit format");
+  if (N == 0) return BBBP_OK;
+  // images per block: every warp of a channel group takes two passes of 4 images
+  const int imgs = 2 * conv::BGL_IMGS * (8 / (Cout / 32));
+  const int smem = (Cin * (Cout + 1) + imgs * Cin) * (int)sizeof(float);
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
+    cudaFuncSetAttribute(conv::bg_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  BBBP_CHECK_ARG(smem <= 200 * 1024, "bg_layer: %d -> %d channels need %d bytes of shared memory", Cin, Cout, smem);
+  conv::bg_layer_kernel<<<ceil_div(N, imgs), 256, smem, as_stream(stream)>>>(wsum, bias, in, ld_in, Cin, Cout, out0, ld0, out1, ld1,
+                                                                           static_cast<uint16_t*>(neg16), fmt, N, imgs);
+  return launch_status("bg_layer");
+}
+
+extern "C" int bbbp_fc_weight_channel_sums(const float* w, float* out, int rows, int C, int HW, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(w && out && rows > 0 && C > 0 && HW > 0, "fc_weight_channel_sums: bad argument");
+  conv::fc_weight_channel_sums_kernel<<<ceil_div(rows * C * 32, 256), 256, 0, as_stream(stream)>>>(w, out, rows * C, HW);
+  return launch_status("fc_weight_channel_sums");
+}
+
+extern "C" int bbbp_conv1_from_image_bg16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats,
+                                          const void* wprep, const float* bg_in, const float* tab, void* y_nhwc, int N, int H,
+                                          int W, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img_chw && wprep && bg_in && tab && y_nhwc, "conv1_from_image_bg: null operand");
+  BBBP_CHECK_ARG(fmt == BBBP_FMT_F16 && (split == 1 || split == 2), "conv1_from_image_bg: built for fp16, split 1 or 2");
+  BBBP_CHECK_ARG(!img_is_u8 || stats, "conv1_from_image_bg: uint8 input needs the per-image (mean, 1/std) table");
+  BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
+                 "conv1_from_image_bg: H=%d must be a multiple of 32 and W=%d of 16", H, W);
+  BBBP_CHECK_ARG(((uintptr_t)tab % 16) == 0 && ((uintptr_t)y_nhwc % 16) == 0, "conv1_from_image_bg: table and output must be 16-byte aligned");
+  if (N == 0) return BBBP_OK;
+  cudaStream_t s = as_stream(stream);
+  const conv::BgArgs bg{bg_in, tab};
+  if (img_is_u8) {
+    if (split == 2)
+      return conv::launch<1, 32, conv::SRC_CHW_U8, BBBP_FMT_F16, 2, 1>(img_chw, nullptr, stats, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
+    return conv::launch<1, 32, conv::SRC_CHW_U8, BBBP_FMT_F16, 1, 1>(img_chw, nullptr, stats, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
+  }
+  if (split == 2)
+    return conv::launch<1, 32, conv::SRC_CHW_F32, BBBP_FMT_F16, 2, 1>(img_chw, nullptr, nullptr, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
+  return conv::launch<1, 32, conv::SRC_CHW_F32, BBBP_FMT_F16, 1, 1>(img_chw, nullptr, nullptr, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
+}
+
+extern "C" int bbbp_conv3x3_relu_pool_bg16(int fmt, const void* x_nhwc, const void* wprep, const void* neg_bg_in, const float* tab,
+                                           void* y_nhwc, int N, int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(x_nhwc && wprep && neg_bg_in && tab && y_nhwc, "conv3x3_relu_pool_bg: null operand");
+  BBBP_CHECK_ARG(fmt == BBBP_FMT_F16 && Cin_pad == 32 && Cout == 64, "conv3x3_relu_pool_bg: built for fp16, 32 -> 64 channels");
+  BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
+                 "conv3x3_relu_pool_bg: H=%d must be a multiple of 32 and W=%d of 16", H, W);
+  BBBP_CHECK_ARG(((uintptr_t)x_nhwc % 16) == 0 && ((uintptr_t)y_nhwc % 16) == 0 && ((uintptr_t)wprep % 16) == 0 &&
+                     ((uintptr_t)tab % 16) == 0 && ((uintptr_t)neg_bg_in % 16) == 0,
+                 "conv3x3_relu_pool_bg: operands must be 16-byte aligned");
+  if (N == 0) return BBBP_OK;
+  return conv::launch<4, 64, conv::SRC_NHWC_BF16, BBBP_FMT_F16, 1, 1>(x_nhwc, nullptr, nullptr, wprep, nullptr, y_nhwc, nullptr, N, H, W,
+                                                                      as_stream(stream), conv::BgArgs{neg_bg_in, tab});
 }
 
 // debug: probe = device array of 16 uint64 counters (zero it first), or NULL to switch the probe off

@@ -113,6 +113,10 @@ struct Params {
   //   (128B swizzle), the canonical MN-major layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) with SBO = 1024 (8 K-rows) and
   //   LBO = 8192 (next 64-wide block); a K = 16 MMA step advances the start address by 16 rows = 2048 bytes.
   int a_mn, b_mn;
+  // optional fp32 [M][N] addend applied BEFORE the activation (a per-row bias: the background-referenced strict mode adds
+  // what the constant part of the activation contributes, bbbp_gemm16_pre)
+  const float* pre_add;
+  int ld_pre;
 };
 
 // 32 fp32 values -> 32 16-bit values as four 16-byte stores (and the matching lo parts when lo != nullptr)
@@ -323,6 +327,12 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
           v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
           v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
         }
+        if (p.pre_add && row < p.M) {
+          const float* pa = p.pre_add + (size_t)row * p.ld_pre + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += pa[j];
+        }
         if (p.act == BBBP_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -396,13 +406,15 @@ __global__ void __launch_bounds__(256) splitk_finish_bf16_kernel(const float* __
                                                                  float* __restrict__ out, int ld_out,
                                                                  uint16_t* __restrict__ out16,
                                                                  uint16_t* __restrict__ out16_lo, int ld_out16,
-                                                                 int act, int fmt) {
+                                                                 int act, int fmt, const float* __restrict__ pre_add,
+                                                                 int ld_pre) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= (size_t)M * N) return;
   const int m = i / N, n = i % N;
   float v = 0.0f;
   for (int s = 0; s < splits; ++s) v += partial[((size_t)s * M_pad + m) * N_pad + n];
   v += bias ? bias[n] : 0.0f;
+  if (pre_add) v += pre_add[(size_t)m * ld_pre + n];
   v = apply_act(v, act);
   if (residual) v += residual[(size_t)m * ld_res + n];
   if (out) out[(size_t)m * ld_out + n] = v;
@@ -476,7 +488,7 @@ int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   const size_t total = (size_t)pr.M * pr.N;
   splitk_finish_bf16_kernel<<<(unsigned)ceil_div(total, (size_t)256), 256, 0, stream>>>(
       p.partial, p.splits, pr.M, pr.N, p.M_pad, p.N_pad, p.bias, p.residual, p.ld_res, p.out, p.ld_out, p.out16, p.out16_lo,
-      p.ld_out16, p.act, p.fmt);
+      p.ld_out16, p.act, p.fmt, p.pre_add, p.ld_pre);
   return launch_status("gemm_bf16 split-k finish");
 }
 
@@ -582,10 +594,32 @@ static int check_fmt(const char* who, int fmt) {
   return BBBP_OK;
 }
 
+static int gemm16_impl(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
+                       const void* W_lo, int ldw, const float* bias, const float* pre_add, int ld_pre, const float* residual,
+                       int ld_res, float* out_f32, int ld_out, void* out16_hi, void* out16_lo, int ld_out16, int act,
+                       int split_k, void* workspace, size_t workspace_bytes, bbbp_stream_t stream);
+
 extern "C" int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
                            const void* W_lo, int ldw, const float* bias, const float* residual, int ld_res, float* out_f32,
                            int ld_out, void* out16_hi, void* out16_lo, int ld_out16, int act, int split_k, void* workspace,
                            size_t workspace_bytes, bbbp_stream_t stream) {
+  return gemm16_impl(fmt, M, N, K, A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, nullptr, 0, residual, ld_res, out_f32, ld_out,
+                     out16_hi, out16_lo, ld_out16, act, split_k, workspace, workspace_bytes, stream);
+}
+
+extern "C" int bbbp_gemm16_pre(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
+                               const void* W_lo, int ldw, const float* bias, const float* pre_add, int ld_pre, float* out_f32,
+                               int ld_out, void* out16_hi, void* out16_lo, int ld_out16, int act, int split_k, void* workspace,
+                               size_t workspace_bytes, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(!pre_add || ld_pre >= N, "gemm16_pre: ld_pre < N");
+  return gemm16_impl(fmt, M, N, K, A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, pre_add, ld_pre, nullptr, 0, out_f32, ld_out,
+                     out16_hi, out16_lo, ld_out16, act, split_k, workspace, workspace_bytes, stream);
+}
+
+static int gemm16_impl(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
+                       const void* W_lo, int ldw, const float* bias, const float* pre_add, int ld_pre, const float* residual,
+                       int ld_res, float* out_f32, int ld_out, void* out16_hi, void* out16_lo, int ld_out16, int act,
+                       int split_k, void* workspace, size_t workspace_bytes, bbbp_stream_t stream) {
   using namespace bbbp;
   int st = check_fmt("gemm16", fmt);
   if (st != BBBP_OK) return st;
@@ -612,6 +646,7 @@ extern "C" int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const
   pr.M = M, pr.N = N, pr.K = K, pr.batches = 1;
   pr.A = A_hi, pr.A_lo = A_lo, pr.lda = lda, pr.W = W_hi, pr.W_lo = W_lo, pr.ldw = ldw;
   pr.p.bias = bias, pr.p.residual = residual, pr.p.ld_res = ld_res;
+  pr.p.pre_add = pre_add, pr.p.ld_pre = ld_pre;
   pr.p.out = out_f32, pr.p.ld_out = ld_out;
   pr.p.out16 = static_cast<uint16_t*>(out16_hi), pr.p.out16_lo = static_cast<uint16_t*>(out16_lo), pr.p.ld_out16 = ld_out16;
   pr.p.act = act, pr.p.partial = static_cast<float*>(workspace), pr.p.fmt = fmt;

@@ -178,11 +178,12 @@ def standardize_chunks(x: torch.Tensor, chunk_rows: int = 100, out: torch.Tensor
 
 
 def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, out_bf16=False, split_k=1,
-              ld_out=None, ld_out16=None, fmt=FMT_BF16, a_lo=None, w_lo=None, out16_lo=None):
+              ld_out=None, ld_out16=None, fmt=FMT_BF16, a_lo=None, w_lo=None, out16_lo=None, pre_add=None):
     """act(a16[:, :K] @ w16[:N, :K]^T + bias) (+ residual) on the tcgen05 path.  Returns (f32 | None, 16-bit | None);
     outputs are (M, ld) buffers whose first N columns are the result (16-bit pad columns are zero).  ``fmt``: operand
     format; ``a_lo`` / ``w_lo``: optional low parts (one more MMA each per K step); ``out16_lo`` (True / False, default
-    None): return a 3-tuple (f32, hi, lo) whose lo is the low part of the 16-bit output when True, None when False."""
+    None): return a 3-tuple (f32, hi, lo) whose lo is the low part of the 16-bit output when True, None when False.
+    ``pre_add``: an (M, >= N) float32 addend applied before the activation (per-row bias; excludes ``residual``)."""
     M = a16.shape[0]
     ld_out = N if ld_out is None else ld_out
     ld16 = -(-N // 8) * 8 if ld_out16 is None else ld_out16
@@ -195,6 +196,12 @@ def gemm_bf16(a16, K, w16, N, bias=None, residual=None, act=None, out_f32=True, 
         fill_zero(o16[:, N:])          # the split-K finish kernel writes only the N result columns
         if o16lo is not None:
             fill_zero(o16lo[:, N:])
+    if pre_add is not None:
+        assert residual is None and pre_add.dtype == torch.float32 and pre_add.shape[0] == M and pre_add.stride(1) == 1
+        check(lib.bbbp_gemm16_pre(fmt, M, N, K, a16.data_ptr(), _ptr(a_lo), a16.stride(0), w16.data_ptr(), _ptr(w_lo),
+                                  w16.stride(0), _ptr(bias), pre_add.data_ptr(), pre_add.stride(0), _ptr(o32), ld_out, _ptr(o16),
+                                  _ptr(o16lo), ld16, _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm16_pre")
+        return (o32, o16, o16lo) if out16_lo is not None else (o32, o16)
     check(lib.bbbp_gemm16(fmt, M, N, K, a16.data_ptr(), _ptr(a_lo), a16.stride(0), w16.data_ptr(), _ptr(w_lo), w16.stride(0),
                           _ptr(bias), _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(o32), ld_out,
                           _ptr(o16), _ptr(o16lo), ld16, _ACT[act], split_k, _ptr(ws), ws_bytes, _stream()), "gemm16")
@@ -405,6 +412,71 @@ def conv1_from_image_bf16(img: torch.Tensor, wprep: torch.Tensor, bias: torch.Te
                                       bias.data_ptr(), y.data_ptr(), _ptr(y_lo), N, H, W, _stream()), "conv1_from_image16")
     KERNEL_TIMER.stop("conv1", t0, N)
     return (y, y_lo) if split else y
+
+
+# ---- background-referenced strict mode of the image branch (conv_umma.cu, BG = 1) ---------------------------------------
+def image_background(img: torch.Tensor, stats=None, H=128, W=128) -> torch.Tensor:
+    """(N, 4) float32: the background value of every image per channel (column 3 is zero); uint8 images are normalised
+    with ``stats`` exactly as the first layer's producers do."""
+    N = img.numel() // (3 * H * W)
+    is_u8 = img.dtype == torch.uint8
+    assert is_u8 or img.dtype == torch.float32
+    bg = torch.empty((N, 4), device=img.device, dtype=torch.float32)
+    check(lib.bbbp_image_background(img.data_ptr(), int(is_u8), _ptr(stats), bg.data_ptr(), N, H, W, _stream()), "image_background")
+    return bg
+
+
+def fc_weight_channel_sums(w: torch.Tensor, C: int, HW: int) -> torch.Tensor:
+    """(rows, C) float32: sum over the HW positions of w[o, c*HW:(c+1)*HW] (nn.Flatten's (C, H, W) order; HW = 9: a 3x3
+    convolution weight summed over its taps)."""
+    rows = w.shape[0]
+    w = _f32(w, "w")
+    out = torch.empty((rows, C), device=w.device, dtype=torch.float32)
+    check(lib.bbbp_fc_weight_channel_sums(w.data_ptr(), out.data_ptr(), rows, C, HW, _stream()), "fc_weight_channel_sums")
+    return out
+
+
+def bg_layer(wsum: torch.Tensor, bias, bg_in: torch.Tensor, fmt: int = -1, want_neg16: bool = False, table: bool = True):
+    """One step of the background chain (bbbp_bg_layer).  ``table``: returns (tab (N, 2, Cout) = {T, bg_out}, neg16 | None)
+    for a convolution layer; otherwise just T (N, Cout) (the Linear's per-row addend)."""
+    Cout, Cin = wsum.shape
+    N = bg_in.shape[0]
+    if not table:
+        out = torch.empty((N, Cout), device=wsum.device, dtype=torch.float32)
+        check(lib.bbbp_bg_layer(wsum.data_ptr(), _ptr(bias), bg_in.data_ptr(), bg_in.stride(0), Cin, Cout, out.data_ptr(), Cout,
+                                None, 0, None, -1, N, _stream()), "bg_layer")
+        return out
+    tab = torch.empty((N, 2, Cout), device=wsum.device, dtype=torch.float32)
+    neg = torch.empty((N, Cout), device=wsum.device, dtype=_DT16[fmt]) if want_neg16 else None
+    check(lib.bbbp_bg_layer(wsum.data_ptr(), _ptr(bias), bg_in.data_ptr(), bg_in.stride(0), Cin, Cout, tab.data_ptr(), 2 * Cout,
+                            tab[:, 1].data_ptr(), 2 * Cout, _ptr(neg), fmt, N, _stream()), "bg_layer")
+    return tab, neg
+
+
+def conv1_from_image_bg(img: torch.Tensor, wprep: torch.Tensor, stats, bg_in, tab, H=128, W=128, fmt=FMT_F16, split=True):
+    """First layer on x - bg_in (staged as a (hi, lo) pair when ``split``); returns maxpool(relu(conv1(x))) - tab[:, 1] as
+    ONE NHWC 16-bit tensor."""
+    N = img.numel() // (3 * H * W)
+    y = torch.empty((N, H // 2, W // 2, 32), device=img.device, dtype=_DT16[fmt])
+    is_u8 = img.dtype == torch.uint8
+    t0 = KERNEL_TIMER.start("conv1")
+    check(lib.bbbp_conv1_from_image_bg16(fmt, 2 if split else 1, img.data_ptr(), int(is_u8), _ptr(stats), wprep.data_ptr(),
+                                         bg_in.data_ptr(), tab.data_ptr(), y.data_ptr(), N, H, W, _stream()),
+          "conv1_from_image_bg16")
+    KERNEL_TIMER.stop("conv1", t0, N)
+    return y
+
+
+def conv3x3_relu_pool_bg(x_nhwc: torch.Tensor, wprep: torch.Tensor, neg_bg_in, tab, Cout: int, fmt=FMT_F16):
+    """Second layer on background-referenced NHWC input (``neg_bg_in``: what its padding holds); returns
+    maxpool(relu(conv(x))) - tab[:, 1]."""
+    N, H, W, Cin_pad = x_nhwc.shape
+    y = torch.empty((N, H // 2, W // 2, Cout), device=x_nhwc.device, dtype=_DT16[fmt])
+    t0 = KERNEL_TIMER.start("conv2")
+    check(lib.bbbp_conv3x3_relu_pool_bg16(fmt, x_nhwc.data_ptr(), wprep.data_ptr(), neg_bg_in.data_ptr(), tab.data_ptr(), y.data_ptr(),
+                                          N, Cin_pad, Cout, H, W, _stream()), "conv3x3_relu_pool_bg16")
+    KERNEL_TIMER.stop("conv2", t0, N)
+    return y
 
 
 def fc_weight_to_hwc_bf16(w: torch.Tensor, C: int, HW: int, fmt=FMT_BF16) -> torch.Tensor:

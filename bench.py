@@ -50,6 +50,9 @@ CONFIG = {"workload": "screen_maccs_b256", "model": "MixedInputModel(167,128) 20
 # molecules per staged chunk of the host pipeline: a chunk's replay costs ~0.55 ms + its compute, its copy 0.94 ms per 1 024
 # (tools/e2e_sweep.py on B200, strict mode, 16 384 molecules: 1 024 -> 20.0 ms, 2 048 -> 16.4 ms, 4 096 -> 17.5 ms)
 E2E_CHUNK = 2048
+# sparse depictions cut the copy to ~5 KB per molecule, so the fixed per-chunk latency decides instead of the PCIe overlap:
+# tools/e2e_sweep.py --sparse, strict: 2 048 -> 14.9 ms, 4 096 -> 12.9, 8 192 -> 12.5, 16 384 -> 12.4 (profiles/r02_e2e_sweep_sparse_strict.txt)
+E2E_CHUNK_SPARSE = 8192
 DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (hi+lo pairs, fp32 accumulate)"}
 
 
@@ -352,7 +355,7 @@ def main():
             dist.all_gather_into_tensor(gathered, s)
 
     def step_e2e_sparse():
-        _, s = model.predict_from_host(packed_host, sparse_host, BATCH, chunk_molecules=E2E_CHUNK, packed=True, out_host=scores_host,
+        _, s = model.predict_from_host(packed_host, sparse_host, BATCH, chunk_molecules=E2E_CHUNK_SPARSE, packed=True, out_host=scores_host,
                                        return_device=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
@@ -419,7 +422,7 @@ def main():
                 step_resident()
             m_res = timed(step_resident, args.steps)
             for _ in range(2):
-                step_e2e_compact()
+                step_e2e_sparse()          # (captures this mode's chunk graphs outside the timed region)
             m_e2e = timed(step_e2e_sparse, args.steps)
             by_precision[mode] = {"value": world * n * args.steps / (m_res * 1e-3), "e2e": world * n * args.steps / (m_e2e * 1e-3),
                                   "unit": UNIT, "dtype": DTYPE[mode], "ms_per_step": m_res / args.steps}

@@ -103,6 +103,13 @@ int bbbp_gemm16(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo
                 int ldw, const float* bias, const float* residual, int ld_res, float* out_f32, int ld_out, void* out16_hi,
                 void* out16_lo, int ld_out16, int act, int split_k, void* workspace, size_t workspace_bytes,
                 bbbp_stream_t stream);
+/* bbbp_gemm16 with an fp32 [M][N] addend applied BEFORE the activation (a per-row bias; pitch ld_pre >= N, NULL to skip):
+ * out = act((A_hi + A_lo) W_hi^T + A_hi W_lo^T + bias + pre_add).  Used by the background-referenced strict mode, where
+ * the Linear(65536,128) of the image branch (20250113.py:92) sees activations relative to a per-image background. */
+int bbbp_gemm16_pre(int fmt, int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi, const void* W_lo,
+                    int ldw, const float* bias, const float* pre_add, int ld_pre, float* out_f32, int ld_out, void* out16_hi,
+                    void* out16_lo, int ld_out16, int act, int split_k, void* workspace, size_t workspace_bytes,
+                    bbbp_stream_t stream);
 /* Operands read in place in their TRANSPOSED storage (the backward products of a Linear layer and the convolution weight
  * gradient over im2col rows need no transposed copies): trans_a != 0: A is stored [K][M] (M contiguous, lda >= M);
  * trans_w != 0: W is stored [K][N] (N contiguous, ldw >= N).  out = act(opA(A) opW(W)^T + bias).  UMMA MN-major operand
@@ -184,6 +191,32 @@ int bbbp_conv3x3_relu_pool16(int fmt, int split, const void* x_nhwc, const void*
 int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
                             const float* bias, void* y_nhwc, void* y_lo, int N, int H, int W, bbbp_stream_t stream);
 int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int C, int HW, bbbp_stream_t stream);
+/* Background-referenced strict mode of the same two blocks (conv_umma.cu, BG = 1).  A depiction is
+ * mostly one value per channel, so each layer works on activations RELATIVE to a per-image background (exactly 0 on the
+ * canvas: rounding them to fp16 costs nothing there) and its epilogue adds back, in fp32 and from the fp32 weights, what the
+ * constant part contributes:  conv(x)[p] = conv(x - bg)[p] + T[image][cout],  T = bias + sum over all taps of w . bg  (the
+ * zero padding of x is staged as -bg, so this holds at the image border too).
+ *   bbbp_image_background   bg[n][0..2] = background value of image n per channel (majority of 8 probe pixels), bg[n][3] = 0;
+ *                           uint8 input: normalised with stats exactly as the first layer's producers do
+ *   bbbp_fc_weight_channel_sums  out[o][c] = sum_j w[o][c*HW + j]: a Linear over a flattened (C, HW) activation, or (HW = 9)
+ *                           a 3x3 convolution, applied to a per-channel constant
+ *   bbbp_bg_layer           one step of the background chain: out0[n][co] = bias[co] + sum_ci wsum[co][ci] * in[n][ci]
+ *                           (pitches ld_in / ld0; bias may be NULL); out1 (may be NULL) = relu(out0), rounded to the 16-bit
+ *                           format fmt when fmt >= 0 (-1: no rounding) = the background of the layer's OUTPUT; neg16 (may be
+ *                           NULL) = -out1 in that format, [n][Cout] = what the next layer's padding holds.  Cout 32..256
+ *   bbbp_conv1_from_image_bg16 / bbbp_conv3x3_relu_pool_bg16: the layers.  tab[n] = {T[Cout], bg_out[Cout]} (out0 / out1 of
+ *                           bbbp_bg_layer written with pitch 2*Cout); bg_in = bbbp_image_background's table; neg_bg_in = the
+ *                           previous layer's neg16.  split = 2: the first layer's producers stage x - bg as a (hi, lo) pair.
+ *                           Output: ONE fp16 NHWC tensor holding maxpool(relu(conv(x))) - bg_out.  Built for fp16. */
+int bbbp_image_background(const void* img_chw, int img_is_u8, const float* stats, float* bg, int N, int H, int W,
+                          bbbp_stream_t stream);
+int bbbp_fc_weight_channel_sums(const float* w, float* out, int rows, int C, int HW, bbbp_stream_t stream);
+int bbbp_bg_layer(const float* wsum, const float* bias, const float* in, int ld_in, int Cin, int Cout, float* out0, int ld0,
+                  float* out1, int ld1, void* neg16, int fmt, int N, bbbp_stream_t stream);
+int bbbp_conv1_from_image_bg16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
+                               const float* bg_in, const float* tab, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream);
+int bbbp_conv3x3_relu_pool_bg16(int fmt, const void* x_nhwc, const void* wprep, const void* neg_bg_in, const float* tab,
+                                void* y_nhwc, int N, int Cin_pad, int Cout, int H, int W, bbbp_stream_t stream);
 /* Lossless sparse depictions (extension, sparse_depictions.cu): rebuilds out[n][3][128][128] uint8 from mask[n][2048]
  * (bit p, little-endian, set where pixel p is not white), values (the RGB triples of the marked pixels in scan order) and
  * offsets[n + 1] (running pixel counts; only differences to offsets[0] are used).  ~5.5 KB per molecule instead of 49 152. */

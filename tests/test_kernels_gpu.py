@@ -720,6 +720,97 @@ def test_conv_stack_tcgen05_fp16_and_strict(ops, N, source):
     assert e2 <= 2.5e-3 * max(1.0, float(ref2.abs().max())) and e2 < 0.6 * f2, (e2, f2)
 
 
+def _bg_row_reference(w, b, bg):
+    """T[n][co] = the layer's response to a constant image equal to bg away from the border (float64)."""
+    return b.double()[None, :] + torch.einsum("ocij,nc->no", w.double(), bg.double())
+
+
+@pytest.mark.parametrize("N", [1, 3, 37])
+@pytest.mark.parametrize("source", ["fp32", "uint8"])
+@pytest.mark.parametrize("split", [True, False])
+def test_conv_stack_background_referenced(ops, N, source, split):
+    """The strict mode's background-referenced layers (conv_umma.cu BG = 1): background rows against their definition, the
+    stack against the float64 convolution of the unrounded operands (image borders included: the padding is staged as -bg),
+    exact zeros on the canvas, and the first layer staged in one or two passes.  Depiction-like inputs: one value per
+    channel with sparse strokes (also touching every border)."""
+    from oracle import preprocess
+    rng = np.random.default_rng(100 + N)
+    img8 = np.full((N, 3, 128, 128), 255, dtype=np.uint8)
+    strokes = rng.random((N, 1, 128, 128)) < 0.05
+    strokes[:, :, 0:2, 30:60] = True                                              # strokes on all four borders
+    strokes[:, :, 126:128, 70:90] = True
+    strokes[:, :, 40:70, 0:2] = True
+    strokes[:, :, 80:100, 126:128] = True
+    strokes[:, :, 20:110, 18:50] = False                                          # a stroke-free band
+    img8[np.broadcast_to(strokes, img8.shape)] = rng.integers(0, 200, size=int(strokes.sum()) * 3, dtype=np.uint8)
+    if N > 1:
+        img8[1, :, 0, 0] = 7                                                      # a corner that is NOT background: outvoted
+    img = torch.from_numpy(preprocess.u8_image_zscore(img8)).view(N, 3, 128, 128)
+    if source == "uint8":
+        dev = torch.from_numpy(img8).cuda()
+        stats = ops.u8_image_stats(dev)
+    else:
+        dev, stats = img.cuda(), None
+    w1, b1 = rnd(32, 3, 3, 3, seed=231, scale=0.2), rnd(32, seed=232, scale=0.1)
+    w2, b2 = rnd(64, 32, 3, 3, seed=233, scale=0.06), rnd(64, seed=234, scale=0.1)
+    ref1 = F.max_pool2d(F.relu(F.conv2d(img.double(), w1.double(), b1.double(), padding=1)), 2)
+    ref2 = F.max_pool2d(F.relu(F.conv2d(ref1, w2.double(), b2.double(), padding=1)), 2)
+    # the background chain
+    bg1 = ops.image_background(dev, stats)
+    white = img[:, :, 64, 22]                                                     # inside the stroke-free band
+    close(bg1[:, :3], white, atol=2e-6, what="background value")
+    assert float(bg1[:, 3].abs().max()) == 0.0
+    ws1, ws2 = ops.fc_weight_channel_sums(w1.cuda(), 3, 9), ops.fc_weight_channel_sums(w2.cuda(), 32, 9)
+    close(ws1, w1.double().sum((2, 3)).float(), atol=1e-6, what="tap sums 1")
+    close(ws2, w2.double().sum((2, 3)).float(), atol=1e-6, what="tap sums 2")
+    tab1, neg2 = ops.bg_layer(ws1, b1.cuda(), bg1, fmt=1, want_neg16=True)
+    tab2, none = ops.bg_layer(ws2, b2.cuda(), tab1[:, 1], fmt=-1)
+    assert none is None and tab1.shape == (N, 2, 32) and tab2.shape == (N, 2, 64) and neg2.dtype == torch.float16
+    bg2, bg3 = tab1[:, 1], tab2[:, 1]
+    close(tab1[:, 0], _bg_row_reference(w1, b1, bg1[:, :3].cpu()).float(), atol=2e-5, what="T1")
+    assert torch.equal(bg2, torch.relu(tab1[:, 0]).half().float()), "bg2 = rn16(relu(T1))"
+    assert torch.equal(neg2.float(), -bg2), "the next layer's padding value is exactly -bg2"
+    close(tab2[:, 0], _bg_row_reference(w2, b2, bg2.cpu()).float(), atol=5e-5, what="T2")
+    assert torch.equal(bg3, torch.relu(tab2[:, 0])), "bg3 = relu(T2)"
+    # layers
+    wp1, wp2 = ops.conv3x3_prepare_bf16(w1.cuda(), 1), ops.conv3x3_prepare_bf16(w2.cuda(), 1)
+    y1 = ops.conv1_from_image_bg(dev, wp1, stats, bg1, tab1, fmt=1, split=split)
+    y2 = ops.conv3x3_relu_pool_bg(y1, wp2, neg2, tab2, 64, fmt=1)
+    assert y1.dtype == torch.float16 and y1.shape == (N, 64, 64, 32) and y2.shape == (N, 32, 32, 64)
+    got1 = y1.float().cpu() + bg2.cpu()[:, None, None, :]
+    got2 = y2.float().cpu() + bg3.cpu()[:, None, None, :]
+    r1, r2 = ref1.float().permute(0, 2, 3, 1), ref2.float().permute(0, 2, 3, 1)
+    e1, e2 = float((got1 - r1).abs().max()), float((got2 - r2).abs().max())
+    print(f"[conv bg] N={N} {source} split={split}: conv1 {e1:.2e} (|ref| {float(r1.abs().max()):.1f}), conv2 {e2:.2e} "
+          f"(|ref| {float(r2.abs().max()):.1f})")
+    # fp16 round-off of the (small) stroke responses only: the canvas carries no error at all
+    assert e1 <= 4e-3 * max(1.0, float(r1.abs().max())), e1
+    assert e2 <= 4e-3 * max(1.0, float(r2.abs().max())), e2
+    band1 = y1[:, 12:52, 11:12, :].float().cpu()        # pooled pixels whose 3x3 neighbourhoods see canvas only
+    resid = (torch.relu(tab1[:, 0]) - bg2).cpu()[:, None, None, :]        # relu(T1) - rn16(relu(T1)): at most half an fp16 ulp
+    assert float((band1 - resid.half().float()).abs().max()) == 0.0, "the canvas carries only the rounding residue of bg2"
+    band2 = y2[:, 8:24, 7:10, :].float()                # pooled pixels of layer 2 that see pure-canvas pixels of layer 1 only
+    assert float(band2.abs().max()) <= 1e-3 * float(bg3.abs().max()), "canvas after the second layer"
+    if split:                                           # two passes over x - bg: fp32-class against the ONCE-ROUNDED weights
+        r1h = F.max_pool2d(F.relu(F.conv2d(img.double(), w1.half().double(), b1.double(), padding=1)), 2).float().permute(0, 2, 3, 1)
+        y1f = (y1.float().cpu() + bg2.cpu()[:, None, None, :])
+        # y1 itself is one fp16 rounding of (value - bg2): compare before that rounding matters, i.e. at half an fp16 ulp
+        e1h = float((y1f - r1h).abs().max())
+        assert e1h <= 6e-4 * max(1.0, float(r1.abs().max())), e1h
+
+
+@pytest.mark.parametrize("M,N,K,split_k", [(5, 128, 4096, 1), (300, 128, 65536, 32), (130, 70, 1000, 3)])
+def test_gemm16_pre_activation_addend(ops, M, N, K, split_k):
+    """bbbp_gemm16_pre: relu(A W^T + bias + pre) with the addend applied before the activation, one-shot and split-K."""
+    a, w, b = rnd(M, K, seed=260), rnd(N, K, seed=261, scale=K ** -0.5), rnd(N, seed=262)
+    pre = rnd(M, N, seed=263)
+    a16, _ = ops.cast16(a.cuda(), 1)
+    w16, _ = ops.cast16(w.cuda(), 1)
+    o, _ = ops.gemm_bf16(a16, K, w16, N, bias=b.cuda(), act="relu", split_k=split_k, fmt=1, pre_add=pre.cuda())
+    ref = torch.relu(a.half().double() @ w.half().double().t() + b.double() + pre.double()).float()
+    close(o, ref, atol=2e-4 * max(1.0, math.sqrt(K) / 64), rtol=1e-4, what="gemm16_pre")
+
+
 def test_attention_many_small_heads_fp16(ops):
     groups, seq, heads, d = 2, 100, 32, 8
     E = heads * d
