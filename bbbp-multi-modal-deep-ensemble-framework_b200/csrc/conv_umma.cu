@@ -128,6 +128,19 @@ __host__ __device__ constexpr TapPair conv1_pair(int dx, int i) {
   return TapPair{t1, t0, pad ? 0 : -1};
 }
 
+// t / d and t % d for a run-time d without the ~40-instruction integer-division sequence: the role loops below locate
+// every tile (image, tile row, tile column) on latency-bound single warps.  q = umulhi(t, ceil(2^32 / d)) is exact for
+// t < 2^32 / d (the launcher checks the tile count).
+struct FastDiv {
+  uint32_t d, m;
+  __device__ explicit FastDiv(int dd) : d((uint32_t)dd), m(dd == 1 ? 0u : 0xFFFFFFFFu / (uint32_t)dd + 1u) {}
+  __device__ __forceinline__ int div(int t) const { return m ? (int)__umulhi((uint32_t)t, m) : t; }
+  __device__ __forceinline__ void divmod(int t, int& q, int& r) const {
+    q = div(t);
+    r = t - q * (int)d;
+  }
+};
+
 struct MmaOp {
   uint32_t a_off, a_lbo, b_off, b_lbo, d_col, n, accumulate;
 };
@@ -244,6 +257,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
   const int tiles_x = (W / 2) / TILE_PW, tiles_y = (H / 2) / TILE_PH;
   const int tiles_per_img = tiles_x * tiles_y;
   const int num_tiles = n_img * tiles_per_img;
+  const FastDiv fd_img(tiles_per_img), fd_x(tiles_x);
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // ---- one-time setup: weights + bias to smem, barriers, TMEM -----------------------------------------------------
@@ -284,8 +298,10 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       const int my_units = my_tiles * SPLIT;
       for (int i = 0; i < my_units; ++i) {
         const int t = blockIdx.x + (i / SPLIT) * gridDim.x;
-        const int n = t / tiles_per_img, r = t % tiles_per_img;
-        const int y0 = 2 * (r / tiles_x) * TILE_PH - 1, x0 = 2 * (r % tiles_x) * TILE_PW - 1;
+        int n, r, ty, tx;
+        fd_img.divmod(t, n, r);
+        fd_x.divmod(r, ty, tx);
+        const int y0 = 2 * ty * TILE_PH - 1, x0 = 2 * tx * TILE_PW - 1;
         const int s = i % STAGES;
         long long tp = probe ? clock64() : 0;
         mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
@@ -349,10 +365,11 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       }
       auto tile_origin = [&](int i, int& n, int& y0, int& x0) {
         const int t = blockIdx.x + i * gridDim.x;
-        n = t / tiles_per_img;
-        const int r = t % tiles_per_img;
-        y0 = 2 * (r / tiles_x) * TILE_PH - 1;
-        x0 = 2 * (r % tiles_x) * TILE_PW - 1;
+        int r, ty, tx;
+        fd_img.divmod(t, n, r);
+        fd_x.divmod(r, ty, tx);
+        y0 = 2 * ty * TILE_PH - 1;
+        x0 = 2 * tx * TILE_PW - 1;
       };
       auto load_tile = [&](int i, Vec (&v)[TPT][CH], uint32_t& okmask) {
         int n, y0, x0;
@@ -383,12 +400,12 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       auto store_tile = [&](int i, const Vec (&v)[TPT][CH], uint32_t okmask) {
         float scale = 1.0f, shift = 0.0f;   // (u/255 - mean) * rstd == u * scale + shift
         if constexpr (SRC == SRC_CHW_U8) {
-          const float2 st = __ldg(stats + (blockIdx.x + i * gridDim.x) / tiles_per_img);
+          const float2 st = __ldg(stats + fd_img.div(blockIdx.x + i * gridDim.x));
           scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
         }
         [[maybe_unused]] float bgc[CH] = {0.0f, 0.0f, 0.0f};   // BG: this image's background value per channel
         if constexpr (BG) {
-          const float* bp = static_cast<const float*>(bg_in) + 4 * (size_t)((blockIdx.x + i * gridDim.x) / tiles_per_img);
+          const float* bp = static_cast<const float*>(bg_in) + 4 * (size_t)fd_img.div(blockIdx.x + i * gridDim.x);
 #pragma unroll
           for (int c = 0; c < CH; ++c) bgc[c] = __ldg(bp + c);
         }
@@ -470,15 +487,17 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
     const int PH = H / 2;
     for (int i = 0; i < my_tiles; ++i) {
       const int t = blockIdx.x + i * gridDim.x;
-      const int n = t / tiles_per_img, r = t % tiles_per_img;
+      int n, r, ty, tx;
+      fd_img.divmod(t, n, r);
+      fd_x.divmod(r, ty, tx);
       if (lane == 0 && i >= 2) bulk_store_wait_read<1>();   // the store of tile i-2 has finished reading buffer i & 1
       __syncwarp();
       named_bar_arrive(1, EPI_THREADS + 32);
       named_bar_sync(2, EPI_THREADS + 32);
       if (lane == 0) {
-        tma_store_3d(&tmOut, sOut + (i & 1) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
+        tma_store_3d(&tmOut, sOut + (i & 1) * C::OUT_BYTES, 0, tx * TILE_PW, n * PH + ty * TILE_PH);
         if constexpr (C::OSPLIT == 2)   // the lo tile travels in the same bulk group
-          tma_store_3d(&tmOutLo, sOut + (2 + (i & 1)) * C::OUT_BYTES, 0, (r % tiles_x) * TILE_PW, n * PH + (r / tiles_x) * TILE_PH);
+          tma_store_3d(&tmOutLo, sOut + (2 + (i & 1)) * C::OUT_BYTES, 0, tx * TILE_PW, n * PH + ty * TILE_PH);
         bulk_store_commit();
       }
     }
@@ -560,7 +579,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       if constexpr (BG) {
         const int e = threadIdx.x;
         if (it < my_tiles && e < C::TAB_FLOATS / 4) {
-          const int n = (blockIdx.x + it * gridDim.x) / tiles_per_img;
+          const int n = fd_img.div(blockIdx.x + it * gridDim.x);
           cp_async_16(smem_u32(sTab + (it & 1) * C::TAB_FLOATS + 4 * e), bg_tab + (size_t)n * C::TAB_FLOATS + 4 * e, 16u);
         }
         cp_async_commit();
@@ -914,6 +933,10 @@ int launch(const void* x, const void* x_lo, const float* stats, const void* wpre
     if (C::OSPLIT == 1) tmOutLo = tmOut;
   }
   const int tiles = N * ((W / 2) / TILE_PW) * ((H / 2) / TILE_PH);
+  if ((long long)tiles * (((W / 2) / TILE_PW) * ((H / 2) / TILE_PH)) >= (1ll << 32)) {
+    set_error("conv3x3_relu_pool16: %d tiles of %dx%d images exceed the kernel's tile index range", tiles, H, W);
+    return BBBP_EINVAL;
+  }
   const int per_sm = C::MIN_CTAS;
   const int grid = tiles < sms * per_sm ? tiles : sms * per_sm;
   conv3x3_umma_kernel<KC, COUT, SRC, FMT, SPLIT, BG><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(

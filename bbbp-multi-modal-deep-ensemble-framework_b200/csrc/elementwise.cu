@@ -404,53 +404,74 @@ __global__ void __launch_bounds__(128) unpack_zscore_kernel(const uint8_t* __res
   for (int i = lane; i < n_bits; i += 32) out[(size_t)row * ld_out + i] = ((pr[i >> 3] >> (i & 7)) & 1) ? v1 : v0;
 }
 
-// Contiguous output (ld_out == n_bits, 16-byte aligned base): a block owns 32 consecutive rows, whose 32 * n_bits floats
+// Contiguous output (ld_out == n_bits, 16-byte aligned base): a block owns 128 consecutive rows, whose 128 * n_bits floats
 // start on a 16-byte boundary whatever n_bits is, and writes them as 128-bit stores (the warp-per-row kernel above writes
-// rows of 167 floats with scalar stores: 0.27 of the HBM roofline).  Same float64 statistics, same two values per row.
-constexpr int UZ_ROWS = 32;
+// rows of 167 floats with scalar stores: 0.27 of the HBM roofline).  The packed rows are staged in shared memory with one
+// coalesced pass, the statistics take one thread per row (same float64 formula, same two values per row), and the store
+// loop carries its (row, bit) position incrementally: no division, two shared-memory bytes and one 128-bit store per four
+// outputs.
+constexpr int UZ_ROWS = 128;
 __global__ void __launch_bounds__(256) unpack_zscore_vec_kernel(const uint8_t* __restrict__ packed, int bytes_per_row,
                                                                 float* __restrict__ out, int rows, int n_bits) {
-  extern __shared__ uint8_t sm_bits[];                 // UZ_ROWS rows of packed bytes
+  extern __shared__ __align__(16) uint8_t sm_bits[];   // UZ_ROWS rows of packed bytes (+ 4 bytes of slack for the 2-byte reads)
   __shared__ float2 sval[UZ_ROWS];
-  const int row0 = blockIdx.x * UZ_ROWS, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row0 = blockIdx.x * UZ_ROWS;
   const int nrows = min(UZ_ROWS, rows - row0);
-  for (int r = warp; r < nrows; r += 8) {              // a warp computes the statistics of rows warp, warp + 8, ...
-    const uint8_t* pr = packed + (size_t)(row0 + r) * bytes_per_row;
+  const int nbytes = nrows * bytes_per_row;
+  const uint8_t* src = packed + (size_t)row0 * bytes_per_row;
+  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    for (int i = threadIdx.x; i < nbytes / 4; i += 256) reinterpret_cast<uint32_t*>(sm_bits)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    for (int i = (nbytes / 4) * 4 + threadIdx.x; i < nbytes; i += 256) sm_bits[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += 256) sm_bits[i] = src[i];
+  }
+  if (threadIdx.x < 4) sm_bits[nbytes + threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x < nrows) {
+    const uint8_t* pr = sm_bits + threadIdx.x * bytes_per_row;
     int pop = 0;
-    for (int b = lane; b < bytes_per_row; b += 32) {
+    for (int b = 0; b < bytes_per_row; ++b) {
       uint32_t byte = pr[b];
-      sm_bits[r * bytes_per_row + b] = (uint8_t)byte;
       const int valid = n_bits - b * 8;
       if (valid < 8) byte &= (1u << (valid > 0 ? valid : 0)) - 1u;
       pop += __popc(byte);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pop += __shfl_xor_sync(0xffffffffu, pop, o);
-    if (lane == 0) {
-      const double mean = (double)pop / n_bits;
-      const double var = ((double)pop * (1.0 - mean) * (1.0 - mean) + (double)(n_bits - pop) * mean * mean) / n_bits;
-      double sd = sqrt(var);
-      if (sd == 0.0) sd = 1.0;
-      sval[r] = make_float2((float)((0.0 - mean) / sd), (float)((1.0 - mean) / sd));
-    }
+    const double mean = (double)pop / n_bits;
+    const double var = ((double)pop * (1.0 - mean) * (1.0 - mean) + (double)(n_bits - pop) * mean * mean) / n_bits;
+    double sd = sqrt(var);
+    if (sd == 0.0) sd = 1.0;
+    sval[threadIdx.x] = make_float2((float)((0.0 - mean) / sd), (float)((1.0 - mean) / sd));
   }
   __syncthreads();
   const int total = nrows * n_bits, total4 = total / 4;                   // total % 4 != 0 only for the last, ragged block
   float* obase = out + (size_t)row0 * n_bits;
+  // element 4 * g = (row r, bit i); a step of 256 threads advances it by 1 024 elements = (dr rows, di bits)
+  const int dr = 1024 / n_bits, di = 1024 - dr * n_bits;
+  int r = (4 * (int)threadIdx.x) / n_bits, i = 4 * (int)threadIdx.x - r * n_bits;
   for (int g = threadIdx.x; g < total4; g += 256) {
-    int r = (4 * g) / n_bits, i = 4 * g - r * n_bits;                     // one division per 128-bit store
     float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    if (i + 4 <= n_bits) {                                               // the four outputs belong to one row
+      const uint8_t* pb = sm_bits + r * bytes_per_row + (i >> 3);
+      const uint32_t bits = (((uint32_t)pb[0] | ((uint32_t)pb[1] << 8)) >> (i & 7));
       const float2 two = sval[r];
-      v[k] = ((sm_bits[r * bytes_per_row + (i >> 3)] >> (i & 7)) & 1) ? two.y : two.x;
-      if (++i == n_bits) i = 0, ++r;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ((bits >> k) & 1u) ? two.y : two.x;
+    } else {
+      int rr = r, ii = i;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 two = sval[rr];
+        v[k] = ((sm_bits[rr * bytes_per_row + (ii >> 3)] >> (ii & 7)) & 1) ? two.y : two.x;
+        if (++ii == n_bits) ii = 0, ++rr;
+      }
     }
     reinterpret_cast<float4*>(obase)[g] = make_float4(v[0], v[1], v[2], v[3]);
+    i += di, r += dr;
+    if (i >= n_bits) i -= n_bits, ++r;
   }
   for (int e = total4 * 4 + threadIdx.x; e < total; e += 256) {
-    const int r = e / n_bits, i = e - r * n_bits;
-    obase[e] = ((sm_bits[r * bytes_per_row + (i >> 3)] >> (i & 7)) & 1) ? sval[r].y : sval[r].x;
+    const int rr = e / n_bits, ii = e - rr * n_bits;
+    obase[e] = ((sm_bits[rr * bytes_per_row + (ii >> 3)] >> (ii & 7)) & 1) ? sval[rr].y : sval[rr].x;
   }
 }
 
@@ -772,9 +793,9 @@ extern "C" int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, 
   BBBP_CHECK_ARG(packed && out && rows >= 0 && n_bits > 0 && bytes_per_row * 8 >= n_bits && ld_out >= n_bits,
                  "unpack_zscore: bad argument");
   if (rows == 0) return BBBP_OK;
-  if (ld_out == n_bits && ((uintptr_t)out & 15) == 0 && bytes_per_row <= 1024)
-    unpack_zscore_vec_kernel<<<ceil_div(rows, UZ_ROWS), 256, UZ_ROWS * bytes_per_row, as_stream(stream)>>>(packed, bytes_per_row, out,
-                                                                                                           rows, n_bits);
+  if (ld_out == n_bits && ((uintptr_t)out & 15) == 0 && bytes_per_row <= 256)
+    unpack_zscore_vec_kernel<<<ceil_div(rows, UZ_ROWS), 256, UZ_ROWS * bytes_per_row + 4, as_stream(stream)>>>(packed, bytes_per_row,
+                                                                                                               out, rows, n_bits);
   else
     unpack_zscore_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(packed, bytes_per_row, out, ld_out, rows, n_bits);
   return launch_status("unpack_zscore");

@@ -422,7 +422,8 @@ def test_adamw_state_interchanges_with_torch_adamw(cuda_device):
 
 
 # ---- packed input contracts (bit-exact) ----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,n_bits", [(1, 167), (64, 167), (33, 2048), (5, 8), (3, 13)])
+@pytest.mark.parametrize("rows,n_bits", [(1, 167), (64, 167), (33, 2048), (5, 8), (3, 13), (301, 167), (1000, 167), (129, 3), (260, 1),
+                                         (257, 2048), (131, 1031)])
 def test_unpack_zscore_bit_exact(ops, rows, n_bits):
     from oracle import preprocess
     rng = np.random.default_rng(n_bits + rows)
