@@ -17,11 +17,12 @@ from .data_parallel import FlatGradients  # noqa: F401
 from .ensemble import OutOfFoldScores, stack_columns  # noqa: F401
 from .screening import (  # noqa: F401
     SparseDepictions, average_gradients, gather_scores, pack_fingerprint_bits, partition_batches, screen, screen_library)
+from .c_host import CHostForward  # noqa: F401
 from .preprocess import pca_transform, standardize_chunks, unpack_zscore, u8_image_zscore  # noqa: F401
 
 __all__ = [
     "MixedInputModel", "MixedInputModelBig", "MixedInputModelNoFusion", "MixedInputModelMLP", "MixedInputModelMLPMore",
     "MixedInputModelMLPRdkit", "MultiHeadAttentionFusion", "AttentionFusion", "MultiModalAttentionFusion", "MSELoss",
     "BCEWithLogitsLoss", "AdamW", "build", "VARIANTS", "ops", "partition_batches", "gather_scores", "screen",
-    "average_gradients", "FlatGradients", "DeviceBatchFeeder", "GraphedTrainStep", "OutOfFoldScores", "stack_columns", "screen_library", "pack_fingerprint_bits", "SparseDepictions", "pca_transform", "standardize_chunks", "unpack_zscore", "u8_image_zscore",
+    "average_gradients", "FlatGradients", "DeviceBatchFeeder", "GraphedTrainStep", "OutOfFoldScores", "stack_columns", "screen_library", "pack_fingerprint_bits", "SparseDepictions", "pca_transform", "standardize_chunks", "unpack_zscore", "u8_image_zscore", "CHostForward",
 ]

@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(PKG_DIR, "..", "include", "bbbp_b200.h")
 
 _SCALARS = {
     "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t, "uint64_t": ctypes.c_uint64,
-    "int64_t": ctypes.c_int64, "long": ctypes.c_longlong, "int32_t": ctypes.c_int32, "bbbp_stream_t": ctypes.c_void_p,
+    "int64_t": ctypes.c_int64, "long": ctypes.c_longlong, "int32_t": ctypes.c_int32, "bbbp_stream_t": ctypes.c_void_p, "bbbp_comm_t": ctypes.c_void_p,
 }
 _PROTO = re.compile(r"\n((?:int|size_t|uint64_t|const char\s*\*)\s*)(bbbp_\w+)\s*\(([^;]*?)\)\s*;", re.S)
 

@@ -41,7 +41,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libbbbp_b200.so")
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *sources()]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *sources(), "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

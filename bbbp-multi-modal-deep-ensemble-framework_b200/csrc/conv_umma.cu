@@ -92,7 +92,8 @@ struct Cfg {
   static constexpr int NISSUE = PACK4 ? 6 : KC == 1 ? 4 * NMMA : 24 * (KC / 2);
   static constexpr int W8_BYTES = 2 * 5 * 2 * COUT * 16;                  // conv1 weight image for the NHWC8 source
   static constexpr int W_BYTES = PACK4 ? 3 * 2 * (2 * COUT) * 16 : KC == 1 ? W8_BYTES : 9 * KC * COUT * 16;
-  static constexpr int W_OFFSET = PACK4 ? W8_BYTES : 0;                   // the prepared blob holds both conv1 images
+  // the prepared blob of the first layer: NHWC8 image | PACK4 hi | PACK4 lo | PACK4 with the channel sums in the spare channel
+  static constexpr int W_OFFSET = PACK4 ? (BG == 2 ? W8_BYTES + 2 * (3 * 2 * (2 * COUT) * 16) : W8_BYTES) : 0;
   static constexpr int ACC_COLS = 4 * COUT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -107,7 +108,8 @@ struct Cfg {
   // is the largest remaining term of the strict mode's error budget (tests/precision_study.py: 6e-4 of 8e-4)
   static constexpr int W_PARTS = (SPLIT == 2 && PACK4 && !BG) ? 2 : 1;
   // BG: the current and the next tile's per-image table rows (T and bg_out), double-buffered
-  static constexpr int TAB_FLOATS = 2 * COUT, TAB_BYTES = BG ? 2 * TAB_FLOATS * 4 : 0;
+  // (BG == 2: + the image's (mean, 1/std) pair, the epilogue's scale, in a 16-byte slot of its own)
+  static constexpr int TAB_FLOATS = 2 * COUT, TAB_SLOT = TAB_FLOATS + (BG == 2 ? 4 : 0), TAB_BYTES = BG ? 2 * TAB_SLOT * 4 : 0;
   static constexpr int SMEM_BYTES = 1024 + OUT_BUFS * OUT_BYTES + STAGES * STAGE_BYTES + W_PARTS * W_BYTES + COUT * 4 + BAR_BYTES + TAB_BYTES;
 };
 
@@ -230,6 +232,15 @@ __device__ unsigned long long* g_conv_probe = nullptr;
 // letting cp.async zero-fill them.  bg_tab[image] = {T[COUT], bg_out[COUT]} (bbbp_bg_layer); after ReLU + pooling the
 // epilogue subtracts bg_out before rounding.  bg_in: first layer float[image][4]; later layers the NEGATED background of the
 // input in the operand format, [image][8 * KC].
+//
+// BG = 2, raw uint8 depictions only: the EXACT-INTEGER form of the same idea, one pass.  With x = scale*u + shift (scale =
+// rstd/255, shift = -mean*rstd) and r[c] the background's raw byte per channel, the producers stage d = u - r[c]: an integer
+// of magnitude <= 255, exact in fp16, 0 on the canvas -- there is no activation rounding at all, so no (hi, lo) pair is needed.
+// x = scale*d + bg[c] with bg[c] = scale*r[c] + shift, hence  conv(x) = scale * conv(d) + (T - bias)  and the epilogue forms
+// relu(scale * max(acc) + T) - bg_out (scale > 0 commutes with the max).  The zero padding of x is d_pad = 255*mean - r[c]:
+// its integer part floor(255*mean) - r[c] goes into the channel, the fraction in [0, 1) into the SPARE fourth channel of the
+// pixel, whose weights are the filter's sum over its input channels (the third PACK4 weight image) -- the fraction is the same
+// for all three channels.  bg_in[image][3] carries r as packed bytes (bbbp_image_background).
 template <int KC, int COUT, int SRC, int FMT, int SPLIT, int BG>
 __global__ void __launch_bounds__(Cfg<KC, COUT, SRC, FMT, SPLIT, BG>::THREADS, Cfg<KC, COUT, SRC, FMT, SPLIT, BG>::MIN_CTAS)
 conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ src_lo_any, const float2* __restrict__ stats,
@@ -238,6 +249,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
                     const float* __restrict__ bg_tab) {
   using C = Cfg<KC, COUT, SRC, FMT, SPLIT, BG>;
   static_assert(SRC == SRC_NHWC_BF16 || KC == 1, "planar sources feed the 3-channel first layer only");
+  static_assert(BG != 2 || (SRC == SRC_CHW_U8 && SPLIT == 1), "the exact-integer form reads raw uint8 depictions in one pass");
     constexpr int THREADS = C::THREADS, EPI_THREADS = C::EPI_THREADS, PROD_WARP0 = C::PROD_WARP0, MMA_WARP = C::MMA_WARP;
   constexpr int PROD_THREADS = C::PROD_THREADS, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -399,15 +411,27 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       };
       auto store_tile = [&](int i, const Vec (&v)[TPT][CH], uint32_t okmask) {
         float scale = 1.0f, shift = 0.0f;   // (u/255 - mean) * rstd == u * scale + shift
+        [[maybe_unused]] float pad_frac = 0.0f;   // BG == 2: fraction of the padding value 255 * mean (spare channel)
+        [[maybe_unused]] float bgc[CH] = {0.0f, 0.0f, 0.0f};   // BG: this image's background value per channel
+        if constexpr (BG == 2) {
+          // exact integers: in the image u - r[c], outside floor(255 * mean) - r[c] (+ the fraction in the spare channel)
+          const int n = fd_img.div(blockIdx.x + i * gridDim.x);
+          const float m255 = 255.0f * __ldg(stats + n).x;
+          shift = floorf(m255);
+          pad_frac = m255 - shift;
+          const uint32_t r = __float_as_uint(__ldg(static_cast<const float*>(bg_in) + 4 * (size_t)n + 3));
+#pragma unroll
+          for (int c = 0; c < CH; ++c) bgc[c] = (float)((r >> (8 * c)) & 255u);
+        } else {
         if constexpr (SRC == SRC_CHW_U8) {
           const float2 st = __ldg(stats + fd_img.div(blockIdx.x + i * gridDim.x));
           scale = st.y * (1.0f / 255.0f), shift = -st.x * st.y;
         }
-        [[maybe_unused]] float bgc[CH] = {0.0f, 0.0f, 0.0f};   // BG: this image's background value per channel
         if constexpr (BG) {
           const float* bp = static_cast<const float*>(bg_in) + 4 * (size_t)fd_img.div(blockIdx.x + i * gridDim.x);
 #pragma unroll
           for (int c = 0; c < CH; ++c) bgc[c] = __ldg(bp + c);
+        }
         }
         // one ring slot per tile; part 1 (the lo halves x - rn16(x) of the same pixels) follows part 0 inside the slot
         const int s = i % STAGES;
@@ -432,8 +456,10 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
                 }
               } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)   // zero padding applies to the NORMALISED image
-                  px[e][c] = (ok ? fmaf((float)((v[k][c] >> (8 * e)) & 255u), scale, shift) : 0.0f) - bgc[c];
+                for (int e = 0; e < 4; ++e) {   // zero padding applies to the NORMALISED image
+                  if constexpr (BG == 2) px[e][c] = (ok ? (float)((v[k][c] >> (8 * e)) & 255u) : shift) - bgc[c];
+                  else px[e][c] = (ok ? fmaf((float)((v[k][c] >> (8 * e)) & 255u), scale, shift) : 0.0f) - bgc[c];
+                }
               }
             }
 #pragma unroll
@@ -442,7 +468,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
               if (X >= 0 && X < HALO_W) {
                 uint2 pix;
                 if (part == 0) {
-                  pix = make_uint2(pack16<FMT>(px[e][0], px[e][1]), pack16<FMT>(px[e][2], 0.0f));
+                  pix = make_uint2(pack16<FMT>(px[e][0], px[e][1]), pack16<FMT>(px[e][2], (BG == 2 && !ok) ? pad_frac : 0.0f));
                 } else {
                   pix = make_uint2(pack16<FMT>(px[e][0] - round16<FMT>(px[e][0]), px[e][1] - round16<FMT>(px[e][1])),
                                    pack16<FMT>(px[e][2] - round16<FMT>(px[e][2]), 0.0f));
@@ -580,13 +606,17 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
         const int e = threadIdx.x;
         if (it < my_tiles && e < C::TAB_FLOATS / 4) {
           const int n = fd_img.div(blockIdx.x + it * gridDim.x);
-          cp_async_16(smem_u32(sTab + (it & 1) * C::TAB_FLOATS + 4 * e), bg_tab + (size_t)n * C::TAB_FLOATS + 4 * e, 16u);
+          cp_async_16(smem_u32(sTab + (it & 1) * C::TAB_SLOT + 4 * e), bg_tab + (size_t)n * C::TAB_FLOATS + 4 * e, 16u);
+        }
+        if constexpr (BG == 2) {
+          if (it < my_tiles && e == C::TAB_FLOATS / 4)      // the image's (mean, 1/std)
+            cp_async_8(smem_u32(sTab + (it & 1) * C::TAB_SLOT + C::TAB_FLOATS), stats + fd_img.div(blockIdx.x + it * gridDim.x));
         }
         cp_async_commit();
       }
     };
     if constexpr (BG) {
-      static_assert(C::TAB_FLOATS / 4 <= EPI_THREADS, "one 16-byte copy per epilogue thread");
+      static_assert(C::TAB_FLOATS / 4 < EPI_THREADS, "one 16-byte copy per epilogue thread");
       fetch_tab(0);
       cp_async_wait<0>();
     }
@@ -603,7 +633,9 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * C::ACC_COLS + half * CH;
       uint8_t* orow = otile + m * C::OUT_ROW_B;
       [[maybe_unused]] uint8_t* orow_lo = sOut + (2 + b) * C::OUT_BYTES + m * C::OUT_ROW_B;
-      [[maybe_unused]] const uint32_t tb_s = BG ? smem_u32(sTab + b * C::TAB_FLOATS + half * CH) : 0u;   // this tile's {T, bg_out}
+      [[maybe_unused]] const uint32_t tb_s = BG ? smem_u32(sTab + b * C::TAB_SLOT + half * CH) : 0u;   // this tile's {T, bg_out}
+      [[maybe_unused]] float acc_scale = 1.0f;   // BG == 2: rstd / 255, formed exactly as bbbp_image_background forms it
+      if constexpr (BG == 2) acc_scale = ld_shared_f32(smem_u32(sTab + b * C::TAB_SLOT + C::TAB_FLOATS + 1)) * (1.0f / 255.0f);
       // CS channels per step (CS/8 output chunks): 4*CS live accumulator registers.  The first layer uses 8 so that its
       // variants fit the register cap of two CTAs per SM with eight producer warps; conv2 (no cap) uses 16.
       constexpr int CS = COUT >= 64 ? 16 : (C::PACK4 ? BBBP_CONV1_CS : 8);
@@ -631,9 +663,11 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
             const float e[4] = {t.x, t.y, t.z, t.w}, o[4] = {bo.x, bo.y, bo.z, bo.w};
             float v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              v[k] = fmaxf(fmaxf(fmaxf(__uint_as_float(r0[j + k]), __uint_as_float(r1[j + k])),
-                                 fmaxf(__uint_as_float(r2[j + k]), __uint_as_float(r3[j + k]))) + e[k], 0.0f) - o[k];
+            for (int k = 0; k < 4; ++k) {
+              const float mx = fmaxf(fmaxf(__uint_as_float(r0[j + k]), __uint_as_float(r1[j + k])),
+                                     fmaxf(__uint_as_float(r2[j + k]), __uint_as_float(r3[j + k])));
+              v[k] = fmaxf(BG == 2 ? fmaf(mx, acc_scale, e[k]) : mx + e[k], 0.0f) - o[k];
+            }
             packed[j / 2] = pack16<FMT>(v[0], v[1]);
             packed[j / 2 + 1] = pack16<FMT>(v[2], v[3]);
           } else {
@@ -714,15 +748,18 @@ __global__ void prep_weights_c8_kernel(const float* __restrict__ w, uint16_t* __
 }
 // PACK4 image (planar sources): wp[kh][chunk][n2][8], n2 = dx*Cout + n.  K index k = chunk*8 + e = j*4 + c addresses pixel
 // X + j of the halo row (X = 2*pw) and channel c; member dx uses tap kw = j - dx: zero where that is not in 0..2 or c >= Cin
-// lo != 0: the low part rn(w - rn(w)) of the same image (strict mode)
+// lo == 1: the low part rn(w - rn(w)) of the same image (strict mode, pair design); lo == 2: the image with the filter's sum
+// over its input channels in the spare fourth channel (exact-integer uint8 form, BG == 2)
 __global__ void prep_weights_pack4_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Cin, int Cout, int fmt,
                                           int lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * 2 * (2 * Cout) * 8) return;
   const int e = i % 8, n2 = (i / 8) % (2 * Cout), chunk = (i / (16 * Cout)) % 2, kh = i / (32 * Cout);
   const int k = chunk * 8 + e, j = k / 4, c = k % 4, dx = n2 / Cout, n = n2 % Cout, kw = j - dx;
-  const float v = (kw >= 0 && kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f;
-  wp[i] = cvt16_rt(lo ? v - round16_rt(v, fmt) : v, fmt);
+  float v = (kw >= 0 && kw < 3 && c < Cin) ? w[((size_t)n * Cin + c) * 9 + kh * 3 + kw] : 0.0f;
+  if (lo == 2 && kw >= 0 && kw < 3 && c == Cin)     // spare channel: the tap summed over the input channels (BG == 2)
+    for (int ci = 0; ci < Cin; ++ci) v += w[((size_t)n * Cin + ci) * 9 + kh * 3 + kw];
+  wp[i] = cvt16_rt(lo == 1 ? v - round16_rt(v, fmt) : v, fmt);
 }
 // fp32 NCHW image (C <= 8 planes) -> bf16 NHWC with 8 channels per pixel (zero padded): one 16-byte store per pixel
 __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ img, uint4* __restrict__ out,
@@ -838,7 +875,18 @@ __global__ void __launch_bounds__(128) image_background_kernel(const void* __res
     for (int k = 1; k < 8; ++k) kv = best == k ? key[k][c] : kv;
     bg[4 * (size_t)n + c] = is_u8 ? fmaf((float)kv, scale, shift) : __uint_as_float(kv);
   }
-  bg[4 * (size_t)n + 3] = 0.0f;
+  // column 3: the raw background bytes r | g << 8 | b << 16 of a uint8 image (read by the exact-integer first layer only)
+  uint32_t raw = 0;
+  if (is_u8) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t kv = key[0][c];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) kv = best == k ? key[k][c] : kv;
+      raw |= kv << (8 * c);
+    }
+  }
+  bg[4 * (size_t)n + 3] = __uint_as_float(raw);
 }
 
 // One "layer" of the background chain:  T[n][co] = bias[co] + sum_ci wsum[co][ci] * in[n][ci]  (wsum = the layer's weights
@@ -965,7 +1013,7 @@ int dispatch(int fmt, int split, const void* x, const void* x_lo, const float* s
 using namespace bbbp;
 
 extern "C" size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout) {
-  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)2 * 3 * 2 * (2 * Cout) * 16;   // NHWC8 image | PACK4 hi | PACK4 lo
+  if (Cin <= 8) return (size_t)2 * 5 * 2 * Cout * 16 + (size_t)3 * 3 * 2 * (2 * Cout) * 16;   // NHWC8 | PACK4 hi | PACK4 lo | PACK4 + channel sums
   return (size_t)9 * (Cin / 8) * Cout * 16;
 }
 
@@ -981,7 +1029,8 @@ extern "C" int bbbp_conv3x3_prepare16(int fmt, const float* w, void* wprep, int 
     conv::prep_weights_c8_kernel<<<ceil_div(n8, 256), 256, 0, as_stream(stream)>>>(w, wp, Cin, Cout, fmt);
     conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(w, wp + n8, Cin, Cout, fmt, 0);
     conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(w, wp + n8 + n4, Cin, Cout, fmt, 1);
-    note_launches(2);
+    conv::prep_weights_pack4_kernel<<<ceil_div(n4, 256), 256, 0, as_stream(stream)>>>(w, wp + n8 + 2 * n4, Cin, Cout, fmt, 2);
+    note_launches(3);
   } else
     conv::prep_weights_kc_kernel<<<ceil_div(total / 9, 256), 256, 0, as_stream(stream)>>>(w, wp, Cin, Cout, fmt);
   return launch_status("conv3x3_prepare");
@@ -1115,7 +1164,8 @@ extern "C" int bbbp_conv1_from_image_bg16(int fmt, int split, const void* img_ch
   if (img_is_u8) {
     if (split == 2)
       return conv::launch<1, 32, conv::SRC_CHW_U8, BBBP_FMT_F16, 2, 1>(img_chw, nullptr, stats, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
-    return conv::launch<1, 32, conv::SRC_CHW_U8, BBBP_FMT_F16, 1, 1>(img_chw, nullptr, stats, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
+    // one pass on exact integers (BG = 2): u - background byte is exact in fp16, so raw depictions need no (hi, lo) pair
+    return conv::launch<1, 32, conv::SRC_CHW_U8, BBBP_FMT_F16, 1, 2>(img_chw, nullptr, stats, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);
   }
   if (split == 2)
     return conv::launch<1, 32, conv::SRC_CHW_F32, BBBP_FMT_F16, 2, 1>(img_chw, nullptr, nullptr, wprep, nullptr, y_nhwc, nullptr, N, H, W, s, bg);

@@ -154,6 +154,14 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_8(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t smem_src) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_src));
+  return v;
+}
 __device__ __forceinline__ void st_shared_16(uint32_t smem_dst, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

@@ -399,6 +399,7 @@ class TransformerCnnModel(_KernelModule):
     # input staged as a (hi, lo) pair (two passes); the environment switches exist for the measurements in DESIGN.md
     strict_background = os.environ.get("BBBP_STRICT_BACKGROUND", "1") != "0"
     strict_conv1_split = os.environ.get("BBBP_STRICT_CONV1_SPLIT", "1") != "0"
+    strict_u8_exact = os.environ.get("BBBP_STRICT_U8_EXACT", "1") != "0"
     tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
     im2col_chunk = 256      # images per pass of the im2col route (bounds the im2col buffer: 4.7 MB per image at 64 -> 128)
 
@@ -468,7 +469,10 @@ class TransformerCnnModel(_KernelModule):
                 tab1, neg2 = ops.bg_layer(ws1, conv1.bias, bg1, fmt=fmt, want_neg16=True)      # {T1, bg2}, -bg2 as fp16
                 tab2, _ = ops.bg_layer(ws2, conv2.bias, tab1[:, 1], fmt=-1)                     # {T2, bg3}
                 fc_add = ops.bg_layer(wsf, None, tab2[:, 1], table=False)                       # what bg3 contributes to the fc
-                y1 = ops.conv1_from_image_bg(part, w1, stats, bg1, tab1, fmt=fmt, split=self.strict_conv1_split)
+                # raw uint8 depictions: u - background byte is an exact fp16 integer, so ONE pass has no activation rounding
+                # at all (conv_umma.cu, BG = 2); standardised fp32 planes need the (hi, lo) pair
+                exact = self.strict_u8_exact and part.dtype == torch.uint8
+                y1 = ops.conv1_from_image_bg(part, w1, stats, bg1, tab1, fmt=fmt, split=self.strict_conv1_split and not exact)
                 y2 = ops.conv3x3_relu_pool_bg(y1, w2, neg2, tab2, 64, fmt=fmt)
                 o, _ = ops.gemm_bf16(y2.view(y2.shape[0], 65536), 65536, wfc, fc.out_features, bias=fc.bias, act="relu",
                                      split_k=ops.fixed_split_k_strict(65536), fmt=fmt, pre_add=fc_add)

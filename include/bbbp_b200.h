@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BBBP_ABI_VERSION 3
+#define BBBP_ABI_VERSION 4
 
 enum { BBBP_OK = 0, BBBP_EINVAL = -1, BBBP_ECUDA = -2, BBBP_EWORKSPACE = -3, BBBP_EUNSUPPORTED = -4 };
 
@@ -36,7 +36,10 @@ enum { BBBP_ACT_NONE = 0, BBBP_ACT_RELU = 1, BBBP_ACT_TANH = 2 };
 /* arithmetic mode of the fused forward */
 enum {
   BBBP_PREC_FP32 = 0, /* CUDA-core fp32 FMA everywhere (validation mode, 1e-4 class parity)       */
-  BBBP_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 TMEM accumulation, fp32 statistics (default)  */
+  BBBP_PREC_BF16 = 1, /* tcgen05 bf16 operands, fp32 TMEM accumulation, fp32 statistics (fastest)  */
+  BBBP_PREC_F16 = 2,  /* tcgen05 fp16 operands, one pass (11-bit operand mantissa = a TF32 operand)   */
+  BBBP_PREC_STRICT = 3 /* tcgen05 fp16 operands, background-referenced image branch, split small GEMMs:
+                          |d logBB| <= 1e-3 vs the fp32 reference at trained output scale          */
 };
 
 /* 16-bit operand format of the tensor-core entry points (the *16 functions; the *_bf16 names are the fmt = BF16 forms) */
@@ -196,8 +199,9 @@ int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int 
  * canvas: rounding them to fp16 costs nothing there) and its epilogue adds back, in fp32 and from the fp32 weights, what the
  * constant part contributes:  conv(x)[p] = conv(x - bg)[p] + T[image][cout],  T = bias + sum over all taps of w . bg  (the
  * zero padding of x is staged as -bg, so this holds at the image border too).
- *   bbbp_image_background   bg[n][0..2] = background value of image n per channel (majority of 8 probe pixels), bg[n][3] = 0;
- *                           uint8 input: normalised with stats exactly as the first layer's producers do
+ *   bbbp_image_background   bg[n][0..2] = background value of image n per channel (majority of 8 probe pixels); uint8 input:
+ *                           normalised with stats exactly as the first layer's producers do, and bg[n][3] carries the raw
+ *                           background bytes r | g << 8 | b << 16 as a bit pattern (fp32 input: 0)
  *   bbbp_fc_weight_channel_sums  out[o][c] = sum_j w[o][c*HW + j]: a Linear over a flattened (C, HW) activation, or (HW = 9)
  *                           a 3x3 convolution, applied to a per-channel constant
  *   bbbp_bg_layer           one step of the background chain: out0[n][co] = bias[co] + sum_ci wsum[co][ci] * in[n][ci]
@@ -207,6 +211,9 @@ int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int 
  *   bbbp_conv1_from_image_bg16 / bbbp_conv3x3_relu_pool_bg16: the layers.  tab[n] = {T[Cout], bg_out[Cout]} (out0 / out1 of
  *                           bbbp_bg_layer written with pitch 2*Cout); bg_in = bbbp_image_background's table; neg_bg_in = the
  *                           previous layer's neg16.  split = 2: the first layer's producers stage x - bg as a (hi, lo) pair.
+ *                           split = 1 on a uint8 image is the EXACT-INTEGER form: the producers stage u - background byte
+ *                           (an integer, exact in fp16; the padding's fraction rides in the pixel's spare channel) and the
+ *                           epilogue scales the accumulator by rstd / 255 -- one pass, no activation rounding at all.
  *                           Output: ONE fp16 NHWC tensor holding maxpool(relu(conv(x))) - bg_out.  Built for fp16. */
 int bbbp_image_background(const void* img_chw, int img_is_u8, const float* stats, float* bg, int N, int H, int W,
                           bbbp_stream_t stream);
@@ -436,6 +443,58 @@ int bbbp_unpack_zscore_f32(const uint8_t* packed, int bytes_per_row, float* out,
                            bbbp_stream_t stream);
 /* uint8 depictions (rows x n values) -> x/255 -> per-molecule z-score, fp32 */
 int bbbp_u8_zscore_f32(const uint8_t* img, float* out, int rows, int n, bbbp_stream_t stream);
+
+/* ---- whole-model inference (bbbp_fwd / bbbp_workspace_bytes) ------------------------------------------
+ * MixedInputModel.forward of Models/multi_input_data_regression_opt_transformer_cnn_20250113.py:109-119 in eval mode as
+ * ONE call for a host written in C / C++ / anything with an FFI: the same kernel sequence bbbp_b200.model runs from Python
+ * (bit-identical scores), orchestrated by the library.  Nothing is allocated: the caller passes
+ *   params    HOST array of bbbp_model_param_count() DEVICE pointers, fp32, in the order of the reference's
+ *             model.state_dict() (bbbp_model_param_name(i) is the key, bbbp_model_param_numel(i) the element count;
+ *             fc.2.num_batches_tracked is listed but never read and may be NULL),
+ *   prepared  bbbp_model_prepared_bytes() bytes, filled by bbbp_model_prepare() from the parameters (16-bit copies, the conv
+ *             kernels' shared-memory weight images, the (H,W,C) re-laid Linear(65536,128) weight, stacked fusion heads,
+ *             tap / position sums for the strict mode); call it again whenever a parameter changes,
+ *   workspace bbbp_workspace_bytes() bytes of scratch (activations; contents undefined between calls),
+ * all 256-byte aligned.  A call scores desc->groups independent reference batches of desc->seq molecules each (attention
+ * runs ACROSS the molecules of a batch) and writes out[groups*seq] fp32.  Everything is enqueued on `stream`
+ * (graph-capturable: no synchronisation, no allocation, no host reads of device memory).
+ * Built: variant BBBP_MODEL_TCNN_20250113, precisions BF16 / F16 / STRICT; fingerprint sizes whose encoder has one head
+ * (F <= 192, e.g. MACCS-167; any seq) or heads of dimension 8 / 16 (e.g. Morgan-2048: 256 x 8).  The fp32 validation mode
+ * and training stay behind the per-kernel entry points above (orchestrated by bbbp_b200.autograd). */
+enum { BBBP_MODEL_TCNN_20250113 = 0 };
+typedef struct bbbp_model_desc {
+  int abi_version;      /* BBBP_ABI_VERSION the caller was compiled against */
+  int variant;          /* BBBP_MODEL_TCNN_20250113 */
+  int fingerprint_size; /* F (constructor argument fingerprint_size, 20250113.py:69) */
+  int precision;        /* BBBP_PREC_BF16 | BBBP_PREC_F16 | BBBP_PREC_STRICT */
+  int groups;           /* reference batches per call */
+  int seq;              /* molecules per reference batch (the reference's batch_size) */
+  int image_is_u8;      /* 0: fp32 standardised (B, 3*128*128) CHW rows (contract P2); 1: raw uint8 CHW depictions */
+} bbbp_model_desc;
+int bbbp_model_param_count(const bbbp_model_desc* desc);
+const char* bbbp_model_param_name(const bbbp_model_desc* desc, int index);
+size_t bbbp_model_param_numel(const bbbp_model_desc* desc, int index);
+size_t bbbp_model_prepared_bytes(const bbbp_model_desc* desc);
+int bbbp_model_prepare(const bbbp_model_desc* desc, const void* const* params, void* prepared, size_t prepared_bytes,
+                       bbbp_stream_t stream);
+size_t bbbp_workspace_bytes(const bbbp_model_desc* desc);
+int bbbp_fwd(const bbbp_model_desc* desc, const void* fingerprint, const void* image, const void* const* params,
+             const void* prepared, float* out, void* workspace, size_t workspace_bytes, bbbp_stream_t stream);
+
+/* ---- multi-GPU: the two exchanges of the path over NCCL ------------------------------------------
+ * comm is an ncclComm_t (one per process / GPU).  NCCL is resolved at first use with dlopen("libnccl.so.2") -- the copy
+ * already loaded in the process (e.g. torch's) when there is one -- so the library has no link-time dependency on it;
+ * BBBP_EUNSUPPORTED when it cannot be found.  id128 is a HOST buffer of 128 bytes (ncclUniqueId).
+ *   bbbp_comm_gather_scores      screening: every rank contributes count fp32 scores, all ranks receive
+ *                                recv[rank*count .. ) (ncclAllGather; the only collective of the screening path)
+ *   bbbp_comm_average_gradients  data-parallel training: the flat fp32 gradient buffer averaged in place over the ranks
+ *                                (ncclAllReduce, ncclAvg), 20250113.py:190-191 run as replicas */
+typedef void* bbbp_comm_t;
+int bbbp_comm_unique_id(void* id128);
+int bbbp_comm_init_rank(bbbp_comm_t* comm, int nranks, const void* id128, int rank);
+int bbbp_comm_destroy(bbbp_comm_t comm);
+int bbbp_comm_gather_scores(bbbp_comm_t comm, const float* send, float* recv, size_t count, bbbp_stream_t stream);
+int bbbp_comm_average_gradients(bbbp_comm_t comm, float* flat_grads, size_t count, bbbp_stream_t stream);
 
 #ifdef __cplusplus
 }

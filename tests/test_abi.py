@@ -18,7 +18,7 @@ def test_header_symbols_all_exported():
 
 
 def test_abi_version_and_no_torch_in_signatures():
-    assert bbbp_b200.ABI_VERSION == 3
+    assert bbbp_b200.ABI_VERSION == 4
     header = open(_lib.HEADER_PATH).read()
     code = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
     assert "torch" not in code.lower() and "Tensor" not in code and "at::" not in code
@@ -64,3 +64,40 @@ def test_cuda_sources_are_blackwell_native():
     assert "UTMALDG" in sass      # TMA tensor loads
     assert "LDTM" in sass         # tcgen05.ld
     assert "HGMMA" not in sass
+
+
+def test_whole_model_entry_points_describe_the_reference_state_dict():
+    """bbbp_model_param_name / _numel enumerate MixedInputModel.state_dict() (20250113.py:69-107) key for key."""
+    import ctypes
+    from oracle import nets
+    from bbbp_b200 import c_host
+    for fp_dim in (167, 2048, 64):
+        ref = nets.build("tcnn", fp_dim, 128)
+        desc = c_host.make_desc(fp_dim, "strict")
+        names = c_host.param_names(desc)
+        state = ref.state_dict()
+        assert names == list(state.keys())
+        for i, n in enumerate(names):
+            assert _lib.lib.bbbp_model_param_numel(ctypes.byref(desc), i) == state[n].numel(), n
+        assert _lib.lib.bbbp_model_prepared_bytes(ctypes.byref(desc)) > 128 * 65536 * 2
+        desc = c_host.make_desc(fp_dim, "bf16", 4, 256)
+        assert _lib.lib.bbbp_workspace_bytes(ctypes.byref(desc)) > 1024 * (64 * 64 * 32 + 65536) * 2
+
+
+def test_whole_model_entry_points_reject_what_is_not_built():
+    import ctypes
+    from bbbp_b200 import c_host
+    lib = _lib.lib
+    desc = c_host.make_desc(167, "strict", 1, 32)
+    desc.precision = 0                                   # BBBP_PREC_FP32: validation mode, per-kernel entry points only
+    assert lib.bbbp_workspace_bytes(ctypes.byref(desc)) == 0 and "BF16, F16 and STRICT" in bbbp_b200.last_error()
+    desc = c_host.make_desc(167, "strict", 1, 32)
+    desc.abi_version = 1
+    assert lib.bbbp_model_param_count(ctypes.byref(desc)) == -1 and "abi_version" in bbbp_b200.last_error()
+    desc = c_host.make_desc(200, "bf16", 1, 32)          # 25 heads of dimension 8 are built ...
+    assert lib.bbbp_model_param_count(ctypes.byref(desc)) == 109
+    desc = c_host.make_desc(201, "bf16", 1, 32)          # ... 3 heads of dimension 67 are not
+    assert lib.bbbp_model_param_count(ctypes.byref(desc)) == -4
+    desc = c_host.make_desc(167, "bf16", 1, 32)
+    assert lib.bbbp_fwd(ctypes.byref(desc), None, None, None, None, None, None, 0, None) == -1
+    assert lib.bbbp_comm_gather_scores(None, None, None, 0, None) == -1

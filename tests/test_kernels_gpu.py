@@ -760,7 +760,10 @@ def test_conv_stack_background_referenced(ops, N, source, split):
     bg1 = ops.image_background(dev, stats)
     white = img[:, :, 64, 22]                                                     # inside the stroke-free band
     close(bg1[:, :3], white, atol=2e-6, what="background value")
-    assert float(bg1[:, 3].abs().max()) == 0.0
+    if source == "uint8":       # column 3: the raw background bytes r | g << 8 | b << 16 (read by the exact-integer first layer)
+        assert bool((bg1[:, 3].view(torch.int32) == 0x00FFFFFF).all())
+    else:
+        assert float(bg1[:, 3].abs().max()) == 0.0
     ws1, ws2 = ops.fc_weight_channel_sums(w1.cuda(), 3, 9), ops.fc_weight_channel_sums(w2.cuda(), 32, 9)
     close(ws1, w1.double().sum((2, 3)).float(), atol=1e-6, what="tap sums 1")
     close(ws2, w2.double().sum((2, 3)).float(), atol=1e-6, what="tap sums 2")
@@ -792,7 +795,9 @@ def test_conv_stack_background_referenced(ops, N, source, split):
     assert float((band1 - resid.half().float()).abs().max()) == 0.0, "the canvas carries only the rounding residue of bg2"
     band2 = y2[:, 8:24, 7:10, :].float()                # pooled pixels of layer 2 that see pure-canvas pixels of layer 1 only
     assert float(band2.abs().max()) <= 1e-3 * float(bg3.abs().max()), "canvas after the second layer"
-    if split:                                           # two passes over x - bg: fp32-class against the ONCE-ROUNDED weights
+    # two passes over x - bg, or ONE pass over the exact integers u - background byte of a raw uint8 depiction (BG = 2: the
+    # padding's fraction rides in the pixel's spare channel): fp32-class against the ONCE-ROUNDED weights
+    if split or source == "uint8":
         r1h = F.max_pool2d(F.relu(F.conv2d(img.double(), w1.half().double(), b1.double(), padding=1)), 2).float().permute(0, 2, 3, 1)
         y1f = (y1.float().cpu() + bg2.cpu()[:, None, None, :])
         # y1 itself is one fp16 rounding of (value - bg2): compare before that rounding matters, i.e. at half an fp16 ulp

@@ -814,3 +814,85 @@ def test_sparse_depictions_decode_and_host_pipeline(cuda_device):
     assert torch.equal(got, want)
     got2 = ours.predict_from_host(packed, sd, 32, chunk_molecules=128, packed=True)      # another chunking, graphs re-captured
     assert torch.equal(got2, want)
+
+
+@pytest.mark.parametrize("precision", ["strict", "fp16", "bf16"])
+@pytest.mark.parametrize("fp_dim,rows,groups,u8", [(167, 512, 2, False), (167, 96, 3, True), (167, 600, 1, False), (2048, 24, 2, True),
+                                                   (64, 40, 1, False)])
+def test_c_host_forward_is_bit_identical_to_the_python_host(cuda_device, precision, fp_dim, rows, groups, u8):
+    """bbbp_fwd (csrc/model_fwd.cu: the whole eval forward of 20250113.py:109-119 orchestrated by the library for a host that
+    is not Python) runs the same kernels with the same pitches and split-K factors as model.py: equal scores, bit for bit;
+    and within the mode's tolerance of the oracle on the reference's own input contract."""
+    import bbbp_b200
+    ref, ours = make_pair("tcnn", fp_dim, 128, 31, cuda_device)
+    ours.eval().set_precision(precision)
+    ours.use_cuda_graphs = False
+    fp, img, _ = seeded_inputs(77, rows, fp_dim, IMG)
+    if u8:
+        g = torch.Generator().manual_seed(5)
+        img_u8 = torch.full((rows, IMG), 255, dtype=torch.uint8)
+        mask = torch.rand(rows, IMG, generator=g) < 0.07
+        img_u8[mask] = torch.randint(0, 255, (int(mask.sum()),), generator=g, dtype=torch.uint8)
+        img_dev = img_u8.cuda()
+    else:
+        img_dev = img.cuda()
+    host = bbbp_b200.CHostForward(ours, precision)
+    with torch.no_grad():
+        want = ours.forward_groups(fp.cuda(), img_dev, groups)
+        got = host(fp.cuda(), img_dev, groups)
+        again = host(fp.cuda(), img_dev, groups)
+    torch.cuda.synchronize()
+    assert got.shape == (rows, 1)
+    assert torch.equal(got, want), float((got - want).abs().max())
+    assert torch.equal(got, again)
+    if not u8 and precision == "strict":
+        seq = rows // groups
+        ref.eval()
+        with torch.no_grad():
+            oracle = torch.cat([ref(fp[i:i + seq], img[i:i + seq]) for i in range(0, rows, seq)])
+        np.testing.assert_allclose(got.cpu().numpy(), oracle.numpy(), rtol=0, atol=1e-3)
+
+
+def test_c_host_forward_tracks_parameter_updates_and_reports_errors(cuda_device):
+    import ctypes
+    import bbbp_b200
+    from bbbp_b200 import c_host, _lib
+    _, ours = make_pair("tcnn", 167, 128, 3, cuda_device)
+    ours.eval().set_precision("fp16")
+    ours.use_cuda_graphs = False
+    fp, img, _ = seeded_inputs(9, 64, 167, IMG)
+    host = bbbp_b200.CHostForward(ours, "fp16")
+    with torch.no_grad():
+        before = host(fp.cuda(), img.cuda())
+        for p in ours.parameters():
+            p.mul_(1.01)
+        host.prepare()
+        after = host(fp.cuda(), img.cuda())
+        want = ours(fp.cuda(), img.cuda())
+    assert not torch.equal(before, after) and torch.equal(after, want)
+    desc = c_host.make_desc(167, "fp16", 1, 64)
+    small = torch.empty(1024, device="cuda", dtype=torch.uint8)
+    rc = _lib.lib.bbbp_fwd(ctypes.byref(desc), fp.cuda().data_ptr(), img.cuda().data_ptr(), host._table, host._prepared.data_ptr(),
+                           after.data_ptr(), small.data_ptr(), small.numel(), None)
+    assert rc == -3 and "bbbp_workspace_bytes" in bbbp_b200.last_error()
+
+
+def test_comm_entry_points_single_rank(cuda_device):
+    """bbbp_comm_* over NCCL with a one-rank communicator (the two-rank form runs in tools/comm_check.py)."""
+    import ctypes
+    import bbbp_b200
+    from bbbp_b200 import _lib
+    lib = _lib.lib
+    uid = (ctypes.c_char * 128)()
+    _lib.check(lib.bbbp_comm_unique_id(uid), "comm_unique_id")
+    comm = ctypes.c_void_p()
+    _lib.check(lib.bbbp_comm_init_rank(ctypes.byref(comm), 1, uid, 0), "comm_init_rank")
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(1000, device="cuda")
+    y = torch.empty_like(x)
+    _lib.check(lib.bbbp_comm_gather_scores(comm, x.data_ptr(), y.data_ptr(), x.numel(), s), "gather")
+    g = x.clone()
+    _lib.check(lib.bbbp_comm_average_gradients(comm, g.data_ptr(), g.numel(), s), "average")
+    torch.cuda.synchronize()
+    assert torch.equal(x, y) and torch.equal(x, g)
+    _lib.check(lib.bbbp_comm_destroy(comm), "comm_destroy")
