@@ -176,7 +176,7 @@ void lay_workspace(const Dims& m, Arena& a, Work* w) {
   w->vt = m.heads == 1 ? a.take(size_t(m.groups) * m.F * w->ldp * e) : nullptr;
   w->attn = a.take(R * m.Fq * e);
   w->sum32 = a.take<float>(R * m.Fq * 4);
-  w->hidden = a.take(R * kFF * e);
+  w->hidden = m.F > 176 ? a.take(R * kFF * e) : nullptr;     // narrower models run the feed-forward block as one fused kernel
   w->fp_hi = m.split ? a.take(R * m.Fq * e) : nullptr;
   w->fp_lo = m.split ? a.take(R * m.Fq * e) : nullptr;
   w->both = a.take<float>(R * kFused * 4);
@@ -469,6 +469,14 @@ extern "C" int bbbp_fwd(const bbbp_model_desc* desc, const void* fingerprint, co
     const int mid = cur ^ 1;
     RUN(bbbp_add_layernorm_fwd_pitched16(fmt, w.sum32, Fq, nullptr, 0, fparam(lp, L_N1_W), fparam(lp, L_N1_B), w.x32[mid], Fq,
                                          w.x16[mid], Fq, R, F, kLnEps, s));
+    if (F <= 176) {     // linear1 + ReLU + linear2 + residual + norm2 in one kernel (the hidden activation stays on the chip)
+      RUN(bbbp_ffn_layernorm16(fmt, R, F, kFF, w.x16[mid], Fq, d.w_l1, Fq, fparam(lp, L_L1_B), d.w_l2, kFF, fparam(lp, L_L2_B),
+                               w.x32[mid], Fq, fparam(lp, L_N2_W), fparam(lp, L_N2_B), kLnEps, w.x32[cur], Fq, w.x16[cur], Fq, s));
+      x32 = w.x32[cur];
+      ldx = Fq;
+      x16 = w.x16[cur];
+      continue;
+    }
     RUN(gemm(m, R, kFF, F, w.x16[mid], nullptr, Fq, d.w_l1, nullptr, Fq, fparam(lp, L_L1_B), nullptr, 0, nullptr, 0, nullptr, kFF,
              w.hidden, nullptr, kFF, BBBP_ACT_RELU, 1, nullptr, 0, s));
     RUN(gemm(m, R, F, kFF, w.hidden, nullptr, kFF, d.w_l2, nullptr, kFF, fparam(lp, L_L2_B), w.x32[mid], Fq, nullptr, 0, w.sum32,

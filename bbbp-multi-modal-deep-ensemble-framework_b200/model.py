@@ -334,6 +334,12 @@ class TransformerCnnModel(_KernelModule):
                                    ld_out=Fq, fmt=fmt)
             x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,
                                                  bf16_ld=Fq, fmt=fmt)
+            if self.fused_ffn and F_ <= 176 and layer.linear1.out_features % 128 == 0:
+                # linear1 + ReLU + linear2 + residual + norm2 in one kernel: the (rows, 2048) activation stays on the chip
+                x32, x16 = ops.ffn_layernorm16(x16, F_, w16(layer.linear1.weight), layer.linear1.bias, w16(layer.linear2.weight),
+                                               layer.linear2.bias, x32, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
+                                               ld_y=Fq, ld16=Fq, fmt=fmt)
+                continue
             _, h16 = ops.gemm_bf16(x16, F_, w16(layer.linear1.weight), layer.linear1.out_features,
                                    bias=layer.linear1.bias, act="relu", out_f32=False, out_bf16=True, fmt=fmt)
             f32, _ = ops.gemm_bf16(h16, layer.linear1.out_features, w16(layer.linear2.weight), F_,
@@ -400,6 +406,7 @@ class TransformerCnnModel(_KernelModule):
     strict_background = os.environ.get("BBBP_STRICT_BACKGROUND", "1") != "0"
     strict_conv1_split = os.environ.get("BBBP_STRICT_CONV1_SPLIT", "1") != "0"
     strict_u8_exact = os.environ.get("BBBP_STRICT_U8_EXACT", "1") != "0"
+    fused_ffn = os.environ.get("BBBP_FUSED_FFN", "1") != "0"     # encoder feed-forward + norm2 as one kernel (widths <= 192)
     tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
     im2col_chunk = 256      # images per pass of the im2col route (bounds the im2col buffer: 4.7 MB per image at 64 -> 128)
 

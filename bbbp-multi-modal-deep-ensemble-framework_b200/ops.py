@@ -646,6 +646,23 @@ def layernorm_fwd_pitched(x, dim, gamma, beta, eps=1e-5, ld_y=None, bf16_ld=0, f
     return y, y16
 
 
+def ffn_layernorm16(x16, d, w1_16, b1, w2_16, b2, residual, gamma, beta, eps=1e-5, ld_y=None, ld16=0, fmt=FMT_BF16):
+    """LayerNorm(residual + relu(x16 W1^T + b1) W2^T + b2) in ONE tcgen05 kernel (the hidden activation stays on the chip).
+    x16: (rows, ldx) 16-bit; w1_16: (hidden, >= d); w2_16: (d, >= hidden); residual: (rows, ld_res) fp32 pitched.
+    Returns ((rows, ld_y) fp32, (rows, ld16) 16-bit | None)."""
+    rows, hidden = x16.shape[0], w1_16.shape[0]
+    ld_y = d if ld_y is None else ld_y
+    y = torch.empty((rows, ld_y), device=x16.device, dtype=torch.float32)
+    y16 = torch.empty((rows, ld16), device=x16.device, dtype=_DT16[fmt]) if ld16 else None
+    t0 = KERNEL_TIMER.start("ffn")
+    check(lib.bbbp_ffn_layernorm16(fmt, rows, d, hidden, x16.data_ptr(), x16.stride(0), w1_16.data_ptr(), w1_16.stride(0),
+                                   b1.data_ptr(), w2_16.data_ptr(), w2_16.stride(0), b2.data_ptr(), residual.data_ptr(),
+                                   residual.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps), y.data_ptr(), ld_y, _ptr(y16),
+                                   ld16, _stream()), "ffn_layernorm16")
+    KERNEL_TIMER.stop("ffn", t0, rows)
+    return y, y16
+
+
 def layernorm_bwd(dy, s, mean, rstd, gamma):
     rows, dim = s.shape
     dx = torch.empty_like(s)

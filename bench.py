@@ -53,7 +53,7 @@ E2E_CHUNK = 2048
 # sparse depictions cut the copy to ~5 KB per molecule, so the fixed per-chunk latency decides instead of the PCIe overlap:
 # tools/e2e_sweep.py --sparse, strict: 2 048 -> 14.9 ms, 4 096 -> 12.9, 8 192 -> 12.5, 16 384 -> 12.4 (profiles/r02_e2e_sweep_sparse_strict.txt)
 E2E_CHUNK_SPARSE = 8192
-DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (hi+lo pairs, fp32 accumulate)"}
+DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (background-referenced activations, split small GEMMs, fp32 accumulate)"}
 
 
 def peaks():
@@ -440,18 +440,22 @@ def main():
         per_launch_ms = statistics.mean(conv2_ms)
         flop = CONV2_FLOP_PER_MOL * statistics.mean(conv2_mols)
         ach = flop / (per_launch_ms * 1e-3) / 1e12
-        passes = 2 if args.precision == "strict" else 1        # strict: hi and lo activation parts, two MMAs per K step
+        # strict mode: ONE pass over background-referenced fp16 activations (model.strict_background, the default); its
+        # first form carried (hi, lo) pairs through two MMAs per K step and twice the bytes
+        passes = 2 if (args.precision == "strict" and not model.strict_background) else 1
         traffic = (CONV2_STRICT_DRAM_BYTES_PER_MOL if passes == 2 else CONV2_DRAM_BYTES_PER_MOL) * statistics.mean(conv2_mols)
         roof = {"kernel": "conv2 (3x3, 32->64, +bias+ReLU+maxpool) implicit GEMM", "bound": "tensor", "achieved": ach,
                 "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                 "traffic": traffic, "traffic_unit": "bytes/launch",
-                "traffic_source": ("ncu --set full of the strict-mode kernel (profiles/r02_ncu_conv.txt: tensor pipe 59 %, DRAM = the "
+                "traffic_source": ("ncu --set full of the pair-mode kernel (profiles/r02_ncu_conv.txt: tensor pipe 59 %, DRAM = the "
                                    "algorithmic bytes of the (hi, lo) pairs)" if passes == 2 else
-                                   "ncu --set full of the bf16 launch (profiles/r01_ncu_conv_umma_full.txt)") + ", scaled to this launch's molecules",
+                                   "ncu --set full of the one-pass kernel (profiles/r01_ncu_conv_umma_full.txt; the background-referenced "
+                                   "strict instantiation moves the same 16-bit tensors + 0.5 KB of per-image tables, "
+                                   "profiles/r02_ncu_conv_bg.txt)") + ", scaled to this launch's molecules",
                 "peak_source": pk["src"] + " bf16_tflops_sustained", "launch_ms": per_launch_ms,
                 "mma_passes": passes, "executed_tflops": ach * passes, "executed_frac": ach * passes / pk["tensor"],
-                "note": "achieved = ALGORITHMIC flops (151.0 MFLOP per molecule, SURVEY 8d) / CUDA-event time; the strict mode issues "
-                        "each product twice (hi and lo activation parts), executed_* counts those",
+                "note": "achieved = ALGORITHMIC flops (151.0 MFLOP per molecule, SURVEY 8d) / CUDA-event time; executed_* multiplies by "
+                        "the MMA passes the mode issues (1, or 2 in the pair form of the strict mode)",
                 "share_of_step": sum(conv2_ms) / ms, "whole_model_tflops": FWD_FLOP_PER_MOL * value / 1e12,
                 "conv1_launch_ms": statistics.mean(conv1_ms) if conv1_ms else None}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

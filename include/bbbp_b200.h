@@ -320,6 +320,19 @@ int bbbp_attention_flash16(int fmt, int groups, int seq, int head_dim, const voi
 int bbbp_attention_heads16(int fmt, const void* qkv, int ld, int k_offset, int v_offset, void* out, int ld_out, int groups,
                            int seq, int heads, int head_dim, bbbp_stream_t stream);
 
+/* The feed-forward half of a post-norm nn.TransformerEncoderLayer (linear1 -> ReLU -> linear2 -> + x -> norm2, via
+ * 20250113.py:75-78) in ONE tcgen05 kernel (ffn_fused_umma.cu):
+ *   y = LayerNorm(residual + relu(x16 W1^T + b1) W2^T + b2) * gamma + beta
+ * The (rows x hidden) activation never reaches HBM: a CTA owns 128 rows, walks the hidden units in blocks of 128 (first
+ * product -> TMEM, bias + ReLU -> 16-bit tile in shared memory, second product accumulates in TMEM) and normalises whole rows
+ * straight out of TMEM.  x16 (rows x d, pitch ldx), W1 (hidden x d, pitch ldw1), W2 (d x hidden, pitch ldw2): 16-bit in format
+ * fmt; residual / y32: fp32 rows (pitches multiples of 4); y16 (may be NULL): the 16-bit copy of y, columns [d, ld_y16) zero.
+ * d <= 176, hidden % 128 == 0, ld_y16 <= ceil16(d). */
+int bbbp_ffn_layernorm16(int fmt, int rows, int d, int hidden, const void* x16, int ldx, const void* w1_16, int ldw1,
+                         const float* b1, const void* w2_16, int ldw2, const float* b2, const float* residual, int ld_res,
+                         const float* gamma, const float* beta, float eps, float* y32, int ld_y, void* y16, int ld_y16,
+                         bbbp_stream_t stream);
+
 /* out[r, c] = (x[r, c] - mean_c) / std_c with the statistics of column c taken over the rows of r's CHUNK (chunk_rows
  * consecutive rows; the last chunk may be shorter): StandardScaler().fit_transform per block of 100 molecules,
  * Descriptors/multi_input_data_preprocess_maccs_opt_IsolationForest_fixed_1.py:86-101.  float64 statistics, sklearn's

@@ -960,3 +960,40 @@ def test_gemm16_operands_in_transposed_storage(ops, M, N, K, trans_a, trans_w):
     split = 4 if K >= 2048 else 1
     y, _ = ops.gemm16_tn(a16, w16, M, N, K, trans_a=trans_a, trans_w=trans_w, split_k=split)
     close(y, ref, atol=2e-5 * max(1.0, math.sqrt(K) / 8), what=f"gemm16_tn {M}x{N}x{K} tA={trans_a} tW={trans_w}")
+
+
+@pytest.mark.parametrize("rows,d,hidden", [(1, 167, 2048), (130, 167, 2048), (300, 64, 256), (257, 176, 384), (128, 16, 128),
+                                           (4100, 167, 2048)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_ffn_layernorm_fused(ops, rows, d, hidden, fmt):
+    """bbbp_ffn_layernorm16 = LayerNorm(x + relu(x W1^T + b1) W2^T + b2) in one kernel (linear1 / linear2 / norm2 of
+    nn.TransformerEncoderLayer, 20250113.py:75-78), against float64 on the SAME 16-bit operands with the hidden activation
+    rounded to 16 bits where the kernel rounds it; and against the library's own two-GEMM + LayerNorm route."""
+    dt = torch.bfloat16 if fmt == 0 else torch.float16
+    ldq = -(-d // 8) * 8
+    x = rnd(rows, d, seed=301)
+    w1, b1 = rnd(hidden, d, seed=302, scale=d ** -0.5), rnd(hidden, seed=303, scale=0.1)
+    w2, b2 = rnd(d, hidden, seed=304, scale=hidden ** -0.5), rnd(d, seed=305, scale=0.1)
+    gamma, beta = 1.0 + rnd(d, seed=306, scale=0.1), rnd(d, seed=307, scale=0.1)
+    x32 = torch.zeros(rows, ldq)
+    x32[:, :d] = x
+    x32 = x32.cuda()
+    x16, _ = ops.cast16(x.cuda(), fmt, ld=ldq)
+    w1_16, _ = ops.cast16(w1.cuda(), fmt)
+    w2_16, _ = ops.cast16(w2.cuda(), fmt)
+    y, y16 = ops.ffn_layernorm16(x16, d, w1_16, b1.cuda(), w2_16, b2.cuda(), x32[:, :d], gamma.cuda(), beta.cuda(), 1e-5,
+                                 ld_y=ldq, ld16=ldq, fmt=fmt)
+    torch.cuda.synchronize()
+    xr, w1r, w2r = x.to(dt).double(), w1.to(dt).double(), w2.to(dt).double()
+    h = torch.relu(xr @ w1r.t() + b1.double()).float().to(dt).double()
+    ref = F.layer_norm(x.double() + h @ w2r.t() + b2.double(), (d,), gamma.double(), beta.double(), 1e-5).float()
+    tol = 5e-4 if fmt == 1 else 2e-3          # the 16-bit rounding of h can flip by one ulp where fp32 and fp64 sums straddle a tie
+    close(y[:, :d], ref, atol=tol, rtol=tol, what="fused ffn + layernorm")
+    assert y16.dtype == dt and y16.shape == (rows, ldq)
+    assert torch.equal(y16[:, :d].float(), y[:, :d].to(dt).float()), "16-bit copy = rn16(y)"
+    assert float(y16[:, d:].float().abs().max()) == 0.0 if ldq > d else True
+    # the unfused route of the same library
+    _, h16 = ops.gemm_bf16(x16, d, w1_16, hidden, bias=b1.cuda(), act="relu", out_f32=False, out_bf16=True, fmt=fmt)
+    f32, _ = ops.gemm_bf16(h16, hidden, w2_16, d, bias=b2.cuda(), residual=x32, ld_out=ldq, fmt=fmt)
+    y_ref, _ = ops.layernorm_fwd_pitched(f32, d, gamma.cuda(), beta.cuda(), 1e-5, ld_y=ldq, bf16_ld=ldq, fmt=fmt)
+    close(y[:, :d], y_ref[:, :d], atol=5e-5, rtol=5e-5, what="fused vs two GEMMs + LayerNorm")

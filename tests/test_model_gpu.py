@@ -896,3 +896,52 @@ def test_comm_entry_points_single_rank(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(x, y) and torch.equal(x, g)
     _lib.check(lib.bbbp_comm_destroy(comm), "comm_destroy")
+
+
+@pytest.mark.parametrize("precision,u8", [("strict", True), ("bf16", False)])
+def test_c_program_scores_equal_the_python_host(cuda_device, tmp_path, precision, u8):
+    """tools/c_host_example.c -- plain C + the CUDA runtime, no torch in the process -- compiled with gcc, fed the model's
+    state_dict as raw floats, must print the Python host's scores bit for bit (and replays the forward as a CUDA graph)."""
+    import os
+    import shutil
+    import subprocess
+    import bbbp_b200
+    from bbbp_b200 import c_host
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.dirname(bbbp_b200.LIB_PATH)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "lib64", "libcudart.so")):
+        pytest.skip("gcc / libcudart.so not available")
+    exe = str(tmp_path / "c_host_example")
+    subprocess.run(["gcc", "-O2", "-std=c99", os.path.join(root, "tools", "c_host_example.c"), "-I" + os.path.join(root, "include"),
+                    "-I" + os.path.join(cuda, "include"), "-L" + pkg, "-lbbbp_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+                    "-o", exe], check=True)
+    groups, seq, fp_dim = 2, 48, 167
+    rows = groups * seq
+    _, ours = make_pair("tcnn", fp_dim, 128, 41, cuda_device)
+    ours.eval().set_precision(precision)
+    ours.use_cuda_graphs = False
+    fp, img, _ = seeded_inputs(55, rows, fp_dim, IMG)
+    if u8:
+        g = torch.Generator().manual_seed(6)
+        img = torch.full((rows, IMG), 255, dtype=torch.uint8)
+        mask = torch.rand(rows, IMG, generator=g) < 0.06
+        img[mask] = torch.randint(0, 255, (int(mask.sum()),), generator=g, dtype=torch.uint8)
+    state = ours.state_dict()
+    desc = c_host.make_desc(fp_dim, precision)
+    with open(tmp_path / "params.bin", "wb") as f:
+        for name in c_host.param_names(desc):
+            f.write(state[name].detach().float().cpu().contiguous().numpy().tobytes())
+    with open(tmp_path / "inputs.bin", "wb") as f:
+        f.write(fp.numpy().tobytes())
+        f.write(img.numpy().tobytes())
+    env = dict(os.environ, LD_LIBRARY_PATH=pkg + ":" + os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    run = subprocess.run([exe, str(tmp_path / "params.bin"), str(tmp_path / "inputs.bin"), str(tmp_path / "scores.bin"), str(fp_dim),
+                          str(groups), str(seq), str(c_host.PRECISION_CODES[precision]), str(int(u8))], env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    print("[c host]", run.stdout.strip())
+    got = np.fromfile(tmp_path / "scores.bin", dtype=np.float32)
+    with torch.no_grad():
+        want = ours.forward_groups(fp.cuda(), img.cuda(), groups).cpu().numpy().ravel()
+    assert got.shape == want.shape and np.array_equal(got, want), float(np.abs(got - want).max())
