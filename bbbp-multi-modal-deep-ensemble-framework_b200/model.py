@@ -675,7 +675,18 @@ class TransformerCnnModel(_KernelModule):
         chunks) 8.6-8.9 ms -- a chunk's graph replay costs ~0.55 ms + 0.34 ms per 1 024 molecules (the encoder is a chain
         of ~85 dependent kernels), so chunks much shorter than 1 024 no longer hide behind their own copy."""
         full = n // batch_size * batch_size
-        spans = [(a, min(full, a + chunk)) for a in range(0, full, chunk)]
+        if isinstance(chunk, (tuple, list)):
+            # a SCHEDULE of chunk lengths (the last one repeats): a short first chunk exposes little of its own copy, and --
+            # where the link outruns the arithmetic, as with sparse depictions (5 KB per molecule) -- every later copy hides
+            # behind the chunk before it however long it is, so the remaining chunks can be few and long
+            spans, a, i = [], 0, 0
+            while a < full:
+                b = min(full, a + chunk[min(i, len(chunk) - 1)])
+                spans.append((a, b))
+                a, i = b, i + 1
+            chunk = max(chunk)
+        else:
+            spans = [(a, min(full, a + chunk)) for a in range(0, full, chunk)]
         if n > full:
             if spans and spans[-1][1] - spans[-1][0] + (n - full) <= chunk:
                 spans[-1] = (spans[-1][0], n)
@@ -684,7 +695,7 @@ class TransformerCnnModel(_KernelModule):
         return spans
 
     @torch.no_grad()
-    def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int = 1024,
+    def predict_from_host(self, fingerprint_host, image_host, batch_size: int, chunk_molecules: int | tuple = 1024,
                           packed: bool = False, out_host: torch.Tensor | None = None, return_device: bool = False,
                           synchronize: bool = True):
         """End-to-end scoring of HOST-resident molecules (pinned tensors recommended): the host->device copy of chunk
@@ -705,7 +716,12 @@ class TransformerCnnModel(_KernelModule):
                 return self.predict_from_host(fingerprint_host, image_host, batch_size, chunk_molecules, packed, out_host,
                                               return_device, synchronize)
         n = fingerprint_host.shape[0]
-        chunk = max(1, chunk_molecules // batch_size) * batch_size
+        if isinstance(chunk_molecules, (tuple, list)):           # a schedule of chunk lengths, see _pipeline_spans
+            schedule = tuple(max(1, int(c) // batch_size) * batch_size for c in chunk_molecules)
+            chunk = max(schedule)
+        else:
+            chunk = max(1, chunk_molecules // batch_size) * batch_size
+            schedule = chunk
         scores = torch.empty((n,), device=dev, dtype=torch.float32)
         compute = torch.cuda.current_stream(dev)
         # the copy stream and the two staging slots are created once and reused: a fresh stream per call would defeat
@@ -732,7 +748,7 @@ class TransformerCnnModel(_KernelModule):
             pipe[1].wait_stream(compute)
         _, copier, slots, freed = pipe               # freed[s]: last compute that read slot s (this call or a previous one)
         ready = [None, None]
-        spans = self._pipeline_spans(n, chunk, batch_size)
+        spans = self._pipeline_spans(n, schedule, batch_size)
 
         def stage(i):
             a, b = spans[i]

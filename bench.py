@@ -50,9 +50,11 @@ CONFIG = {"workload": "screen_maccs_b256", "model": "MixedInputModel(167,128) 20
 # molecules per staged chunk of the host pipeline: a chunk's replay costs ~0.55 ms + its compute, its copy 0.94 ms per 1 024
 # (tools/e2e_sweep.py on B200, strict mode, 16 384 molecules: 1 024 -> 20.0 ms, 2 048 -> 16.4 ms, 4 096 -> 17.5 ms)
 E2E_CHUNK = 2048
-# sparse depictions cut the copy to ~5 KB per molecule, so the fixed per-chunk latency decides instead of the PCIe overlap:
-# tools/e2e_sweep.py --sparse, strict: 2 048 -> 14.9 ms, 4 096 -> 12.9, 8 192 -> 12.5, 16 384 -> 12.4 (profiles/r02_e2e_sweep_sparse_strict.txt)
-E2E_CHUNK_SPARSE = 8192
+# sparse depictions cut the copy to ~5 KB per molecule: the link outruns the arithmetic 5:1, so only the FIRST chunk's copy is
+# exposed and every later copy hides behind the chunk before it -- a short first chunk, then one long one (a schedule of chunk
+# lengths).  SPARSE=1 SCHEDULES=1 tools/e2e_sweep.py, strict, 16 384 molecules: equal chunks of 8 192 -> 7.68 ms, one chunk of
+# 16 384 -> 7.98, (2 048, 14 336) -> 7.27, (4 096, 12 288) -> 7.38, (2 048, 6 144, 8 192) -> 7.74 (profiles/r02_e2e_sweep_sparse_strict.txt)
+E2E_CHUNK_SPARSE = (2048, 14336)
 DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (background-referenced activations, split small GEMMs, fp32 accumulate)"}
 
 

@@ -295,6 +295,20 @@ def test_host_pipeline_chunk_spans_cover_whole_batches():
         assert all((b - a) % bs == 0 for a, b in sp[:-1])           # only the last span may carry the ragged tail batch
 
 
+def test_host_pipeline_chunk_schedules():
+    """A schedule of chunk lengths (short first chunk, the last length repeating) keeps the same invariants."""
+    import bbbp_b200
+    spans = bbbp_b200.TransformerCnnModel._pipeline_spans
+    assert spans(16384, (2048, 6144, 8192), 256) == [(0, 2048), (2048, 8192), (8192, 16384)]
+    assert spans(16384 + 100, (2048, 14336), 256) == [(0, 2048), (2048, 16384), (16384, 16484)]
+    assert spans(5000, (1024, 2048), 256) == [(0, 1024), (1024, 3072), (3072, 5000)]      # tail batch rides on the last span
+    assert spans(100, (1024, 2048), 256) == [(0, 100)]
+    for n, sched, bs in [(10_000, (512, 1024, 4096), 256), (1058, (64, 96), 32), (777, (256,), 256)]:
+        sp = spans(n, sched, bs)
+        assert sp[0][0] == 0 and sp[-1][1] == n and all(a[1] == b[0] for a, b in zip(sp, sp[1:]))
+        assert all(a % bs == 0 for a, _ in sp) and all(b - a <= max(max(sched), bs) for a, b in sp)
+
+
 def test_graphed_train_step_rejects_foreign_optimizers():
     """The captured update reads its scalars from device memory: only bbbp_b200.AdamW provides that entry point."""
     import pytest

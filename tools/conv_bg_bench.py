@@ -25,6 +25,7 @@ tab1, neg2 = ops.bg_layer(ws1, b1, bg1, fmt=1, want_neg16=True)
 tab2, _ = ops.bg_layer(ws2, b2, tab1[:, 1], fmt=-1)
 y1, y1lo = ops.conv1_from_image_bf16(img, w1, b1, fmt=1, split=True)
 y1b = ops.conv1_from_image_bg(img, w1, None, bg1, tab1, fmt=1, split=True)
+bg1_u8 = ops.image_background(img8, stats)          # carries the raw background bytes the exact-integer form reads
 cases = [
     ("conv1 fp16 one pass (fp32 planes)", lambda: ops.conv1_from_image_bf16(img, w1, b1, fmt=1)),
     ("conv1 strict pairs  (fp32 planes)", lambda: ops.conv1_from_image_bf16(img, w1, b1, fmt=1, split=True)),
@@ -32,6 +33,7 @@ cases = [
     ("conv1 BG 1 pass     (fp32 planes)", lambda: ops.conv1_from_image_bg(img, w1, None, bg1, tab1, fmt=1, split=False)),
     ("conv1 fp16 one pass (uint8)", lambda: ops.conv1_from_image_bf16(img8, w1, b1, stats, fmt=1)),
     ("conv1 BG 2 passes   (uint8)", lambda: ops.conv1_from_image_bg(img8, w1, stats, bg1, tab1, fmt=1, split=True)),
+    ("conv1 BG exact ints, 1 pass (uint8)", lambda: ops.conv1_from_image_bg(img8, w1, stats, bg1_u8, tab1, fmt=1, split=False)),
     ("conv2 fp16 one pass", lambda: ops.conv3x3_relu_pool_bf16(y1, w2, b2, 64, fmt=1)),
     ("conv2 strict pairs", lambda: ops.conv3x3_relu_pool_bf16(y1, w2, b2, 64, fmt=1, x_lo=y1lo)),
     ("conv2 BG", lambda: ops.conv3x3_relu_pool_bg(y1b, w2, neg2, tab2, 64, fmt=1)),
@@ -44,7 +46,7 @@ for label, fn in cases:
     print(f"{label:36s} {t(fn):.3f} ms")
 names = ["mma: wait acc_empty", "mma: wait full", "mma: issue+commit", "mma: tiles", "epi: wait acc_full", "epi: tmem+math+sts",
          "epi: wait buffer free (bar1)", "epi: fence + arrive", "prod: wait empty", "prod: issue loads", "prod: wait data+arrive"]
-for label, fn in cases[:9]:
+for label, fn in cases[:10]:
     probe = torch.zeros(16, dtype=torch.int64, device="cuda")
     check(lib.bbbp_debug_conv_probe(probe.data_ptr()))
     fn(); torch.cuda.synchronize()

@@ -14,16 +14,18 @@ if os.environ.get("SPARSE", "0") == "1":            # mostly-white depictions in
     img8[strokes.expand(-1, 3, -1, -1)] = 40
     img8 = bbbp_b200.SparseDepictions.encode(img8.numpy())
 res = {}
-for chunk in (256, 512, 1024, 2048, 4096, 8192, 16384):
-    if chunk > n: continue
+schedules = [(1024, 5120, 10240), (2048, 14336), (2048, 6144, 8192), (1024, 3072, 4096, 8192), (4096, 12288), (2048, 4096, 10240)]
+chunks = [256, 512, 1024, 2048, 4096, 8192, 16384] if os.environ.get("SCHEDULES", "0") != "only" else []
+for chunk in chunks + (schedules if os.environ.get("SCHEDULES", "0") != "0" else []):
+    if (max(chunk) if isinstance(chunk, tuple) else chunk) > n: continue
     fn = lambda: m.predict_from_host(packed, img8, 256, chunk_molecules=chunk, packed=True, out_host=out_host)
     for _ in range(3): fn()
     torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(8): fn()
     e1.record(); torch.cuda.synchronize()
-    res[chunk] = e0.elapsed_time(e1) / 8
-    print(chunk, res[chunk], n / res[chunk] * 1e3, flush=True)
+    res[str(chunk)] = e0.elapsed_time(e1) / 8
+    print(chunk, res[str(chunk)], n / res[str(chunk)] * 1e3, flush=True)
 # H2D alone
 if not torch.is_tensor(img8): sys.exit(0)
 d = torch.empty_like(img8, device=dev)
