@@ -75,7 +75,8 @@ struct Cfg {
   static constexpr int PROD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + PROD_WARPS, STORE_WARP = MMA_WARP + 1;
   // the first layer runs two small CTAs per SM (measured: one CTA with 8 + 8 + 1 warps and a 6-deep ring is slower,
   // 1.65 ms vs 1.42 ms per 8 192 images)
-  static constexpr int MIN_CTAS = KC == 1 ? 2 : 1;
+  // (64 output channels need all 512 TMEM columns for the double-buffered accumulators: one CTA per SM)
+  static constexpr int MIN_CTAS = (KC == 1 && COUT <= 32) ? 2 : 1;
   static constexpr int A_BYTES = KC * KC_B;
   // planar first-layer sources in two parts: BOTH parts of a tile's halo share one ring slot (hi image, then lo image), so
   // the producers pay one wait / fence / arrive round per tile instead of two (they, not the MMAs, bound that kernel)
@@ -1020,8 +1021,8 @@ extern "C" size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout) {
 extern "C" int bbbp_conv3x3_prepare16(int fmt, const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream) {
   BBBP_CHECK_ARG(fmt == BBBP_FMT_BF16 || fmt == BBBP_FMT_F16, "conv3x3_prepare: bad fmt %d", fmt);
   BBBP_CHECK_ARG(w && wprep, "conv3x3_prepare: null operand");
-  BBBP_CHECK_ARG((Cin == 3 && Cout == 32) || (Cin == 32 && Cout == 64),
-                 "conv3x3_prepare: only (3->32) and (32->64) are built for the tcgen05 path, got %d->%d", Cin, Cout);
+  BBBP_CHECK_ARG((Cin == 3 && (Cout == 32 || Cout == 64)) || (Cin == 32 && Cout == 64),
+                 "conv3x3_prepare: only (3->32), (3->64) and (32->64) are built for the tcgen05 path, got %d->%d", Cin, Cout);
   const int total = (int)(bbbp_conv3x3_prepared_bytes(Cin, Cout) / 2);
   uint16_t* wp = static_cast<uint16_t*>(wprep);
   if (Cin <= 8) {
@@ -1105,6 +1106,17 @@ extern "C" int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, 
   if (img_is_u8)
     return conv::dispatch<1, 32, conv::SRC_CHW_U8>(fmt, split, img_chw, nullptr, stats, wprep, bias, y_nhwc, y_lo, N, H, W, s);
   return conv::dispatch<1, 32, conv::SRC_CHW_F32>(fmt, split, img_chw, nullptr, nullptr, wprep, bias, y_nhwc, y_lo, N, H, W, s);
+}
+// First layer of the big variant (nn.Conv2d(3, 64, 3, padding=1) + ReLU + MaxPool2d(2), 20250107_network.py:133-135): the same
+// fused kernel with 64 output channels (N = 128 MMAs, all 512 TMEM columns, one CTA per SM), bf16, fp32 planar input.
+extern "C" int bbbp_conv1_from_image_c64_bf16(const float* img_chw, const void* wprep, const float* bias, void* y_nhwc, int N,
+                                              int H, int W, bbbp_stream_t stream) {
+  BBBP_CHECK_ARG(img_chw && wprep && bias && y_nhwc, "conv1_from_image_c64: null operand");
+  BBBP_CHECK_ARG(N >= 0 && H > 0 && W > 0 && H % 32 == 0 && W % 16 == 0,
+                 "conv1_from_image_c64: H=%d must be a multiple of 32 and W=%d of 16", H, W);
+  if (N == 0) return BBBP_OK;
+  return conv::launch<1, 64, conv::SRC_CHW_F32, BBBP_FMT_BF16, 1>(img_chw, nullptr, nullptr, wprep, bias, y_nhwc, nullptr, N, H, W,
+                                                                  as_stream(stream));
 }
 extern "C" int bbbp_conv1_from_image_bf16(const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
                                           const float* bias, void* y_nhwc, int N, int H, int W, bbbp_stream_t stream) {

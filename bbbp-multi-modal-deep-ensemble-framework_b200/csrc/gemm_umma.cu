@@ -117,6 +117,11 @@ struct Params {
   // what the constant part of the activation contributes, bbbp_gemm16_pre)
   const float* pre_add;
   int ld_pre;
+  // implicit 3x3 convolution (bbbp_conv3x3_gemm16): the A operand is an NHWC activation read through a 4-D tensor map.
+  // A GEMM row is a pixel, an M tile = 128 consecutive pixels = conv_rows whole image rows; K block kb = (tap, 64-channel
+  // block) is ONE shifted box {64 channels, W, conv_rows, 1} at (x, y) offset (kw - 1, kh - 1): the im2col matrix never
+  // exists, and the zero padding is the TMA's out-of-bounds fill.  conv_cblocks = C / 64 (0: plain GEMM).
+  int conv_cblocks, conv_rows, conv_tiles_per_img;
 };
 
 // 32 fp32 values -> 32 16-bit values as four 16-byte stores (and the matching lo parts when lo != nullptr)
@@ -140,6 +145,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -196,7 +209,11 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         uint8_t* st = tiles + s * stage_bytes;
         const int kc = (kb_begin + i) * BK;
-        if (p.a_mn) {
+        if (p.conv_cblocks) {
+          const int kbg = kb_begin + i, tap = kbg / p.conv_cblocks, cb = kbg - tap * p.conv_cblocks;
+          const int img = (int)blockIdx.y / p.conv_tiles_per_img, y0 = ((int)blockIdx.y - img * p.conv_tiles_per_img) * p.conv_rows;
+          tma_load_4d(&tmA, &full[s], st, cb * 64, tap % 3 - 1, y0 + tap / 3 - 1, img);
+        } else if (p.a_mn) {
           for (int mb = 0; mb < BM / 64; ++mb) tma_load_3d(&tmA, &full[s], st + mb * 8192, m0 + mb * 64, kc, batch);
         } else {
           tma_load_3d(&tmA, &full[s], st, kc, m0, batch);
@@ -434,6 +451,7 @@ struct Problem {
   const void* A_lo = nullptr;   // optional lo parts (same pitch / batch stride as the hi parts)
   const void* W_lo = nullptr;
   bool a_mn = false, b_mn = false;   // A stored [K][M] / W stored [K][N]
+  int conv_n = 0, conv_h = 0, conv_w = 0, conv_c = 0;   // implicit 3x3 convolution over an NHWC activation (conv_c != 0)
 };
 
 template <int BN, int EPI>
@@ -442,10 +460,29 @@ int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   // (fp16 tiles go through the same 2-byte tensor maps: the element type only selects the out-of-bounds fill, zero in both)
   CUtensorMap tmA, tmB, tmA2, tmB2;
   // K-major: rows = M (N), cols = K, box = tile rows x 64.  MN-major: rows = K, cols = M (N), box = 64 K-rows x 64 columns.
-  int st = pr.a_mn ? make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.K, (uint64_t)pr.M, (uint64_t)pr.lda, (uint64_t)pr.batches,
-                                       (uint64_t)pr.a_bs, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B)
-                   : make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
-                                       (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  int st = BBBP_OK;
+  if (pr.conv_c) {
+    // NHWC activation as {C, W, H, N}; one box = 64 channels of conv_rows whole image rows = the 128 x 64 A tile of a K block
+    tensormap_encode_fn enc = get_tensormap_encoder();
+    if (!enc) return BBBP_ECUDA;
+    const cuuint64_t C = (cuuint64_t)pr.conv_c, Wd = (cuuint64_t)pr.conv_w, Hd = (cuuint64_t)pr.conv_h;
+    cuuint64_t dims[4] = {C, Wd, Hd, (cuuint64_t)pr.conv_n};
+    cuuint64_t strides[3] = {C * 2, Wd * C * 2, Hd * Wd * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)pr.conv_w, (cuuint32_t)(BM / pr.conv_w), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(pr.A), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv3x3_gemm16: cuTensorMapEncodeTiled failed (%d) for %d x %d x %d x %d", (int)r, pr.conv_n, pr.conv_h, pr.conv_w, pr.conv_c);
+      return BBBP_ECUDA;
+    }
+  } else {
+    st = pr.a_mn ? make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.K, (uint64_t)pr.M, (uint64_t)pr.lda, (uint64_t)pr.batches,
+                                     (uint64_t)pr.a_bs, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+                 : make_tmap_bf16_3d(&tmA, pr.A, (uint64_t)pr.M, (uint64_t)pr.K, (uint64_t)pr.lda, (uint64_t)pr.batches,
+                                     (uint64_t)pr.a_bs, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   if (st != BBBP_OK) return st;
   st = pr.b_mn ? make_tmap_bf16_3d(&tmB, pr.W, (uint64_t)pr.K, (uint64_t)pr.N, (uint64_t)pr.ldw, (uint64_t)pr.batches,
                                    (uint64_t)pr.w_bs, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B)
@@ -467,6 +504,9 @@ int launch(const Problem& pr, int split_k, cudaStream_t stream) {
   p.n_a = pr.A_lo ? 2 : 1;
   p.n_w = pr.W_lo ? 2 : 1;
   p.a_mn = pr.a_mn, p.b_mn = pr.b_mn;
+  p.conv_cblocks = pr.conv_c / 64;
+  p.conv_rows = pr.conv_c ? BM / pr.conv_w : 0;
+  p.conv_tiles_per_img = pr.conv_c ? pr.conv_h * pr.conv_w / BM : 0;
   p.stages = C::stages(p.n_a, p.n_w);
   const int smem_bytes = C::smem_bytes(p.n_a, p.n_w);
   p.M = pr.M;
@@ -654,6 +694,34 @@ static int gemm16_impl(int fmt, int M, int N, int K, const void* A_hi, const voi
   if (N <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, split_k, s);
   if (N >= 512 && split_k == 1) return gemm::launch<256, gemm::EPI_LINEAR>(pr, split_k, s);
   return gemm::launch<128, gemm::EPI_LINEAR>(pr, split_k, s);
+}
+
+// 3x3 convolution (stride 1, padding 1) + bias + activation as an IMPLICIT GEMM over an NHWC 16-bit activation: rows = pixels,
+// K = 9 * C in (tap, channel) order, the A tiles fetched as shifted TMA boxes (see Params::conv_cblocks).
+extern "C" int bbbp_conv3x3_gemm16(int fmt, const void* x_nhwc, int N, int H, int W, int C, const void* w_taps, int Cout,
+                                   const float* bias, int act, void* y_nhwc, bbbp_stream_t stream) {
+  using namespace bbbp;
+  int st = check_fmt("conv3x3_gemm16", fmt);
+  if (st != BBBP_OK) return st;
+  BBBP_CHECK_ARG(x_nhwc && w_taps && y_nhwc && N >= 0, "conv3x3_gemm16: null operand");
+  BBBP_CHECK_ARG(C >= 64 && C % 64 == 0 && Cout >= 8 && Cout % 8 == 0, "conv3x3_gemm16: C=%d must be a multiple of 64, Cout=%d of 8", C, Cout);
+  BBBP_CHECK_ARG(W >= 8 && W <= gemm::BM && gemm::BM % W == 0 && H >= 1 && (H * W) % gemm::BM == 0,
+                 "conv3x3_gemm16: W=%d must divide %d and H*W=%d be a multiple of it", W, gemm::BM, H * W);
+  BBBP_CHECK_ARG(((uintptr_t)x_nhwc % 16) == 0 && ((uintptr_t)w_taps % 16) == 0 && ((uintptr_t)y_nhwc % 16) == 0,
+                 "conv3x3_gemm16: operands must be 16-byte aligned");
+  BBBP_CHECK_ARG((long long)N * H * W / gemm::BM <= 65535, "conv3x3_gemm16: %d x %d x %d pixels exceed 65 535 row tiles per launch", N, H, W);
+  if (N == 0) return BBBP_OK;
+  gemm::Problem pr{};
+  pr.M = N * H * W, pr.N = Cout, pr.K = 9 * C, pr.batches = 1;
+  pr.A = x_nhwc, pr.lda = 9 * C, pr.W = w_taps, pr.ldw = 9 * C;
+  pr.conv_n = N, pr.conv_h = H, pr.conv_w = W, pr.conv_c = C;
+  pr.p.bias = bias;
+  pr.p.out16 = static_cast<uint16_t*>(y_nhwc), pr.p.ld_out16 = Cout;
+  pr.p.act = act, pr.p.fmt = fmt;
+  cudaStream_t s = as_stream(stream);
+  if (Cout <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, 1, s);
+  if (Cout >= 512) return gemm::launch<256, gemm::EPI_LINEAR>(pr, 1, s);
+  return gemm::launch<128, gemm::EPI_LINEAR>(pr, 1, s);
 }
 
 // out[M,N] = opA(A) opW(W)^T with either operand read in place in its MN-major storage (see Params::a_mn).

@@ -408,6 +408,8 @@ class TransformerCnnModel(_KernelModule):
     strict_u8_exact = os.environ.get("BBBP_STRICT_U8_EXACT", "1") != "0"
     fused_ffn = os.environ.get("BBBP_FUSED_FFN", "1") != "0"     # encoder feed-forward + norm2 as one kernel (widths <= 192)
     tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
+    implicit_conv = os.environ.get("BBBP_IMPLICIT_CONV", "1") != "0"    # big variant: no im2col matrix for the 64 / 128-channel layers
+    implicit_chunk = 1024   # images per pass when no im2col matrix is built (bounds the NHWC activations: 1.5 MB per image)
     im2col_chunk = 256      # images per pass of the im2col route (bounds the im2col buffer: 4.7 MB per image at 64 -> 128)
 
     def _image_branch_im2col(self, image, mods):
@@ -427,16 +429,28 @@ class TransformerCnnModel(_KernelModule):
         wfc = ag.derived_weight(fc.weight, "hwc_bf16",
                                 lambda w: ops.fc_weight_to_hwc_bf16(w, convs[-1].out_channels, final_side * final_side))
         outs = []
-        for a in range(0, n, self.im2col_chunk):
-            part = img[a:a + self.im2col_chunk]
-            x = ops.image_to_nhwc8_bf16(part, 3, side, side)              # (n, H, W, 8): channels 3..7 zero
-            for conv in convs:
+        # first block on the fused tcgen05 kernel of the canonical network (instantiated for 64 output channels): conv + ReLU +
+        # pool straight from the planar image, no NHWC8 copy, no im2col, no separate pooling pass
+        fused_first = self.implicit_conv and side == 128 and convs[0].in_channels == 3 and convs[0].out_channels == 64
+        chunk = self.implicit_chunk if fused_first else self.im2col_chunk
+        for a in range(0, n, chunk):
+            part = img[a:a + chunk]
+            if fused_first:
+                w1 = ag.derived_weight(convs[0].weight, "conv_umma_0", lambda w: ops.conv3x3_prepare_bf16(w, ops.FMT_BF16))
+                x = ops.conv1_from_image_c64(part, w1, convs[0].bias, side, side)
+            else:
+                x = ops.image_to_nhwc8_bf16(part, 3, side, side)              # (n, H, W, 8): channels 3..7 zero
+            for conv in (convs[1:] if fused_first else convs):
                 nb, H, W, C = x.shape
                 w16 = ag.derived_weight(conv.weight, f"im2col_{C}", lambda w, C=C: ops.conv3x3_weight_im2col_bf16(w, C))
-                cols = ops.im2col3x3_bf16(x)
-                _, y = ops.gemm_bf16(cols, 9 * C, w16, conv.out_channels, bias=conv.bias, act="relu", out_f32=False,
-                                     out_bf16=True)
-                del cols
+                if self.implicit_conv and C % 64 == 0 and 128 % W == 0 and (H * W) % 128 == 0:
+                    # 64 -> 128 and 128 -> 256: implicit GEMM, the A tiles are shifted TMA boxes of the activation itself
+                    y = ops.conv3x3_gemm16(x, w16, conv.bias, "relu")
+                else:
+                    cols = ops.im2col3x3_bf16(x)
+                    _, y = ops.gemm_bf16(cols, 9 * C, w16, conv.out_channels, bias=conv.bias, act="relu", out_f32=False,
+                                         out_bf16=True)
+                    del cols
                 x = ops.maxpool2x2_nhwc_bf16(y.view(nb, H, W, conv.out_channels))
             flat = x.view(x.shape[0], -1)
             K = flat.shape[1]

@@ -414,6 +414,18 @@ def conv1_from_image_bf16(img: torch.Tensor, wprep: torch.Tensor, bias: torch.Te
     return (y, y_lo) if split else y
 
 
+def conv1_from_image_c64(img: torch.Tensor, wprep: torch.Tensor, bias: torch.Tensor, H=128, W=128) -> torch.Tensor:
+    """Conv2d(3, 64) + ReLU + MaxPool2d(2) of the big variant straight from the planar fp32 (N, 3, H, W) input -> bf16 NHWC."""
+    N = img.numel() // (3 * H * W)
+    assert img.dtype == torch.float32
+    y = torch.empty((N, H // 2, W // 2, 64), device=img.device, dtype=torch.bfloat16)
+    t0 = KERNEL_TIMER.start("conv1")
+    check(lib.bbbp_conv1_from_image_c64_bf16(img.data_ptr(), wprep.data_ptr(), bias.data_ptr(), y.data_ptr(), N, H, W, _stream()),
+          "conv1_from_image_c64")
+    KERNEL_TIMER.stop("conv1", t0, N)
+    return y
+
+
 # ---- background-referenced strict mode of the image branch (conv_umma.cu, BG = 1) ---------------------------------------
 def image_background(img: torch.Tensor, stats=None, H=128, W=128) -> torch.Tensor:
     """(N, 4) float32: the background value of every image per channel (column 3 is zero); uint8 images are normalised
@@ -492,6 +504,19 @@ def im2col3x3_bf16(x_nhwc: torch.Tensor) -> torch.Tensor:
     out = torch.empty((N * H * W, 9 * C), device=x_nhwc.device, dtype=torch.bfloat16)
     check(lib.bbbp_im2col3x3_bf16(x_nhwc.data_ptr(), out.data_ptr(), N, H, W, C, _stream()), "im2col3x3_bf16")
     return out
+
+
+def conv3x3_gemm16(x_nhwc: torch.Tensor, w_taps: torch.Tensor, bias, act="relu", fmt=FMT_BF16) -> torch.Tensor:
+    """act(conv3x3(x) + bias) on NHWC 16-bit activations as an implicit GEMM (no im2col matrix); C % 64 == 0.
+    w_taps: (Cout, 9*C) in (tap, channel) order (conv3x3_weight_im2col_bf16)."""
+    N, H, W, C = x_nhwc.shape
+    Cout = w_taps.shape[0]
+    y = torch.empty((N, H, W, Cout), device=x_nhwc.device, dtype=x_nhwc.dtype)
+    t0 = KERNEL_TIMER.start("conv_gemm")
+    check(lib.bbbp_conv3x3_gemm16(fmt, x_nhwc.data_ptr(), N, H, W, C, w_taps.data_ptr(), Cout, _ptr(bias), _ACT[act], y.data_ptr(),
+                                  _stream()), "conv3x3_gemm16")
+    KERNEL_TIMER.stop("conv_gemm", t0, N)
+    return y
 
 
 def maxpool2x2_nhwc_bf16(x_nhwc: torch.Tensor) -> torch.Tensor:

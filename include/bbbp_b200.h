@@ -171,7 +171,7 @@ int bbbp_conv3x3_flip_weights_f32(const float* w, float* w_t, int Cin, int Cout,
 
 /* tcgen05 inference path of the same block: NHWC bf16 activations with 8*k channels per pixel, implicit GEMM with the
  * halo tile staged once in shared memory, bias + ReLU + 2x2 max-pool fused into the TMEM epilogue (conv_umma.cu).
- * Built for the reference's two layers: (Cin 3 -> padded 8, Cout 32) and (Cin 32, Cout 64). */
+ * Built for the reference's layers: (Cin 3 -> padded 8, Cout 32), (Cin 32, Cout 64) and -- planar fp32 input only -- (3, 64). */
 size_t bbbp_conv3x3_prepared_bytes(int Cin, int Cout);
 /* w[Cout,Cin,3,3] fp32 -> the kernel's bf16 shared-memory weight image (call again whenever w changes) */
 int bbbp_conv3x3_prepare_bf16(const float* w, void* wprep, int Cin, int Cout, bbbp_stream_t stream);
@@ -194,6 +194,10 @@ int bbbp_conv3x3_relu_pool16(int fmt, int split, const void* x_nhwc, const void*
 int bbbp_conv1_from_image16(int fmt, int split, const void* img_chw, int img_is_u8, const float* stats, const void* wprep,
                             const float* bias, void* y_nhwc, void* y_lo, int N, int H, int W, bbbp_stream_t stream);
 int bbbp_fc_weight_to_hwc16(int fmt, const float* w, void* out16, int rows, int C, int HW, bbbp_stream_t stream);
+/* First block of the big variant (Conv2d(3, 64) + ReLU + MaxPool2d(2), 20250107_network.py:133-135) on the same fused kernel:
+ * fp32 planar (N, 3, H, W) in, bf16 NHWC (N, H/2, W/2, 64) out; wprep from bbbp_conv3x3_prepare_bf16(w, wprep, 3, 64). */
+int bbbp_conv1_from_image_c64_bf16(const float* img_chw, const void* wprep, const float* bias, void* y_nhwc, int N, int H, int W,
+                                   bbbp_stream_t stream);
 /* Background-referenced strict mode of the same two blocks (conv_umma.cu, BG = 1).  A depiction is
  * mostly one value per channel, so each layer works on activations RELATIVE to a per-image background (exactly 0 on the
  * canvas: rounding them to fp16 costs nothing there) and its epilogue adds back, in fp32 and from the fp32 weights, what the
@@ -249,6 +253,14 @@ int bbbp_fc_weight_to_hwc_bf16(const float* w, void* out_bf16, int rows, int C, 
  * stack of 20250107_network.py:133-141): explicit bf16 im2col -> bbbp_gemm_bf16 (bias + ReLU epilogue) -> 2x2 max-pool.
  * out[(n*H + y)*W + x][tap*C + c] = x[n][y+dy][x+dx][c], zero outside the image, tap = 3*(dy+1) + (dx+1); C % 8 == 0. */
 int bbbp_im2col3x3_bf16(const void* x_nhwc, void* out, int N, int H, int W, int C, bbbp_stream_t stream);
+/* The same convolution WITHOUT the im2col matrix (channel counts that are multiples of 64: the 64 -> 128 and 128 -> 256 layers
+ * of 20250107_network.py:136-141): y[N,H,W,Cout] = act(conv3x3(x[N,H,W,C]) + bias), 16-bit NHWC in and out, as an implicit GEMM
+ * on the tcgen05 GEMM kernel -- a GEMM row is a pixel, a K block is one (tap, 64-channel block), and its A tile is fetched as
+ * ONE shifted 4-D TMA box of the activation (the zero padding is the TMA's out-of-bounds fill), so the activation is read from
+ * L2 nine times instead of a 9x larger matrix being written to and read from HBM.  w_taps: [Cout][9*C] in (tap, channel)
+ * order (bbbp_conv3x3_weight_im2col16).  W must divide 128, H*W % 128 == 0, N*H*W/128 <= 65535. */
+int bbbp_conv3x3_gemm16(int fmt, const void* x_nhwc, int N, int H, int W, int C, const void* w_taps, int Cout, const float* bias,
+                        int act, void* y_nhwc, bbbp_stream_t stream);
 /* y[N,H/2,W/2,C] = 2x2 max-pool of x[N,H,W,C], bf16 NHWC, C % 8 == 0 */
 int bbbp_maxpool2x2_nhwc_bf16(const void* x_nhwc, void* y_nhwc, int N, int H, int W, int C, bbbp_stream_t stream);
 /* out[Cout][9*Cpad] bf16 with out[co][tap*Cpad + c] = w[co][c][tap] (zero for c >= Cin): the W operand matching the

@@ -997,3 +997,39 @@ def test_ffn_layernorm_fused(ops, rows, d, hidden, fmt):
     f32, _ = ops.gemm_bf16(h16, hidden, w2_16, d, bias=b2.cuda(), residual=x32, ld_out=ldq, fmt=fmt)
     y_ref, _ = ops.layernorm_fwd_pitched(f32, d, gamma.cuda(), beta.cuda(), 1e-5, ld_y=ldq, bf16_ld=ldq, fmt=fmt)
     close(y[:, :d], y_ref[:, :d], atol=5e-5, rtol=5e-5, what="fused vs two GEMMs + LayerNorm")
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout", [(1, 64, 64, 64, 128), (3, 32, 32, 128, 256), (2, 16, 16, 64, 64), (5, 8, 16, 64, 136),
+                                          (2, 2, 128, 64, 128)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_conv3x3_implicit_gemm(ops, N, H, W, C, Cout, fmt):
+    """bbbp_conv3x3_gemm16 (the big variant's 64 -> 128 -> 256 layers, 20250107_network.py:136-141, without an im2col matrix)
+    against conv2d in float64 on the same 16-bit operands, and bit for bit against the library's explicit im2col + GEMM route
+    (same products, same accumulation order per K block)."""
+    dt = torch.bfloat16 if fmt == 0 else torch.float16
+    x = rnd(N, C, H, W, seed=401)
+    w, b = rnd(Cout, C, 3, 3, seed=402, scale=(9 * C) ** -0.5), rnd(Cout, seed=403, scale=0.1)
+    x16 = x.permute(0, 2, 3, 1).contiguous().to(dt).cuda()
+    w16 = ops.conv3x3_weight_im2col16(w.cuda(), C, fmt)
+    y = ops.conv3x3_gemm16(x16, w16, b.cuda(), "relu", fmt=fmt)
+    torch.cuda.synchronize()
+    assert y.shape == (N, H, W, Cout) and y.dtype == dt
+    ref = torch.relu(F.conv2d(x.to(dt).double(), w.to(dt).double(), b.double(), padding=1)).permute(0, 2, 3, 1).float()
+    tol = 2e-2 if fmt == 0 else 3e-3
+    close(y, ref, atol=tol, rtol=tol, what="implicit-GEMM conv")
+    cols = ops.im2col3x3_16(x16)
+    _, y2 = ops.gemm_bf16(cols, 9 * C, w16, Cout, bias=b.cuda(), act="relu", out_f32=False, out_bf16=True, fmt=fmt)
+    assert torch.equal(y.view(-1, Cout), y2[:, :Cout]), "implicit and explicit im2col routes differ"
+
+
+@pytest.mark.parametrize("N", [1, 5])
+def test_conv1_fused_with_64_output_channels(ops, N):
+    """Conv2d(3, 64) + ReLU + MaxPool2d(2) of the big variant (20250107_network.py:133-135) on the fused first-layer kernel."""
+    img = rnd(N, 3, 128, 128, seed=411)
+    w, b = rnd(64, 3, 3, 3, seed=412, scale=0.2), rnd(64, seed=413, scale=0.1)
+    wp = ops.conv3x3_prepare_bf16(w.cuda(), 0)
+    y = ops.conv1_from_image_c64(img.cuda(), wp, b.cuda())
+    torch.cuda.synchronize()
+    assert y.shape == (N, 64, 64, 64) and y.dtype == torch.bfloat16
+    ref = F.max_pool2d(F.relu(F.conv2d(img.bfloat16().double(), w.bfloat16().double(), b.double(), padding=1)), 2)
+    close(y, ref.permute(0, 2, 3, 1).float(), atol=2e-2, rtol=1e-2, what="conv1 with 64 output channels")
