@@ -720,7 +720,7 @@ extern "C" int bbbp_conv3x3_gemm16(int fmt, const void* x_nhwc, int N, int H, in
   pr.p.act = act, pr.p.fmt = fmt;
   cudaStream_t s = as_stream(stream);
   if (Cout <= 64) return gemm::launch<64, gemm::EPI_LINEAR>(pr, 1, s);
-  if (Cout >= 512) return gemm::launch<256, gemm::EPI_LINEAR>(pr, 1, s);
+  if (Cout >= 512) return gemm::launch<256, gemm::EPI_LINEAR>(pr, 1, s);     // (256-wide tiles at Cout = 256: measured, no gain)
   return gemm::launch<128, gemm::EPI_LINEAR>(pr, 1, s);
 }
 

@@ -86,14 +86,13 @@ int parse(const bbbp_model_desc* d, Dims* m, bool need_batch) {
   if (need_batch) {
     BBBP_CHECK_ARG(d->groups >= 1 && d->seq >= 1, "bbbp_model: groups %d, seq %d", d->groups, d->seq);
     BBBP_CHECK_ARG(m->R <= (1ll << 22), "bbbp_model: %lld molecules per call (limit 4 194 304)", m->R);
-    if (m->heads == 1 && m->seq > 256) {
-      if (m->F > 192) {
-        bbbp::set_error("bbbp_model: one head of dimension %d with %d molecules per batch is not built (head_dim <= 192)",
-                        m->F, m->seq);
-        return BBBP_EUNSUPPORTED;
-      }
-      m->flash = true;
+    if (m->heads == 1 && m->seq > 256 && m->F > 192) {
+      bbbp::set_error("bbbp_model: one head of dimension %d with %d molecules per batch is not built (head_dim <= 192)", m->F,
+                      m->seq);
+      return BBBP_EUNSUPPORTED;
     }
+    // scopes of 129 molecules or more take the streaming-softmax kernel (model.py: flash_min_seq)
+    m->flash = m->heads == 1 && m->F <= 192 && m->seq >= 129;
   }
   return BBBP_OK;
 }

@@ -316,7 +316,7 @@ class TransformerCnnModel(_KernelModule):
             w_in = ag.derived_weight(attn.in_proj_weight, f"qkv_pad16_{fmt}", padded_in_proj)
             b_in = ag.derived_weight(attn.in_proj_bias, "qkv_pad", padded_in_bias)
             _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True, fmt=fmt)
-            if attn.num_heads == 1 and seq > 256 and F_ <= 192:
+            if attn.num_heads == 1 and seq >= self.flash_min_seq and F_ <= 192:
                 # scopes wider than one score tile: streaming-softmax kernel, the seq x seq logits stay in TMEM / shared memory
                 ldp = -(-seq // 8) * 8
                 vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
@@ -406,6 +406,10 @@ class TransformerCnnModel(_KernelModule):
     strict_background = os.environ.get("BBBP_STRICT_BACKGROUND", "1") != "0"
     strict_conv1_split = os.environ.get("BBBP_STRICT_CONV1_SPLIT", "1") != "0"
     strict_u8_exact = os.environ.get("BBBP_STRICT_U8_EXACT", "1") != "0"
+    # shortest attention scope that takes the streaming-softmax kernel (one launch instead of scores GEMM + P V GEMM).  Measured at
+    # the reference's batch 256 (16 384 molecules per step): 7.23 -> 7.17 ms strict, 5.95 -> 5.72 ms bf16; 257 restores the
+    # two-GEMM route for scopes that fit one score tile
+    flash_min_seq = int(os.environ.get("BBBP_FLASH_MIN_SEQ", "129"))
     fused_ffn = os.environ.get("BBBP_FUSED_FFN", "1") != "0"     # encoder feed-forward + norm2 as one kernel (widths <= 192)
     tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
     implicit_conv = os.environ.get("BBBP_IMPLICIT_CONV", "1") != "0"    # big variant: no im2col matrix for the 64 / 128-channel layers
