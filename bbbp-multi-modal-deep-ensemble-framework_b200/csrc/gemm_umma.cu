@@ -67,7 +67,10 @@ namespace gemm {
 using namespace sm100;
 
 constexpr int BM = 128, BK = 64;
-constexpr int THREADS = 256;
+// warps: 0 TMA producer, 1 MMA issue, 2 TMEM allocation, 3 idle, 4-11 epilogue.  TWO epilogue warps per TMEM lane quadrant
+// (quadrant = warp % 4) take alternate 32-column chunks: the epilogue is a serial, latency-bound walk over the tile's
+// columns, and for the encoder's K = 167 products it -- not the MMAs -- is the tile's critical path.
+constexpr int THREADS = 384;
 enum { EPI_LINEAR = 0, EPI_SOFTMAX = 1 };
 
 constexpr int MAX_STAGES = 4;
@@ -256,7 +259,9 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;  // TMEM lane quadrant == warp_id % 4
+    const int q = warp & 3;  // TMEM lane quadrant == warp_id % 4
+    const int half = (warp - 4) >> 2;   // which of the quadrant's two epilogue warps
+    if (EPI == EPI_SOFTMAX && half != 0) goto done;   // a softmax row is owned by ONE thread (three passes over its lane)
     mbar_wait(accum, 0);
     tc_fence_after_sync();
     const int row = m0 + q * 32 + lane;
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
       const bool alres = p.residual && p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && p.res_bs % 4 == 0;
       const float4* bias4 = reinterpret_cast<const float4*>(sBias);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n0 + c * 32;
         if (!p.partial && col0 >= max(p.N, p.out16 ? p.ld_out16 : 0)) break;
         uint32_t r[32];
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(const __grid_constan
       }
     }
   }
+done:
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) {
