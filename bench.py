@@ -42,6 +42,9 @@ CONV2_DRAM_BYTES_PER_MOL = (2.186054e9 + 1.046418e9) / 8192
 # ... and of its strict-mode instantiation (profiles/r02_ncu_conv.txt: 2.148330 GB + 1.042366 GB per 4 096-molecule launch);
 # algorithmic: (hi, lo) pairs in and out = 2 x (256 KiB + 128 KiB) = 786 432 B, i.e. no re-reads either
 CONV2_STRICT_DRAM_BYTES_PER_MOL = (2.148330e9 + 1.042366e9) / 4096
+# ... and of the background-referenced strict instantiation, one pass over single fp16 tensors (profiles/r02_ncu_conv_ffn_flash.txt:
+# 1.076648 GB + 0.506714 GB per 4 096-molecule launch = 386.6 KB per molecule against 393 216 B algorithmic: no re-reads)
+CONV2_BG_DRAM_BYTES_PER_MOL = (1.076648e9 + 0.506714e9) / 4096
 FWD_FLOP_PER_MOL = 207.2e6
 IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
 # the workload both arms run (identical dict in both JSON lines; per-arm sample sizes live outside it)
@@ -445,15 +448,17 @@ def main():
         # strict mode: ONE pass over background-referenced fp16 activations (model.strict_background, the default); its
         # first form carried (hi, lo) pairs through two MMAs per K step and twice the bytes
         passes = 2 if (args.precision == "strict" and not model.strict_background) else 1
-        traffic = (CONV2_STRICT_DRAM_BYTES_PER_MOL if passes == 2 else CONV2_DRAM_BYTES_PER_MOL) * statistics.mean(conv2_mols)
+        bg = args.precision == "strict" and model.strict_background
+        traffic = (CONV2_STRICT_DRAM_BYTES_PER_MOL if passes == 2 else CONV2_BG_DRAM_BYTES_PER_MOL if bg else
+                   CONV2_DRAM_BYTES_PER_MOL) * statistics.mean(conv2_mols)
         roof = {"kernel": "conv2 (3x3, 32->64, +bias+ReLU+maxpool) implicit GEMM", "bound": "tensor", "achieved": ach,
                 "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                 "traffic": traffic, "traffic_unit": "bytes/launch",
                 "traffic_source": ("ncu --set full of the pair-mode kernel (profiles/r02_ncu_conv.txt: tensor pipe 59 %, DRAM = the "
                                    "algorithmic bytes of the (hi, lo) pairs)" if passes == 2 else
-                                   "ncu --set full of the one-pass kernel (profiles/r01_ncu_conv_umma_full.txt; the background-referenced "
-                                   "strict instantiation moves the same 16-bit tensors + 0.5 KB of per-image tables, "
-                                   "profiles/r02_ncu_conv_bg.txt)") + ", scaled to this launch's molecules",
+                                   "ncu --set full of the background-referenced strict kernel (profiles/r02_ncu_conv_ffn_flash.txt: tensor "
+                                   "pipe 63 %, DRAM 1.58 GB per 4 096 molecules = the algorithmic bytes)" if bg else
+                                   "ncu --set full of the one-pass kernel (profiles/r01_ncu_conv_umma_full.txt)") + ", scaled to this launch's molecules",
                 "peak_source": pk["src"] + " bf16_tflops_sustained", "launch_ms": per_launch_ms,
                 "mma_passes": passes, "executed_tflops": ach * passes, "executed_frac": ach * passes / pk["tensor"],
                 "note": "achieved = ALGORITHMIC flops (151.0 MFLOP per molecule, SURVEY 8d) / CUDA-event time; executed_* multiplies by "
