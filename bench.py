@@ -58,6 +58,9 @@ E2E_CHUNK = 2048
 # lengths).  SPARSE=1 SCHEDULES=1 tools/e2e_sweep.py, strict, 16 384 molecules: equal chunks of 8 192 -> 7.68 ms, one chunk of
 # 16 384 -> 7.98, (2 048, 14 336) -> 7.27, (4 096, 12 288) -> 7.38, (2 048, 6 144, 8 192) -> 7.74 (profiles/r02_e2e_sweep_sparse_strict.txt)
 E2E_CHUNK_SPARSE = (2048, 14336)
+# four or more ranks share host bridges (tools/h2d_probe.py: 55 GB/s per GPU alone, 23-29 GB/s with 4-8 active), so the long second
+# chunk's copy (72 MB) no longer hides behind the first chunk's arithmetic: three chunks keep every copy shorter than the chunk before
+E2E_CHUNK_SPARSE_SHARED_LINK = (2048, 6144, 8192)
 DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (background-referenced activations, split small GEMMs, fp32 accumulate)"}
 
 
@@ -359,8 +362,10 @@ def main():
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
 
+    sparse_schedule = E2E_CHUNK_SPARSE_SHARED_LINK if world >= 4 else E2E_CHUNK_SPARSE
+
     def step_e2e_sparse():
-        _, s = model.predict_from_host(packed_host, sparse_host, BATCH, chunk_molecules=E2E_CHUNK_SPARSE, packed=True, out_host=scores_host,
+        _, s = model.predict_from_host(packed_host, sparse_host, BATCH, chunk_molecules=sparse_schedule, packed=True, out_host=scores_host,
                                        return_device=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
@@ -476,7 +481,7 @@ def main():
             "by_precision": by_precision,
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(sparse_bytes), "d2h_bytes_per_step": n * 4,
-                    "ms_per_step": ms_e2e_sparse / args.steps,
+                    "ms_per_step": ms_e2e_sparse / args.steps, "chunk_schedule": list(sparse_schedule),
                     "api": "model.predict_from_host(packed MACCS bits uint8, bbbp_b200.SparseDepictions, packed=True): pinned host -> "
                            "chunked H2D overlapped with [sparse decode to uint8 CHW + unpack + z-score + in-kernel image "
                            "normalisation + forward] -> D2H scores, readable in host memory when the call returns",
