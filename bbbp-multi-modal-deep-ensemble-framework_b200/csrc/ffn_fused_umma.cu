@@ -111,10 +111,12 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_layernorm_kernel(const __grid_
   uint64_t* w2_empty = bars + 6;       // 1
   uint64_t* s_full = bars + 7;         // [2]
   uint64_t* s_empty = bars + 9;        // [2]   (128 arrivals)
-  uint64_t* p_full = bars + 11;        // 1     (128 arrivals)
-  uint64_t* o_done = bars + 12;        // 1     second product of a block finished: P buffer free
-  uint64_t* o_full = bars + 13;        // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  // the 16-bit tile P is handed over in its two K-blocks (64 hidden units each): the second product of K-block 0 runs while
+  // the activation warps still write K-block 1, and the next block's K-block 0 may be written as soon as ITS reader has finished
+  uint64_t* p_full = bars + 11;        // [2]   (128 arrivals each)
+  uint64_t* o_done = bars + 13;        // [2]   second product has read K-block kk of P
+  uint64_t* o_full = bars + 15;        // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* sB2 = reinterpret_cast<float*>(base + sm.vec);      // every per-column vector the activation / epilogue threads need
   float* sGamma = sB2 + p.dn;                                //   lives in shared memory: read from global memory at their point
   float* sBeta = sGamma + p.dn;                              //   of use, each one cost an exposed L2 round trip per 16 columns
@@ -137,8 +139,10 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_layernorm_kernel(const __grid_
     }
     mbar_init(w2_full, 1);
     mbar_init(w2_empty, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_done, 1);
+    for (int kk = 0; kk < 2; ++kk) {
+      mbar_init(&p_full[kk], 128);
+      mbar_init(&o_done[kk], 1);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -175,20 +179,21 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_layernorm_kernel(const __grid_
     const uint32_t idesc_o = make_idesc_16(BM, (uint32_t)p.dn, p.fmt);
     const int last_steps = (p.d - (p.d_kb - 1) * KB + 15) / 16;       // K steps of 16 in the last K-block of the model width
     auto second = [&](int i) {
-      mbar_wait(p_full, i & 1);
       mbar_wait(w2_full, i & 1);
-      tc_fence_after_sync();
-      if (elect_one_sync()) {
-        const uint32_t a0 = smem_u32(sP), b0 = smem_u32(sW2);
-        for (int kk = 0; kk < 2; ++kk)
+      for (int kk = 0; kk < 2; ++kk) {
+        mbar_wait(&p_full[kk], i & 1);
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          const uint32_t a0 = smem_u32(sP), b0 = smem_u32(sW2);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
             umma_bf16(tmem_o, make_smem_desc(a0 + kk * TILE_B + k4 * 32, 0, 1024, kLayoutSw128),
                       make_smem_desc(b0 + kk * w2_kb + k4 * 32, 0, 1024, kLayoutSw128), idesc_o, (i | kk | k4) != 0);
-        umma_commit(w2_empty);
-        umma_commit(o_done);
+          umma_commit(&o_done[kk]);
+          if (kk == 1) umma_commit(w2_empty);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     };
     mbar_wait(x_full, 0);
     for (int j = 0; j < p.nb; ++j) {
@@ -242,7 +247,6 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_layernorm_kernel(const __grid_
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&s_empty[sb]);                          // the pre-activations are in registers: S[sb] may be overwritten
-      if (j > 0) mbar_wait(o_done, (j - 1) & 1);          // the second product of the previous block has read the P buffer
       // P = relu(S + b1), 16-bit, into the swizzled A-operand tile: 16-byte chunk c of row r at position c ^ (r % 8)
       const uint32_t bias = smem_u32(sB1 + sb * BH);                            // the same for every thread: broadcast loads
 #define BBBP_ACT_STORE(ARR, KK, CH0, COL0)                                                                 \
@@ -257,14 +261,19 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_layernorm_kernel(const __grid_
     }                                                                                                      \
     *reinterpret_cast<uint4*>(prow + (KK) * TILE_B + ((((CH0) + q) ^ swz) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]); \
   }
+      if (j > 0) mbar_wait(&o_done[0], (j - 1) & 1);      // the previous block's second product has read K-block 0 of P
       BBBP_ACT_STORE(s0, 0, 0, 0)
       BBBP_ACT_STORE(s1, 0, 4, 32)
+      fence_proxy_async_smem();                           // generic-proxy writes of P -> visible to tcgen05.mma
+      tc_fence_before_sync();
+      mbar_arrive(&p_full[0]);
+      if (j > 0) mbar_wait(&o_done[1], (j - 1) & 1);
       BBBP_ACT_STORE(s2, 1, 0, 64)
       BBBP_ACT_STORE(s3, 1, 4, 96)
 #undef BBBP_ACT_STORE
-      fence_proxy_async_smem();                           // generic-proxy writes of P -> visible to tcgen05.mma
+      fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[1]);
       sB1[(sb ^ 1) * BH + r] = b1_next;                   // (that buffer was last read in block j - 1: every thread is past it)
       named_bar_sync(1, 128);
     }

@@ -448,9 +448,17 @@ extern "C" int bbbp_fwd(const bbbp_model_desc* desc, const void* fingerprint, co
     RUN(gemm(m, R, 3 * Fq, F, x16, nullptr, Fq, d.w_in, nullptr, Fq, d.b_in, nullptr, 0, nullptr, 0, nullptr, 3 * Fq, w.qkv,
              nullptr, 3 * Fq, BBBP_ACT_NONE, 1, nullptr, 0, s));
     const void *q = w.qkv, *k = at16(w.qkv, Fq), *v = at16(w.qkv, 2 * Fq);
+    bool tail_done = false;
     if (m.heads == 1) {
       RUN(bbbp_transpose_bf16(groups, seq, F, v, 3 * Fq, (long long)seq * 3 * Fq, w.vt, w.ldp, (long long)F * w.ldp, s));
-      if (m.flash) {
+      if (m.flash && F <= 176) {
+        // streaming attention with out_proj + residual + norm1 fused into its tail (model.py: fused_attention_tail)
+        const int mid = cur ^ 1;
+        RUN(bbbp_attention_flash_proj_ln16(fmt, groups, seq, F, q, 3 * Fq, k, 3 * Fq, (long long)seq * 3 * Fq, w.vt, w.ldp,
+                                           (long long)F * w.ldp, scale, d.w_out, Fq, fparam(lp, L_OUT_B), x32, ldx,
+                                           fparam(lp, L_N1_W), fparam(lp, L_N1_B), kLnEps, w.x32[mid], Fq, w.x16[mid], Fq, s));
+        tail_done = true;
+      } else if (m.flash) {
         if (Fq > ceil16(F)) RUN(bbbp_fill_zero(at16(w.attn, ceil16(F)), R, (Fq - ceil16(F)) * 2ll, Fq * 2ll, s));
         RUN(bbbp_attention_flash16(fmt, groups, seq, F, q, 3 * Fq, k, 3 * Fq, (long long)seq * 3 * Fq, w.vt, w.ldp,
                                    (long long)F * w.ldp, scale, w.attn, Fq, (long long)seq * Fq, s));
@@ -463,11 +471,13 @@ extern "C" int bbbp_fwd(const bbbp_model_desc* desc, const void* fingerprint, co
     } else {
       RUN(bbbp_attention_heads16(fmt, w.qkv, 3 * Fq, Fq, 2 * Fq, w.attn, Fq, groups, seq, m.heads, m.head_dim, s));
     }
-    RUN(gemm(m, R, F, F, w.attn, nullptr, Fq, d.w_out, nullptr, Fq, fparam(lp, L_OUT_B), x32, ldx, nullptr, 0, w.sum32, Fq,
-             nullptr, nullptr, Fq, BBBP_ACT_NONE, 1, nullptr, 0, s));
     const int mid = cur ^ 1;
-    RUN(bbbp_add_layernorm_fwd_pitched16(fmt, w.sum32, Fq, nullptr, 0, fparam(lp, L_N1_W), fparam(lp, L_N1_B), w.x32[mid], Fq,
-                                         w.x16[mid], Fq, R, F, kLnEps, s));
+    if (!tail_done) {
+      RUN(gemm(m, R, F, F, w.attn, nullptr, Fq, d.w_out, nullptr, Fq, fparam(lp, L_OUT_B), x32, ldx, nullptr, 0, w.sum32, Fq,
+               nullptr, nullptr, Fq, BBBP_ACT_NONE, 1, nullptr, 0, s));
+      RUN(bbbp_add_layernorm_fwd_pitched16(fmt, w.sum32, Fq, nullptr, 0, fparam(lp, L_N1_W), fparam(lp, L_N1_B), w.x32[mid], Fq,
+                                           w.x16[mid], Fq, R, F, kLnEps, s));
+    }
     if (F <= 176) {     // linear1 + ReLU + linear2 + residual + norm2 in one kernel (the hidden activation stays on the chip)
       RUN(bbbp_ffn_layernorm16(fmt, R, F, kFF, w.x16[mid], Fq, d.w_l1, Fq, fparam(lp, L_L1_B), d.w_l2, kFF, fparam(lp, L_L2_B),
                                w.x32[mid], Fq, fparam(lp, L_N2_W), fparam(lp, L_N2_B), kLnEps, w.x32[cur], Fq, w.x16[cur], Fq, s));

@@ -316,11 +316,19 @@ class TransformerCnnModel(_KernelModule):
             w_in = ag.derived_weight(attn.in_proj_weight, f"qkv_pad16_{fmt}", padded_in_proj)
             b_in = ag.derived_weight(attn.in_proj_bias, "qkv_pad", padded_in_bias)
             _, qkv16 = ops.gemm_bf16(x16, F_, w_in, 3 * Fq, bias=b_in, out_f32=False, out_bf16=True, fmt=fmt)
+            fused_tail = False
             if attn.num_heads == 1 and seq >= self.flash_min_seq and F_ <= 192:
                 # scopes wider than one score tile: streaming-softmax kernel, the seq x seq logits stay in TMEM / shared memory
                 ldp = -(-seq // 8) * 8
                 vt = ops.transpose_bf16(qkv16[:, 2 * Fq:], groups, seq, F_, 3 * Fq, seq * 3 * Fq, ldp)
-                a16 = ops.attention_flash16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, vt, ldp, fmt=fmt, ld_out=Fq)
+                if self.fused_attention_tail and F_ <= 176:
+                    # ... with out_proj + residual + norm1 in the kernel's tail: the attention output never reaches HBM
+                    x32, x16 = ops.attention_flash_proj_ln16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, vt, ldp,
+                                                             w16(attn.out_proj.weight), attn.out_proj.bias, x32, layer.norm1.weight,
+                                                             layer.norm1.bias, layer.norm1.eps, ld_y=Fq, ld16=Fq, fmt=fmt)
+                    fused_tail = True
+                else:
+                    a16 = ops.attention_flash16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, vt, ldp, fmt=fmt, ld_out=Fq)
             elif attn.num_heads == 1:
                 p16 = ops.attention_scores_softmax_bf16(qkv16, qkv16[:, Fq:], 3 * Fq, groups, seq, F_, F_ ** -0.5, fmt=fmt)
                 ldp = p16.shape[1]
@@ -330,10 +338,11 @@ class TransformerCnnModel(_KernelModule):
             else:       # 256 heads x 8 (2048-bit fingerprints): warp-level MMA flash kernel on the packed qkv, 16-bit out
                 a16 = ops.attention_heads_bf16(qkv16, Fq, 2 * Fq, groups, seq, attn.num_heads, F_ // attn.num_heads, ld_out=Fq,
                                                fmt=fmt)
-            s32, _ = ops.gemm_bf16(a16, F_, w16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32,
-                                   ld_out=Fq, fmt=fmt)
-            x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,
-                                                 bf16_ld=Fq, fmt=fmt)
+            if not fused_tail:
+                s32, _ = ops.gemm_bf16(a16, F_, w16(attn.out_proj.weight), F_, bias=attn.out_proj.bias, residual=x32,
+                                       ld_out=Fq, fmt=fmt)
+                x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,
+                                                     bf16_ld=Fq, fmt=fmt)
             if self.fused_ffn and F_ <= 176 and layer.linear1.out_features % 128 == 0:
                 # linear1 + ReLU + linear2 + residual + norm2 in one kernel: the (rows, 2048) activation stays on the chip
                 x32, x16 = ops.ffn_layernorm16(x16, F_, w16(layer.linear1.weight), layer.linear1.bias, w16(layer.linear2.weight),
@@ -410,6 +419,7 @@ class TransformerCnnModel(_KernelModule):
     # the reference's batch 256 (16 384 molecules per step): 7.23 -> 7.17 ms strict, 5.95 -> 5.72 ms bf16; 257 restores the
     # two-GEMM route for scopes that fit one score tile
     flash_min_seq = int(os.environ.get("BBBP_FLASH_MIN_SEQ", "129"))
+    fused_attention_tail = os.environ.get("BBBP_FUSED_ATTENTION_TAIL", "1") != "0"   # out_proj + residual + norm1 in the flash kernel
     fused_ffn = os.environ.get("BBBP_FUSED_FFN", "1") != "0"     # encoder feed-forward + norm2 as one kernel (widths <= 192)
     tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
     implicit_conv = os.environ.get("BBBP_IMPLICIT_CONV", "1") != "0"    # big variant: no im2col matrix for the 64 / 128-channel layers

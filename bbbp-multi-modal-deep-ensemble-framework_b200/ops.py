@@ -295,6 +295,24 @@ def attention_flash16(q16, k16, ld, groups, seq, head_dim, scale, vt, ld_vt, fmt
     return out
 
 
+def attention_flash_proj_ln16(q16, k16, ld, groups, seq, head_dim, scale, vt, ld_vt, w_out16, b_out, residual, gamma, beta,
+                              eps=1e-5, ld_y=None, ld16=0, fmt=FMT_BF16):
+    """LayerNorm(residual + softmax(scale Q K^T) V W_out^T + b_out): the streaming attention kernel with out_proj + residual +
+    norm1 fused into its tail.  Returns ((groups*seq, ld_y) fp32, (groups*seq, ld16) 16-bit | None)."""
+    rows = groups * seq
+    ld_y = head_dim if ld_y is None else ld_y
+    y = torch.empty((rows, ld_y), device=q16.device, dtype=torch.float32)
+    y16 = torch.empty((rows, ld16), device=q16.device, dtype=_DT16[fmt]) if ld16 else None
+    t0 = KERNEL_TIMER.start("attn_flash")
+    check(lib.bbbp_attention_flash_proj_ln16(fmt, groups, seq, head_dim, q16.data_ptr(), ld, k16.data_ptr(), ld, seq * ld, vt.data_ptr(),
+                                             ld_vt, head_dim * ld_vt, float(scale), w_out16.data_ptr(), w_out16.stride(0),
+                                             b_out.data_ptr(), residual.data_ptr(), residual.stride(0), gamma.data_ptr(),
+                                             beta.data_ptr(), float(eps), y.data_ptr(), ld_y, _ptr(y16), ld16, _stream()),
+          "attention_flash_proj_ln16")
+    KERNEL_TIMER.stop("attn_flash", t0, rows)
+    return y, y16
+
+
 def transpose_bf16(src, batches, rows, cols, ld_src, src_bs, ld_dst):
     """(batches, rows, cols) pitched bf16 -> (batches, cols, ld_dst) with zero fill of columns >= rows."""
     dst = torch.empty((batches, cols, ld_dst), device=src.device, dtype=src.dtype)

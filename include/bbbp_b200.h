@@ -329,6 +329,18 @@ int bbbp_attention_heads_bf16(const void* qkv_bf16, int ld, int k_offset, int v_
 int bbbp_attention_flash16(int fmt, int groups, int seq, int head_dim, const void* q, int ldq, const void* k, int ldk,
                            long long group_stride, const void* v_t, int ld_vt, long long vt_group_stride, float scale, void* out,
                            int ld_out, long long out_group_stride, bbbp_stream_t stream);
+/* The same kernel with the REST of the attention half of a post-norm encoder layer fused into its tail (out_proj, + bias,
+ * + residual, norm1: nn.TransformerEncoderLayer via 20250113.py:75-78):
+ *   y[g*seq + r] = LayerNorm(residual[g*seq + r] + softmax(scale Q K^T) V  W_out^T + b_out) * gamma + beta
+ * After the last P V product the CTA writes O / l as a 16-bit operand into the dead Q tiles, fetches W_out (head_dim x head_dim,
+ * 16-bit, pitch ldw) into the dead K stages, runs one more product into the dead S columns of TMEM and normalises whole rows
+ * out of TMEM; the attention output never reaches HBM and three launches become one.  residual / y32: fp32 rows (pitches
+ * multiples of 4); y16 (may be NULL): 16-bit copy, columns [head_dim, ld_y16) zero, ld_y16 <= ceil16(head_dim).  head_dim <= 176. */
+int bbbp_attention_flash_proj_ln16(int fmt, int groups, int seq, int head_dim, const void* q, int ldq, const void* k, int ldk,
+                                   long long group_stride, const void* v_t, int ld_vt, long long vt_group_stride, float scale,
+                                   const void* w_out16, int ldw, const float* b_out, const float* residual, int ld_res,
+                                   const float* gamma, const float* beta, float eps, float* y32, int ld_y, void* y16, int ld_y16,
+                                   bbbp_stream_t stream);
 int bbbp_attention_heads16(int fmt, const void* qkv, int ld, int k_offset, int v_offset, void* out, int ld_out, int groups,
                            int seq, int heads, int head_dim, bbbp_stream_t stream);
 

@@ -1033,3 +1033,40 @@ def test_conv1_fused_with_64_output_channels(ops, N):
     assert y.shape == (N, 64, 64, 64) and y.dtype == torch.bfloat16
     ref = F.max_pool2d(F.relu(F.conv2d(img.bfloat16().double(), w.bfloat16().double(), b.double(), padding=1)), 2)
     close(y, ref.permute(0, 2, 3, 1).float(), atol=2e-2, rtol=1e-2, what="conv1 with 64 output channels")
+
+
+@pytest.mark.parametrize("groups,seq,d", [(2, 300, 167), (1, 129, 64), (3, 256, 167), (1, 1000, 176), (2, 40, 16)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_attention_flash_with_fused_projection_and_layernorm(ops, groups, seq, d, fmt):
+    """bbbp_attention_flash_proj_ln16 = LayerNorm(x + softmax(QK^T/sqrt(d)) V W_out^T + b_out): the attention half of a post-norm
+    encoder layer in one kernel, against the library's own three-launch route (flash + out_proj GEMM + LayerNorm: same 16-bit
+    rounding of the attention output) and against float64 on the same 16-bit operands."""
+    dt = torch.bfloat16 if fmt == 0 else torch.float16
+    ldq = -(-d // 8) * 8
+    rows = groups * seq
+    qkv = rnd(rows, 3 * ldq, seed=501, scale=0.8)
+    x = rnd(rows, d, seed=502)
+    w_out, b_out = rnd(d, d, seed=503, scale=d ** -0.5), rnd(d, seed=504, scale=0.1)
+    gamma, beta = 1.0 + rnd(d, seed=505, scale=0.1), rnd(d, seed=506, scale=0.1)
+    qkv16 = qkv.to(dt).cuda()
+    x32 = torch.zeros(rows, ldq)
+    x32[:, :d] = x
+    x32 = x32.cuda()
+    w16, _ = ops.cast16(w_out.cuda(), fmt)
+    ldp = -(-seq // 8) * 8
+    vt = ops.transpose_bf16(qkv16[:, 2 * ldq:], groups, seq, d, 3 * ldq, seq * 3 * ldq, ldp)
+    scale = d ** -0.5
+    y, y16 = ops.attention_flash_proj_ln16(qkv16, qkv16[:, ldq:], 3 * ldq, groups, seq, d, scale, vt, ldp, w16, b_out.cuda(), x32[:, :d],
+                                           gamma.cuda(), beta.cuda(), 1e-5, ld_y=ldq, ld16=ldq, fmt=fmt)
+    torch.cuda.synchronize()
+    a16 = ops.attention_flash16(qkv16, qkv16[:, ldq:], 3 * ldq, groups, seq, d, scale, vt, ldp, fmt=fmt, ld_out=ldq)
+    s32, _ = ops.gemm_bf16(a16, d, w16, d, bias=b_out.cuda(), residual=x32, ld_out=ldq, fmt=fmt)
+    y_ref, _ = ops.layernorm_fwd_pitched(s32, d, gamma.cuda(), beta.cuda(), 1e-5, ld_y=ldq, bf16_ld=ldq, fmt=fmt)
+    close(y[:, :d], y_ref[:, :d], atol=2e-5, rtol=2e-5, what="fused tail vs flash + GEMM + LayerNorm")
+    assert torch.equal(y16[:, :d].float(), y[:, :d].to(dt).float()) and y16.shape == (rows, ldq)
+    q = qkv16.cpu().double().view(groups, seq, 3 * ldq)
+    att = F.scaled_dot_product_attention(q[:, :, :d], q[:, :, ldq:ldq + d], q[:, :, 2 * ldq:2 * ldq + d]).reshape(rows, d)
+    ref = F.layer_norm(x.double() + att.float().to(dt).double() @ w_out.to(dt).double().t() + b_out.double(), (d,), gamma.double(),
+                       beta.double(), 1e-5).float()
+    tol = 3e-2 if fmt == 0 else 4e-3      # P and O / l are rounded to 16 bits inside the kernel
+    close(y[:, :d], ref, atol=tol, rtol=tol, what="fused attention tail vs float64")
