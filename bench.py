@@ -51,6 +51,9 @@ CONV1_OUT_BYTES_PER_MOL = 64 * 64 * 32 * 2
 # DRAM bytes per molecule of the uint8 / exact-integer instantiation (profiles/r02_ncu_conv_ffn_flash.txt: 0.203347 GB read +
 # 1.022220 GB written per 4 096-molecule launch = 299 KB against 311 296 B algorithmic)
 CONV1_U8_DRAM_BYTES_PER_MOL = (0.203347e9 + 1.022220e9) / 4096
+# ... and of the fp32-plane strict instantiation, (hi, lo) staging (profiles/r02_ncu_conv_fp32_planes.txt: 0.812390 GB + 1.032090 GB
+# per 4 096-molecule launch = 450 KB against 458 752 B algorithmic: no re-reads)
+CONV1_F32_DRAM_BYTES_PER_MOL = (0.812390e9 + 1.032090e9) / 4096
 FWD_FLOP_PER_MOL = 207.2e6
 IN_BYTES_PER_MOL = (F_BITS + IMG + 1) * 4
 # the workload both arms run (identical dict in both JSON lines; per-arm sample sizes live outside it)
@@ -485,9 +488,12 @@ def main():
         bytes1 = (IMG * 4 + CONV1_OUT_BYTES_PER_MOL) * statistics.mean(conv2_mols)
         gbs = bytes1 / (t1 * 1e-3) / 1e9
         roof1 = {"kernel": "conv1 (3x3, 3->32, +bias+ReLU+maxpool) implicit GEMM straight from the planar fp32 input", "bound": "hbm",
-                 "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
-                 "traffic_note": "not captured for the fp32-plane instantiation; the uint8 / exact-integer instantiation moves "
-                                 f"{CONV1_U8_DRAM_BYTES_PER_MOL:.0f} B per molecule against 311 296 B algorithmic (profiles/r02_ncu_conv_ffn_flash.txt)",
+                 "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                 "traffic": CONV1_F32_DRAM_BYTES_PER_MOL * statistics.mean(conv2_mols), "traffic_unit": "bytes/launch",
+                 "traffic_source": "ncu --set full of the strict-mode launch from fp32 planes (profiles/r02_ncu_conv_fp32_planes.txt: 450 KB "
+                                   "per molecule = the algorithmic bytes; one-pass modes move the same tensors), scaled to this launch's "
+                                   f"molecules; the uint8 / exact-integer instantiation moves {CONV1_U8_DRAM_BYTES_PER_MOL:.0f} B per molecule "
+                                   "against 311 296 B algorithmic (profiles/r02_ncu_conv_ffn_flash.txt)",
                  "peak_source": pk["src"] + " hbm_gbs", "launch_ms": t1, "share_of_step": sum(conv1_ms) / ms,
                  "note": "achieved = ALGORITHMIC bytes (196 608 B fp32 planes in + 262 144 B 16-bit NHWC out per molecule) / CUDA-event "
                          "time; the kernel is bound by its producers / epilogue warps, not by DRAM (DESIGN.md section 5b item 1)"}
