@@ -67,9 +67,8 @@ E2E_CHUNK = 2048
 # lengths).  SPARSE=1 SCHEDULES=1 tools/e2e_sweep.py, strict, 16 384 molecules: equal chunks of 8 192 -> 7.68 ms, one chunk of
 # 16 384 -> 7.98, (2 048, 14 336) -> 7.27, (4 096, 12 288) -> 7.38, (2 048, 6 144, 8 192) -> 7.74 (profiles/r02_e2e_sweep_sparse_strict.txt)
 E2E_CHUNK_SPARSE = (2048, 14336)
-# four or more ranks share host bridges (tools/h2d_probe.py: 55 GB/s per GPU alone, 23-29 GB/s with 4-8 active), so the long second
-# chunk's copy (72 MB) no longer hides behind the first chunk's arithmetic: three chunks keep every copy shorter than the chunk before
-E2E_CHUNK_SPARSE_SHARED_LINK = (2048, 6144, 8192)
+# (four ranks behind one host bridge, tools/gpu_r2_multi3.sh: (2 048, 14 336) 7.19 ms, (4 096, 12 288) 7.12, (2 048, 6 144, 8 192) 7.35
+# against 7.10 resident -- the schedule holds when ranks share a link, profiles/r02_e2e_schedules_n4.txt)
 DTYPE = {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "strict": "f16 (background-referenced activations, split small GEMMs, fp32 accumulate)"}
 
 
@@ -371,7 +370,9 @@ def main():
         if world > 1:
             dist.all_gather_into_tensor(gathered, s)
 
-    sparse_schedule = E2E_CHUNK_SPARSE_SHARED_LINK if world >= 4 else E2E_CHUNK_SPARSE
+    sparse_schedule = E2E_CHUNK_SPARSE
+    if os.environ.get("BBBP_E2E_SCHEDULE"):          # measurement override, e.g. "2048,14336"
+        sparse_schedule = tuple(int(c) for c in os.environ["BBBP_E2E_SCHEDULE"].split(","))
 
     def step_e2e_sparse():
         _, s = model.predict_from_host(packed_host, sparse_host, BATCH, chunk_molecules=sparse_schedule, packed=True, out_host=scores_host,
