@@ -41,7 +41,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libbbbp_b200.so")
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *sources(), "-ldl"]
+    # BBBP_NVCC_FLAGS: extra flags for measurement builds (e.g. -DBBBP_CONV1_PF_MERGED=3, the kernels' tuning macros)
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BBBP_NVCC_FLAGS", "").split(), "-o", tmp, *sources(), "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

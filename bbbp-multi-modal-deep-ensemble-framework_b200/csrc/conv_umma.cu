@@ -39,6 +39,9 @@ using namespace sm100;
 #ifndef BBBP_CONV1_PF
 #define BBBP_CONV1_PF 3
 #endif
+#ifndef BBBP_CONV1_PF_MERGED
+#define BBBP_CONV1_PF_MERGED 2     // prefetch depth of the (hi, lo) first-layer kernels (their conversion code needs more registers)
+#endif
 #ifndef BBBP_CONV1_PROD_WARPS
 #define BBBP_CONV1_PROD_WARPS 8
 #endif
@@ -489,7 +492,7 @@ conv3x3_umma_kernel(const void* __restrict__ src_any, const void* __restrict__ s
       // Register prefetch ring, PF tiles deep (loop unrolled by PF, no register copies): PF - 1 tile loads stay in flight
       // per CTA while tile i is converted and stored.  With the store warp in place the producers' global-load latency
       // is what the first layer waits for (cycle probe: producers 1 766 cycles per tile in "wait data").
-      constexpr int PF = BBBP_CONV1_PF;
+      constexpr int PF = C::MERGED ? BBBP_CONV1_PF_MERGED : BBBP_CONV1_PF;
       Vec buf[PF][TPT][CH];
       uint32_t okm[PF];
 #pragma unroll

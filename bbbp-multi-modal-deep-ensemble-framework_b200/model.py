@@ -53,6 +53,12 @@ def _stack_rows(parts):
     return out
 
 
+def _copy_scores(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst[:] = src for two contiguous float32 score vectors, through the library's copy kernel (no ATen kernel on the path)."""
+    from . import ops
+    ops.copy2d(src.reshape(1, -1), dst.reshape(1, -1))
+
+
 def _encoder(fingerprint_size: int, nhead: int, layers: int) -> nn.TransformerEncoder:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # "enable_nested_tensor is True, but ... batch_first was not True"
@@ -806,7 +812,7 @@ class TransformerCnnModel(_KernelModule):
             fp, img = slots[slot][0][: b - a], slots[slot][1][: b - a]
             encoded = (slots[slot][2][: b - a], slots[slot][3], slots[slot][4][: b - a + 1]) if sparse else None
             part = self._score_staged_chunk(slot, fp, img, batch_size, chunk, packed, encoded)
-            scores[a:b].copy_(part)
+            _copy_scores(scores[a:b], part)
             freed[slot] = torch.cuda.Event()
             freed[slot].record(compute)
         if out_host is None:
@@ -885,10 +891,10 @@ class TransformerCnnModel(_KernelModule):
         while start < full:
             stop = min(full, start + per_pass)
             y = self.forward_groups(fingerprint[start:stop], image[start:stop], (stop - start) // batch_size)
-            out[start:stop].copy_(y.reshape(-1))
+            _copy_scores(out[start:stop], y)
             start = stop
         if full < n:
-            out[full:].copy_(self.forward_groups(fingerprint[full:], image[full:], 1).reshape(-1))
+            _copy_scores(out[full:], self.forward_groups(fingerprint[full:], image[full:], 1))
         return out
 
 
