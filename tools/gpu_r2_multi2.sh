@@ -1,12 +1,12 @@
 #!/bin/bash
-# 8-GPU box: bench.py --gpus 8 (strict, sparse e2e) and the C ABI's NCCL exchanges on 8 and 2 ranks
+# G-GPU box: bench.py --gpus G (strict, sparse e2e) and the C ABI's NCCL exchanges on G ranks
 cd "$(dirname "$0")/.."
+G=${G:-$(nvidia-smi -L | wc -l)}
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 1000)) "${@:2}"; }
-run 8 bench.py --gpus 8 --steps 8 --warmup 3 2>gpurun_out/r2m_bench8.err | tail -1 > gpurun_out/r02_bench_n8.json
-python - <<'PY'
+run $G bench.py --gpus $G --steps 8 --warmup 3 2>gpurun_out/r2m_bench$G.err | tail -1 > gpurun_out/r02_bench_n$G.json
+python - <<PY
 import json
-d=json.load(open('gpurun_out/r02_bench_n8.json'))
+d=json.load(open('gpurun_out/r02_bench_n$G.json'))
 print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, 'e2e', d['e2e']['value'], 'dense', d['e2e_dense_u8']['value'], {k:(v['value'],v['e2e']) for k,v in d['by_precision'].items()})
 PY
-run 8 tools/comm_check.py 2>/dev/null | tail -1 | tee gpurun_out/r02_comm_check_n8.json
-run 2 tools/comm_check.py 2>/dev/null | tail -1 | tee gpurun_out/r02_comm_check_n2.json
+run $G tools/comm_check.py 2>/dev/null | tail -1 | tee gpurun_out/r02_comm_check_n$G.json
