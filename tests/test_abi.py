@@ -101,3 +101,24 @@ def test_whole_model_entry_points_reject_what_is_not_built():
     desc = c_host.make_desc(167, "bf16", 1, 32)
     assert lib.bbbp_fwd(ctypes.byref(desc), None, None, None, None, None, None, 0, None) == -1
     assert lib.bbbp_comm_gather_scores(None, None, None, 0, None) == -1
+
+
+def test_header_is_plain_c_and_the_c_host_example_compiles():
+    """include/bbbp_b200.h must be consumable by a C compiler (the drop-in boundary is a C ABI): gcc -std=c99 -fsyntax-only on
+    the header alone, and on tools/c_host_example.c (a complete C host of bbbp_fwd) when the CUDA runtime headers are present."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    probe = '#include "bbbp_b200.h"\nint main(void) { bbbp_model_desc d = {BBBP_ABI_VERSION, BBBP_MODEL_TCNN_20250113, 167, BBBP_PREC_STRICT, 1, 32, 0}; return d.seq == 32 ? 0 : 1; }\n'
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, "-x", "c", "-"], input=probe,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-I" + inc, "-I" + cuda_inc,
+                            os.path.join(root, "tools", "c_host_example.c")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
