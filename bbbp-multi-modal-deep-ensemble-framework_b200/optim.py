@@ -19,6 +19,13 @@ from ._lib import lib as _lib
 _CHUNK = _lib.bbbp_adamw_chunk()      # elements per CTA of the fused update
 
 
+def _zeros_like(p: torch.Tensor) -> torch.Tensor:
+    """Moment buffers zeroed by the library's fill kernel (contiguous CUDA parameters; anything else falls back to torch)."""
+    if p.is_cuda and p.is_contiguous():
+        return ops.fill_zero(torch.empty_like(p))
+    return torch.zeros_like(p, memory_format=torch.preserve_format)
+
+
 class AdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
@@ -71,8 +78,8 @@ class AdamW(torch.optim.Optimizer):
         for p in params:
             st = self.state[p]
             if "exp_avg" not in st:
-                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg"] = _zeros_like(p)
+                st["exp_avg_sq"] = _zeros_like(p)
         for sel in (lambda p: p, lambda p: p.grad, lambda p: self.state[p]["exp_avg"],
                     lambda p: self.state[p]["exp_avg_sq"]):
             ptrs += [sel(p).data_ptr() for p in params]
@@ -105,8 +112,8 @@ class AdamW(torch.optim.Optimizer):
                     raise RuntimeError("bbbp_b200.AdamW needs contiguous float32 CUDA parameters")
                 st = self.state[p]
                 if "exp_avg" not in st:
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg"] = _zeros_like(p)
+                    st["exp_avg_sq"] = _zeros_like(p)
             sizes, chunk_t, chunk_o = [], [], []
             for t, p in enumerate(params):
                 sizes.append(p.numel())
