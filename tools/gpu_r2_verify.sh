@@ -1,8 +1,9 @@
 #!/bin/bash
-# final check of the committed state: full GPU suite, smoke, both bench arms
+# check of the committed state: full GPU suite, smoke, (with "bench") both bench arms
 cd "$(dirname "$0")/.."
 timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 600 --timeout-method=thread 2>&1 | tee gpurun_out/r2v_tests.log | grep -E "passed|failed|FAILED|Error" | tail -20
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+[ "$1" == "bench" ] || exit 0
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_ref_n1.json 2>/dev/null
 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r2v_bench.err && python - <<'PY'
 import json
