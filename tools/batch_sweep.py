@@ -33,7 +33,8 @@ with torch.no_grad():
         ms = e0.elapsed_time(e1) / reps
         flop = B * (206.0e6 + 2 * 6 * 2 * B * 167)           # + the S = B attention term
         rows.append({"batch": B, "latency_ms": ms, "molecules_per_s": B / ms * 1e3, "tflops": flop / ms / 1e9,
-                     "attention": "QK^T GEMM with softmax epilogue" if B <= 256 else "streaming-softmax tcgen05 kernel (logits stay on chip)"})
+                     "attention": "QK^T GEMM with softmax epilogue + P V GEMM" if B < model.flash_min_seq else
+                     "streaming-softmax tcgen05 kernel with out_proj + norm1 in its tail (logits stay on chip)"})
         print(f"B={B:6d}  {ms:10.3f} ms  {B / ms * 1e3:12.0f} mol/s  {flop / ms / 1e9:8.1f} TFLOP/s  {rows[-1]['attention']}", flush=True)
         del fp, img, out
 os.makedirs("gpurun_out", exist_ok=True)
