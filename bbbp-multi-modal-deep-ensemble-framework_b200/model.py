@@ -349,7 +349,7 @@ class TransformerCnnModel(_KernelModule):
                                        ld_out=Fq, fmt=fmt)
                 x32, x16 = ops.layernorm_fwd_pitched(s32, F_, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, ld_y=Fq,
                                                      bf16_ld=Fq, fmt=fmt)
-            if self.fused_ffn and F_ <= 176 and layer.linear1.out_features % 128 == 0:
+            if self.fused_ffn and F_ <= 176 and layer.linear1.out_features % 128 == 0 and rows >= self.fused_ffn_min_rows:
                 # linear1 + ReLU + linear2 + residual + norm2 in one kernel: the (rows, 2048) activation stays on the chip
                 x32, x16 = ops.ffn_layernorm16(x16, F_, w16(layer.linear1.weight), layer.linear1.bias, w16(layer.linear2.weight),
                                                layer.linear2.bias, x32, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
@@ -426,7 +426,11 @@ class TransformerCnnModel(_KernelModule):
     # two-GEMM route for scopes that fit one score tile
     flash_min_seq = int(os.environ.get("BBBP_FLASH_MIN_SEQ", "129"))
     fused_attention_tail = os.environ.get("BBBP_FUSED_ATTENTION_TAIL", "1") != "0"   # out_proj + residual + norm1 in the flash kernel
-    fused_ffn = os.environ.get("BBBP_FUSED_FFN", "1") != "0"     # encoder feed-forward + norm2 as one kernel (widths <= 192)
+    fused_ffn = os.environ.get("BBBP_FUSED_FFN", "1") != "0"     # encoder feed-forward + norm2 as one kernel (widths <= 176)
+    # ... from this many rows up.  The fused kernel walks the 16 hidden blocks of a row tile serially (~42 us whatever the row
+    # count), yet a reference-sized call is still faster with it than with two GEMMs + LayerNorm (graph-replayed call at batch
+    # 32: 0.493 vs 0.525 ms, batch 256: 0.614 vs 0.657 ms with a threshold of 1 024), so the default is 0
+    fused_ffn_min_rows = int(os.environ.get("BBBP_FUSED_FFN_MIN_ROWS", "0"))
     tensor_core_train_min_batch = 64   # below this the training step is launch-latency-bound and keeps the fp32 kernels
     implicit_conv = os.environ.get("BBBP_IMPLICIT_CONV", "1") != "0"    # big variant: no im2col matrix for the 64 / 128-channel layers
     implicit_chunk = 1024   # images per pass when no im2col matrix is built (bounds the NHWC activations: 1.5 MB per image)

@@ -818,7 +818,7 @@ def test_sparse_depictions_decode_and_host_pipeline(cuda_device):
 
 @pytest.mark.parametrize("precision", ["strict", "fp16", "bf16"])
 @pytest.mark.parametrize("fp_dim,rows,groups,u8", [(167, 512, 2, False), (167, 96, 3, True), (167, 600, 1, False), (2048, 24, 2, True),
-                                                   (64, 40, 1, False)])
+                                                   (64, 40, 1, False), (167, 1280, 5, True)])
 def test_c_host_forward_is_bit_identical_to_the_python_host(cuda_device, precision, fp_dim, rows, groups, u8):
     """bbbp_fwd (csrc/model_fwd.cu: the whole eval forward of 20250113.py:109-119 orchestrated by the library for a host that
     is not Python) runs the same kernels with the same pitches and split-K factors as model.py: equal scores, bit for bit;
