@@ -2,14 +2,14 @@
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bbbp_b200
-from oracle import nets
+
 
 dev = torch.device("cuda:0")
 out = {}
 for prec in os.environ.get("PRECS", "fp32,bf16").split(","):
     for B in [int(b) for b in os.environ.get("BATCHES", "32,256").split(",")]:
         torch.manual_seed(0)
-        m = bbbp_b200.MixedInputModel(167, 128).to(dev); nets.zero_dropout(m); m.train().set_precision(prec)
+        m = bbbp_b200.MixedInputModel(167, 128).to(dev); bbbp_b200.zero_dropout(m); m.train().set_precision(prec)
         opt = bbbp_b200.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5); crit = bbbp_b200.MSELoss()
         fp, img, y = torch.randn(B, 167, device=dev), torch.randn(B, 49152, device=dev), torch.randn(B, device=dev)
 

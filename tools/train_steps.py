@@ -2,10 +2,10 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bbbp_b200
-from oracle import nets
+
 B = int(os.environ.get("B", 32)); STEPS = int(os.environ.get("STEPS", 4))
 dev = torch.device("cuda:0"); torch.manual_seed(0)
-m = bbbp_b200.MixedInputModel(167, 128).to(dev); nets.zero_dropout(m); m.train()
+m = bbbp_b200.MixedInputModel(167, 128).to(dev); bbbp_b200.zero_dropout(m); m.train()
 opt = bbbp_b200.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5); crit = bbbp_b200.MSELoss()
 fp, img, y = torch.randn(B, 167, device=dev), torch.randn(B, 49152, device=dev), torch.randn(B, device=dev)
 for i in range(STEPS):

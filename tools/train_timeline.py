@@ -3,12 +3,12 @@ longest kernels, to see which branch of the captured graph is the critical path.
 import os, sys, json, tempfile, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bbbp_b200
-from oracle import nets
+
 from torch.profiler import profile, ProfilerActivity
 
 B = int(os.environ.get("B", 32)); prec = os.environ.get("PREC", "fp32")
 dev = torch.device("cuda:0"); torch.manual_seed(0)
-m = bbbp_b200.MixedInputModel(167, 128).to(dev); nets.zero_dropout(m); m.train().set_precision(prec)
+m = bbbp_b200.MixedInputModel(167, 128).to(dev); bbbp_b200.zero_dropout(m); m.train().set_precision(prec)
 opt = bbbp_b200.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5); crit = bbbp_b200.MSELoss()
 fp, img, y = torch.randn(B, 167, device=dev), torch.randn(B, 49152, device=dev), torch.randn(B, device=dev)
 step = bbbp_b200.GraphedTrainStep(m, opt, crit, fork_image_branch=os.environ.get("FORK", "1") == "1")

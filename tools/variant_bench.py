@@ -25,9 +25,9 @@ for name, variant, F, img_dim, groups in [("Morgan-2048 canonical", "tcnn", 2048
         print(f"{name:24s} {prec}: {n} molecules in {ms:8.2f} ms = {n / ms * 1e3:10.0f} mol/s", flush=True)
     del m, fp, img
 # training step of the Morgan-2048 variant (BASELINE configs[2]: BCE loss, batch 32): eager loop body vs graph replay
-from oracle import nets
+
 torch.manual_seed(0)
-m = bbbp_b200.build("tcnn", 2048, 128).to(dev); nets.zero_dropout(m); m.train()
+m = bbbp_b200.build("tcnn", 2048, 128).to(dev); bbbp_b200.zero_dropout(m); m.train()
 opt = bbbp_b200.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5); crit = bbbp_b200.BCEWithLogitsLoss()
 fp, img, y = torch.randn(32, 2048, device=dev), torch.randn(32, 49152, device=dev), (torch.rand(32, device=dev) < 0.64).float()
 def eager():
